@@ -1,0 +1,96 @@
+#!/usr/bin/env python3
+"""Build a syntax-dumping copy of the reference's hooked HM-16.0 decoder (TEST INFRASTRUCTURE).
+
+Only runs where /root/reference exists (the build container).  It copies
+HM_16.0_features/{source,build} to a scratch directory, applies the minimal patch set
+listed in SURVEY.md section 0.5 (drop -Werror, drop system("pause"), replace the OpenCV
+block of TDecGop.cpp by a binary dump of TDecCu::{bits,MV,CUPU,Pred}), runs the
+reference's own linux makefiles on the copy and leaves the binary in oracle/_ref/.
+No reference source is copied into this repository.
+
+Dump record (little endian), one per slice/picture:
+    int32 poc, int32 nctu, then per CTU (raster order):
+        int32 bytes, int32 n_cupu, int32 n_pred, int32 n_mv,
+        int16 cupu[n_cupu], int16 pred[n_pred], int16 mv[n_mv]
+"""
+import os, re, shutil, subprocess, sys
+
+REF = "/root/reference/HM_16.0_features"
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "_ref")
+WORK = os.environ.get("HM_DUMP_WORK", "/tmp/hm_dump_build")
+
+DUMP = r'''
+  /* ---- syntax dump (replaces the reference's OpenCV saliency block) ---- */
+  {
+    static FILE* s_dump = NULL;
+    if (!s_dump) { const char* pth = getenv("HM_SYNTAX_DUMP"); s_dump = fopen(pth ? pth : "syntax_dump.bin", "wb"); }
+    int poc = pcSlice->getPOC();
+    int nctu = (int)rpcPic->getNumCUsInFrame();
+    fwrite(&poc, 4, 1, s_dump); fwrite(&nctu, 4, 1, s_dump);
+    for (int a = 0; a < nctu; a++) {
+      int hdr[4]; hdr[0] = (int)TDecCu::bits[a];
+      int n[3]; float* src[3] = { TDecCu::CUPU[a], TDecCu::Pred[a], TDecCu::MV[a] };
+      for (int s = 0; s < 3; s++) { n[s] = 0; while (src[s][n[s]] != 999) n[s]++; hdr[1+s] = n[s]; }
+      fwrite(hdr, 4, 4, s_dump);
+      for (int s = 0; s < 3; s++) for (int i = 0; i < n[s]; i++) { short v = (short)src[s][i]; fwrite(&v, 2, 1, s_dump); }
+    }
+    fflush(s_dump);
+  }
+}
+'''
+
+STATICS = r'''
+#include <stdio.h>
+#include <stdlib.h>
+float TDecCu::bits[LCUNUM] = {0};
+float TDecCu::MV[LCUNUM][1000] = {0};
+float TDecCu::CUPU[LCUNUM][1000] = {0};
+float TDecCu::Pred[LCUNUM][1000] = {0};
+extern Bool g_md5_mismatch;
+static Void calcAndPrintHashStatus(TComPicYuv& pic, const SEIDecodedPictureHash* pictureHashSEI);
+'''
+
+def main():
+    if not os.path.isdir(REF):
+        print("reference tree absent; nothing to build"); return 0
+    if os.path.isdir(WORK): shutil.rmtree(WORK)
+    os.makedirs(WORK)
+    for d in ("source", "build"):
+        shutil.copytree(os.path.join(REF, d), os.path.join(WORK, d))
+    subprocess.check_call(["chmod", "-R", "u+w", WORK])
+    # (i) -Werror
+    mb = os.path.join(WORK, "build/linux/common/makefile.base")
+    s = open(mb).read().replace("-Werror", ""); open(mb, "w").write(s)
+    # (ii) system("pause")
+    for f in ("source/App/TAppDecoder/TAppDecTop.cpp", "source/App/TAppDecoder/decmain.cpp"):
+        p = os.path.join(WORK, f); s = open(p, encoding="latin-1").read()
+        s = s.replace('system("pause");', ''); open(p, "w", encoding="latin-1").write(s)
+    # geometry macro: one binary for every resolution (only sizes static arrays)
+    p = os.path.join(WORK, "source/Lib/TLibDecoder/TDecCu.h")
+    s = open(p, encoding="latin-1").read()
+    s = re.sub(r"#define LCUNUM\s+\d+", "#define LCUNUM 2100", s); open(p, "w", encoding="latin-1").write(s)
+    # (iii) TDecGop.cpp: keep 1-46, 119-224, 337-end (1-based)
+    p = os.path.join(WORK, "source/Lib/TLibDecoder/TDecGop.cpp")
+    L = open(p, encoding="latin-1").read().replace("\r", "").lstrip("﻿").lstrip("\xef\xbb\xbf").split("\n")
+    head = [l for l in L[:46] if "Math.h" not in l]
+    mid = L[118:224]
+    tail = L[336:472]
+    # drop prototypes of the removed OpenCV helpers from the middle block
+    mid = [l for l in mid if "Mat" not in l and "vote_alg" not in l and "Umean" not in l
+           and "MergeSort" not in l and "Merge(" not in l and "MeanArry" not in l
+           and "int max(int" not in l and "g_md5_mismatch" not in l
+           and not l.startswith("static Void calcAndPrintHashStatus")]
+    out = "\n".join(head) + "\n#include <math.h>\n" + STATICS + "\n".join(mid) + DUMP + "\n".join(tail) + "\n"
+    open(p, "w", encoding="latin-1").write(out)
+    env = dict(os.environ)
+    for lib in ("TLibVideoIO", "TLibCommon", "TLibDecoder", "TAppCommon"):
+        subprocess.check_call(["make", "-j8", "-C", os.path.join(WORK, "build/linux/lib", lib), "release"], env=env)
+    subprocess.check_call(["make", "-C", os.path.join(WORK, "build/linux/app/TAppDecoder"), "release"], env=env)
+    os.makedirs(OUT, exist_ok=True)
+    shutil.copy(os.path.join(WORK, "bin/TAppDecoderStatic"), os.path.join(OUT, "hm_syntax_dump"))
+    print("built", os.path.join(OUT, "hm_syntax_dump"))
+    return 0
+
+if __name__ == "__main__":
+    sys.exit(main())
