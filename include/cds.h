@@ -82,7 +82,9 @@ int cds_getframe_dev(int w, int h, int nframes, const int32_t* hdr, const int16_
 
 /* Synthetic syntax producer (stands in for HM CABAC parsing in throughput runs).
  * Fills hdr[nctu*4], tok (capacity tok_cap int16), ctu_bytes[nctu] for picture `poc` of the clip
- * identified by `seed`.  Returns the number of tokens written or <0. */
+ * identified by `seed`.  Seed bit 60 selects adversarial statistics (deep trees, many intra / NxN /
+ * AMP CUs, small MVs that collide with PU labels) used by the differential fuzz tests.
+ * Returns the number of tokens written or <0. */
 long cds_synth_frame(int w, int h, uint64_t seed, int poc, int32_t* hdr, int16_t* tok, size_t tok_cap,
                      uint16_t* ctu_bytes);
 
@@ -157,6 +159,10 @@ int cds_clip_process(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* c
                      void* maps_out, int* cam_out);
 /* Drop all temporal state (start a new clip). */
 int cds_reset(cds_ctx* ctx);
+/* Measure this device's issue ceilings with micro-kernels (lane-instructions per second): the
+ * contrast kernel's FADD+FFMA pair mix, pure FFMA, and MUFU.EX2.  Used as roofline denominators
+ * for the FP32/MUFU-bound kernels (MEASURED_PEAKS.json has only HBM and bf16 tensor numbers). */
+int cds_measure_peaks(double* fp32_pair_ips, double* ffma_ips, double* mufu_ips);
 /* Number of kernel launches issued by this library since the last call (bench bookkeeping). */
 long cds_take_launch_count(void);
 

@@ -1,0 +1,107 @@
+"""CPU-only: pin the oracle (oracle/cds_oracle.c) against the reference's golden vectors and, where
+oracle/_ref exists (the reference's own sources compiled in the build container), against the
+reference code itself."""
+import numpy as np
+import pytest
+
+import _oracle as o
+
+GOLDEN = ["BasketballDrill", "BasketballDrive"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_getframe_oracle_matches_authors_golden_mat(name):
+    d = np.load(f"{o.ROOT}/tests/golden/stage_a_{name}.npz")
+    w, h = int(d["w"]), int(d["h"])
+    for f in range(len(d["pocs"])):
+        tok = d["tok"][d["tok_base"][f]:d["tok_base"][f + 1]]
+        mx, my, dp = o.orc_getframe(w, h, d["hdr"][f], tok)
+        assert np.array_equal(mx, d["mvx"][f]), (name, int(d["pocs"][f]))
+        assert np.array_equal(my, d["mvy"][f])
+        assert np.array_equal(dp, d["depth"][f])
+        assert np.array_equal(d["ctu_bytes"][f].reshape(d["bitmap"][f].shape), d["bitmap"][f])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_reference_getframe_matches_golden(name):
+    d = np.load(f"{o.ROOT}/tests/golden/stage_a_{name}.npz")
+    w, h = int(d["w"]), int(d["h"])
+    if o.ref(f"getframe_{w}x{h}") is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for f in range(min(3, len(d["pocs"]))):
+        tok = d["tok"][d["tok_base"][f]:d["tok_base"][f + 1]]
+        mx, my, dp = o.ref_getframe(w, h, d["hdr"][f], tok)
+        assert np.array_equal(mx, d["mvx"][f]) and np.array_equal(my, d["mvy"][f]) and np.array_equal(dp, d["depth"][f])
+
+
+@pytest.mark.parametrize("wh", [(416, 240), (832, 480), (1280, 800), (1920, 1080)])
+@pytest.mark.parametrize("adv", [0, 1])
+def test_getframe_oracle_vs_verbatim_reference_fuzz(wh, adv):
+    w, h = wh
+    if o.ref(f"getframe_{w}x{h}") is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from compressd_domain_saliencyprediction_b200 import ops
+    for poc in (0, 1, 5):
+        hdr, tok, _ = ops.synth_frame(w, h, 99 + (adv << 60), poc)
+        mx, my, dp = o.orc_getframe(w, h, hdr, tok)
+        r = o.ref_getframe(w, h, hdr, tok)
+        assert np.array_equal(mx, r[0]) and np.array_equal(my, r[1]) and np.array_equal(dp, r[2])
+
+
+def _rand_map(rng, rows, cols, signed):
+    a = rng.standard_normal((rows, cols)) if signed else rng.uniform(0, 1, (rows, cols))
+    a[rng.uniform(size=a.shape) < 0.1] = a.min() if signed else 0.0   # ties at the minimum -> exact zeros after pm_norm
+    return a
+
+
+@pytest.mark.parametrize("case", [(23, 31, 11.0, 1, 48, True), (20, 17, 13.0, 2, 48, False), (9, 12, 3.0, 16, 80, False)])
+def test_contrast_oracle_vs_verbatim_reference(case):
+    rows, cols, delta, cusize, patch, signed = case
+    if o.ref("contrast") is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(5)
+    a = _rand_map(rng, rows, cols, signed)
+    pad, W, ln, win = o.sudoku_inputs(a, delta, cusize, patch)
+    # MATLAB view: the map is m x n = rows x cols
+    got = o.orc_computecontrast5(pad, W, ln, win, rows, cols)
+    want = o.ref_computecontrast5(pad, W, ln, win, rows, cols)
+    assert np.array_equal(got, want)      # same arithmetic, same order -> identical doubles
+    # the row-major Sudoku restatement must agree with the mex-level composition
+    sud = o.orc_sudoku(a, delta, cusize, patch)
+    np.testing.assert_allclose(sud, want / want.max(), rtol=1e-12, atol=0)
+
+
+def test_contrast_constant_map_gives_nan_like_reference():
+    a = np.zeros((12, 14))
+    with np.errstate(all="ignore"):
+        out = o.orc_cu_contrast5(a, 1, 11.0, 48)
+    assert np.isnan(out).all()          # 0/0, then main.m:237-238 turns NaN into 0
+
+
+def test_cu_contrast5_block_mean_and_replication():
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 1, (21, 27))
+    out = o.orc_cu_contrast5(a, 4, 3.0, 20)
+    assert out.shape == a.shape and abs(out.max() - 1.0) < 1e-12
+    assert np.all(out[0:4, 0:4] == out[0, 0]) and np.all(out[20:21, 24:27] == out[20, 24])
+
+
+@pytest.mark.parametrize("nsv,nfeat", [(300, 9), (130, 13)])
+def test_svm_oracle_vs_reference_libsvm(nsv, nfeat):
+    if o.ref("svm") is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    SV, coef, rho, gamma, labels = o.synth_model(nsv, nfeat)
+    SV[::7, 2] = 0.0                       # zeros are dropped from the sparse SV rows like MATLAB does
+    X = np.random.default_rng(1).standard_normal((500, nfeat))
+    dec, lab = o.orc_svm_predict(SV, coef, rho, gamma, labels, X)
+    rdec, rlab = o.ref_svm_predict(SV, coef, rho, gamma, labels, X)
+    assert np.array_equal(dec, rdec) and np.array_equal(lab, rlab)
+
+
+def test_svm_heart_scale_known_answer():
+    """libsvm-3.17/matlab/README:179-181: svm-train -c 1 -g 0.07 heart_scale -> 86.6667 % (234/270)."""
+    d = np.load(f"{o.ROOT}/tests/golden/svm_heart_scale.npz")
+    dec, lab = o.orc_svm_predict(d["SV"], d["coef"], float(d["rho"]), float(d["gamma"]), d["labels"], d["X"])
+    assert d["SV"].shape[0] == 130
+    assert int((lab == d["y"]).sum()) == 234
+    assert np.array_equal(dec, d["dec_ref"])
