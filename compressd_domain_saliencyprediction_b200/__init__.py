@@ -6,5 +6,6 @@ runs in libcds_b200.so.  There is no CPU fallback: calls raise CdsError without 
 """
 from ._lib import CdsError, lib, lib_path, device_ok, take_launch_count  # noqa: F401
 from . import ops  # noqa: F401
+from .saliency import SaliencyClip  # noqa: F401
 
-__all__ = ["CdsError", "lib", "lib_path", "device_ok", "take_launch_count", "ops"]
+__all__ = ["CdsError", "lib", "lib_path", "device_ok", "take_launch_count", "ops", "SaliencyClip"]

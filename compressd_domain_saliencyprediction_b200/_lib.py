@@ -50,6 +50,9 @@ def _declare(L):
         "cds_clip_process": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, sz, c_p, c_p]),
         "cds_reset": (i32, [c_p]),
         "cds_measure_peaks": (i32, [c_p, c_p, c_p]),
+        "cds_seek": (i32, [c_p, i32]),
+        "cds_clip_context_dev": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, c_p]),
+        "cds_debug_copy": (i32, [c_p, C.c_char_p, i32, c_p, sz]),
     }
     missing = []
     for name, (res, args) in sig.items():

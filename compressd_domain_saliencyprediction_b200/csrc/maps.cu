@@ -1,0 +1,538 @@
+// maps.cu — stage (e): normalisation, smoothing, temporal difference, replicate+Gaussian, resize.
+//
+// Replaces main.m:144-257 and 275-305 with upsample.m, fourX2.m, pm_norm.m, mysterythrehold.m,
+// immove.m, getdistMatrix.m and MATLAB's imfilter/fspecial/imresize as used there.  The MATLAB code
+// materialises nine H x W double maps per frame; here
+//   * fourX2 + imfilter(gaussian) is evaluated as a polyphase filter on the h/4 x w/4 map (each
+//     full-res sample is a <=k/4+1 tap combination of cells), horizontal pass to an (h/4 x W)
+//     intermediate, vertical pass straight into min/max/sum reductions (pm_norm needs only those);
+//   * imresize(pm_norm(Y),[200 200]) is affine in imresize(Y) (weights sum to 1), and
+//     imresize(imfilter(fourX2(X))) is one composite banded operator applied to X, so the six
+//     non-temporal features never exist at full resolution;
+//   * the three temporal features need a clamp at full resolution (mysterythrehold, main.m:255-257)
+//     and are the only maps stored at H x W;
+//   * every global reduction (pm_norm min/max, mysterythrehold sums) is block partials + a
+//     deterministic finalize, so results do not depend on scheduling.
+// All of these passes are bandwidth/latency class (HBM / L2), not FLOP class.
+#include "maps.cuh"
+#include <math.h>
+
+namespace cds {
+
+// =================================================================================================
+// host-side operator construction (double precision, once per context)
+// =================================================================================================
+static double matlab_round(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); }
+
+static std::vector<double> gauss1d(int k, double sigma) {   // fspecial('gaussian',k,sigma) is separable: normalised 1-D factor
+  std::vector<double> g(k);
+  const double siz = (k - 1) / 2.0; double s = 0;
+  for (int i = 0; i < k; i++) { const double x = i - siz; g[i] = exp(-(x * x) / (2 * sigma * sigma)); s += g[i]; }
+  for (int i = 0; i < k; i++) g[i] /= s;
+  return g;
+}
+
+void build_gauss_polyphase(int k, double sigma, Polyphase* out) {
+  const std::vector<double> g = gauss1d(k, sigma);
+  const int c0 = (k + 1) / 2 - 1;                         // imfilter origin: floor((k+1)/2), 1-based
+  auto fdiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+  const int dmin = fdiv(0 - c0, 4), dmax = fdiv(3 + k - 1 - c0, 4);
+  out->dmin = dmin; out->nt = dmax - dmin + 1;
+  std::vector<double> acc((size_t)out->nt * 4, 0.0);
+  for (int ph = 0; ph < 4; ph++)
+    for (int u = 0; u < k; u++) { const int d = fdiv(ph + u - c0, 4); acc[(size_t)(d - dmin) * 4 + ph] += g[u]; }
+  out->g.resize(acc.size());
+  for (size_t i = 0; i < acc.size(); i++) out->g[i] = (float)acc[i];
+}
+
+std::vector<double> dense_gauss_rep4(int n_cells, int k, double sigma) {
+  const std::vector<double> g = gauss1d(k, sigma);
+  const int c0 = (k + 1) / 2 - 1, n = 4 * n_cells;
+  std::vector<double> A((size_t)n * n_cells, 0.0);
+  for (int y = 0; y < n; y++)
+    for (int u = 0; u < k; u++) { const int s = y + u - c0; if (s >= 0 && s < n) A[(size_t)y * n_cells + s / 4] += g[u]; }
+  return A;
+}
+
+std::vector<double> dense_gauss(int n, int k, double sigma) {
+  const std::vector<double> g = gauss1d(k, sigma);
+  const int c0 = (k + 1) / 2 - 1;
+  std::vector<double> A((size_t)n * n, 0.0);
+  for (int y = 0; y < n; y++)
+    for (int u = 0; u < k; u++) { const int s = y + u - c0; if (s >= 0 && s < n) A[(size_t)y * n + s] += g[u]; }
+  return A;
+}
+
+// MATLAB imresize 'bilinear' contributions(): triangle kernel, widened by 1/scale when shrinking,
+// weights normalised to 1, symmetric boundary indices aux = [1:n, n:-1:1].
+std::vector<double> dense_imresize(int n_in, int n_out) {
+  const double scale = (double)n_out / n_in;
+  double kw = 2.0; const bool aa = scale < 1;
+  if (aa) kw /= scale;
+  const int P = (int)ceil(kw) + 2;
+  std::vector<double> A((size_t)n_out * n_in, 0.0);
+  std::vector<double> wt(P);
+  for (int x = 1; x <= n_out; x++) {
+    const double u = x / scale + 0.5 * (1 - 1 / scale);
+    const int left = (int)floor(u - kw / 2);
+    double s = 0;
+    for (int p = 0; p < P; p++) {
+      double t = u - (left + p);
+      if (aa) t *= scale;
+      double v = (t >= -1 && t < 0) ? t + 1 : (t >= 0 && t <= 1) ? 1 - t : 0;
+      if (aa) v *= scale;
+      wt[p] = v; s += v;
+    }
+    for (int p = 0; p < P; p++) {
+      const int mm = 2 * n_in;
+      const int q = (((left + p - 1) % mm) + mm) % mm;
+      const int idx = q < n_in ? q : mm - 1 - q;
+      A[(size_t)(x - 1) * n_in + idx] += wt[p] / s;
+    }
+  }
+  return A;
+}
+
+std::vector<double> dense_mul(const std::vector<double>& A, int ar, int ac, const std::vector<double>& B, int bc) {
+  std::vector<double> C((size_t)ar * bc, 0.0);
+  for (int i = 0; i < ar; i++)
+    for (int k = 0; k < ac; k++) {
+      const double a = A[(size_t)i * ac + k];
+      if (a == 0) continue;
+      const double* b = &B[(size_t)k * bc]; double* c = &C[(size_t)i * bc];
+      for (int j = 0; j < bc; j++) c[j] += a * b[j];
+    }
+  return C;
+}
+
+void banded_from_dense(const std::vector<double>& A, int n_out, int n_in, Banded* out) {
+  out->n_out = n_out; out->n_in = n_in; out->start.assign(n_out, 0);
+  int nt = 1;
+  std::vector<int> lo(n_out, 0), hi(n_out, 0);
+  for (int i = 0; i < n_out; i++) {
+    int l = -1, h = -1;
+    for (int j = 0; j < n_in; j++) if (A[(size_t)i * n_in + j] != 0) { if (l < 0) l = j; h = j; }
+    if (l < 0) { l = 0; h = 0; }
+    lo[i] = l; hi[i] = h; if (h - l + 1 > nt) nt = h - l + 1;
+  }
+  out->nt = nt; out->w.assign((size_t)n_out * nt, 0.f);
+  for (int i = 0; i < n_out; i++) {
+    out->start[i] = lo[i];
+    for (int j = lo[i]; j <= hi[i]; j++) out->w[(size_t)i * nt + (j - lo[i])] = (float)A[(size_t)i * n_in + j];
+  }
+}
+
+int Banded::upload() {
+  CDS_CUDA(cudaMalloc(&d_w, w.size() * 4));
+  CDS_CUDA(cudaMalloc(&d_start, start.size() * 4));
+  CDS_CUDA(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  CDS_CUDA(cudaMemcpy(d_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+  return CDS_OK;
+}
+void Banded::release() { if (d_w) cudaFree(d_w); if (d_start) cudaFree(d_start); d_w = nullptr; d_start = nullptr; }
+int Polyphase::upload() {
+  CDS_CUDA(cudaMalloc(&d_g, g.size() * 4));
+  CDS_CUDA(cudaMemcpy(d_g, g.data(), g.size() * 4, cudaMemcpyHostToDevice));
+  return CDS_OK;
+}
+void Polyphase::release() { if (d_g) cudaFree(d_g); d_g = nullptr; }
+
+// =================================================================================================
+// block reductions (deterministic: fixed tree)
+// =================================================================================================
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T* red, Op op) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  T r = red[0];
+  for (int i = 1; i < nw; i++) r = op(r, red[i]);
+  return r;
+}
+struct OpMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct OpAddI { __device__ int operator()(int a, int b) const { return a + b; } };
+
+// =================================================================================================
+// smoothing: causal mean over the last PS pictures (main.m:144-165)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+smooth_kernel(int n4, int PS, int RL, int first_poc, const float* __restrict__ Vx, const float* __restrict__ Vy,
+              const float* __restrict__ mvn, const float* __restrict__ bitn, const float* __restrict__ depn,
+              float* __restrict__ mvx_s, float* __restrict__ mvy_s, float* __restrict__ bit_s, float* __restrict__ dep_s,
+              float* __restrict__ mv_s) {
+  const int o = blockIdx.x * 256 + threadIdx.x, f = blockIdx.y;
+  if (o >= n4) return;
+  const int poc = first_poc + f;
+  const int cnt = min(PS, poc + 1);
+  float a = 0.f, b = 0.f, c = 0.f, d = 0.f, e = 0.f;
+  for (int ii = poc - cnt + 1; ii <= poc; ii++) {                 // ascending, like the reference loop
+    const size_t s = (size_t)(ii % RL) * n4 + o;
+    a += mvn[s]; b += Vx[s]; c += Vy[s]; d += bitn[s]; e += depn[s];
+  }
+  const float fc = (float)cnt;
+  const size_t so = (size_t)(poc % RL) * n4 + o;
+  mv_s[(size_t)f * n4 + o] = a / fc; mvx_s[so] = b / fc; mvy_s[so] = c / fc; bit_s[so] = d / fc; dep_s[so] = e / fc;
+}
+
+int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const float* Vx, const float* Vy, const float* mvn,
+                  const float* bitn, const float* depn, float* mvx_s, float* mvy_s, float* bit_s, float* dep_s, float* mv_s,
+                  cudaStream_t st) {
+  dim3 grid(ceil_div(n4, 256), B);
+  smooth_kernel<<<grid, 256, 0, st>>>(n4, PS, ring_len, first_poc, Vx, Vy, mvn, bitn, depn, mvx_s, mvy_s, bit_s, dep_s, mv_s);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// =================================================================================================
+// mysterythrehold.m:3-7 on the smoothed h4 x w4 maps (main.m:170-172).  One CTA per (picture, map).
+// =================================================================================================
+__global__ void __launch_bounds__(1024)
+myst_small_kernel(int n4, double inv_hw, int RL, int first_poc, const float* __restrict__ mv_s,
+                  const float* __restrict__ bit_ring, const float* __restrict__ dep_ring, float* __restrict__ Xmaps) {
+  __shared__ float redf[32];
+  __shared__ double redd[32];
+  __shared__ int redi[32];
+  const int f = blockIdx.x, which = blockIdx.y;       // 0 mv, 1 bit, 2 depth
+  const size_t slot = (size_t)((first_poc + f) % RL) * n4;
+  const float* __restrict__ src = which == 0 ? mv_s + (size_t)f * n4 : which == 1 ? bit_ring + slot : dep_ring + slot;
+  float* __restrict__ dst = Xmaps + ((size_t)f * 9 + which * 3) * n4;
+  double s = 0; float mx = -INFINITY;
+  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[o]; s += v; mx = fmaxf(mx, v); }
+  s = block_reduce(s, redd, OpAddD());
+  mx = block_reduce(mx, redf, OpMax());
+  const float lim = mx - (float)(s * inv_hw);                     // max - ave, ave over im_height*im_width (:3-4)
+  double sb = 0; int nb = 0;
+  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[o]; if (v > lim) { sb += v; nb++; } }
+  sb = block_reduce(sb, redd, OpAddD());
+  nb = block_reduce(nb, redi, OpAddI());
+  const float thresh = nb > 0 ? (float)(sb / nb) : NAN;           // :5
+  const float M = nb > 0 ? fminf(thresh, mx) : mx;                // max after the clamp
+  const float inv = 1.f / (M + 0.000001f);                        // :7
+  for (int o = threadIdx.x; o < n4; o += 1024) { float v = src[o]; if (v > thresh) v = thresh; dst[o] = v * inv; }
+}
+
+int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float* bit_s_ring,
+                      const float* dep_s_ring, float* Xmaps, cudaStream_t st) {
+  dim3 grid(B, 3);
+  myst_small_kernel<<<grid, 1024, 0, st>>>(n4, 1.0 / ((double)H * W), ring_len, first_poc, mv_s, bit_s_ring, dep_s_ring, Xmaps);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// =================================================================================================
+// temporal difference with accumulated camera motion (main.m:174-199, immove.m)
+// grid: x = picture in batch (fast, so the pictures that share ring data run together), y = cell tile
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float* __restrict__ mvx_s, const float* __restrict__ mvy_s,
+                const float* __restrict__ bit_s, const float* __restrict__ dep_s, const int* __restrict__ cam,
+                const float* __restrict__ wtab /*[PT][4]: exp(-j/26), exp(-j/46), exp(-j/46)*/, float* __restrict__ Xmaps) {
+  const int f = blockIdx.x, n4 = h4 * w4;
+  const int o = blockIdx.y * 256 + threadIdx.x;
+  if (o >= n4) return;
+  const int r = o / w4, c = o - r * w4;
+  const int poc = first_poc + f;
+  const size_t cur = (size_t)(poc % RL) * n4 + o;
+  const float rx = mvx_s[cur], ry = mvy_s[cur], rb = bit_s[cur], rd = dep_s[cur];
+  float am = 0.f, ab = 0.f, ad = 0.f;
+  int camX = 0, camY = 0;
+  const int jmax = min(PT - 1, poc);
+  for (int j = 1; j <= jmax; j++) {
+    const int cs = ((poc - j + 1) % RL) * 2;
+    camX += cam[cs]; camY += cam[cs + 1];                          // :189-190
+    const int sx = camX >= 0 ? (camX + 2) >> 2 : -((-camX + 2) >> 2);   // round(camX/4), half away from zero
+    const int sy = camY >= 0 ? (camY + 2) >> 2 : -((-camY + 2) >> 2);
+    const int sr = r - sy, sc = c - sx;                            // immove: +x moves content right, +y down, zero fill
+    float tx = 0.f, ty = 0.f, tb = 0.f, td = 0.f;
+    if (sr >= 0 && sr < h4 && sc >= 0 && sc < w4) {
+      const size_t s = (size_t)((poc - j) % RL) * n4 + (size_t)sr * w4 + sc;
+      tx = mvx_s[s]; ty = mvy_s[s]; tb = bit_s[s]; td = dep_s[s];
+    }
+    const float4 wj = *reinterpret_cast<const float4*>(wtab + 4 * j);
+    const float dx = rx - tx, dy = ry - ty;
+    am = fmaf(wj.x, sqrtf(fmaf(dx, dx, dy * dy)), am);            // :195
+    ab = fmaf(wj.y, fabsf(rb - tb), ab);                           // :196
+    ad = fmaf(wj.z, fabsf(rd - td), ad);                           // :197
+  }
+  float* X = Xmaps + (size_t)f * 9 * n4 + o;
+  X[(size_t)1 * n4] = am; X[(size_t)4 * n4] = ab; X[(size_t)7 * n4] = ad;
+}
+
+int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float* mvx_s, const float* mvy_s,
+                    const float* bit_s, const float* dep_s, const int* cam_ring, const float* wtab, float* Xmaps, cudaStream_t st) {
+  dim3 grid(B, ceil_div(h4 * w4, 256));
+  temporal_kernel<<<grid, 256, 0, st>>>(h4, w4, PT, ring_len, first_poc, mvx_s, mvy_s, bit_s, dep_s, cam_ring, wtab, Xmaps);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// =================================================================================================
+// contrast input preparation (cu_contrast5.m:8-32 block mean; Sudoku_contrastcpp5.m:18-34) and
+// output post-processing (Sudoku :50, cu_contrast5.m:36-55/:60, main.m:237-241)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+contrast_sub_kernel(const float* __restrict__ src, long frame_stride, int RL, int first_slot, int rows, int cols, int cus,
+                    int srows, int scols, float* __restrict__ sub, unsigned* __restrict__ keys) {
+  const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  const float* __restrict__ S = src + (size_t)(RL > 0 ? (first_slot + f) % RL : f) * frame_stride;
+  float v = 0.f; bool ok = i < srows * scols;
+  if (ok) {
+    const int k = i / scols, j = i - k * scols;
+    if (cus == 1) v = S[i];
+    else {
+      const int r0 = k * cus, c0 = j * cus, r1 = min(rows, r0 + cus), c1 = min(cols, c0 + cus);
+      float acc = 0.f;
+      for (int c = c0; c < c1; c++) {                               // mean(mean(temp)): column means first
+        float cs = 0.f;
+        for (int r = r0; r < r1; r++) cs += S[(size_t)r * cols + c];
+        acc += cs / (float)(r1 - r0);
+      }
+      v = acc / (float)(c1 - c0);
+    }
+    v += 0.00000001f;                                               // Sudoku :18
+    sub[(size_t)f * srows * scols + i] = v;
+  }
+  // min / max over the map (the zero padding joins in contrast_pad_kernel)
+  float mn = ok ? v : INFINITY, mx = ok ? v : -INFINITY;
+  mn = warp_min(mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(keys + 2 * f, float_key(mn)); atomicMax(keys + 2 * f + 1, float_key(mx)); }
+}
+
+int contrast_sub_launch(const float* src, long src_frame_stride, int ring_len, int first_slot, int B, int rows, int cols,
+                        int cusize, float* sub, unsigned* minmax_keys, cudaStream_t st) {
+  const int srows = ceil_div(rows, cusize), scols = ceil_div(cols, cusize);
+  dim3 grid(ceil_div(srows * scols, 256), B);
+  contrast_sub_kernel<<<grid, 256, 0, st>>>(src, src_frame_stride, ring_len, first_slot, rows, cols, cusize, srows, scols, sub, minmax_keys);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+__global__ void __launch_bounds__(256)
+contrast_pad_kernel(const float* __restrict__ sub, const unsigned* __restrict__ keys, int srows, int scols, int len,
+                    float* __restrict__ pad) {
+  const int f = blockIdx.y, pr = srows + 2 * len, pc = scols + 2 * len;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= pr * pc) return;
+  const float mn = fminf(key_float(keys[2 * f]), 0.f), mx = fmaxf(key_float(keys[2 * f + 1]), 0.f);   // zero padding takes part in pm_norm
+  const int r = i / pc, c = i - r * pc;
+  float v = 0.f;
+  if (r >= len && r < len + srows && c >= len && c < len + scols) v = sub[(size_t)f * srows * scols + (size_t)(r - len) * scols + (c - len)];
+  pad[(size_t)f * pr * pc + i] = (v - mn) / (mx - mn);               // pm_norm.m (Sudoku :34)
+}
+
+int contrast_pad_launch(const float* sub, const unsigned* minmax_keys, int B, int srows, int scols, int len, float* pad,
+                        cudaStream_t st) {
+  dim3 grid(ceil_div((srows + 2 * len) * (scols + 2 * len), 256), B);
+  contrast_pad_kernel<<<grid, 256, 0, st>>>(sub, minmax_keys, srows, scols, len, pad);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+__global__ void __launch_bounds__(256)
+contrast_post_kernel(const float* __restrict__ raw, const unsigned* __restrict__ maxbits, int srows, int scols, int cus,
+                     int rows, int cols, float* __restrict__ Xmaps, int slot) {
+  const int f = blockIdx.y, o = blockIdx.x * 256 + threadIdx.x;
+  if (o >= rows * cols) return;
+  const float mx = __uint_as_float(maxbits[f]);
+  const int r = o / cols, c = o - r * cols;
+  const float v = raw[(size_t)f * srows * scols + (size_t)(r / cus) * scols + (c / cus)];
+  // contrast/max (Sudoku :50); an all-zero contrast map is NaN in the reference and ends as 0 (main.m:245-253)
+  Xmaps[((size_t)f * 9 + slot) * rows * cols + o] = mx > 0.f ? v / mx : 0.f;
+}
+
+int contrast_post_launch(const float* raw, const unsigned* maxbits, int B, int srows, int scols, int cusize, int rows, int cols,
+                         float* Xmaps, int slot, cudaStream_t st) {
+  dim3 grid(ceil_div(rows * cols, 256), B);
+  contrast_post_kernel<<<grid, 256, 0, st>>>(raw, maxbits, srows, scols, cusize, rows, cols, Xmaps, slot);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+__global__ void __launch_bounds__(256)
+contrast_post_mv_kernel(const float* __restrict__ rawx, const float* __restrict__ rawy, const unsigned* __restrict__ maxx,
+                        const unsigned* __restrict__ maxy, int n4, float* __restrict__ Xmaps, int slot) {
+  const int f = blockIdx.y, o = blockIdx.x * 256 + threadIdx.x;
+  if (o >= n4) return;
+  const float mx = __uint_as_float(maxx[f]), my = __uint_as_float(maxy[f]);
+  const float a = mx > 0.f ? rawx[(size_t)f * n4 + o] / mx : 0.f;    // NaN -> 0 (main.m:237-238)
+  const float b = my > 0.f ? rawy[(size_t)f * n4 + o] / my : 0.f;
+  Xmaps[((size_t)f * 9 + slot) * n4 + o] = sqrtf(a * a + b * b);     // main.m:241
+}
+
+int contrast_post_mv_launch(const float* rawx, const float* rawy, const unsigned* maxx, const unsigned* maxy, int B, int rows,
+                            int cols, float* Xmaps, int slot, cudaStream_t st) {
+  dim3 grid(ceil_div(rows * cols, 256), B);
+  contrast_post_mv_kernel<<<grid, 256, 0, st>>>(rawx, rawy, maxx, maxy, rows * cols, Xmaps, slot);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// =================================================================================================
+// full-resolution replicate + Gaussian as a polyphase filter
+// =================================================================================================
+// horizontal: T[m][r][4c+ph] = sum_d G[ph][d] X[m][r][c+d].  One CTA per (row, map); the row sits in smem.
+__global__ void __launch_bounds__(256)
+fullres_hpass_kernel(const float* __restrict__ X, int h4, int w4, int dmin, int nt, const float4* __restrict__ G,
+                     float* __restrict__ T) {
+  extern __shared__ float srow[];               // [w4 + nt - 1] zero padded, then nt float4 weights
+  float4* sG = reinterpret_cast<float4*>(srow + ((w4 + nt - 1 + 3) / 4) * 4);
+  const int r = blockIdx.x, m = blockIdx.y;
+  const float* __restrict__ xr = X + ((size_t)m * h4 + r) * w4;
+  for (int i = threadIdx.x; i < w4 + nt - 1; i += 256) { const int c = i + dmin; srow[i] = (c >= 0 && c < w4) ? xr[c] : 0.f; }
+  for (int i = threadIdx.x; i < nt; i += 256) sG[i] = G[i];
+  __syncthreads();
+  float4* __restrict__ out = reinterpret_cast<float4*>(T + ((size_t)m * h4 + r) * (size_t)w4 * 4);
+  for (int c = threadIdx.x; c < w4; c += 256) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < nt; t++) {
+      const float x = srow[c + t]; const float4 g = sG[t];
+      a.x = fmaf(g.x, x, a.x); a.y = fmaf(g.y, x, a.y); a.z = fmaf(g.z, x, a.z); a.w = fmaf(g.w, x, a.w);
+    }
+    out[c] = a;
+  }
+}
+
+int fullres_hpass_launch(const float* X, int nmaps, int h4, int w4, const Polyphase& P, float* T, cudaStream_t st) {
+  dim3 grid(h4, nmaps);
+  const size_t smem = (size_t)(((w4 + P.nt - 1 + 3) / 4) * 4) * 4 + (size_t)P.nt * 16;
+  fullres_hpass_kernel<<<grid, 256, smem, st>>>(X, h4, w4, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g), T);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// vertical + reductions: Y[m][4r+ph][x] = sum_d G[ph][d] T[m][r+d][x]; thread = column x, CTA = 128 columns x VP_CELLS cell rows.
+constexpr int VP_CELLS = 8;
+__global__ void __launch_bounds__(128)
+fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int nt, const float4* __restrict__ G,
+                     float* __restrict__ Ystore, const int* __restrict__ store_index, float* __restrict__ partial) {
+  extern __shared__ float4 sGv[];               // nt float4
+  __shared__ float redf[4];
+  __shared__ double redd[4];
+  const int m = blockIdx.z, x = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * VP_CELLS;
+  for (int i = threadIdx.x; i < nt; i += 128) sGv[i] = G[i];
+  __syncthreads();
+  const float* __restrict__ Tm = T + (size_t)m * h4 * W;
+  const int sidx = store_index ? store_index[m] : -1;
+  float* __restrict__ Ys = sidx >= 0 ? Ystore + (size_t)sidx * (size_t)h4 * 4 * W : nullptr;
+  float mn = INFINITY, mx = -INFINITY; double sum = 0;
+  if (x < W) {
+    for (int rc = 0; rc < VP_CELLS; rc++) {
+      const int r = r0 + rc;
+      if (r >= h4) break;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int t_lo = max(0, -(r + dmin)), t_hi = min(nt, h4 - (r + dmin));
+      for (int t = t_lo; t < t_hi; t++) {
+        const float v = __ldg(Tm + (size_t)(r + dmin + t) * W + x); const float4 g = sGv[t];
+        a.x = fmaf(g.x, v, a.x); a.y = fmaf(g.y, v, a.y); a.z = fmaf(g.z, v, a.z); a.w = fmaf(g.w, v, a.w);
+      }
+      mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
+      mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+      sum += (double)a.x + (double)a.y + (double)a.z + (double)a.w;
+      if (Ys) {
+        float* y = Ys + (size_t)(4 * r) * W + x;
+        y[0] = a.x; y[W] = a.y; y[2 * (size_t)W] = a.z; y[3 * (size_t)W] = a.w;
+      }
+    }
+  }
+  mn = block_reduce(mn, redf, OpMin());
+  mx = block_reduce(mx, redf, OpMax());
+  sum = block_reduce(sum, redd, OpAddD());
+  if (threadIdx.x == 0) {
+    const size_t nb = (size_t)gridDim.x * gridDim.y;
+    float* p = partial + ((size_t)m * nb + (size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+    p[0] = mn; p[1] = mx; reinterpret_cast<double*>(p + 2)[0] = sum;
+  }
+}
+
+int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polyphase& P, float* Ystore, const int* store_index,
+                         float* partial, int* nblocks_out, cudaStream_t st) {
+  dim3 grid(ceil_div(W, 128), ceil_div(h4, VP_CELLS), nmaps);
+  fullres_vpass_kernel<<<grid, 128, (size_t)P.nt * 16, st>>>(T, h4, W, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g),
+                                                           Ystore, store_index, partial);
+  CDS_LAUNCH_CHECK();
+  *nblocks_out = grid.x * grid.y;
+  return CDS_OK;
+}
+
+// partial[m][nb][4] = (min, max, sum as double) -> stats[m][4] = (min, max, sum as double); one warp per map, fixed order.
+__global__ void __launch_bounds__(32)
+stats_finalize_kernel(const float* __restrict__ partial, int nb, float* __restrict__ stats) {
+  const int m = blockIdx.x, lane = threadIdx.x;
+  float mn = INFINITY, mx = -INFINITY; double s = 0;
+  for (int i = lane; i < nb; i += 32) {
+    const float* p = partial + ((size_t)m * nb + i) * 4;
+    mn = fminf(mn, p[0]); mx = fmaxf(mx, p[1]); s += reinterpret_cast<const double*>(p + 2)[0];
+  }
+  mn = warp_min(mn); mx = warp_max(mx); s = warp_sum(s);
+  if (lane == 0) { float* o = stats + (size_t)m * 4; o[0] = mn; o[1] = mx; reinterpret_cast<double*>(o + 2)[0] = s; }
+}
+
+int stats_finalize_launch(const float* partial, int nmaps, int nblocks, float* stats, cudaStream_t st) {
+  stats_finalize_kernel<<<nmaps, 32, 0, st>>>(partial, nblocks, stats);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// =================================================================================================
+// generic banded operators
+// =================================================================================================
+// out[m][i][x] = sum_t w[i][t] * f(in[m][start[i]+t][x]);  f = identity or min((v-a)*b, thr) per map.
+__global__ void __launch_bounds__(128)
+banded_rows_kernel(const float* __restrict__ in, int in_rows, int cols, const float* __restrict__ w, const int* __restrict__ start,
+                   int nt, int n_out, const float* __restrict__ xf, float* __restrict__ out) {
+  extern __shared__ float sw[];                 // nt weights of this output row
+  const int i = blockIdx.y, m = blockIdx.z;
+  for (int t = threadIdx.x; t < nt; t += 128) sw[t] = w[(size_t)i * nt + t];
+  __syncthreads();
+  const int s0 = start[i];
+  const int t_hi = min(nt, in_rows - s0);
+  float a = 0.f, b = 1.f, thr = INFINITY;
+  if (xf) { a = xf[4 * m]; b = xf[4 * m + 1]; thr = xf[4 * m + 2]; }
+  const float* __restrict__ src = in + (size_t)m * in_rows * cols;
+  for (int x = blockIdx.x * 128 + threadIdx.x; x < cols; x += gridDim.x * 128) {
+    float acc = 0.f;
+    if (xf) { for (int t = 0; t < t_hi; t++) acc = fmaf(sw[t], fminf((__ldg(src + (size_t)(s0 + t) * cols + x) - a) * b, thr), acc); }
+    else    { for (int t = 0; t < t_hi; t++) acc = fmaf(sw[t], __ldg(src + (size_t)(s0 + t) * cols + x), acc); }
+    out[((size_t)m * n_out + i) * cols + x] = acc;
+  }
+}
+
+int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const Banded& B, const float* xf, float* out, cudaStream_t st) {
+  dim3 grid(min(ceil_div(cols, 128), 64), B.n_out, nmaps);
+  banded_rows_kernel<<<grid, 128, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// out[m][r][j] = sum_t w[j][t] * in[m][r][start[j]+t].  One CTA per (row, map): the input row sits in smem.
+__global__ void __launch_bounds__(256)
+banded_cols_kernel(const float* __restrict__ in, int rows, int in_cols, const float* __restrict__ w, const int* __restrict__ start,
+                   int nt, int n_out, float* __restrict__ out) {
+  extern __shared__ float srow2[];              // in_cols
+  const int r = blockIdx.x, m = blockIdx.y;
+  const float* __restrict__ src = in + ((size_t)m * rows + r) * in_cols;
+  for (int i = threadIdx.x; i < in_cols; i += 256) srow2[i] = src[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_out; j += 256) {
+    const int s0 = start[j], t_hi = min(nt, in_cols - s0);
+    const float* __restrict__ wj = w + (size_t)j * nt;
+    float acc = 0.f;
+    for (int t = 0; t < t_hi; t++) acc = fmaf(__ldg(wj + t), srow2[s0 + t], acc);
+    out[((size_t)m * rows + r) * n_out + j] = acc;
+  }
+}
+
+int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st) {
+  dim3 grid(rows, nmaps);
+  banded_cols_kernel<<<grid, 256, (size_t)in_cols * 4, st>>>(in, rows, in_cols, B.d_w, B.d_start, B.nt, B.n_out, out);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+}  // namespace cds

@@ -1,0 +1,701 @@
+// pipeline.cu — per-clip context and batch orchestration of the whole hot path
+// (main.m:77-305 with the RBF-SVM branch, or the linear branch; TDecGop.cpp:225-333 hook surface).
+//
+// One context owns every device buffer for batches of up to B pictures plus ring buffers holding the
+// temporal history (PS raw pictures for smoothing, PT smoothed pictures for the temporal features).
+// A batch is ~35 kernel launches on one stream; nothing synchronises with the host inside
+// cds_clip_process_dev.  Stages: (a) getframe.cu, (c) vote.cu, (e) maps.cu, (b) contrast.cu,
+// (d) svm.cu, final map below.
+#include "maps.cuh"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+struct cds_svm_model;
+
+namespace cds {
+// from the other translation units
+int getframe_launch(int w, int h, int nframes, const int32_t* hdr, const int16_t* tok, const int64_t* tok_base,
+                    int16_t* mvx, int16_t* mvy, uint8_t* depth, int* err, cudaStream_t st);
+int camera_motion_launch(int w, int h, int nframes, const int16_t* mvx, const int16_t* mvy, const uint16_t* byts,
+                         const uint8_t* depth, float* Vx, float* Vy, float* mvn, float* bitn, float* depn, int* cam,
+                         double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st);
+int contrast_sep_launch(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C, int win,
+                        const float* gr, const float* gc, float* dW_scratch, cudaStream_t st);
+void gaussian_factor(int win, double delta, float* g);
+int contrast_generic_launch(const float* pad, const float* dW, float* out, unsigned* mx, int nmaps,
+                            int R, int C, int win, int len, cudaStream_t st);
+int svm_predict_launch(const cds_svm_model* m, const float* X, long N, float* dec, cudaStream_t st);
+}  // namespace cds
+
+using namespace cds;
+
+static const float kFeatureWeight[9] = {0.058f, 0.171f, -0.095f, 0.068f, -0.01f, 0.509f, -0.051f, 0.154f, 0.196f};   // main.m:115
+
+struct cds_ctx {
+  cds_params p;
+  int w, h, h4, w4, n4, ncol, nrow, nctu, B, RL, PS, PT, gk;
+  double gs;
+  int next_poc = 0;
+  long HW;
+  // operators
+  Polyphase poly;                      // fourX2 + gaussian, both directions (square kernel)
+  Banded Av, Ah;                       // imresize(.,[200 200]) o imfilter o fourX2 on h4 / w4 cells
+  Banded Rv, Rh;                       // imresize(.,[200 200]) on H / W pixels (temporal features)
+  Banded Bv, Bh;                       // imfilter o imresize(.,[H W]) from 200 (final map)
+  float *d_dist = nullptr, *d_wtab = nullptr, *d_w5 = nullptr;
+  // stage (a) batch outputs
+  int16_t *d_mvx = nullptr, *d_mvy = nullptr; uint8_t* d_dep = nullptr; int* d_err = nullptr;
+  // rings [RL][n4]
+  float *r_Vx = nullptr, *r_Vy = nullptr, *r_mvn = nullptr, *r_bitn = nullptr, *r_depn = nullptr;
+  float *r_mvx_s = nullptr, *r_mvy_s = nullptr, *r_bit_s = nullptr, *r_dep_s = nullptr;
+  int* r_cam = nullptr;                // [RL][2]
+  // batch buffers
+  float *d_mv_s = nullptr, *d_X = nullptr;           // [B][n4], [B][9][n4]
+  float *d_subB = nullptr, *d_padB = nullptr, *d_rawB = nullptr;   // bit contrast (17x30 @1080p)
+  float *d_subD = nullptr, *d_padD = nullptr, *d_rawD = nullptr;   // depth contrast
+  float *d_subM = nullptr, *d_padM = nullptr, *d_rawM = nullptr;   // mvx | mvy: [2B]
+  unsigned *d_keys = nullptr, *d_maxbits = nullptr;   // [4][B][2], [4][B]
+  float *d_T = nullptr;                // [9B][h4][W]
+  float *d_Y = nullptr;                // [3B or 9B][H][W]
+  int* d_store_index = nullptr;        // [9B]
+  float *d_partial = nullptr, *d_stats9 = nullptr;   // [9B][nblk][4], [9B][4]
+  float *d_partial2 = nullptr, *d_xf = nullptr;      // temporal thresholds: [3B][nblk2][4], [3B][4]
+  float *d_A1 = nullptr, *d_F200 = nullptr;          // [9B][200][w4], [9B][200][200]
+  float *d_R1 = nullptr, *d_Ft = nullptr;            // [3B][200][W], [3B][200][200]
+  float *d_xsvm = nullptr, *d_dec = nullptr;         // [B][40000][9], [B][40000]
+  float *d_fparam = nullptr, *d_C = nullptr;         // [9][4] mean, 1/std, weight; [B][200][200]
+  float *d_T2 = nullptr, *d_raw = nullptr;           // [B][200][W], [B][H][W]
+  float *d_fpartial = nullptr, *d_fstats = nullptr;  // final min/max
+  void* d_out = nullptr;               // [B][H][W] f32 or u8 (hook API)
+  // staging for host-buffer entry points
+  uint16_t* d_bytes = nullptr; int32_t* d_hdr = nullptr; int16_t* d_tok = nullptr; int64_t* d_tokbase = nullptr;
+  size_t tok_cap = 0;
+  // hook API state
+  std::vector<uint16_t> h_bytes; std::vector<int32_t> h_hdr; std::vector<int16_t> h_tok; std::vector<int64_t> h_base;
+  int pending = 0, pending_first = 0, last_first = -1, last_n = 0;
+  std::vector<int> h_cam;
+  cudaStream_t stream = nullptr;
+  int nblk = 0, nblk2 = 0, nblkf = 0;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(cds_ctx* c, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return CDS_ENOMEM; }
+  c->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return CDS_OK;
+}
+
+double mround(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); }
+
+// ------------------------------------------------------------------------------------------------
+// small kernels private to the pipeline
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_u32_kernel(unsigned* p, size_t n, unsigned v0, unsigned v1) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (i & 1) ? v1 : v0;
+}
+
+// temporal features: pm_norm -> NaN->0 -> mysterythrehold statistics on the stored full-res maps (main.m:255-257)
+__global__ void __launch_bounds__(256)
+temporal_thresh_partial_kernel(const float* __restrict__ Y, long HW, const float* __restrict__ stats9, float* __restrict__ partial2,
+                               int nine_stored /*1: Y holds all nine maps per picture (linear branch)*/) {
+  __shared__ double redd[8];
+  __shared__ int redi[8];
+  const int tm = blockIdx.y;                     // f*3 + j
+  const int f = tm / 3, j = tm - 3 * f;
+  const float* st = stats9 + (size_t)(f * 9 + 1 + 3 * j) * 4;
+  const float mn = st[0], mx = st[1]; const double sum = reinterpret_cast<const double*>(st + 2)[0];
+  const bool valid = mx > mn;
+  const float inv = valid ? 1.f / (mx - mn) : 0.f;
+  const double sumn = valid ? (sum - (double)HW * mn) / ((double)mx - (double)mn) : 0.0;
+  const float lim = (valid ? 1.f : 0.f) - (float)(sumn / (double)HW);       // max(Yn) - ave
+  const float* __restrict__ y = Y + (size_t)(nine_stored ? f * 9 + 1 + 3 * j : tm) * HW;
+  double sb = 0; int nb = 0;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < HW; i += (long)gridDim.x * 256) {
+    const float v = valid ? (y[i] - mn) * inv : 0.f;
+    if (v > lim) { sb += v; nb++; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sb += __shfl_xor_sync(0xffffffffu, sb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
+  if ((threadIdx.x & 31) == 0) { redd[threadIdx.x >> 5] = sb; redi[threadIdx.x >> 5] = nb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0; int n = 0;
+    for (int i = 0; i < 8; i++) { s += redd[i]; n += redi[i]; }
+    float* p = partial2 + ((size_t)tm * gridDim.x + blockIdx.x) * 4;
+    reinterpret_cast<double*>(p)[0] = s; reinterpret_cast<int*>(p)[2] = n;
+  }
+}
+__global__ void __launch_bounds__(32)
+temporal_thresh_finalize_kernel(const float* __restrict__ partial2, int nb2, const float* __restrict__ stats9, float* __restrict__ xf) {
+  const int tm = blockIdx.x, lane = threadIdx.x;
+  const int f = tm / 3, j = tm - 3 * f;
+  double s = 0; int n = 0;
+  for (int i = lane; i < nb2; i += 32) {
+    const float* p = partial2 + ((size_t)tm * nb2 + i) * 4;
+    s += reinterpret_cast<const double*>(p)[0]; n += reinterpret_cast<const int*>(p)[2];
+  }
+  s = warp_sum(s); n = warp_sum(n);
+  if (lane == 0) {
+    const float* st = stats9 + (size_t)(f * 9 + 1 + 3 * j) * 4;
+    const float mn = st[0], mx = st[1];
+    const bool valid = mx > mn;
+    const float mxn = valid ? 1.f : 0.f;
+    const float thresh = n > 0 ? (float)(s / n) : INFINITY;                // mysterythrehold.m:5 (empty set -> no clamp)
+    const float M = n > 0 ? fminf(thresh, mxn) : mxn;
+    float* o = xf + (size_t)tm * 4;
+    o[0] = mn; o[1] = valid ? 1.f / (mx - mn) : 0.f; o[2] = thresh; o[3] = 1.f / (M + 0.000001f);   // :6-7
+  }
+}
+
+// featuresTest (main.m:284-294): 9 features at 200x200, z-scored, row-major pixel order n = r*200 + c
+__global__ void __launch_bounds__(256)
+assemble_features_kernel(const float* __restrict__ F200, const float* __restrict__ Ft, const float* __restrict__ stats9,
+                         const float* __restrict__ xf, const float* __restrict__ fparam /*[9][4] = mean, 1/std, weight, 0*/, float* __restrict__ xsvm) {
+  const int f = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= 40000) return;
+  float* o = xsvm + ((size_t)f * 40000 + n) * 9;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    float v;
+    if (i % 3 == 1) {
+      const int tm = f * 3 + i / 3;
+      v = Ft[(size_t)tm * 40000 + n] * xf[(size_t)tm * 4 + 3];
+    } else {
+      const float* st = stats9 + (size_t)(f * 9 + i) * 4;
+      const float mn = st[0], mx = st[1];
+      v = mx > mn ? (F200[(size_t)(f * 9 + i) * 40000 + n] - mn) / (mx - mn) : 0.f;     // pm_norm, NaN -> 0
+    }
+    o[i] = (v - fparam[4 * i]) * fparam[4 * i + 1];
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+dec_minmax_norm_kernel(const float* __restrict__ dec, float* __restrict__ C) {
+  __shared__ float red[32];
+  const int f = blockIdx.x;
+  const float* d = dec + (size_t)f * 40000;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < 40000; i += 1024) { const float v = d[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  float m0 = red[0]; for (int i = 1; i < 32; i++) m0 = fminf(m0, red[i]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  float m1 = red[0]; for (int i = 1; i < 32; i++) m1 = fmaxf(m1, red[i]);
+  const float inv = m1 > m0 ? 1.f / (m1 - m0) : 0.f;                        // pm_norm (main.m:299); flat -> 0 (reference: NaN)
+  for (int i = threadIdx.x; i < 40000; i += 1024) C[(size_t)f * 40000 + i] = (d[i] - m0) * inv;
+}
+
+// final map: Y = Bv * T2 (imfilter o imresize), times the centre prior, stored raw + min/max partials (main.m:300-304)
+__global__ void __launch_bounds__(128)
+final_rows_kernel(const float* __restrict__ T2, int W, int H, const float* __restrict__ w, const int* __restrict__ start, int nt,
+                  const float* __restrict__ dist, float* __restrict__ raw, float* __restrict__ partial) {
+  extern __shared__ float swf[];
+  __shared__ float redf[4];
+  const int y = blockIdx.y, f = blockIdx.z;
+  for (int t = threadIdx.x; t < nt; t += 128) swf[t] = w[(size_t)y * nt + t];
+  __syncthreads();
+  const int s0 = start[y], t_hi = min(nt, 200 - s0);
+  const float* __restrict__ src = T2 + (size_t)f * 200 * W;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int x = blockIdx.x * 128 + threadIdx.x; x < W; x += gridDim.x * 128) {
+    float acc = 0.f;
+    for (int t = 0; t < t_hi; t++) acc = fmaf(swf[t], __ldg(src + (size_t)(s0 + t) * W + x), acc);
+    acc *= dist[(size_t)y * W + x];
+    raw[((size_t)f * H + y) * W + x] = acc;
+    mn = fminf(mn, acc); mx = fmaxf(mx, acc);
+  }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  const float m0 = fminf(fminf(redf[0], redf[1]), fminf(redf[2], redf[3]));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  const float m1 = fmaxf(fmaxf(redf[0], redf[1]), fmaxf(redf[2], redf[3]));
+  if (threadIdx.x == 0) {
+    const size_t nb = (size_t)gridDim.x * gridDim.y;
+    float* p = partial + ((size_t)f * nb + (size_t)y * gridDim.x + blockIdx.x) * 4;
+    p[0] = m0; p[1] = m1; reinterpret_cast<double*>(p + 2)[0] = 0.0;
+  }
+}
+
+// linear fusion (main.m:258-272) from the nine stored full-res maps, times the centre prior
+__global__ void __launch_bounds__(256)
+linear_comb_kernel(const float* __restrict__ Y, long HW, const float* __restrict__ stats9, const float* __restrict__ xf,
+                   const float* __restrict__ fparam, const float* __restrict__ dist, float* __restrict__ raw,
+                   float* __restrict__ partial) {
+  __shared__ float redf[8];
+  const int f = blockIdx.y;
+  float a[9], b[9], thr[9], sc[9];
+  for (int i = 0; i < 9; i++) {
+    const float* st = stats9 + (size_t)(f * 9 + i) * 4;
+    const bool valid = st[1] > st[0];
+    a[i] = st[0]; b[i] = valid ? 1.f / (st[1] - st[0]) : 0.f; thr[i] = INFINITY; sc[i] = 1.f;
+    if (i % 3 == 1) { const float* x = xf + (size_t)(f * 3 + i / 3) * 4; thr[i] = x[2]; sc[i] = x[3]; }
+  }
+  float mn = INFINITY, mx = -INFINITY;
+  for (long p = blockIdx.x * 256L + threadIdx.x; p < HW; p += (long)gridDim.x * 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      const float v = fminf((Y[((size_t)f * 9 + i) * HW + p] - a[i]) * b[i], thr[i]) * sc[i];
+      s += (v - fparam[4 * i]) * fparam[4 * i + 1] * fparam[4 * i + 2];
+    }
+    s *= dist[p];
+    raw[(size_t)f * HW + p] = s;
+    mn = fminf(mn, s); mx = fmaxf(mx, s);
+  }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  float m0 = redf[0]; for (int i = 1; i < 8; i++) m0 = fminf(m0, redf[i]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  float m1 = redf[0]; for (int i = 1; i < 8; i++) m1 = fmaxf(m1, redf[i]);
+  if (threadIdx.x == 0) { float* p = partial + ((size_t)f * gridDim.x + blockIdx.x) * 4; p[0] = m0; p[1] = m1; reinterpret_cast<double*>(p + 2)[0] = 0.0; }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+normalize_out_kernel(const float* __restrict__ raw, long HW, const float* __restrict__ fstats, OutT* __restrict__ out) {
+  const int f = blockIdx.y;
+  const float mn = fstats[(size_t)f * 4], mx = fstats[(size_t)f * 4 + 1];
+  const float inv = mx > mn ? 1.f / (mx - mn) : 0.f;                        // pm_norm (main.m:304)
+  for (long p = blockIdx.x * 256L + threadIdx.x; p < HW; p += (long)gridDim.x * 256) {
+    const float v = (raw[(size_t)f * HW + p] - mn) * inv;
+    if (sizeof(OutT) == 1) out[(size_t)f * HW + p] = (OutT)__float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * 255.f);
+    else out[(size_t)f * HW + p] = (OutT)v;
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// context
+// =================================================================================================
+namespace {
+
+int build_operators(cds_ctx* c) {
+  const int H = c->h, W = c->w, h4 = c->h4, w4 = c->w4;
+  build_gauss_polyphase(c->gk, c->gs, &c->poly);
+  if (int e = c->poly.upload()) return e;
+  // composite 200 x cells operators:  imresize o imfilter o fourX2
+  {
+    std::vector<double> Kv = dense_gauss_rep4(h4, c->gk, c->gs), Rv = dense_imresize(H, 200);
+    banded_from_dense(dense_mul(Rv, 200, H, Kv, h4), 200, h4, &c->Av);
+    banded_from_dense(Rv, 200, H, &c->Rv);
+    std::vector<double> Kh = dense_gauss_rep4(w4, c->gk, c->gs), Rh = dense_imresize(W, 200);
+    banded_from_dense(dense_mul(Rh, 200, W, Kh, w4), 200, w4, &c->Ah);
+    banded_from_dense(Rh, 200, W, &c->Rh);
+  }
+  // final: imfilter o imresize(200 -> H / W)
+  {
+    std::vector<double> Gv = dense_gauss(H, c->gk, c->gs), Uv = dense_imresize(200, H);
+    banded_from_dense(dense_mul(Gv, H, H, Uv, 200), H, 200, &c->Bv);
+    std::vector<double> Gh = dense_gauss(W, c->gk, c->gs), Uh = dense_imresize(200, W);
+    banded_from_dense(dense_mul(Gh, W, W, Uh, 200), W, 200, &c->Bh);
+  }
+  for (Banded* b : {&c->Av, &c->Ah, &c->Rv, &c->Rh, &c->Bv, &c->Bh}) if (int e = b->upload()) return e;
+  // centre prior, getdistMatrix.m:1-17
+  {
+    std::vector<float> dist((size_t)H * W);
+    const int mx_ = H / 2, my_ = W / 2; double dmax = 0;
+    std::vector<double> d((size_t)H * W);
+    for (int x = 1; x <= H; x++) for (int y = 1; y <= W; y++) {
+      const double v = floor(sqrt((double)(x - mx_) * (x - mx_) + (double)(y - my_) * (y - my_)));
+      d[(size_t)(x - 1) * W + (y - 1)] = v; if (v > dmax) dmax = v;
+    }
+    for (size_t i = 0; i < d.size(); i++) dist[i] = (float)(1.0 - d[i] / dmax);
+    if (int e = dalloc(c, &c->d_dist, dist.size())) return e;
+    CDS_CUDA(cudaMemcpy(c->d_dist, dist.data(), dist.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // 5x5 bit-contrast weights exp(-R^2/(2*3^2)), Sudoku_contrastcpp5.m:8-14 with delta_bit_spacial = 3
+  {
+    float g[8], W5[25];
+    gaussian_factor(5, 3.0, g);
+    for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) W5[i * 5 + j] = g[i] * g[j];
+    CDS_CUDA(cudaMemcpy(c->d_w5, W5, sizeof(W5), cudaMemcpyHostToDevice));
+  }
+  // temporal weights exp(-j/delta), main.m:120-122,195-197
+  {
+    std::vector<float> wt((size_t)(c->PT + 1) * 4, 0.f);
+    for (int j = 0; j <= c->PT; j++) { wt[4 * j] = (float)exp(-j / 26.0); wt[4 * j + 1] = (float)exp(-j / 46.0); wt[4 * j + 2] = (float)exp(-j / 46.0); }
+    if (int e = dalloc(c, &c->d_wtab, wt.size())) return e;
+    CDS_CUDA(cudaMemcpy(c->d_wtab, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return CDS_OK;
+}
+
+}  // namespace
+
+extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
+  if (int e = ensure_device()) return e;
+  if (!p || !out) { set_error("cds_create: null argument"); return CDS_EINVAL; }
+  if (p->w < 64 || p->h < 64 || (p->w % 8) || (p->h % 8) || p->w > 8192 || p->h > 8192) {
+    set_error("cds_create: %dx%d unsupported (multiples of 8, 64..8192)", p->w, p->h); return CDS_EINVAL;
+  }
+  if (!(p->fps >= 4) || p->fps > 240) { set_error("cds_create: fps %.3f out of range", p->fps); return CDS_EINVAL; }
+  if (p->use_rbf && (!p->model || cds_svm_model_nfeat(p->model) != 9)) {
+    set_error("cds_create: use_rbf needs a 9-feature RBF model (svmRBFmodel_all.mat stand-in)"); return CDS_EINVAL;
+  }
+  for (int i = 0; i < 9; i++) if (!(p->std_vec[i] != 0)) { set_error("cds_create: std_vec[%d] is zero", i); return CDS_EINVAL; }
+  cds_ctx* c = new cds_ctx();
+  c->p = *p;
+  c->w = p->w; c->h = p->h; c->h4 = p->h / 4; c->w4 = p->w / 4; c->n4 = c->h4 * c->w4;
+  c->ncol = (p->w + 63) / 64; c->nrow = (p->h + 63) / 64; c->nctu = c->ncol * c->nrow;
+  c->HW = (long)p->w * p->h;
+  c->B = p->max_batch > 0 ? p->max_batch : 32;
+  c->PS = (int)mround(p->fps * 0.3);                       // main.m:119
+  c->PT = (int)mround(c->PS * 7.0);                        // main.m:129
+  c->gk = (int)mround(p->h / 7.5); c->gs = mround(p->h / 30.0);   // main.m:211
+  if (c->gk < 1 || c->gs <= 0) { delete c; set_error("cds_create: picture too small for the Gaussian"); return CDS_EINVAL; }
+  c->RL = c->B + c->PT + c->PS;
+  const int B = c->B, n4 = c->n4, H = c->h, W = c->w, h4 = c->h4, w4 = c->w4;
+  const size_t HW = (size_t)c->HW;
+  int e = CDS_OK;
+  cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { delete c; set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); return CDS_ECUDA; }
+#define A(ptr, count) if (!e) e = dalloc(c, &c->ptr, (size_t)(count))
+  A(d_mvx, (size_t)B * n4); A(d_mvy, (size_t)B * n4); A(d_dep, (size_t)B * n4); A(d_err, 4);
+  A(r_Vx, (size_t)c->RL * n4); A(r_Vy, (size_t)c->RL * n4); A(r_mvn, (size_t)c->RL * n4); A(r_bitn, (size_t)c->RL * n4);
+  A(r_depn, (size_t)c->RL * n4); A(r_mvx_s, (size_t)c->RL * n4); A(r_mvy_s, (size_t)c->RL * n4); A(r_bit_s, (size_t)c->RL * n4);
+  A(r_dep_s, (size_t)c->RL * n4); A(r_cam, (size_t)c->RL * 2);
+  A(d_mv_s, (size_t)B * n4); A(d_X, (size_t)B * 9 * n4);
+  const int sbR = (h4 + 15) / 16, sbC = (w4 + 15) / 16, sdR = (h4 + 1) / 2, sdC = (w4 + 1) / 2;
+  A(d_subB, (size_t)B * sbR * sbC); A(d_padB, (size_t)B * (sbR + 4) * (sbC + 4)); A(d_rawB, (size_t)B * sbR * sbC);
+  A(d_subD, (size_t)B * sdR * sdC); A(d_padD, (size_t)B * (sdR + 24) * (sdC + 24)); A(d_rawD, (size_t)B * sdR * sdC);
+  A(d_subM, (size_t)2 * B * n4); A(d_padM, (size_t)2 * B * (h4 + 48) * (w4 + 48)); A(d_rawM, (size_t)2 * B * n4);
+  A(d_keys, (size_t)4 * B * 2); A(d_maxbits, (size_t)4 * B); A(d_w5, 64 * 64);
+  A(d_T, (size_t)9 * B * h4 * W);
+  A(d_Y, (size_t)(p->use_rbf ? 3 : 9) * B * HW);
+  A(d_store_index, (size_t)9 * B);
+  c->nblk = ((W + 127) / 128) * ((h4 + 7) / 8);
+  c->nblk2 = 64;
+  c->nblkf = p->use_rbf ? std::min((W + 127) / 128, 64) * H : 128;
+  A(d_partial, (size_t)9 * B * c->nblk * 4); A(d_stats9, (size_t)9 * B * 4);
+  A(d_partial2, (size_t)3 * B * c->nblk2 * 4); A(d_xf, (size_t)3 * B * 4);
+  A(d_A1, (size_t)9 * B * 200 * w4); A(d_F200, (size_t)9 * B * 40000);
+  A(d_R1, (size_t)3 * B * 200 * W); A(d_Ft, (size_t)3 * B * 40000);
+  A(d_xsvm, (size_t)B * 40000 * 9); A(d_dec, (size_t)B * 40000); A(d_C, (size_t)B * 40000);
+  A(d_T2, (size_t)B * 200 * W); A(d_raw, (size_t)B * HW);
+  A(d_fpartial, (size_t)B * c->nblkf * 4); A(d_fstats, (size_t)B * 4);
+  A(d_bytes, (size_t)B * c->nctu); A(d_hdr, (size_t)B * c->nctu * 4); A(d_tokbase, (size_t)B + 1);
+  c->tok_cap = (size_t)B * c->nctu * 160;
+  A(d_tok, c->tok_cap);
+  if (!e) { void* q = nullptr; ce = cudaMalloc(&q, (size_t)B * HW * (p->out_u8 ? 1 : 4) + 256); if (ce != cudaSuccess) { set_error("cudaMalloc out"); e = CDS_ENOMEM; } else { c->allocs.push_back(q); c->d_out = q; } }
+#undef A
+  float* d_fparam = nullptr;
+  if (!e) e = dalloc(c, &d_fparam, 36);
+  if (!e) {
+    float fp[36];
+    for (int i = 0; i < 9; i++) { fp[4 * i] = (float)p->mean_vec[i]; fp[4 * i + 1] = (float)(1.0 / p->std_vec[i]); fp[4 * i + 2] = kFeatureWeight[i]; fp[4 * i + 3] = 0.f; }
+    if (cudaMemcpy(d_fparam, fp, sizeof(fp), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("cudaMemcpy fparam"); e = CDS_ECUDA; }
+    c->d_fparam = d_fparam;
+  }
+  if (!e) e = build_operators(c);
+  if (!e) {
+    std::vector<int> si((size_t)9 * B);
+    for (int f = 0; f < B; f++) for (int i = 0; i < 9; i++)
+      si[(size_t)f * 9 + i] = p->use_rbf ? ((i % 3 == 1) ? f * 3 + i / 3 : -1) : f * 9 + i;
+    if (cudaMemcpy(c->d_store_index, si.data(), si.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("cudaMemcpy store_index"); e = CDS_ECUDA; }
+  }
+  if (e) { cds_destroy(c); return e; }
+  c->h_bytes.resize((size_t)B * c->nctu); c->h_hdr.resize((size_t)B * c->nctu * 4); c->h_base.assign(B + 1, 0);
+  c->h_cam.assign((size_t)2 * B, 0);
+  cds_seek(c, 0);
+  *out = c;
+  return CDS_OK;
+}
+
+extern "C" void cds_destroy(cds_ctx* c) {
+  if (!c) return;
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  for (void* q : c->allocs) cudaFree(q);
+  c->poly.release();
+  for (Banded* b : {&c->Av, &c->Ah, &c->Rv, &c->Rh, &c->Bv, &c->Bh}) b->release();
+  delete c;
+}
+
+extern "C" int cds_seek(cds_ctx* c, int poc) {
+  if (!c || poc < 0) { set_error("cds_seek: bad arguments"); return CDS_EINVAL; }
+  cudaStreamSynchronize(c->stream);
+  const size_t rb = (size_t)c->RL * c->n4 * 4;
+  for (float* r : {c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn, c->r_depn, c->r_mvx_s, c->r_mvy_s, c->r_bit_s, c->r_dep_s})
+    CDS_CUDA(cudaMemset(r, 0, rb));
+  CDS_CUDA(cudaMemset(c->r_cam, 0, (size_t)c->RL * 8));
+  c->next_poc = poc; c->pending = 0; c->pending_first = poc; c->last_first = -1; c->last_n = 0;
+  c->h_tok.clear();
+  return CDS_OK;
+}
+extern "C" int cds_reset(cds_ctx* c) { return cds_seek(c, 0); }
+
+namespace {
+
+// stages (a), (c) and smoothing: everything later pictures need from this one as temporal context
+int run_context_stages(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
+                       const int64_t* tok_base, cudaStream_t st) {
+  if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
+  if (int e = camera_motion_launch(c->w, c->h, n, c->d_mvx, c->d_mvy, bytes, c->d_dep, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn,
+                                   c->r_depn, c->r_cam, nullptr, nullptr, first_poc % c->RL, c->RL, st)) return e;
+  return smooth_launch(c->n4, c->PS, c->RL, first_poc, n, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn, c->r_depn, c->r_mvx_s, c->r_mvy_s,
+                       c->r_bit_s, c->r_dep_s, c->d_mv_s, st);
+}
+
+template <typename OutT>
+int launch_normalize(cds_ctx* c, int n, void* out, cudaStream_t st) {
+  dim3 grid(256, n);
+  normalize_out_kernel<OutT><<<grid, 256, 0, st>>>(c->d_raw, c->HW, c->d_fstats, reinterpret_cast<OutT*>(out));
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
+              const int64_t* tok_base, void* maps_out, int* cam_out, cudaStream_t st) {
+  const int h4 = c->h4, w4 = c->w4, n4 = c->n4, H = c->h, W = c->w, RL = c->RL;
+  const float* fparam = c->d_fparam;
+  if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, st)) return e;
+  // ---- thresholded smoothed maps and temporal features -> X slots 0,3,6 / 1,4,7 ----
+  if (int e = myst_small_launch(n4, H, W, RL, first_poc, n, c->d_mv_s, c->r_bit_s, c->r_dep_s, c->d_X, st)) return e;
+  if (int e = temporal_launch(h4, w4, c->PT, RL, first_poc, n, c->r_mvx_s, c->r_mvy_s, c->r_bit_s, c->r_dep_s, c->r_cam, c->d_wtab,
+                              c->d_X, st)) return e;
+  // ---- (b) contrast: bit (cusize 16, delta 3, win 5), depth (2, 13, 24), mvx / mvy (1, 11, 48)  main.m:226-235 ----
+  {
+    const size_t nk = (size_t)4 * n * 2;
+    fill_u32_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(c->d_keys, nk, 0xffffffffu, 0u);
+    CDS_LAUNCH_CHECK();
+    CDS_CUDA(cudaMemsetAsync(c->d_maxbits, 0, (size_t)4 * n * 4, st));
+    unsigned *kB = c->d_keys, *kD = c->d_keys + 2 * n, *kX = c->d_keys + 4 * n, *kY = c->d_keys + 6 * n;
+    unsigned *mB = c->d_maxbits, *mD = c->d_maxbits + n, *mX = c->d_maxbits + 2 * n, *mY = c->d_maxbits + 3 * n;
+    const int sbR = (h4 + 15) / 16, sbC = (w4 + 15) / 16, sdR = (h4 + 1) / 2, sdC = (w4 + 1) / 2;
+    float g[64];
+    // bit
+    if (int e = contrast_sub_launch(c->d_X + (size_t)3 * n4, (long)9 * n4, 0, 0, n, h4, w4, 16, c->d_subB, kB, st)) return e;
+    if (int e = contrast_pad_launch(c->d_subB, kB, n, sbR, sbC, 2, c->d_padB, st)) return e;
+    if (int e = contrast_generic_launch(c->d_padB, c->d_w5, c->d_rawB, mB, n, sbR, sbC, 5, 2, st)) return e;
+    if (int e = contrast_post_launch(c->d_rawB, mB, n, sbR, sbC, 16, h4, w4, c->d_X, 5, st)) return e;
+    // depth
+    if (int e = contrast_sub_launch(c->d_X + (size_t)6 * n4, (long)9 * n4, 0, 0, n, h4, w4, 2, c->d_subD, kD, st)) return e;
+    if (int e = contrast_pad_launch(c->d_subD, kD, n, sdR, sdC, 12, c->d_padD, st)) return e;
+    gaussian_factor(24, 13.0, g);
+    if (int e = contrast_sep_launch(c->d_padD, c->d_rawD, mD, n, sdR, sdC, 24, g, g, nullptr, st)) return e;
+    if (int e = contrast_post_launch(c->d_rawD, mD, n, sdR, sdC, 2, h4, w4, c->d_X, 8, st)) return e;
+    // mvx | mvy as 2n maps in one launch
+    if (int e = contrast_sub_launch(c->r_mvx_s, (long)n4, RL, first_poc % RL, n, h4, w4, 1, c->d_subM, kX, st)) return e;
+    if (int e = contrast_sub_launch(c->r_mvy_s, (long)n4, RL, first_poc % RL, n, h4, w4, 1, c->d_subM + (size_t)n * n4, kY, st)) return e;
+    if (int e = contrast_pad_launch(c->d_subM, kX, 2 * n, h4, w4, 24, c->d_padM, st)) return e;   // kX,kY contiguous: keys [2n][2]
+    gaussian_factor(48, 11.0, g);
+    if (int e = contrast_sep_launch(c->d_padM, c->d_rawM, mX, 2 * n, h4, w4, 48, g, g, nullptr, st)) return e;   // mX,mY contiguous
+    if (int e = contrast_post_mv_launch(c->d_rawM, c->d_rawM + (size_t)n * n4, mX, mY, n, h4, w4, c->d_X, 2, st)) return e;
+  }
+  // ---- fourX2 + imfilter(gaussian) at full resolution: statistics (and the temporal maps themselves) ----
+  int nb = 0;
+  if (int e = fullres_hpass_launch(c->d_X, 9 * n, h4, w4, c->poly, c->d_T, st)) return e;
+  if (int e = fullres_vpass_launch(c->d_T, 9 * n, h4, W, c->poly, c->d_Y, c->d_store_index, c->d_partial, &nb, st)) return e;
+  if (int e = stats_finalize_launch(c->d_partial, 9 * n, nb, c->d_stats9, st)) return e;
+  {
+    dim3 grid(c->nblk2, 3 * n);
+    temporal_thresh_partial_kernel<<<grid, 256, 0, st>>>(c->d_Y, c->HW, c->d_stats9, c->d_partial2, c->p.use_rbf ? 0 : 1);
+    CDS_LAUNCH_CHECK();
+    temporal_thresh_finalize_kernel<<<3 * n, 32, 0, st>>>(c->d_partial2, c->nblk2, c->d_stats9, c->d_xf);
+    CDS_LAUNCH_CHECK();
+  }
+  int nbf = 0;
+  if (c->p.use_rbf) {
+    // ---- features at 200x200 (main.m:275-294) ----
+    if (int e = banded_rows_launch(c->d_X, 9 * n, h4, w4, c->Av, nullptr, c->d_A1, st)) return e;
+    if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, c->d_F200, st)) return e;
+    if (int e = banded_rows_launch(c->d_Y, 3 * n, H, W, c->Rv, c->d_xf, c->d_R1, st)) return e;
+    if (int e = banded_cols_launch(c->d_R1, 3 * n, 200, W, c->Rh, c->d_Ft, st)) return e;
+    {
+      dim3 grid(ceil_div(40000, 256), n);
+      assemble_features_kernel<<<grid, 256, 0, st>>>(c->d_F200, c->d_Ft, c->d_stats9, c->d_xf, fparam, c->d_xsvm);
+      CDS_LAUNCH_CHECK();
+    }
+    // ---- (d) RBF-SVM, then pm_norm -> imresize -> imfilter -> centre prior (main.m:297-304) ----
+    if (int e = svm_predict_launch(c->p.model, c->d_xsvm, (long)n * 40000, c->d_dec, st)) return e;
+    dec_minmax_norm_kernel<<<n, 1024, 0, st>>>(c->d_dec, c->d_C);
+    CDS_LAUNCH_CHECK();
+    if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, st)) return e;
+    {
+      dim3 grid(std::min(ceil_div(W, 128), 64), H, n);
+      final_rows_kernel<<<grid, 128, (size_t)c->Bv.nt * 4, st>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
+      CDS_LAUNCH_CHECK();
+      nbf = grid.x * grid.y;
+    }
+  } else {
+    dim3 grid(128, n);
+    linear_comb_kernel<<<grid, 256, 0, st>>>(c->d_Y, c->HW, c->d_stats9, c->d_xf, fparam, c->d_dist, c->d_raw, c->d_fpartial);
+    CDS_LAUNCH_CHECK();
+    nbf = 128;
+  }
+  if (int e = stats_finalize_launch(c->d_fpartial, n, nbf, c->d_fstats, st)) return e;
+  if (maps_out) {
+    if (int e = c->p.out_u8 ? launch_normalize<uint8_t>(c, n, maps_out, st) : launch_normalize<float>(c, n, maps_out, st)) return e;
+  }
+  if (cam_out) {
+    // cam_out is a DEVICE pointer here: gather the ring slots of this batch
+    for (int f = 0; f < n; f++)
+      CDS_CUDA(cudaMemcpyAsync(cam_out + 2 * f, c->r_cam + 2 * ((first_poc + f) % RL), 8, cudaMemcpyDeviceToDevice, st));
+  }
+  return CDS_OK;
+}
+
+}  // namespace
+
+extern "C" int cds_clip_context_dev(cds_ctx* c, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
+                                    const int16_t* tok, const int64_t* tok_base, void* stream) {
+  if (int e = ensure_device()) return e;
+  if (!c || !ctu_bytes || !hdr || !tok || !tok_base || nframes < 1) { set_error("cds_clip_context_dev: bad arguments"); return CDS_EINVAL; }
+  if (first_poc != c->next_poc) { set_error("cds_clip_context_dev: expected poc %d, got %d (use cds_seek)", c->next_poc, first_poc); return CDS_EINVAL; }
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  for (int done = 0; done < nframes; done += c->B) {
+    const int n = std::min(c->B, nframes - done);
+    if (int e = run_context_stages(c, first_poc + done, n, ctu_bytes + (size_t)done * c->nctu, hdr + (size_t)done * c->nctu * 4, tok,
+                                   tok_base + done, st)) return e;
+  }
+  c->next_poc = first_poc + nframes;
+  return CDS_OK;
+}
+
+extern "C" int cds_clip_process_dev(cds_ctx* c, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
+                                    const int16_t* tok, const int64_t* tok_base, void* maps_out, int* cam_out, void* stream) {
+  if (int e = ensure_device()) return e;
+  if (!c || !ctu_bytes || !hdr || !tok || !tok_base || nframes < 1) { set_error("cds_clip_process_dev: bad arguments"); return CDS_EINVAL; }
+  if (first_poc != c->next_poc) { set_error("cds_clip_process_dev: expected poc %d, got %d (use cds_seek)", c->next_poc, first_poc); return CDS_EINVAL; }
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
+  for (int done = 0; done < nframes; done += c->B) {
+    const int n = std::min(c->B, nframes - done);
+    if (int e = run_batch(c, first_poc + done, n, ctu_bytes + (size_t)done * c->nctu, hdr + (size_t)done * c->nctu * 4, tok,
+                          tok_base + done, maps_out ? (char*)maps_out + (size_t)done * px : nullptr,
+                          cam_out ? cam_out + 2 * done : nullptr, st)) return e;
+  }
+  c->next_poc = first_poc + nframes;
+  return CDS_OK;
+}
+
+// host buffers in, results rendered into c->d_out batch by batch and copied to host_out when given
+static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
+                        const int16_t* tok, const int64_t* tok_base, size_t ntok, void* host_out, int* cam_out) {
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
+  for (int done = 0; done < nframes; done += c->B) {
+    const int n = std::min(c->B, nframes - done);
+    const int64_t t0 = tok_base[done], t1 = tok_base[done + n];
+    if (t0 < 0 || t1 < t0 || (size_t)t1 > ntok) { set_error("cds_clip_process: tok_base out of range"); return CDS_EFORMAT; }
+    if ((size_t)(t1 - t0) > c->tok_cap) { set_error("cds_clip_process: %lld tokens exceed the staging capacity %zu", (long long)(t1 - t0), c->tok_cap); return CDS_ENOMEM; }
+    std::vector<int64_t> base(n + 1);
+    for (int i = 0; i <= n; i++) base[i] = tok_base[done + i] - t0;
+    CDS_CUDA(cudaMemcpyAsync(c->d_bytes, ctu_bytes + (size_t)done * c->nctu, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, st));
+    CDS_CUDA(cudaMemcpyAsync(c->d_hdr, hdr + (size_t)done * c->nctu * 4, (size_t)n * c->nctu * 16, cudaMemcpyHostToDevice, st));
+    CDS_CUDA(cudaMemcpyAsync(c->d_tok, tok + t0, (size_t)(t1 - t0) * 2, cudaMemcpyHostToDevice, st));
+    CDS_CUDA(cudaMemcpyAsync(c->d_tokbase, base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CDS_CUDA(cudaStreamSynchronize(st));   // `base` is a host temporary
+    if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out, nullptr, st)) return e;
+    if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)done * px, c->d_out, (size_t)n * px, cudaMemcpyDeviceToHost, st));
+    if (cam_out)
+      for (int f = 0; f < n; f++)
+        CDS_CUDA(cudaMemcpyAsync(cam_out + 2 * (done + f), c->r_cam + 2 * ((first_poc + done + f) % c->RL), 8, cudaMemcpyDeviceToHost, st));
+    int herr = 0;
+    CDS_CUDA(cudaMemcpyAsync(&herr, c->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CDS_CUDA(cudaStreamSynchronize(st));
+    if (herr) { CDS_CUDA(cudaMemset(c->d_err, 0, 4)); set_error("cds_clip_process: malformed CU token stream in pictures %d..%d", first_poc + done, first_poc + done + n - 1); return CDS_EFORMAT; }
+    c->last_first = first_poc + done; c->last_n = n;
+  }
+  c->next_poc = first_poc + nframes;
+  return CDS_OK;
+}
+
+extern "C" int cds_clip_process(cds_ctx* c, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
+                                const int16_t* tok, const int64_t* tok_base, size_t ntok, void* maps_out, int* cam_out) {
+  if (int e = ensure_device()) return e;
+  if (!c || !ctu_bytes || !hdr || !tok || !tok_base || nframes < 1) { set_error("cds_clip_process: bad arguments"); return CDS_EINVAL; }
+  if (first_poc != c->next_poc) { set_error("cds_clip_process: expected poc %d, got %d (use cds_seek)", c->next_poc, first_poc); return CDS_EINVAL; }
+  if (c->pending) { set_error("cds_clip_process: %d pictures submitted through cds_submit_frame are still pending (cds_flush first)", c->pending); return CDS_EINVAL; }
+  if (int e = process_host(c, first_poc, nframes, ctu_bytes, hdr, tok, tok_base, ntok, maps_out, cam_out)) return e;
+  c->pending_first = c->next_poc;
+  return CDS_OK;
+}
+
+// ---- hook-style API (TDecGop.cpp:270-332): one picture at a time, batched internally ----
+static int hook_flush(cds_ctx* c) {
+  if (c->pending == 0) return CDS_OK;
+  const int n = c->pending, first = c->pending_first;
+  c->h_base[n] = (int64_t)c->h_tok.size();
+  c->pending = 0;
+  std::vector<int> cam((size_t)2 * n);
+  int e = process_host(c, first, n, c->h_bytes.data(), c->h_hdr.data(), c->h_tok.data(), c->h_base.data(), c->h_tok.size(),
+                       nullptr, cam.data());
+  c->h_tok.clear();
+  if (e) return e;
+  c->h_cam = cam;
+  return CDS_OK;
+}
+
+extern "C" int cds_submit_frame(cds_ctx* c, int poc, const uint16_t* ctu_bytes, const int32_t* hdr, const int16_t* tok, size_t ntok) {
+  if (int e = ensure_device()) return e;
+  if (!c || !ctu_bytes || !hdr || !tok) { set_error("cds_submit_frame: null argument"); return CDS_EINVAL; }
+  if (poc != c->pending_first + c->pending) { set_error("cds_submit_frame: pictures must arrive in POC order (expected %d, got %d)", c->pending_first + c->pending, poc); return CDS_EINVAL; }
+  const int k = c->pending;
+  memcpy(c->h_bytes.data() + (size_t)k * c->nctu, ctu_bytes, (size_t)c->nctu * 2);
+  memcpy(c->h_hdr.data() + (size_t)k * c->nctu * 4, hdr, (size_t)c->nctu * 16);
+  c->h_base[k] = (int64_t)c->h_tok.size();
+  c->h_tok.insert(c->h_tok.end(), tok, tok + ntok);
+  c->pending = k + 1;
+  if (c->pending == c->B) { if (int e = hook_flush(c)) return e; c->pending_first = poc + 1; }
+  return CDS_OK;
+}
+
+extern "C" int cds_flush(cds_ctx* c) {
+  if (!c) { set_error("cds_flush: null context"); return CDS_EINVAL; }
+  const int n = c->pending, first = c->pending_first;
+  if (int e = hook_flush(c)) return e;
+  c->pending_first = first + n;
+  return CDS_OK;
+}
+
+extern "C" int cds_get_map(cds_ctx* c, int poc, void* dst, int* cam_xy) {
+  if (!c || !dst) { set_error("cds_get_map: null argument"); return CDS_EINVAL; }
+  if (poc >= c->pending_first && poc < c->pending_first + c->pending) { if (int e = cds_flush(c)) return e; }
+  if (poc < c->last_first || poc >= c->last_first + c->last_n) {
+    set_error("cds_get_map: picture %d is not in the most recent batch [%d, %d)", poc, c->last_first, c->last_first + c->last_n); return CDS_EINVAL;
+  }
+  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
+  CDS_CUDA(cudaMemcpy(dst, (char*)c->d_out + (size_t)(poc - c->last_first) * px, px, cudaMemcpyDeviceToHost));
+  if (cam_xy) CDS_CUDA(cudaMemcpy(cam_xy, c->r_cam + 2 * (poc % c->RL), 8, cudaMemcpyDeviceToHost));
+  return CDS_OK;
+}
+
+// Test hook: copy an intermediate of the most recent batch to the host.  which: "xmaps" [9][n4], "stats" [9][4],
+// "feat200" [9][40000] (raw, before pm_norm), "ft" [3][40000], "xsvm" [40000][9], "dec" [40000], "raw" [H][W].
+extern "C" int cds_debug_copy(cds_ctx* c, const char* which, int frame_in_batch, void* dst, size_t bytes) {
+  if (!c || !which || !dst || frame_in_batch < 0 || frame_in_batch >= c->B) { set_error("cds_debug_copy: bad arguments"); return CDS_EINVAL; }
+  const int f = frame_in_batch; const void* src = nullptr; size_t n = 0;
+  if (!strcmp(which, "xmaps")) { src = c->d_X + (size_t)f * 9 * c->n4; n = (size_t)9 * c->n4 * 4; }
+  else if (!strcmp(which, "stats")) { src = c->d_stats9 + (size_t)f * 36; n = 36 * 4; }
+  else if (!strcmp(which, "feat200")) { src = c->d_F200 + (size_t)f * 9 * 40000; n = (size_t)9 * 40000 * 4; }
+  else if (!strcmp(which, "ft")) { src = c->d_Ft + (size_t)f * 3 * 40000; n = (size_t)3 * 40000 * 4; }
+  else if (!strcmp(which, "xf")) { src = c->d_xf + (size_t)f * 12; n = 12 * 4; }
+  else if (!strcmp(which, "xsvm")) { src = c->d_xsvm + (size_t)f * 40000 * 9; n = (size_t)40000 * 9 * 4; }
+  else if (!strcmp(which, "dec")) { src = c->d_dec + (size_t)f * 40000; n = (size_t)40000 * 4; }
+  else if (!strcmp(which, "raw")) { src = c->d_raw + (size_t)f * c->HW; n = (size_t)c->HW * 4; }
+  else { set_error("cds_debug_copy: unknown intermediate %s", which); return CDS_EINVAL; }
+  if (bytes < n) { set_error("cds_debug_copy: %s needs %zu bytes", which, n); return CDS_EINVAL; }
+  CDS_CUDA(cudaStreamSynchronize(c->stream));
+  CDS_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost));
+  return CDS_OK;
+}

@@ -171,3 +171,37 @@ def libsvmpredict(testing_label_vector, testing_instance_matrix, model):
     scc = ((n * sumpt - sump * sumt) ** 2) / den if den != 0 else float("nan")
     accuracy = np.array([correct / n * 100.0, float((err * err).sum()) / n, scc])   # svmpredict.c:233-238
     return lab.reshape(-1, 1), accuracy.reshape(3, 1), dec.reshape(-1, 1)
+
+
+# ------------------------------------------------------------------------------------------ (c)
+def camera_motion(w, h, mvx, mvy, ctu_bytes, depth):
+    """main.m:77-105 for one picture.  Returns dict(Vx, Vy, mv_norm, bit_norm, depth_norm, cam, ave, flag)."""
+    h4, w4 = h // 4, w // 4
+    mvx = np.ascontiguousarray(mvx, np.int16); mvy = np.ascontiguousarray(mvy, np.int16)
+    byts = np.ascontiguousarray(ctu_bytes, np.uint16).reshape(-1); depth = np.ascontiguousarray(depth, np.uint8)
+    if mvx.shape != (h4, w4) or byts.size != nctu(w, h):
+        raise CdsError("camera_motion: map shapes do not match the picture size")
+    outs = [np.zeros((h4, w4), np.float32) for _ in range(5)]
+    cam = np.zeros(2, np.int32); ave = np.zeros(2, np.float64); flag = C.c_int()
+    check(lib().cds_camera_motion(w, h, _ptr(mvx), _ptr(mvy), _ptr(byts), _ptr(depth), *[_ptr(a) for a in outs],
+                                  _ptr(cam), _ptr(ave), C.byref(flag)), "cds_camera_motion")
+    return dict(Vx=outs[0], Vy=outs[1], mv_norm=outs[2], bit_norm=outs[3], depth_norm=outs[4], cam=cam, ave=ave,
+                flag=flag.value)
+
+
+def mv_vote(eVx, eVy):
+    """[x_ave, y_ave] = mv_vote(eVx, eVy)   (mv_vote.m; values are multiples of 1/8 pixel)."""
+    vx = np.asarray(eVx, np.float64).reshape(-1) * 8; vy = np.asarray(eVy, np.float64).reshape(-1) * 8
+    if np.any(vx != np.round(vx)) or np.any(vy != np.round(vy)):
+        raise CdsError("mv_vote: inputs must be multiples of 1/8 pixel (medfilt2 of quarter-pel MVs / 4)")
+    vx8 = np.ascontiguousarray(vx, np.int32); vy8 = np.ascontiguousarray(vy, np.int32)
+    xa = C.c_double(); ya = C.c_double()
+    check(lib().cds_mv_vote(_ptr(vx8), _ptr(vy8), vx8.size, C.byref(xa), C.byref(ya)), "cds_mv_vote")
+    return xa.value, ya.value
+
+
+def magnitude_vote(value):
+    v = np.ascontiguousarray(value, np.float64).reshape(-1)
+    out = C.c_double()
+    check(lib().cds_magnitude_vote(_ptr(v), v.size, C.byref(out)), "cds_magnitude_vote")
+    return out.value

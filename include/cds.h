@@ -149,16 +149,29 @@ int cds_get_map(cds_ctx* ctx, int poc, void* dst, int* cam_xy);
 int cds_flush(cds_ctx* ctx);
 /* Batch entry points used by bench.py.  Process `nframes` pictures [first .. first+nframes) whose
  * packed syntax is resident on the DEVICE (dev pointers; layout as cds_getframe_dev, ctu_bytes
- * [nframes][nctu]) and write maps to a device buffer [nframes][h][w].  `stream` is a cudaStream_t. */
+ * [nframes][nctu]) and write maps to a device buffer [nframes][h][w]; cam_out (may be NULL) is a
+ * DEVICE buffer [nframes][2].  `stream` is a cudaStream_t (NULL = the context's own stream). */
 int cds_clip_process_dev(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* ctu_bytes,
                          const int32_t* hdr, const int16_t* tok, const int64_t* tok_base,
                          void* maps_out, int* cam_out, void* stream);
-/* Same with HOST buffers (pinned or pageable): copies in, computes, copies maps out. */
+/* Same with HOST buffers (pinned or pageable): copies in, computes, copies maps out (maps_out may be
+ * NULL: the last batch then stays retrievable through cds_get_map). */
 int cds_clip_process(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* ctu_bytes,
                      const int32_t* hdr, const int16_t* tok, const int64_t* tok_base, size_t ntok,
                      void* maps_out, int* cam_out);
-/* Drop all temporal state (start a new clip). */
+/* Drop all temporal state (start a new clip at POC 0). */
 int cds_reset(cds_ctx* ctx);
+/* Drop all temporal state and continue at picture `poc` (frame-range sharding: seek to
+ * first - (PS + PT - 2), feed that halo through cds_clip_context_dev, then process the owned range). */
+int cds_seek(cds_ctx* ctx, int poc);
+/* Run only the stages later pictures depend on (syntax->maps, camera motion, smoothing) for `nframes`
+ * pictures of temporal context; no saliency maps are produced.  Device pointers, as cds_clip_process_dev. */
+int cds_clip_context_dev(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
+                         const int16_t* tok, const int64_t* tok_base, void* stream);
+/* Test hook: copy an intermediate of the most recent batch to host memory.  which = "xmaps" ([9][h/4*w/4]),
+ * "stats" ([9][4]), "feat200" ([9][40000]), "ft" ([3][40000]), "xf" ([3][4]), "xsvm" ([40000][9]), "dec" ([40000]),
+ * "raw" ([h][w]); all FP32. */
+int cds_debug_copy(cds_ctx* ctx, const char* which, int frame_in_batch, void* dst, size_t bytes);
 /* Measure this device's issue ceilings with micro-kernels (lane-instructions per second): the
  * contrast kernel's FADD+FFMA pair mix, pure FFMA, and MUFU.EX2.  Used as roofline denominators
  * for the FP32/MUFU-bound kernels (MEASURED_PEAKS.json has only HBM and bf16 tensor numbers). */

@@ -368,24 +368,32 @@ void orc_gauss_kernel(int k, double sigma, double* g) {
   for (int i = 0; i < k; i++) g[i] /= s;
 }
 
-/* imfilter(A, h): correlation, zero padding, 'same'; kernel origin floor((k+1)/2) (1-based) */
+/* imfilter(A, h): correlation, zero padding, 'same'; kernel origin floor((k+1)/2) (1-based).
+ * Loops are ordered tap-outermost so the compiler can vectorise along the row (this only matters
+ * for the CPU-baseline timing; every output still accumulates its taps in ascending order). */
 void orc_imfilter_gauss(const double* a, int rows, int cols, int k, double sigma, double* out) {
   double* g = (double*)malloc(sizeof(double) * k);
-  double* tmp = (double*)malloc(sizeof(double) * (size_t)rows * cols);
+  double* tmp = (double*)calloc((size_t)rows * cols, sizeof(double));
   orc_gauss_kernel(k, sigma, g);
   int c0 = (k + 1) / 2 - 1;   /* 0-based index of the origin tap */
-  for (int r = 0; r < rows; r++)
-    for (int c = 0; c < cols; c++) {
-      double s = 0;
-      for (int u = 0; u < k; u++) { int sc = c + u - c0; if (sc >= 0 && sc < cols) s += g[u] * a[(size_t)r * cols + sc]; }
-      tmp[(size_t)r * cols + c] = s;
+  for (int r = 0; r < rows; r++) {
+    const double* ar = a + (size_t)r * cols; double* tr = tmp + (size_t)r * cols;
+    for (int u = 0; u < k; u++) {
+      int lo = c0 - u < 0 ? 0 : c0 - u, hi = cols + c0 - u > cols ? cols : cols + c0 - u;
+      const double gu = g[u]; const double* src = ar + (u - c0);
+      for (int c = lo; c < hi; c++) tr[c] += gu * src[c];
     }
-  for (int r = 0; r < rows; r++)
-    for (int c = 0; c < cols; c++) {
-      double s = 0;
-      for (int u = 0; u < k; u++) { int sr = r + u - c0; if (sr >= 0 && sr < rows) s += g[u] * tmp[(size_t)sr * cols + c]; }
-      out[(size_t)r * cols + c] = s;
+  }
+  memset(out, 0, sizeof(double) * (size_t)rows * cols);
+  for (int r = 0; r < rows; r++) {
+    double* orow = out + (size_t)r * cols;
+    for (int u = 0; u < k; u++) {
+      int sr = r + u - c0;
+      if (sr < 0 || sr >= rows) continue;
+      const double gu = g[u]; const double* src = tmp + (size_t)sr * cols;
+      for (int c = 0; c < cols; c++) orow[c] += gu * src[c];
     }
+  }
   free(g); free(tmp);
 }
 
@@ -437,4 +445,280 @@ void orc_imresize_bilinear(const double* a, int rows, int cols, int out_rows, in
       out[(size_t)r * out_cols + c] = s;
     }
   free(tmp); free(ir); free(ic); free(wr); free(wc);
+}
+
+/* =====================================================================================
+ * Stage (c) — camera motion (PARITY UNPINNED: restated from the .m text)
+ * ===================================================================================== */
+/* medfilt2(A,[2 2]): MATLAB's ordfilt2 centres an even window on its top-left element
+ * (center = floor((size+1)/2)), pads with zeros, and medfilt2 averages the two middle order
+ * statistics of the four values. */
+void orc_medfilt2_2x2(const double* a, int rows, int cols, double* out) {
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < cols; c++) {
+      double v[4];
+      v[0] = a[(size_t)r * cols + c];
+      v[1] = (r + 1 < rows) ? a[(size_t)(r + 1) * cols + c] : 0.0;
+      v[2] = (c + 1 < cols) ? a[(size_t)r * cols + c + 1] : 0.0;
+      v[3] = (r + 1 < rows && c + 1 < cols) ? a[(size_t)(r + 1) * cols + c + 1] : 0.0;
+      for (int i = 1; i < 4; i++) { double t = v[i]; int j = i - 1; while (j >= 0 && v[j] > t) { v[j + 1] = v[j]; j--; } v[j + 1] = t; }
+      out[(size_t)r * cols + c] = 0.5 * v[1] + 0.5 * v[2];
+    }
+}
+
+static int orc_cmp_double(const void* a, const void* b) {
+  double x = *(const double*)a, y = *(const double*)b;
+  return (x > y) - (x < y);
+}
+
+/* direction_cluster.m:1-50 with k = 16 (mv_vote.m:3-4) */
+void orc_direction_cluster(const double* vx, const double* vy, int n, double* x_ave, double* y_ave) {
+  const double pi = 3.14159265358979323846;
+  int num[16] = {0};
+  int* bin = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) {
+    double t = atan2(vy[i], vx[i]) / pi + 1;                                        /* :9 */
+    int b = (int)floor(t / (2.0 / 16));                                             /* :10 */
+    if (b == 16) b = 15;                                                            /* :11 */
+    bin[i] = b; num[b]++;
+  }
+  int best = 0;
+  for (int k = 1; k < 16; k++) if (num[k] > num[best]) best = k;                    /* first maximum, :18-20 */
+  int Len = num[best];
+  if (Len == 0) { *x_ave = 0; *y_ave = 0; free(bin); return; }
+  double* xs = (double*)malloc(sizeof(double) * Len);
+  double* ys = (double*)malloc(sizeof(double) * Len);
+  int m = 0;
+  for (int i = 0; i < n; i++) if (bin[i] == best) { xs[m] = vx[i]; ys[m] = vy[i]; m++; }
+  qsort(xs, Len, sizeof(double), orc_cmp_double);                                   /* :26-27, sorted independently */
+  qsort(ys, Len, sizeof(double), orc_cmp_double);
+  int Lencut = Len / 2;                                                             /* :25 */
+  double* srt[2] = {xs, ys}; double* res[2] = {x_ave, y_ave};
+  for (int q = 0; q < 2; q++) {
+    double* s = srt[q]; double sum = 0;
+    if (Len < 2) { *res[q] = s[0]; continue; }   /* Len == 1 indexes element 0 / divides by 0 in MATLAB: defined here as the value itself */
+    if (fabs(s[0]) > fabs(s[Len - 1])) {                                            /* :40-44 */
+      for (int i = Lencut - 1; i < Len; i++) sum += s[i];                           /* x_sort(Lencut:Len), 1-based */
+      *res[q] = sum / (Len - Lencut + 1);
+    } else {
+      for (int i = 0; i < Lencut; i++) sum += s[i];                                 /* x_sort(1:Lencut) */
+      *res[q] = sum / Lencut;
+    }
+  }
+  free(bin); free(xs); free(ys);
+}
+
+/* magnitude_vote.m:1-27 */
+double orc_magnitude_vote(const double* value, int n) {
+  const int max_class = 20;
+  double mn = INFINITY, mx = -INFINITY;
+  for (int i = 0; i < n; i++) { if (value[i] < mn) mn = value[i]; if (value[i] > mx) mx = value[i]; }
+  double step = (mx - mn + 1) / max_class;                                          /* :5 */
+  double range[64]; int len = 0;
+  /* MATLAB colon: min:step:max has floor((max-min)/step + tol) + 1 elements */
+  int cnt = (int)floor((mx - mn) / step + 1e-10) + 1;
+  for (int i = 0; i < cnt && i < 64; i++) range[len++] = mn + i * step;
+  int label[64];
+  for (int ii = 0; ii < len - 1; ii++) {                                            /* :10-14 */
+    int l1 = 0, l2 = 0;
+    for (int i = 0; i < n; i++) { if (value[i] >= range[ii]) l1++; if (value[i] >= range[ii + 1]) l2++; }
+    label[ii] = l1 - l2;
+  }
+  { int l = 0; for (int i = 0; i < n; i++) if (value[i] >= range[len - 1]) l++; label[len - 1] = l; }   /* :15 */
+  int lmax = label[0];
+  for (int ii = 1; ii < len; ii++) if (label[ii] > lmax) lmax = label[ii];
+  double v_ave = 0; int nmax = 0;
+  for (int ii = 0; ii < len; ii++) if (label[ii] == lmax) {                         /* :16-25 */
+    double s = 0; int c = 0;
+    for (int i = 0; i < n; i++)
+      if (value[i] >= range[ii] && (ii == len - 1 || value[i] < range[ii + 1])) { s += value[i]; c++; }
+    v_ave += s / c; nmax++;
+  }
+  return v_ave / nmax;                                                              /* :26 */
+}
+
+/* main.m:77-105 for one frame */
+void orc_camera_motion(int w, int h, const int16_t* mvx, const int16_t* mvy, const uint16_t* bitmap,
+                       const uint8_t* depth, double* Vx, double* Vy, double* mv_norm,
+                       double* bit_norm, double* depth_norm, int* cam, double* ave, int* flag_out) {
+  const double eps = 2.220446049250313e-16;
+  int h4 = h / 4, w4 = w / 4, ncol = (w + 63) / 64;
+  long n = (long)h4 * w4;
+  double* Bm = (double*)malloc(sizeof(double) * n);
+  double* Vxf = (double*)malloc(sizeof(double) * n);
+  double* Vyf = (double*)malloc(sizeof(double) * n);
+  double* eVx = (double*)malloc(sizeof(double) * n);
+  double* eVy = (double*)malloc(sizeof(double) * n);
+  double bmin = INFINITY, bmax = -INFINITY, dmax = -INFINITY;
+  for (int r = 0; r < h4; r++)
+    for (int c = 0; c < w4; c++) {
+      long o = (long)r * w4 + c;
+      Vx[o] = mvx[o] / 4.0; Vy[o] = mvy[o] / 4.0;                                   /* :78-79 */
+      Bm[o] = bitmap[(r / 16) * ncol + (c / 16)];                                   /* upsample(.,16,.) :80 */
+      if (Bm[o] < bmin) bmin = Bm[o];
+      if (Bm[o] > bmax) bmax = Bm[o];
+      if (depth[o] > dmax) dmax = depth[o];
+    }
+  orc_medfilt2_2x2(Vx, h4, w4, Vxf);                                                /* :82-83 */
+  orc_medfilt2_2x2(Vy, h4, w4, Vyf);
+  long ne = 0, T = 0;
+  for (long o = 0; o < n; o++)
+    if (Bm[o] < bmin + 20) {                                                        /* :81 */
+      eVx[ne] = Vxf[o]; eVy[ne] = Vyf[o];
+      if (eVx[ne] * eVx[ne] + eVy[ne] * eVy[ne] <= 2) T++;                          /* cm_judge.m:5-6 */
+      ne++;
+    }
+  int flag = !(T > 0.5 * ne);                                                       /* cm_judge.m:8-12 */
+  double x_ave = 0, y_ave = 0;
+  if (flag) {
+    orc_direction_cluster(eVx, eVy, (int)ne, &x_ave, &y_ave);                       /* :88 */
+    for (long o = 0; o < n; o++) { Vx[o] = Vxf[o] - x_ave; Vy[o] = Vyf[o] - y_ave; }   /* :89-90 */
+  }
+  double mmax = -INFINITY;
+  for (long o = 0; o < n; o++) { mv_norm[o] = sqrt(Vx[o] * Vx[o] + Vy[o] * Vy[o]); if (mv_norm[o] > mmax) mmax = mv_norm[o]; }
+  for (long o = 0; o < n; o++) {
+    mv_norm[o] = mv_norm[o] / (mmax + eps);                                         /* :102 */
+    bit_norm[o] = Bm[o] / (bmax + eps);                                             /* :103 */
+    depth_norm[o] = depth[o] / (dmax + eps);                                        /* :104 */
+  }
+  cam[0] = (int)orc_round(x_ave); cam[1] = (int)orc_round(y_ave);                   /* :98-99 */
+  if (ave) { ave[0] = x_ave; ave[1] = y_ave; }
+  if (flag_out) *flag_out = flag;
+  free(Bm); free(Vxf); free(Vyf); free(eVx); free(eVy);
+}
+
+/* =====================================================================================
+ * Whole clip — main.m:77-305 (PARITY UNPINNED for everything outside stages a/b/d)
+ * ===================================================================================== */
+static void orc_nan_to_zero(double* a, long n) { for (long i = 0; i < n; i++) if (a[i] != a[i]) a[i] = 0; }
+
+/* fourX2 -> imfilter(gaussian) -> pm_norm (main.m:208-225, 227-233, 239-243) on an h4 x w4 map */
+static void orc_feature_fullres(const double* x4, int h, int w, int gk, double gs, double* rep, double* out) {
+  orc_replicate(x4, h / 4, w / 4, 4, h, w, rep);
+  orc_imfilter_gauss(rep, h, w, gk, gs, out);
+  orc_pm_norm(out, (long)h * w);
+}
+
+int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t* mvy,
+                     const uint8_t* depth, const uint16_t* bitmap, int first_out,
+                     double* out, int* cam_out, double* feat200) {
+  static const double FeatureWeight[9] = {0.058, 0.171, -0.095, 0.068, -0.01, 0.509, -0.051, 0.154, 0.196};   /* main.m:115 */
+  const int w = p->w, h = p->h, F = p->nframes;
+  const int h4 = h / 4, w4 = w / 4, nctu = ((h + 63) / 64) * ((w + 63) / 64);
+  const long n4 = (long)h4 * w4, N = (long)h * w;
+  const int PS = (int)orc_round(p->fps * 0.3);                                      /* main.m:119 */
+  const int PT = (int)orc_round(PS * 7.0);                                          /* main.m:129 */
+  const int gk = (int)orc_round(h / 7.5); const double gs = orc_round(h / 30.0);    /* main.m:211 */
+  const double d_mv_t = 26, d_bit_t = 46, d_dep_t = 46;                             /* main.m:120-122 */
+  if (F < 1 || first_out < 0 || first_out >= F) return -1;
+  size_t mapb = sizeof(double) * n4;
+  double *Vx = (double*)malloc(mapb * F), *Vy = (double*)malloc(mapb * F), *mvn = (double*)malloc(mapb * F);
+  double *bitn = (double*)malloc(mapb * F), *depn = (double*)malloc(mapb * F);
+  double *bit_s = (double*)malloc(mapb * F), *dep_s = (double*)malloc(mapb * F);
+  double *mvx_s = (double*)malloc(mapb * F), *mvy_s = (double*)malloc(mapb * F);
+  int* cam = (int*)malloc(sizeof(int) * 2 * F);
+  /* ---- pass 1: camera motion, main.m:77-105 ---- */
+  for (int ii = 0; ii < F; ii++)
+    orc_camera_motion(w, h, mvx + ii * n4, mvy + ii * n4, bitmap + (size_t)ii * nctu, depth + ii * n4,
+                      Vx + ii * n4, Vy + ii * n4, mvn + ii * n4, bitn + ii * n4, depn + ii * n4, cam + 2 * ii, 0, 0);
+  if (cam_out) memcpy(cam_out, cam, sizeof(int) * 2 * F);
+  double* dist = (double*)malloc(sizeof(double) * N);
+  orc_distmatrix(h, w, dist);                                                       /* main.m:131 */
+  double *mv_c = (double*)malloc(mapb), *bit_c = (double*)malloc(mapb), *dep_c = (double*)malloc(mapb);
+  double *mvT = (double*)malloc(mapb), *bitT = (double*)malloc(mapb), *depT = (double*)malloc(mapb);
+  double *tb = (double*)malloc(mapb), *td = (double*)malloc(mapb), *tx = (double*)malloc(mapb), *ty = (double*)malloc(mapb);
+  double *con = (double*)malloc(mapb), *con2 = (double*)malloc(mapb);
+  double* rep = (double*)malloc(sizeof(double) * N);
+  double* feat[9];
+  for (int i = 0; i < 9; i++) feat[i] = (double*)malloc(sizeof(double) * N);
+  double* comb = (double*)malloc(sizeof(double) * N);
+  double* small = (double*)malloc(sizeof(double) * 200 * 200 * 9);
+  double* X = (double*)malloc(sizeof(double) * 40000 * 9);
+  double* dec = (double*)malloc(sizeof(double) * 40000);
+  double* lab = (double*)malloc(sizeof(double) * 40000);
+  /* ---- pass 2, main.m:137-307 ---- */
+  for (int k = 0; k < F; k++) {
+    int count = 0;
+    double *cx = mvx_s + k * n4, *cy = mvy_s + k * n4, *cb = bit_s + k * n4, *cd = dep_s + k * n4;
+    memset(mv_c, 0, mapb); memset(cx, 0, mapb); memset(cy, 0, mapb); memset(cb, 0, mapb); memset(cd, 0, mapb);
+    for (int ii = k - PS + 1; ii <= k; ii++) {                                      /* :144-153 */
+      if (ii < 0) continue;
+      for (long o = 0; o < n4; o++) {
+        mv_c[o] += mvn[ii * n4 + o]; cx[o] += Vx[ii * n4 + o]; cy[o] += Vy[ii * n4 + o];
+        cb[o] += bitn[ii * n4 + o]; cd[o] += depn[ii * n4 + o];
+      }
+      count++;
+    }
+    for (long o = 0; o < n4; o++) { mv_c[o] /= count; cx[o] /= count; cy[o] /= count; cb[o] /= count; cd[o] /= count; }   /* :161-165 */
+    if (k < first_out) continue;      /* context frame: only its smoothed maps are needed later */
+    memcpy(bit_c, cb, mapb); memcpy(dep_c, cd, mapb);
+    orc_mysterythrehold(mv_c, n4, h, w);                                            /* :170-172 */
+    orc_mysterythrehold(bit_c, n4, h, w);
+    orc_mysterythrehold(dep_c, n4, h, w);
+    /* temporal difference with accumulated camera motion, :174-199 */
+    double camX = 0, camY = 0;
+    memset(mvT, 0, mapb); memset(bitT, 0, mapb); memset(depT, 0, mapb);
+    for (int j = 1; j <= PT - 1; j++) {
+      if (k - j < 0) continue;
+      camX += cam[2 * (k - j + 1)]; camY += cam[2 * (k - j + 1) + 1];               /* :189-190 */
+      int sx = (int)orc_round(camX / 4), sy = (int)orc_round(camY / 4);
+      orc_immove(bit_s + (k - j) * n4, h4, w4, sx, sy, tb);
+      orc_immove(dep_s + (k - j) * n4, h4, w4, sx, sy, td);
+      orc_immove(mvx_s + (k - j) * n4, h4, w4, sx, sy, tx);
+      orc_immove(mvy_s + (k - j) * n4, h4, w4, sx, sy, ty);
+      double wm = exp(-j / d_mv_t), wb = exp(-j / d_bit_t), wd = exp(-j / d_dep_t);
+      for (long o = 0; o < n4; o++) {
+        double dx = cx[o] - tx[o], dy = cy[o] - ty[o];
+        mvT[o] += wm * sqrt(dx * dx + dy * dy);                                     /* :195 */
+        bitT[o] += wb * fabs(cb[o] - tb[o]);                                        /* :196 */
+        depT[o] += wd * fabs(cd[o] - td[o]);                                        /* :197 */
+      }
+    }
+    /* feature order of featuresTest, main.m:284-292 */
+    orc_feature_fullres(mv_c, h, w, gk, gs, rep, feat[0]);                          /* mv_ori :211,214 */
+    orc_feature_fullres(mvT, h, w, gk, gs, rep, feat[1]);                           /* mv_temporal :220,223 */
+    orc_feature_fullres(bit_c, h, w, gk, gs, rep, feat[3]);                         /* bit_ori */
+    orc_feature_fullres(bitT, h, w, gk, gs, rep, feat[4]);                          /* bit_temporal */
+    orc_feature_fullres(dep_c, h, w, gk, gs, rep, feat[6]);                         /* depth_ori */
+    orc_feature_fullres(depT, h, w, gk, gs, rep, feat[7]);                          /* depth_temporal */
+    orc_cu_contrast5(bit_c, h4, w4, 64 / 4, 3, 64 * 5 / 4, con);                    /* :226 */
+    orc_feature_fullres(con, h, w, gk, gs, rep, feat[5]);                           /* bit_spacial :227-229 */
+    orc_cu_contrast5(dep_c, h4, w4, 8 / 4, 13, 8 * 24 / 4, con);                    /* :230 */
+    orc_feature_fullres(con, h, w, gk, gs, rep, feat[8]);                           /* depth_spacial :231-233 */
+    orc_cu_contrast5(cx, h4, w4, 1, 11, 4 * 48 / 4, con);                           /* :234 */
+    orc_cu_contrast5(cy, h4, w4, 1, 11, 4 * 48 / 4, con2);                          /* :235 */
+    orc_nan_to_zero(con, n4); orc_nan_to_zero(con2, n4);                            /* :237-238 */
+    for (long o = 0; o < n4; o++) con[o] = sqrt(con[o] * con[o] + con2[o] * con2[o]);   /* :241 (fourX2 commutes) */
+    orc_feature_fullres(con, h, w, gk, gs, rep, feat[2]);                           /* mv_spacial :242-243 */
+    for (int i = 0; i < 9; i++) orc_nan_to_zero(feat[i], N);                        /* :245-253 */
+    orc_mysterythrehold(feat[7], N, h, w);                                          /* :255-257 */
+    orc_mysterythrehold(feat[4], N, h, w);
+    orc_mysterythrehold(feat[1], N, h, w);
+    if (!p->use_rbf) {                                                              /* :258-272 */
+      for (long o = 0; o < N; o++) {
+        double s = 0;
+        for (int i = 0; i < 9; i++) s += (feat[i][o] - p->meanVec[i]) / p->stdVec[i] * FeatureWeight[i];
+        comb[o] = s;
+      }
+    } else {                                                                        /* :273-301 */
+      for (int i = 0; i < 9; i++) orc_imresize_bilinear(feat[i], h, w, 200, 200, small + (size_t)i * 40000);
+      for (int i = 0; i < 9; i++)
+        for (int r = 0; r < 200; r++)
+          for (int c = 0; c < 200; c++)
+            X[(size_t)i * 40000 + c * 200 + r] = (small[(size_t)i * 40000 + r * 200 + c] - p->meanVec[i]) / p->stdVec[i];   /* (:) is column-major */
+      if (feat200) memcpy(feat200 + (size_t)(k - first_out) * 9 * 40000, small, sizeof(double) * 9 * 40000);
+      orc_svm_rbf_predict(p->nsv, p->nfeat, p->SV, p->coef, p->rho, p->gamma, p->label0, p->label1, X, 40000, dec, lab);
+      for (int r = 0; r < 200; r++) for (int c = 0; c < 200; c++) small[r * 200 + c] = dec[c * 200 + r];   /* reshape(dec_values,dims) :298 */
+      orc_pm_norm(small, 40000);                                                    /* :299 */
+      orc_imresize_bilinear(small, 200, 200, h, w, rep);                            /* :300 */
+      orc_imfilter_gauss(rep, h, w, gk, gs, comb);                                  /* :301 */
+    }
+    for (long o = 0; o < N; o++) comb[o] *= dist[o];                                /* :303 */
+    orc_pm_norm(comb, N);                                                           /* :304 */
+    memcpy(out + (size_t)(k - first_out) * N, comb, sizeof(double) * N);
+  }
+  free(Vx); free(Vy); free(mvn); free(bitn); free(depn); free(bit_s); free(dep_s); free(mvx_s); free(mvy_s); free(cam);
+  free(dist); free(mv_c); free(bit_c); free(dep_c); free(mvT); free(bitT); free(depT); free(tb); free(td); free(tx); free(ty);
+  free(con); free(con2); free(rep); for (int i = 0; i < 9; i++) free(feat[i]); free(comb); free(small); free(X); free(dec); free(lab);
+  return 0;
 }

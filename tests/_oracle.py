@@ -143,3 +143,52 @@ def synth_model(nsv, nfeat=9, seed=7):
     SV = r.standard_normal((nsv, nfeat))
     coef = r.uniform(0, 1, nsv) * np.where(np.arange(nsv) < nsv // 2, 1.0, -1.0)
     return SV, coef, 0.1, 1.0 / nfeat, (1, -1)
+
+
+# ---------------------------------------------------------------------------- stage (c) / clip
+def orc_camera_motion(w, h, mvx, mvy, bitmap, depth):
+    h4, w4 = h // 4, w // 4
+    mvx = np.ascontiguousarray(mvx, np.int16); mvy = np.ascontiguousarray(mvy, np.int16)
+    bitmap = np.ascontiguousarray(bitmap, np.uint16); depth = np.ascontiguousarray(depth, np.uint8)
+    outs = [np.zeros((h4, w4)) for _ in range(5)]
+    cam = np.zeros(2, np.int32); ave = np.zeros(2); flag = C.c_int()
+    oracle().orc_camera_motion(w, h, _ptr(mvx), _ptr(mvy), _ptr(bitmap), _ptr(depth), *[_ptr(a) for a in outs],
+                               _ptr(cam), _ptr(ave), C.byref(flag))
+    return outs, cam, ave, flag.value
+
+
+def orc_direction_cluster(vx, vy):
+    vx = np.ascontiguousarray(vx, np.float64); vy = np.ascontiguousarray(vy, np.float64)
+    xa = C.c_double(); ya = C.c_double()
+    oracle().orc_direction_cluster(_ptr(vx), _ptr(vy), vx.size, C.byref(xa), C.byref(ya))
+    return xa.value, ya.value
+
+
+def orc_magnitude_vote(v):
+    v = np.ascontiguousarray(v, np.float64)
+    return float(oracle().orc_magnitude_vote(_ptr(v), v.size))
+
+
+class ClipParams(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("nframes", C.c_int), ("fps", C.c_double),
+                ("nsv", C.c_int), ("nfeat", C.c_int), ("SV", C.c_void_p), ("coef", C.c_void_p),
+                ("rho", C.c_double), ("gamma", C.c_double), ("label0", C.c_int), ("label1", C.c_int),
+                ("meanVec", C.c_void_p), ("stdVec", C.c_void_p), ("use_rbf", C.c_int)]
+
+
+def orc_process_clip(w, h, fps, mvx, mvy, depth, bitmap, model, mean_vec, std_vec, first_out=0, use_rbf=1, want_feat=False):
+    """mvx/mvy/depth: [F][h4][w4]; bitmap [F][nctu].  Returns (maps [F-first_out][h][w], cam [F][2], feat200 or None)."""
+    F = mvx.shape[0]
+    SV, coef, rho, gamma, labels = model
+    SV = np.ascontiguousarray(SV, np.float64); coef = np.ascontiguousarray(coef, np.float64)
+    mv = np.ascontiguousarray(mean_vec, np.float64); sv = np.ascontiguousarray(std_vec, np.float64)
+    p = ClipParams(w, h, F, float(fps), SV.shape[0], SV.shape[1], SV.ctypes.data, coef.ctypes.data, float(rho), float(gamma),
+                   int(labels[0]), int(labels[1]), mv.ctypes.data, sv.ctypes.data, int(use_rbf))
+    mvx = np.ascontiguousarray(mvx, np.int16); mvy = np.ascontiguousarray(mvy, np.int16)
+    depth = np.ascontiguousarray(depth, np.uint8); bitmap = np.ascontiguousarray(bitmap, np.uint16)
+    out = np.zeros((F - first_out, h, w)); cam = np.zeros((F, 2), np.int32)
+    feat = np.zeros((F - first_out, 9, 200, 200)) if (want_feat and use_rbf) else None
+    rc = oracle().orc_process_clip(C.byref(p), _ptr(mvx), _ptr(mvy), _ptr(depth), _ptr(bitmap), first_out, _ptr(out), _ptr(cam),
+                                   _ptr(feat) if feat is not None else None)
+    assert rc == 0, rc
+    return out, cam, feat
