@@ -52,6 +52,10 @@ def _declare(L):
         "cds_measure_peaks": (i32, [c_p, c_p, c_p]),
         "cds_seek": (i32, [c_p, i32]),
         "cds_clip_context_dev": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, c_p]),
+        "cds_clip_context": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, sz]),
+        "cds_profile_stage_names": (C.c_char_p, []),
+        "cds_profile_enable": (i32, [c_p, i32]),
+        "cds_profile_read": (i32, [c_p, c_p, c_p, i32]),
         "cds_debug_copy": (i32, [c_p, C.c_char_p, i32, c_p, sz]),
     }
     missing = []

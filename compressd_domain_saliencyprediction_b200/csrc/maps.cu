@@ -16,6 +16,7 @@
 // All of these passes are bandwidth/latency class (HBM / L2), not FLOP class.
 #include "maps.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace cds {
 
@@ -154,6 +155,8 @@ __device__ __forceinline__ T block_reduce(T v, T* red, Op op) {
 }
 struct OpMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
 struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpMinD { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
+struct OpMaxD { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
 struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
 struct OpAddI { __device__ int operator()(int a, int b) const { return a + b; } };
 
@@ -161,29 +164,32 @@ struct OpAddI { __device__ int operator()(int a, int b) const { return a + b; } 
 // smoothing: causal mean over the last PS pictures (main.m:144-165)
 // =================================================================================================
 __global__ void __launch_bounds__(256)
-smooth_kernel(int n4, int PS, int RL, int first_poc, const float* __restrict__ Vx, const float* __restrict__ Vy,
+smooth_kernel(int n4, int PS, int RL, int first_poc, const double* __restrict__ Vx, const double* __restrict__ Vy,
               const float* __restrict__ mvn, const float* __restrict__ bitn, const float* __restrict__ depn,
               float* __restrict__ mvx_s, float* __restrict__ mvy_s, float* __restrict__ bit_s, float* __restrict__ dep_s,
-              float* __restrict__ mv_s) {
+              float* __restrict__ mv_s, double* __restrict__ cxy, int B) {
   const int o = blockIdx.x * 256 + threadIdx.x, f = blockIdx.y;
   if (o >= n4) return;
   const int poc = first_poc + f;
   const int cnt = min(PS, poc + 1);
-  float a = 0.f, b = 0.f, c = 0.f, d = 0.f, e = 0.f;
+  float a = 0.f, d = 0.f, e = 0.f;
+  double b = 0.0, c = 0.0;                                         // mv_x / mv_y stay double: see camera_motion_kernel<double>
   for (int ii = poc - cnt + 1; ii <= poc; ii++) {                 // ascending, like the reference loop
     const size_t s = (size_t)(ii % RL) * n4 + o;
     a += mvn[s]; b += Vx[s]; c += Vy[s]; d += bitn[s]; e += depn[s];
   }
   const float fc = (float)cnt;
+  b /= (double)cnt; c /= (double)cnt;
   const size_t so = (size_t)(poc % RL) * n4 + o;
-  mv_s[(size_t)f * n4 + o] = a / fc; mvx_s[so] = b / fc; mvy_s[so] = c / fc; bit_s[so] = d / fc; dep_s[so] = e / fc;
+  mv_s[(size_t)f * n4 + o] = a / fc; mvx_s[so] = (float)b; mvy_s[so] = (float)c; bit_s[so] = d / fc; dep_s[so] = e / fc;
+  if (cxy) { cxy[(size_t)f * n4 + o] = b; cxy[((size_t)B + f) * n4 + o] = c; }     // [mvx: B maps | mvy: B maps]
 }
 
-int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const float* Vx, const float* Vy, const float* mvn,
+int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const double* Vx, const double* Vy, const float* mvn,
                   const float* bitn, const float* depn, float* mvx_s, float* mvy_s, float* bit_s, float* dep_s, float* mv_s,
-                  cudaStream_t st) {
+                  double* cxy, cudaStream_t st) {
   dim3 grid(ceil_div(n4, 256), B);
-  smooth_kernel<<<grid, 256, 0, st>>>(n4, PS, ring_len, first_poc, Vx, Vy, mvn, bitn, depn, mvx_s, mvy_s, bit_s, dep_s, mv_s);
+  smooth_kernel<<<grid, 256, 0, st>>>(n4, PS, ring_len, first_poc, Vx, Vy, mvn, bitn, depn, mvx_s, mvy_s, bit_s, dep_s, mv_s, cxy, B);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
@@ -329,6 +335,54 @@ int contrast_pad_launch(const float* sub, const unsigned* minmax_keys, int B, in
                         cudaStream_t st) {
   dim3 grid(ceil_div((srows + 2 * len) * (scols + 2 * len), 256), B);
   contrast_pad_kernel<<<grid, 256, 0, st>>>(sub, minmax_keys, srows, scols, len, pad);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// ---- mv contrast input (cusize 1) in double ------------------------------------------------------
+// Sudoku_contrastcpp5.m:18-34 on a signed map: +1e-8, zero pad, pm_norm.  The padded map's minimum cell
+// becomes exactly 0 and computecontrast5 skips zeros (`p != 0`), so which cells tie with the minimum must
+// be decided exactly as the reference's double arithmetic does; only the normalised result is cast to FP32.
+__device__ __forceinline__ unsigned long long double_key(double d) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(d);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_double(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__global__ void __launch_bounds__(256)
+contrast_minmax_f64_kernel(const double* __restrict__ src, int n, unsigned long long* __restrict__ keys) {
+  __shared__ double redd[8];
+  const int f = blockIdx.y;
+  double mn = INFINITY, mx = -INFINITY;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const double v = src[(size_t)f * n + i] + 0.00000001;            // Sudoku :18
+    mn = fmin(mn, v); mx = fmax(mx, v);
+  }
+  mn = block_reduce(mn, redd, OpMinD());
+  mx = block_reduce(mx, redd, OpMaxD());
+  if (threadIdx.x == 0 && mn <= mx) { atomicMin(keys + 2 * f, double_key(mn)); atomicMax(keys + 2 * f + 1, double_key(mx)); }
+}
+__global__ void __launch_bounds__(256)
+contrast_pad_f64_kernel(const double* __restrict__ src, const unsigned long long* __restrict__ keys, int rows, int cols, int len,
+                        float* __restrict__ pad) {
+  const int f = blockIdx.y, pr = rows + 2 * len, pc = cols + 2 * len;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= pr * pc) return;
+  const double mn = fmin(key_double(keys[2 * f]), 0.0), mx = fmax(key_double(keys[2 * f + 1]), 0.0);   // the zero padding takes part
+  const int r = i / pc, c = i - r * pc;
+  double v = 0.0;
+  if (r >= len && r < len + rows && c >= len && c < len + cols) v = src[(size_t)f * rows * cols + (size_t)(r - len) * cols + (c - len)] + 0.00000001;
+  pad[(size_t)f * pr * pc + i] = (float)((v - mn) / (mx - mn));     // pm_norm.m:2-4
+}
+int contrast_prep_f64_launch(const double* src, int nmaps, int rows, int cols, int len, unsigned long long* keys, float* pad,
+                             cudaStream_t st) {
+  // keys must have been initialised to {~0, 0} pairs by the caller
+  dim3 g1(std::min(ceil_div(rows * cols, 256), 64), nmaps);
+  contrast_minmax_f64_kernel<<<g1, 256, 0, st>>>(src, rows * cols, keys);
+  CDS_LAUNCH_CHECK();
+  dim3 g2(ceil_div((rows + 2 * len) * (cols + 2 * len), 256), nmaps);
+  contrast_pad_f64_kernel<<<g2, 256, 0, st>>>(src, keys, rows, cols, len, pad);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }

@@ -38,9 +38,14 @@ std::vector<double> dense_mul(const std::vector<double>& A, int ar, int ac, cons
 void banded_from_dense(const std::vector<double>& A, int n_out, int n_in, Banded* out);
 
 // ---- launches (all asynchronous on `st`) ----
-int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const float* Vx, const float* Vy, const float* mvn,
+// Vx / Vy rings are double (the reference's mv_x / mv_y cell arrays); cxy (optional) receives the smoothed
+// mvx_crop | mvy_crop of this batch in double, [2][B][n4], for contrast_prep_f64_launch
+int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const double* Vx, const double* Vy, const float* mvn,
                   const float* bitn, const float* depn, float* mvx_s, float* mvy_s, float* bit_s, float* dep_s, float* mv_s,
-                  cudaStream_t st);
+                  double* cxy, cudaStream_t st);
+// Sudoku :18-34 for the signed mv maps in double -> padded FP32 maps; keys [nmaps][2] preset to {~0ull, 0}
+int contrast_prep_f64_launch(const double* src, int nmaps, int rows, int cols, int len, unsigned long long* keys, float* pad,
+                             cudaStream_t st);
 // mysterythrehold on the three smoothed h4 x w4 maps -> Xmaps slots 0,3,6
 int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float* bit_s_ring,
                       const float* dep_s_ring, float* Xmaps, cudaStream_t st);

@@ -19,9 +19,9 @@ namespace cds {
 // from the other translation units
 int getframe_launch(int w, int h, int nframes, const int32_t* hdr, const int16_t* tok, const int64_t* tok_base,
                     int16_t* mvx, int16_t* mvy, uint8_t* depth, int* err, cudaStream_t st);
-int camera_motion_launch(int w, int h, int nframes, const int16_t* mvx, const int16_t* mvy, const uint16_t* byts,
-                         const uint8_t* depth, float* Vx, float* Vy, float* mvn, float* bitn, float* depn, int* cam,
-                         double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st);
+int camera_motion_launch_f64(int w, int h, int nframes, const int16_t* mvx, const int16_t* mvy, const uint16_t* byts,
+                             const uint8_t* depth, double* Vx, double* Vy, float* mvn, float* bitn, float* depn, int* cam,
+                             double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st);
 int contrast_sep_launch(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C, int win,
                         const float* gr, const float* gc, float* dW_scratch, cudaStream_t st);
 void gaussian_factor(int win, double delta, float* g);
@@ -49,14 +49,17 @@ struct cds_ctx {
   // stage (a) batch outputs
   int16_t *d_mvx = nullptr, *d_mvy = nullptr; uint8_t* d_dep = nullptr; int* d_err = nullptr;
   // rings [RL][n4]
-  float *r_Vx = nullptr, *r_Vy = nullptr, *r_mvn = nullptr, *r_bitn = nullptr, *r_depn = nullptr;
+  double *r_Vx = nullptr, *r_Vy = nullptr;            // mv_x / mv_y stay double up to the contrast's pm_norm (zero-test ties)
+  float *r_mvn = nullptr, *r_bitn = nullptr, *r_depn = nullptr;
   float *r_mvx_s = nullptr, *r_mvy_s = nullptr, *r_bit_s = nullptr, *r_dep_s = nullptr;
   int* r_cam = nullptr;                // [RL][2]
   // batch buffers
   float *d_mv_s = nullptr, *d_X = nullptr;           // [B][n4], [B][9][n4]
+  double* d_cxy = nullptr;                            // smoothed mvx | mvy of the batch, [2][B][n4]
+  unsigned long long* d_keys64 = nullptr;             // [2B][2] double min/max keys
   float *d_subB = nullptr, *d_padB = nullptr, *d_rawB = nullptr;   // bit contrast (17x30 @1080p)
   float *d_subD = nullptr, *d_padD = nullptr, *d_rawD = nullptr;   // depth contrast
-  float *d_subM = nullptr, *d_padM = nullptr, *d_rawM = nullptr;   // mvx | mvy: [2B]
+  float *d_padM = nullptr, *d_rawM = nullptr;        // mvx | mvy: [2B]
   unsigned *d_keys = nullptr, *d_maxbits = nullptr;   // [4][B][2], [4][B]
   float *d_T = nullptr;                // [9B][h4][W]
   float *d_Y = nullptr;                // [3B or 9B][H][W]
@@ -80,7 +83,27 @@ struct cds_ctx {
   cudaStream_t stream = nullptr;
   int nblk = 0, nblk2 = 0, nblkf = 0;
   std::vector<void*> allocs;
+  // per-stage device timing (cds_profile_*): events recorded on the launching stream around each stage
+  bool prof_on = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<std::pair<int, cudaEvent_t>> ev_marks;     // (stage id that STARTS here, event); id -1 closes a batch
+  double prof_ms[16] = {0};
+  long prof_calls[16] = {0};
 };
+
+enum Stage { ST_GETFRAME = 0, ST_VOTE, ST_SMOOTH, ST_THRESH_TEMPORAL, ST_CONTRAST_PREP, ST_CONTRAST_W5, ST_CONTRAST_W24,
+             ST_CONTRAST_W48, ST_FULLRES, ST_RESIZE200, ST_SVM, ST_FINAL, ST_COUNT };
+static const char* kStageNames = "getframe,vote,smooth,thresh_temporal,contrast_prep,contrast_win5,contrast_win24,contrast_win48,"
+                                 "fullres_gauss,resize200,svm_rbf,final_map";
+
+static void prof_mark(cds_ctx* c, int stage, cudaStream_t st) {
+  if (!c->prof_on) return;
+  if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; c->ev_pool.push_back(e); }
+  cudaEvent_t e = c->ev_pool[c->ev_used++];
+  cudaEventRecord(e, st);
+  c->ev_marks.push_back({stage, e});
+}
 
 namespace {
 
@@ -100,6 +123,11 @@ double mround(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); }
 // small kernels private to the pipeline
 // ------------------------------------------------------------------------------------------------
 __global__ void fill_u32_kernel(unsigned* p, size_t n, unsigned v0, unsigned v1) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (i & 1) ? v1 : v0;
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v0, unsigned long long v1) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = (i & 1) ? v1 : v0;
 }
@@ -371,14 +399,15 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   if (ce != cudaSuccess) { delete c; set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); return CDS_ECUDA; }
 #define A(ptr, count) if (!e) e = dalloc(c, &c->ptr, (size_t)(count))
   A(d_mvx, (size_t)B * n4); A(d_mvy, (size_t)B * n4); A(d_dep, (size_t)B * n4); A(d_err, 4);
+  if (!e && cudaMemset(c->d_err, 0, 16) != cudaSuccess) { set_error("cudaMemset d_err"); e = CDS_ECUDA; }
   A(r_Vx, (size_t)c->RL * n4); A(r_Vy, (size_t)c->RL * n4); A(r_mvn, (size_t)c->RL * n4); A(r_bitn, (size_t)c->RL * n4);
   A(r_depn, (size_t)c->RL * n4); A(r_mvx_s, (size_t)c->RL * n4); A(r_mvy_s, (size_t)c->RL * n4); A(r_bit_s, (size_t)c->RL * n4);
   A(r_dep_s, (size_t)c->RL * n4); A(r_cam, (size_t)c->RL * 2);
-  A(d_mv_s, (size_t)B * n4); A(d_X, (size_t)B * 9 * n4);
+  A(d_mv_s, (size_t)B * n4); A(d_X, (size_t)B * 9 * n4); A(d_cxy, (size_t)2 * B * n4); A(d_keys64, (size_t)4 * B);
   const int sbR = (h4 + 15) / 16, sbC = (w4 + 15) / 16, sdR = (h4 + 1) / 2, sdC = (w4 + 1) / 2;
   A(d_subB, (size_t)B * sbR * sbC); A(d_padB, (size_t)B * (sbR + 4) * (sbC + 4)); A(d_rawB, (size_t)B * sbR * sbC);
   A(d_subD, (size_t)B * sdR * sdC); A(d_padD, (size_t)B * (sdR + 24) * (sdC + 24)); A(d_rawD, (size_t)B * sdR * sdC);
-  A(d_subM, (size_t)2 * B * n4); A(d_padM, (size_t)2 * B * (h4 + 48) * (w4 + 48)); A(d_rawM, (size_t)2 * B * n4);
+  A(d_padM, (size_t)2 * B * (h4 + 48) * (w4 + 48)); A(d_rawM, (size_t)2 * B * n4);
   A(d_keys, (size_t)4 * B * 2); A(d_maxbits, (size_t)4 * B); A(d_w5, 64 * 64);
   A(d_T, (size_t)9 * B * h4 * W);
   A(d_Y, (size_t)(p->use_rbf ? 3 : 9) * B * HW);
@@ -425,6 +454,7 @@ extern "C" void cds_destroy(cds_ctx* c) {
   if (!c) return;
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   for (void* q : c->allocs) cudaFree(q);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   c->poly.release();
   for (Banded* b : {&c->Av, &c->Ah, &c->Rv, &c->Rh, &c->Bv, &c->Bh}) b->release();
   delete c;
@@ -434,8 +464,9 @@ extern "C" int cds_seek(cds_ctx* c, int poc) {
   if (!c || poc < 0) { set_error("cds_seek: bad arguments"); return CDS_EINVAL; }
   cudaStreamSynchronize(c->stream);
   const size_t rb = (size_t)c->RL * c->n4 * 4;
-  for (float* r : {c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn, c->r_depn, c->r_mvx_s, c->r_mvy_s, c->r_bit_s, c->r_dep_s})
+  for (float* r : {c->r_mvn, c->r_bitn, c->r_depn, c->r_mvx_s, c->r_mvy_s, c->r_bit_s, c->r_dep_s})
     CDS_CUDA(cudaMemset(r, 0, rb));
+  for (double* r : {c->r_Vx, c->r_Vy}) CDS_CUDA(cudaMemset(r, 0, 2 * rb));
   CDS_CUDA(cudaMemset(c->r_cam, 0, (size_t)c->RL * 8));
   c->next_poc = poc; c->pending = 0; c->pending_first = poc; c->last_first = -1; c->last_n = 0;
   c->h_tok.clear();
@@ -448,11 +479,14 @@ namespace {
 // stages (a), (c) and smoothing: everything later pictures need from this one as temporal context
 int run_context_stages(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
                        const int64_t* tok_base, cudaStream_t st) {
+  prof_mark(c, ST_GETFRAME, st);
   if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
-  if (int e = camera_motion_launch(c->w, c->h, n, c->d_mvx, c->d_mvy, bytes, c->d_dep, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn,
-                                   c->r_depn, c->r_cam, nullptr, nullptr, first_poc % c->RL, c->RL, st)) return e;
+  prof_mark(c, ST_VOTE, st);
+  if (int e = camera_motion_launch_f64(c->w, c->h, n, c->d_mvx, c->d_mvy, bytes, c->d_dep, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn,
+                                       c->r_depn, c->r_cam, nullptr, nullptr, first_poc % c->RL, c->RL, st)) return e;
+  prof_mark(c, ST_SMOOTH, st);
   return smooth_launch(c->n4, c->PS, c->RL, first_poc, n, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn, c->r_depn, c->r_mvx_s, c->r_mvy_s,
-                       c->r_bit_s, c->r_dep_s, c->d_mv_s, st);
+                       c->r_bit_s, c->r_dep_s, c->d_mv_s, c->d_cxy, st);
 }
 
 template <typename OutT>
@@ -469,36 +503,47 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   const float* fparam = c->d_fparam;
   if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, st)) return e;
   // ---- thresholded smoothed maps and temporal features -> X slots 0,3,6 / 1,4,7 ----
+  prof_mark(c, ST_THRESH_TEMPORAL, st);
   if (int e = myst_small_launch(n4, H, W, RL, first_poc, n, c->d_mv_s, c->r_bit_s, c->r_dep_s, c->d_X, st)) return e;
   if (int e = temporal_launch(h4, w4, c->PT, RL, first_poc, n, c->r_mvx_s, c->r_mvy_s, c->r_bit_s, c->r_dep_s, c->r_cam, c->d_wtab,
                               c->d_X, st)) return e;
   // ---- (b) contrast: bit (cusize 16, delta 3, win 5), depth (2, 13, 24), mvx / mvy (1, 11, 48)  main.m:226-235 ----
   {
-    const size_t nk = (size_t)4 * n * 2;
+    const size_t nk = (size_t)2 * n * 2;
     fill_u32_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(c->d_keys, nk, 0xffffffffu, 0u);
     CDS_LAUNCH_CHECK();
     CDS_CUDA(cudaMemsetAsync(c->d_maxbits, 0, (size_t)4 * n * 4, st));
-    unsigned *kB = c->d_keys, *kD = c->d_keys + 2 * n, *kX = c->d_keys + 4 * n, *kY = c->d_keys + 6 * n;
+    unsigned *kB = c->d_keys, *kD = c->d_keys + 2 * n;
     unsigned *mB = c->d_maxbits, *mD = c->d_maxbits + n, *mX = c->d_maxbits + 2 * n, *mY = c->d_maxbits + 3 * n;
     const int sbR = (h4 + 15) / 16, sbC = (w4 + 15) / 16, sdR = (h4 + 1) / 2, sdC = (w4 + 1) / 2;
     float g[64];
-    // bit
+    prof_mark(c, ST_CONTRAST_PREP, st);
+    // block mean (+1e-8), zero pad, pm_norm of the padded map (cu_contrast5.m:8-32, Sudoku_contrastcpp5.m:18-34)
     if (int e = contrast_sub_launch(c->d_X + (size_t)3 * n4, (long)9 * n4, 0, 0, n, h4, w4, 16, c->d_subB, kB, st)) return e;
     if (int e = contrast_pad_launch(c->d_subB, kB, n, sbR, sbC, 2, c->d_padB, st)) return e;
-    if (int e = contrast_generic_launch(c->d_padB, c->d_w5, c->d_rawB, mB, n, sbR, sbC, 5, 2, st)) return e;
-    if (int e = contrast_post_launch(c->d_rawB, mB, n, sbR, sbC, 16, h4, w4, c->d_X, 5, st)) return e;
-    // depth
     if (int e = contrast_sub_launch(c->d_X + (size_t)6 * n4, (long)9 * n4, 0, 0, n, h4, w4, 2, c->d_subD, kD, st)) return e;
     if (int e = contrast_pad_launch(c->d_subD, kD, n, sdR, sdC, 12, c->d_padD, st)) return e;
+    // mvx | mvy (cusize 1) in double up to the pm_norm; d_cxy holds [mvx: n maps | mvy: n maps] (written by smooth_launch)
+    {
+      const size_t nk64 = (size_t)2 * n * 2;
+      fill_u64_kernel<<<(unsigned)((nk64 + 255) / 256), 256, 0, st>>>(c->d_keys64, nk64, ~0ull, 0ull);
+      CDS_LAUNCH_CHECK();
+      if (int e = contrast_prep_f64_launch(c->d_cxy, 2 * n, h4, w4, 24, c->d_keys64, c->d_padM, st)) return e;
+    }
+    // bit: 5x5 window on the CTU grid
+    prof_mark(c, ST_CONTRAST_W5, st);
+    if (int e = contrast_generic_launch(c->d_padB, c->d_w5, c->d_rawB, mB, n, sbR, sbC, 5, 2, st)) return e;
+    // depth: 24x24 window on the 8-px grid
+    prof_mark(c, ST_CONTRAST_W24, st);
     gaussian_factor(24, 13.0, g);
     if (int e = contrast_sep_launch(c->d_padD, c->d_rawD, mD, n, sdR, sdC, 24, g, g, nullptr, st)) return e;
-    if (int e = contrast_post_launch(c->d_rawD, mD, n, sdR, sdC, 2, h4, w4, c->d_X, 8, st)) return e;
-    // mvx | mvy as 2n maps in one launch
-    if (int e = contrast_sub_launch(c->r_mvx_s, (long)n4, RL, first_poc % RL, n, h4, w4, 1, c->d_subM, kX, st)) return e;
-    if (int e = contrast_sub_launch(c->r_mvy_s, (long)n4, RL, first_poc % RL, n, h4, w4, 1, c->d_subM + (size_t)n * n4, kY, st)) return e;
-    if (int e = contrast_pad_launch(c->d_subM, kX, 2 * n, h4, w4, 24, c->d_padM, st)) return e;   // kX,kY contiguous: keys [2n][2]
+    // mvx | mvy as 2n maps in one launch: 48x48 window on the 4-px grid (the dominant FP32 kernel)
+    prof_mark(c, ST_CONTRAST_W48, st);
     gaussian_factor(48, 11.0, g);
     if (int e = contrast_sep_launch(c->d_padM, c->d_rawM, mX, 2 * n, h4, w4, 48, g, g, nullptr, st)) return e;   // mX,mY contiguous
+    prof_mark(c, ST_FULLRES, st);
+    if (int e = contrast_post_launch(c->d_rawB, mB, n, sbR, sbC, 16, h4, w4, c->d_X, 5, st)) return e;
+    if (int e = contrast_post_launch(c->d_rawD, mD, n, sdR, sdC, 2, h4, w4, c->d_X, 8, st)) return e;
     if (int e = contrast_post_mv_launch(c->d_rawM, c->d_rawM + (size_t)n * n4, mX, mY, n, h4, w4, c->d_X, 2, st)) return e;
   }
   // ---- fourX2 + imfilter(gaussian) at full resolution: statistics (and the temporal maps themselves) ----
@@ -516,6 +561,7 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   int nbf = 0;
   if (c->p.use_rbf) {
     // ---- features at 200x200 (main.m:275-294) ----
+    prof_mark(c, ST_RESIZE200, st);
     if (int e = banded_rows_launch(c->d_X, 9 * n, h4, w4, c->Av, nullptr, c->d_A1, st)) return e;
     if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, c->d_F200, st)) return e;
     if (int e = banded_rows_launch(c->d_Y, 3 * n, H, W, c->Rv, c->d_xf, c->d_R1, st)) return e;
@@ -526,7 +572,9 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
       CDS_LAUNCH_CHECK();
     }
     // ---- (d) RBF-SVM, then pm_norm -> imresize -> imfilter -> centre prior (main.m:297-304) ----
+    prof_mark(c, ST_SVM, st);
     if (int e = svm_predict_launch(c->p.model, c->d_xsvm, (long)n * 40000, c->d_dec, st)) return e;
+    prof_mark(c, ST_FINAL, st);
     dec_minmax_norm_kernel<<<n, 1024, 0, st>>>(c->d_dec, c->d_C);
     CDS_LAUNCH_CHECK();
     if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, st)) return e;
@@ -537,6 +585,7 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
       nbf = grid.x * grid.y;
     }
   } else {
+    prof_mark(c, ST_FINAL, st);
     dim3 grid(128, n);
     linear_comb_kernel<<<grid, 256, 0, st>>>(c->d_Y, c->HW, c->d_stats9, c->d_xf, fparam, c->d_dist, c->d_raw, c->d_fpartial);
     CDS_LAUNCH_CHECK();
@@ -551,6 +600,7 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     for (int f = 0; f < n; f++)
       CDS_CUDA(cudaMemcpyAsync(cam_out + 2 * f, c->r_cam + 2 * ((first_poc + f) % RL), 8, cudaMemcpyDeviceToDevice, st));
   }
+  prof_mark(c, -1, st);
   return CDS_OK;
 }
 
@@ -590,14 +640,22 @@ extern "C" int cds_clip_process_dev(cds_ctx* c, int first_poc, int nframes, cons
 
 // host buffers in, results rendered into c->d_out batch by batch and copied to host_out when given
 static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
-                        const int16_t* tok, const int64_t* tok_base, size_t ntok, void* host_out, int* cam_out) {
+                        const int16_t* tok, const int64_t* tok_base, size_t ntok, void* host_out, int* cam_out,
+                        bool context_only = false) {
   cudaStream_t st = c->stream;
   const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
   for (int done = 0; done < nframes; done += c->B) {
     const int n = std::min(c->B, nframes - done);
     const int64_t t0 = tok_base[done], t1 = tok_base[done + n];
     if (t0 < 0 || t1 < t0 || (size_t)t1 > ntok) { set_error("cds_clip_process: tok_base out of range"); return CDS_EFORMAT; }
-    if ((size_t)(t1 - t0) > c->tok_cap) { set_error("cds_clip_process: %lld tokens exceed the staging capacity %zu", (long long)(t1 - t0), c->tok_cap); return CDS_ENOMEM; }
+    if ((size_t)(t1 - t0) > c->tok_cap) {        // grow the token staging buffer (worst case 1237 tokens per CTU)
+      CDS_CUDA(cudaStreamSynchronize(st));
+      const size_t want = (size_t)(t1 - t0) + (size_t)(t1 - t0) / 4;
+      void* q = nullptr;
+      if (cudaMalloc(&q, want * 2 + 256) != cudaSuccess) { set_error("cds_clip_process: cannot stage %zu tokens", want); return CDS_ENOMEM; }
+      for (void*& a : c->allocs) if (a == (void*)c->d_tok) { cudaFree(a); a = q; }
+      c->d_tok = reinterpret_cast<int16_t*>(q); c->tok_cap = want;
+    }
     std::vector<int64_t> base(n + 1);
     for (int i = 0; i <= n; i++) base[i] = tok_base[done + i] - t0;
     CDS_CUDA(cudaMemcpyAsync(c->d_bytes, ctu_bytes + (size_t)done * c->nctu, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, st));
@@ -605,7 +663,11 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
     CDS_CUDA(cudaMemcpyAsync(c->d_tok, tok + t0, (size_t)(t1 - t0) * 2, cudaMemcpyHostToDevice, st));
     CDS_CUDA(cudaMemcpyAsync(c->d_tokbase, base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CDS_CUDA(cudaStreamSynchronize(st));   // `base` is a host temporary
-    if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out, nullptr, st)) return e;
+    if (context_only) {
+      if (int e = run_context_stages(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, st)) return e;
+    } else {
+      if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out, nullptr, st)) return e;
+    }
     if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)done * px, c->d_out, (size_t)n * px, cudaMemcpyDeviceToHost, st));
     if (cam_out)
       for (int f = 0; f < n; f++)
@@ -614,9 +676,20 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
     CDS_CUDA(cudaMemcpyAsync(&herr, c->d_err, 4, cudaMemcpyDeviceToHost, st));
     CDS_CUDA(cudaStreamSynchronize(st));
     if (herr) { CDS_CUDA(cudaMemset(c->d_err, 0, 4)); set_error("cds_clip_process: malformed CU token stream in pictures %d..%d", first_poc + done, first_poc + done + n - 1); return CDS_EFORMAT; }
-    c->last_first = first_poc + done; c->last_n = n;
+    if (!context_only) { c->last_first = first_poc + done; c->last_n = n; }
   }
   c->next_poc = first_poc + nframes;
+  return CDS_OK;
+}
+
+extern "C" int cds_clip_context(cds_ctx* c, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
+                                const int16_t* tok, const int64_t* tok_base, size_t ntok) {
+  if (int e = ensure_device()) return e;
+  if (!c || !ctu_bytes || !hdr || !tok || !tok_base || nframes < 1) { set_error("cds_clip_context: bad arguments"); return CDS_EINVAL; }
+  if (first_poc != c->next_poc) { set_error("cds_clip_context: expected poc %d, got %d (use cds_seek)", c->next_poc, first_poc); return CDS_EINVAL; }
+  if (c->pending) { set_error("cds_clip_context: pictures submitted through cds_submit_frame are still pending"); return CDS_EINVAL; }
+  if (int e = process_host(c, first_poc, nframes, ctu_bytes, hdr, tok, tok_base, ntok, nullptr, nullptr, true)) return e;
+  c->pending_first = c->next_poc;
   return CDS_OK;
 }
 
@@ -677,6 +750,33 @@ extern "C" int cds_get_map(cds_ctx* c, int poc, void* dst, int* cam_xy) {
   const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
   CDS_CUDA(cudaMemcpy(dst, (char*)c->d_out + (size_t)(poc - c->last_first) * px, px, cudaMemcpyDeviceToHost));
   if (cam_xy) CDS_CUDA(cudaMemcpy(cam_xy, c->r_cam + 2 * (poc % c->RL), 8, cudaMemcpyDeviceToHost));
+  return CDS_OK;
+}
+
+// ---- per-stage device timing -------------------------------------------------------------------
+extern "C" const char* cds_profile_stage_names(void) { return kStageNames; }
+
+extern "C" int cds_profile_enable(cds_ctx* c, int on) {
+  if (!c) { set_error("cds_profile_enable: null context"); return CDS_EINVAL; }
+  CDS_CUDA(cudaStreamSynchronize(c->stream));
+  c->prof_on = on != 0; c->ev_used = 0; c->ev_marks.clear();
+  for (int i = 0; i < 16; i++) { c->prof_ms[i] = 0; c->prof_calls[i] = 0; }
+  return CDS_OK;
+}
+
+// Synchronises the device, folds every recorded stage interval into per-stage totals and returns them
+// (milliseconds and number of timed intervals per stage, ST_COUNT entries each) since cds_profile_enable.
+extern "C" int cds_profile_read(cds_ctx* c, double* ms, long* calls, int n) {
+  if (!c || !ms || n < ST_COUNT) { set_error("cds_profile_read: need room for %d stages", (int)ST_COUNT); return CDS_EINVAL; }
+  CDS_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i + 1 < c->ev_marks.size(); i++) {
+    const int id = c->ev_marks[i].first;
+    if (id < 0) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, c->ev_marks[i].second, c->ev_marks[i + 1].second) == cudaSuccess) { c->prof_ms[id] += t; c->prof_calls[id]++; }
+  }
+  c->ev_marks.clear(); c->ev_used = 0;
+  for (int i = 0; i < ST_COUNT; i++) { ms[i] = c->prof_ms[i]; if (calls) calls[i] = c->prof_calls[i]; }
   return CDS_OK;
 }
 

@@ -123,10 +123,13 @@ __device__ __forceinline__ void find_pivot(const unsigned* hist, int nbins, int 
 }
 
 // grid: one CTA per picture f (slot given by slot_of[f] into the ring outputs)
+// VT = double for the clip pipeline: the smoothed mv maps feed Sudoku_contrastcpp5's `p != 0` test after a
+// pm_norm, so ties at the map minimum must round exactly as the reference's double arithmetic does.
+template <typename VT>
 __global__ void __launch_bounds__(CM_THREADS)
 camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const int16_t* __restrict__ mvy_all,
                      const uint16_t* __restrict__ bytes_all, const uint8_t* __restrict__ depth_all,
-                     float* __restrict__ Vx_ring, float* __restrict__ Vy_ring, float* __restrict__ mvn_ring,
+                     VT* __restrict__ Vx_ring, VT* __restrict__ Vy_ring, float* __restrict__ mvn_ring,
                      float* __restrict__ bitn_ring, float* __restrict__ depn_ring, int* __restrict__ cam_ring,
                      double* __restrict__ ave_out, int* __restrict__ flag_out, int first_slot, int ring_len) {
   __shared__ CmShared S;
@@ -138,7 +141,7 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
   const uint16_t* __restrict__ byts = bytes_all + (size_t)f * nctu;
   const uint8_t* __restrict__ dep = depth_all + (size_t)f * n4;
   const int slot = (first_slot + f) % ring_len;
-  float* Vx = Vx_ring + (size_t)slot * n4; float* Vy = Vy_ring + (size_t)slot * n4;
+  VT* Vx = Vx_ring + (size_t)slot * n4; VT* Vy = Vy_ring + (size_t)slot * n4;
   float* mvn = mvn_ring + (size_t)slot * n4; float* bitn = bitn_ring + (size_t)slot * n4; float* depn = depn_ring + (size_t)slot * n4;
   const int tid = threadIdx.x, lane = tid & 31;
 
@@ -264,14 +267,15 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
   // ---- pass 5: compensated field, |V| max ----
   float vmax = 0.f;
   for (int o = tid; o < n4; o += CM_THREADS) {
-    float vx, vy;
+    double dvx, dvy;
     if (flag) {
       const CmCell c = cm_cell(mvx, mvy, byts, h4, w4, ncol, bmn, o);
-      vx = (float)((double)c.kx * 0.125 - x_ave); vy = (float)((double)c.ky * 0.125 - y_ave);   // Vxf - x_ave  (main.m:89-90)
+      dvx = (double)c.kx * 0.125 - x_ave; dvy = (double)c.ky * 0.125 - y_ave;                   // Vxf - x_ave  (main.m:89-90)
     } else {
-      vx = (float)mvx[o] * 0.25f; vy = (float)mvy[o] * 0.25f;                                   // unfiltered (main.m:78-79,93)
+      dvx = (double)mvx[o] * 0.25; dvy = (double)mvy[o] * 0.25;                                 // unfiltered (main.m:78-79,93)
     }
-    Vx[o] = vx; Vy[o] = vy;
+    Vx[o] = (VT)dvx; Vy[o] = (VT)dvy;
+    const float vx = (float)dvx, vy = (float)dvy;
     const float m = sqrtf(vx * vx + vy * vy);
     mvn[o] = m;
     vmax = fmaxf(vmax, m);
@@ -297,8 +301,16 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
 int camera_motion_launch(int w, int h, int nframes, const int16_t* mvx, const int16_t* mvy, const uint16_t* byts,
                          const uint8_t* depth, float* Vx, float* Vy, float* mvn, float* bitn, float* depn, int* cam,
                          double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st) {
-  camera_motion_kernel<<<nframes, CM_THREADS, 0, st>>>(w, h, mvx, mvy, byts, depth, Vx, Vy, mvn, bitn, depn, cam, ave, flag,
-                                                       first_slot, ring_len);
+  camera_motion_kernel<float><<<nframes, CM_THREADS, 0, st>>>(w, h, mvx, mvy, byts, depth, Vx, Vy, mvn, bitn, depn, cam, ave,
+                                                              flag, first_slot, ring_len);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+int camera_motion_launch_f64(int w, int h, int nframes, const int16_t* mvx, const int16_t* mvy, const uint16_t* byts,
+                             const uint8_t* depth, double* Vx, double* Vy, float* mvn, float* bitn, float* depn, int* cam,
+                             double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st) {
+  camera_motion_kernel<double><<<nframes, CM_THREADS, 0, st>>>(w, h, mvx, mvy, byts, depth, Vx, Vy, mvn, bitn, depn, cam, ave,
+                                                               flag, first_slot, ring_len);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }

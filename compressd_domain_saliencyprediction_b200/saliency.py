@@ -71,6 +71,16 @@ class SaliencyClip:
                                      _ptr(maps), _ptr(cam)), "cds_clip_process")
         return maps, cam
 
+    def context(self, first_poc, hdr, tok, tok_base, ctu_bytes):
+        """Feed pictures as temporal context only (frame-range sharding halo): no maps are produced."""
+        hdr = np.ascontiguousarray(hdr, np.int32); tok = np.ascontiguousarray(tok, np.int16)
+        tok_base = np.ascontiguousarray(tok_base, np.int64); byts = np.ascontiguousarray(ctu_bytes, np.uint16)
+        F = hdr.shape[0]
+        if hdr.shape != (F, nctu(self.w, self.h), 4) or byts.shape != (F, nctu(self.w, self.h)) or tok_base.size != F + 1:
+            raise CdsError("context: packed syntax shapes do not match the picture size")
+        check(lib().cds_clip_context(self._h, int(first_poc), F, _ptr(byts), _ptr(hdr), _ptr(tok), _ptr(tok_base), tok.size),
+              "cds_clip_context")
+
     # hook-style surface (TDecGop.cpp:270-332): one picture per call
     def submit_frame(self, poc, ctu_bytes, hdr, tok):
         hdr = np.ascontiguousarray(hdr, np.int32); tok = np.ascontiguousarray(tok, np.int16)

@@ -168,10 +168,19 @@ int cds_seek(cds_ctx* ctx, int poc);
  * pictures of temporal context; no saliency maps are produced.  Device pointers, as cds_clip_process_dev. */
 int cds_clip_context_dev(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
                          const int16_t* tok, const int64_t* tok_base, void* stream);
+/* Same with HOST buffers (as cds_clip_process). */
+int cds_clip_context(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
+                     const int16_t* tok, const int64_t* tok_base, size_t ntok);
 /* Test hook: copy an intermediate of the most recent batch to host memory.  which = "xmaps" ([9][h/4*w/4]),
  * "stats" ([9][4]), "feat200" ([9][40000]), "ft" ([3][40000]), "xf" ([3][4]), "xsvm" ([40000][9]), "dec" ([40000]),
  * "raw" ([h][w]); all FP32. */
 int cds_debug_copy(cds_ctx* ctx, const char* which, int frame_in_batch, void* dst, size_t bytes);
+/* Per-stage device timing of the clip pipeline: CUDA events recorded on the launching stream around
+ * each stage of every batch.  cds_profile_stage_names() is a comma-separated list; cds_profile_read
+ * synchronises and returns accumulated milliseconds / interval counts per stage (same order). */
+const char* cds_profile_stage_names(void);
+int cds_profile_enable(cds_ctx* ctx, int on);
+int cds_profile_read(cds_ctx* ctx, double* ms, long* calls, int n);
 /* Measure this device's issue ceilings with micro-kernels (lane-instructions per second): the
  * contrast kernel's FADD+FFMA pair mix, pure FFMA, and MUFU.EX2.  Used as roofline denominators
  * for the FP32/MUFU-bound kernels (MEASURED_PEAKS.json has only HBM and bf16 tensor numbers). */

@@ -6,6 +6,35 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+
+/* A pthread parallel-for (orc_set_threads) only splits loops whose iterations write disjoint outputs
+ * and keep their own accumulation order, so results are identical for any thread count.  It exists
+ * for the CPU-baseline timing ("all host threads"); the reference itself is single-threaded.
+ * (This image's gcc has no libgomp, hence pthreads instead of OpenMP.) */
+#include <pthread.h>
+static int g_orc_threads = 1;
+void orc_set_threads(int n) { g_orc_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+int orc_threads(void) { return g_orc_threads; }
+typedef void (*orc_range_fn)(long lo, long hi, void* ctx);
+typedef struct { orc_range_fn fn; void* ctx; long lo, hi; } orc_job;
+static void* orc_job_run(void* p) { orc_job* j = (orc_job*)p; j->fn(j->lo, j->hi, j->ctx); return 0; }
+static void orc_parallel_for(long n, orc_range_fn fn, void* ctx) {
+  int T = g_orc_threads;
+  if (T > n) T = (int)(n > 0 ? n : 1);
+  if (T <= 1) { fn(0, n, ctx); return; }
+  pthread_t th[256]; orc_job jobs[256];
+  for (int t = 0; t < T; t++) {
+    jobs[t].fn = fn; jobs[t].ctx = ctx; jobs[t].lo = n * t / T; jobs[t].hi = n * (t + 1) / T;
+    if (t + 1 < T) pthread_create(&th[t], 0, orc_job_run, &jobs[t]);
+  }
+  orc_job_run(&jobs[T - 1]);
+  for (int t = 0; t + 1 < T; t++) pthread_join(th[t], 0);
+}
+static double orc_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+static double g_orc_t_context = 0, g_orc_t_output = 0;
+/* seconds the last orc_process_clip spent in (0) pass 1 + smoothing over all frames, (1) the per-output-frame work */
+double orc_last_seconds(int which) { return which == 0 ? g_orc_t_context : g_orc_t_output; }
 
 #define ORC_MAXTOK 2048
 
@@ -141,16 +170,17 @@ static int orc_subst(int L, const int* mv, int x) {
 int orc_getframe(int w, int h, const int32_t* hdr, const int16_t* tok, int16_t* mvx, int16_t* mvy, uint8_t* depth) {
   int ncol = (w + 63) / 64, nrow = (h + 63) / 64;   /* == int(w/64.0+0.5) for every supported size, code_mat_h.h:20-21 */
   int h4 = h / 4, w4 = w / 4;
-  orc_cu cus[256];
-  int base[256], pux[512], puy[512];
+  int rc_all = 0;
   for (int line = 0; line < nrow * ncol; line++) {
+    orc_cu cus[256];
+    int base[256], pux[512], puy[512];
     const int16_t* cupu = tok + hdr[line * 4 + 0];
     int ncupu = hdr[line * 4 + 1], npred = hdr[line * 4 + 2], nmv = hdr[line * 4 + 3];
     const int16_t* pred = cupu + ncupu;
     const int16_t* mv = pred + npred;
-    if (ncupu > ORC_MAXTOK || npred > ORC_MAXTOK || nmv > ORC_MAXTOK) return -10;
+    if (ncupu > ORC_MAXTOK || npred > ORC_MAXTOK || nmv > ORC_MAXTOK) { rc_all = -10; continue; }
     int ncu = 0, pos = 0;
-    if (orc_walk(cupu, ncupu, &pos, 0, 0, 64, cus, &ncu)) return -1;
+    if (orc_walk(cupu, ncupu, &pos, 0, 0, 64, cus, &ncu)) { rc_all = -1; continue; }
     /* label bookkeeping; `lab15` = label a PartSize-15 CU carries before compaction (negated, :409) */
     int next = 1, next15 = 1;
     int lab15[256];
@@ -184,17 +214,19 @@ int orc_getframe(int w, int h, const int32_t* hdr, const int16_t* tok, int16_t* 
       }
     }
   }
-  return 0;
+  return rc_all;
 }
 
 /* =====================================================================================
  * Stage (b)
  * ===================================================================================== */
 /* computecontrast5.cpp:52-96 (img_extract :11, outer_pro :30, sumup :41); column-major. */
-void orc_computecontrast5(const double* pad, int m1, int n1, const double* W, int len, int win,
-                          int m, int n, double* out) {
-  (void)n1;
-  for (int row = 1 + len; row <= m + len; row++) {
+typedef struct { const double* pad; int m1; const double* W; int len, win, m, n; double* out; } orc_cc5_ctx;
+static void orc_cc5_rows(long lo, long hi, void* vp) {
+  orc_cc5_ctx* a = (orc_cc5_ctx*)vp;
+  const double* pad = a->pad; const double* W = a->W; double* out = a->out;
+  const int m1 = a->m1, len = a->len, win = a->win, m = a->m, n = a->n;
+  for (int row = 1 + len + (int)lo; row < 1 + len + (int)hi; row++) {
     for (int col = 1 + len; col <= n + len; col++) {
       double centre = pad[(size_t)(col - 1) * m1 + row - 1];                      /* :83 */
       double acc = 0;
@@ -209,6 +241,12 @@ void orc_computecontrast5(const double* pad, int m1, int n1, const double* W, in
       out[(size_t)(col - len - 1) * m + row - len - 1] = acc;                      /* :91 */
     }
   }
+}
+void orc_computecontrast5(const double* pad, int m1, int n1, const double* W, int len, int win,
+                          int m, int n, double* out) {
+  (void)n1;
+  orc_cc5_ctx a = {pad, m1, W, len, win, m, n, out};
+  orc_parallel_for(m, orc_cc5_rows, &a);
 }
 
 static double orc_round(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); }  /* MATLAB round */
@@ -284,10 +322,14 @@ void orc_cu_contrast5(const double* map, int rows, int cols, int cusize, double 
  * with the dense instance rows built by matlab/svmpredict.c:165-170.  A dense x against a sparse
  * SV walks every index 1..F in order; a missing SV entry contributes x_j*x_j == (x_j-0)^2.
  * ===================================================================================== */
-void orc_svm_rbf_predict(int nsv, int nfeat, const double* SV, const double* coef, double rho,
-                         double gamma, int label0, int label1, const double* X, int N,
-                         double* dec, double* label) {
-  for (int n = 0; n < N; n++) {
+typedef struct { int nsv, nfeat; const double* SV; const double* coef; double rho, gamma; int label0, label1;
+                 const double* X; int N; double* dec; double* label; } orc_svm_ctx;
+static void orc_svm_rows(long lo, long hi, void* vp) {
+  orc_svm_ctx* a = (orc_svm_ctx*)vp;
+  const int nsv = a->nsv, nfeat = a->nfeat, N = a->N, label0 = a->label0, label1 = a->label1;
+  const double *SV = a->SV, *coef = a->coef, *X = a->X; const double rho = a->rho, gamma = a->gamma;
+  double *dec = a->dec, *label = a->label;
+  for (int n = (int)lo; n < (int)hi; n++) {
     double sum = 0;
     for (int i = 0; i < nsv; i++) {
       double d2 = 0;
@@ -301,6 +343,12 @@ void orc_svm_rbf_predict(int nsv, int nfeat, const double* SV, const double* coe
     dec[n] = sum;
     label[n] = sum > 0 ? label0 : label1;                                          /* :2556-2559 */
   }
+}
+void orc_svm_rbf_predict(int nsv, int nfeat, const double* SV, const double* coef, double rho,
+                         double gamma, int label0, int label1, const double* X, int N,
+                         double* dec, double* label) {
+  orc_svm_ctx a = {nsv, nfeat, SV, coef, rho, gamma, label0, label1, X, N, dec, label};
+  orc_parallel_for(N, orc_svm_rows, &a);
 }
 
 /* =====================================================================================
@@ -371,12 +419,11 @@ void orc_gauss_kernel(int k, double sigma, double* g) {
 /* imfilter(A, h): correlation, zero padding, 'same'; kernel origin floor((k+1)/2) (1-based).
  * Loops are ordered tap-outermost so the compiler can vectorise along the row (this only matters
  * for the CPU-baseline timing; every output still accumulates its taps in ascending order). */
-void orc_imfilter_gauss(const double* a, int rows, int cols, int k, double sigma, double* out) {
-  double* g = (double*)malloc(sizeof(double) * k);
-  double* tmp = (double*)calloc((size_t)rows * cols, sizeof(double));
-  orc_gauss_kernel(k, sigma, g);
-  int c0 = (k + 1) / 2 - 1;   /* 0-based index of the origin tap */
-  for (int r = 0; r < rows; r++) {
+typedef struct { const double* a; int rows, cols, k, c0; const double* g; double* tmp; double* out; } orc_imf_ctx;
+static void orc_imf_hpass(long lo_, long hi_, void* vp) {
+  orc_imf_ctx* q = (orc_imf_ctx*)vp;
+  const double* a = q->a; const double* g = q->g; double* tmp = q->tmp; const int cols = q->cols, k = q->k, c0 = q->c0;
+  for (int r = (int)lo_; r < (int)hi_; r++) {
     const double* ar = a + (size_t)r * cols; double* tr = tmp + (size_t)r * cols;
     for (int u = 0; u < k; u++) {
       int lo = c0 - u < 0 ? 0 : c0 - u, hi = cols + c0 - u > cols ? cols : cols + c0 - u;
@@ -384,8 +431,11 @@ void orc_imfilter_gauss(const double* a, int rows, int cols, int k, double sigma
       for (int c = lo; c < hi; c++) tr[c] += gu * src[c];
     }
   }
-  memset(out, 0, sizeof(double) * (size_t)rows * cols);
-  for (int r = 0; r < rows; r++) {
+}
+static void orc_imf_vpass(long lo_, long hi_, void* vp) {
+  orc_imf_ctx* q = (orc_imf_ctx*)vp;
+  const double* g = q->g; const double* tmp = q->tmp; double* out = q->out; const int rows = q->rows, cols = q->cols, k = q->k, c0 = q->c0;
+  for (int r = (int)lo_; r < (int)hi_; r++) {
     double* orow = out + (size_t)r * cols;
     for (int u = 0; u < k; u++) {
       int sr = r + u - c0;
@@ -394,6 +444,15 @@ void orc_imfilter_gauss(const double* a, int rows, int cols, int k, double sigma
       for (int c = 0; c < cols; c++) orow[c] += gu * src[c];
     }
   }
+}
+void orc_imfilter_gauss(const double* a, int rows, int cols, int k, double sigma, double* out) {
+  double* g = (double*)malloc(sizeof(double) * k);
+  double* tmp = (double*)calloc((size_t)rows * cols, sizeof(double));
+  orc_gauss_kernel(k, sigma, g);
+  orc_imf_ctx q = {a, rows, cols, k, (k + 1) / 2 - 1 /* 0-based index of the origin tap */, g, tmp, out};
+  orc_parallel_for(rows, orc_imf_hpass, &q);
+  memset(out, 0, sizeof(double) * (size_t)rows * cols);
+  orc_parallel_for(rows, orc_imf_vpass, &q);
   free(g); free(tmp);
 }
 
@@ -599,6 +658,26 @@ static void orc_feature_fullres(const double* x4, int h, int w, int gk, double g
   orc_pm_norm(out, (long)h * w);
 }
 
+typedef struct { int w, h; long n4; int nctu; const int16_t *mvx, *mvy; const uint16_t* bitmap; const uint8_t* depth;
+                 double *Vx, *Vy, *mvn, *bitn, *depn; int* cam; } orc_pass1_ctx;
+static void orc_pass1_frames(long lo, long hi, void* vp) {
+  orc_pass1_ctx* a = (orc_pass1_ctx*)vp;
+  const long n4 = a->n4;
+  for (long ii = lo; ii < hi; ii++)
+    orc_camera_motion(a->w, a->h, a->mvx + ii * n4, a->mvy + ii * n4, a->bitmap + (size_t)ii * a->nctu, a->depth + ii * n4,
+                      a->Vx + ii * n4, a->Vy + ii * n4, a->mvn + ii * n4, a->bitn + ii * n4, a->depn + ii * n4, a->cam + 2 * ii, 0, 0);
+}
+typedef struct { long n4; const double *cx, *cy, *cb, *cd, *tx, *ty, *tb, *td; double wm, wb, wd; double *mvT, *bitT, *depT; } orc_tmp_ctx;
+static void orc_temporal_cells(long lo, long hi, void* vp) {
+  orc_tmp_ctx* a = (orc_tmp_ctx*)vp;
+  for (long o = lo; o < hi; o++) {
+    double dx = a->cx[o] - a->tx[o], dy = a->cy[o] - a->ty[o];
+    a->mvT[o] += a->wm * sqrt(dx * dx + dy * dy);                                   /* main.m:195 */
+    a->bitT[o] += a->wb * fabs(a->cb[o] - a->tb[o]);                                /* main.m:196 */
+    a->depT[o] += a->wd * fabs(a->cd[o] - a->td[o]);                                /* main.m:197 */
+  }
+}
+
 int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t* mvy,
                      const uint8_t* depth, const uint16_t* bitmap, int first_out,
                      double* out, int* cam_out, double* feat200) {
@@ -618,10 +697,13 @@ int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t
   double *mvx_s = (double*)malloc(mapb * F), *mvy_s = (double*)malloc(mapb * F);
   int* cam = (int*)malloc(sizeof(int) * 2 * F);
   /* ---- pass 1: camera motion, main.m:77-105 ---- */
-  for (int ii = 0; ii < F; ii++)
-    orc_camera_motion(w, h, mvx + ii * n4, mvy + ii * n4, bitmap + (size_t)ii * nctu, depth + ii * n4,
-                      Vx + ii * n4, Vy + ii * n4, mvn + ii * n4, bitn + ii * n4, depn + ii * n4, cam + 2 * ii, 0, 0);
+  double t_ctx = 0, t_out = 0, t0 = orc_now();
+  {
+    orc_pass1_ctx a = {w, h, n4, nctu, mvx, mvy, bitmap, depth, Vx, Vy, mvn, bitn, depn, cam};
+    orc_parallel_for(F, orc_pass1_frames, &a);
+  }
   if (cam_out) memcpy(cam_out, cam, sizeof(int) * 2 * F);
+  t_ctx += orc_now() - t0;
   double* dist = (double*)malloc(sizeof(double) * N);
   orc_distmatrix(h, w, dist);                                                       /* main.m:131 */
   double *mv_c = (double*)malloc(mapb), *bit_c = (double*)malloc(mapb), *dep_c = (double*)malloc(mapb);
@@ -639,6 +721,7 @@ int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t
   /* ---- pass 2, main.m:137-307 ---- */
   for (int k = 0; k < F; k++) {
     int count = 0;
+    t0 = orc_now();
     double *cx = mvx_s + k * n4, *cy = mvy_s + k * n4, *cb = bit_s + k * n4, *cd = dep_s + k * n4;
     memset(mv_c, 0, mapb); memset(cx, 0, mapb); memset(cy, 0, mapb); memset(cb, 0, mapb); memset(cd, 0, mapb);
     for (int ii = k - PS + 1; ii <= k; ii++) {                                      /* :144-153 */
@@ -650,7 +733,9 @@ int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t
       count++;
     }
     for (long o = 0; o < n4; o++) { mv_c[o] /= count; cx[o] /= count; cy[o] /= count; cb[o] /= count; cd[o] /= count; }   /* :161-165 */
+    t_ctx += orc_now() - t0;
     if (k < first_out) continue;      /* context frame: only its smoothed maps are needed later */
+    t0 = orc_now();
     memcpy(bit_c, cb, mapb); memcpy(dep_c, cd, mapb);
     orc_mysterythrehold(mv_c, n4, h, w);                                            /* :170-172 */
     orc_mysterythrehold(bit_c, n4, h, w);
@@ -667,12 +752,8 @@ int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t
       orc_immove(mvx_s + (k - j) * n4, h4, w4, sx, sy, tx);
       orc_immove(mvy_s + (k - j) * n4, h4, w4, sx, sy, ty);
       double wm = exp(-j / d_mv_t), wb = exp(-j / d_bit_t), wd = exp(-j / d_dep_t);
-      for (long o = 0; o < n4; o++) {
-        double dx = cx[o] - tx[o], dy = cy[o] - ty[o];
-        mvT[o] += wm * sqrt(dx * dx + dy * dy);                                     /* :195 */
-        bitT[o] += wb * fabs(cb[o] - tb[o]);                                        /* :196 */
-        depT[o] += wd * fabs(cd[o] - td[o]);                                        /* :197 */
-      }
+          orc_tmp_ctx ta = {n4, cx, cy, cb, cd, tx, ty, tb, td, wm, wb, wd, mvT, bitT, depT};
+      orc_parallel_for(n4, orc_temporal_cells, &ta);
     }
     /* feature order of featuresTest, main.m:284-292 */
     orc_feature_fullres(mv_c, h, w, gk, gs, rep, feat[0]);                          /* mv_ori :211,214 */
@@ -716,7 +797,9 @@ int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t
     for (long o = 0; o < N; o++) comb[o] *= dist[o];                                /* :303 */
     orc_pm_norm(comb, N);                                                           /* :304 */
     memcpy(out + (size_t)(k - first_out) * N, comb, sizeof(double) * N);
+    t_out += orc_now() - t0;
   }
+  g_orc_t_context = t_ctx; g_orc_t_output = t_out;
   free(Vx); free(Vy); free(mvn); free(bitn); free(depn); free(bit_s); free(dep_s); free(mvx_s); free(mvy_s); free(cam);
   free(dist); free(mv_c); free(bit_c); free(dep_c); free(mvT); free(bitT); free(depT); free(tb); free(td); free(tx); free(ty);
   free(con); free(con2); free(rep); for (int i = 0; i < 9; i++) free(feat[i]); free(comb); free(small); free(X); free(dec); free(lab);

@@ -89,6 +89,12 @@ int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t
                      const uint8_t* depth, const uint16_t* bitmap, int first_out,
                      double* out, int* cam, double* feat200);
 
+/* timing of the last orc_process_clip (CPU-baseline bookkeeping): which = 0 -> seconds in pass 1 +
+ * smoothing over all frames, 1 -> seconds in the per-output-frame work.  orc_threads() = worker threads in use. */
+double orc_last_seconds(int which);
+void orc_set_threads(int n);   /* pthread parallel-for width (default 1; results do not depend on it) */
+int orc_threads(void);
+
 #ifdef __cplusplus
 }
 #endif
