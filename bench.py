@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""Headline benchmark: 1080p saliency frames/s through the whole hot path (packed per-CTU syntax ->
+stage (a) scatter -> (c) camera-motion vote -> (e) smoothing / temporal / Gaussian map passes ->
+(b) centre-surround contrast -> (d) RBF-SVM -> final map), BASELINE.json's metric and config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (default N=1, K=10, W=3)
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port on the host cores
+
+A "step" is one batch of B (default 32) consecutive pictures of a synthetic 1920x1080, 50 fps clip
+(seeded syntax buffers) through the clip context, at steady state (temporal window
+full).  `value` is measured with the syntax resident in HBM (cds_clip_process_dev, CUDA events on
+the launching stream, max over ranks); `e2e` goes through the host-buffer C-ABI call
+(cds_clip_process): pinned host syntax in, FP32 maps out, copies inside the timed region.
+Multi-GPU: one process per GPU, each rank runs its own clip (work shards by video: no collective
+on the data path); torch.distributed is used only for the barrier and the max over ranks.
+
+The oracle (oracle/) is only used for the `cpu_baseline` leg and the `--impl reference` arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "saliency_frames_per_sec_1080p"
+UNIT = "frames/s"
+NINE = 9
+MEAN9 = np.full(NINE, 0.3)      # placeholders for svmRBFmodel_all.mat's meanVec / stdVec (file absent from the reference)
+STD9 = np.full(NINE, 0.2)
+
+
+def synth_model(nsv, seed=7):
+    """Stand-in for svmRBFmodel_all.mat:model: gamma 1/9, SV ~ N(0,1), coef ~ +-U(0,1), rho 0.1."""
+    rng = np.random.default_rng(seed)
+    SV = rng.standard_normal((nsv, NINE))
+    coef = rng.uniform(0, 1, nsv) * np.where(np.arange(nsv) < nsv // 2, 1.0, -1.0)
+    return SV, coef, 0.1, 1.0 / NINE, (1, -1)
+
+
+def contrast_pairs(w, h):
+    """(cell, neighbour) pairs per picture of the three contrast windows."""
+    h4, w4 = h // 4, w // 4
+    c = lambda a, b: -(-a // b)
+    return {"win48": 2 * h4 * w4 * 48 * 48, "win24": c(h4, 2) * c(w4, 2) * 24 * 24, "win5": c(h4, 16) * c(w4, 16) * 25}
+
+
+def workload_name(a):
+    return (f"synthetic {a.width}x{a.height} @{a.fps:g}fps packed syntax, all 9 HEVC features + RBF-SVM nSV={a.nsv} "
+            f"(stand-in model), batch {a.batch} pictures/step")
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, started before and killed after the timed region; exact PID only)
+# ----------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill(); out, _ = self.p.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of main.m (RBF branch) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(a, n_out, ctx_frames, threads, seed=1234):
+    """Times n_out output pictures after ctx_frames pictures of temporal context.  Returns (seconds, detail)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as o                                         # checker / CPU baseline only
+    import compressd_domain_saliencyprediction_b200 as cds
+    L = o.oracle()
+    L.orc_last_seconds.restype = C.c_double
+    L.orc_set_threads(int(threads))
+    F = ctx_frames + n_out
+    hdr, tok, base, byts = cds.ops.synth_clip(a.width, a.height, seed, F, first_poc=1)   # poc 0 is all-intra: skip it
+    t0 = time.perf_counter()
+    maps = [o.orc_getframe(a.width, a.height, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    t_a = (time.perf_counter() - t0) / F
+    mvx = np.stack([m[0] for m in maps]); mvy = np.stack([m[1] for m in maps]); dep = np.stack([m[2] for m in maps])
+    model = synth_model(a.nsv)
+    t0 = time.perf_counter()
+    o.orc_process_clip(a.width, a.height, a.fps, mvx, mvy, dep, byts, model, MEAN9, STD9, first_out=ctx_frames, use_rbf=1)
+    wall = time.perf_counter() - t0
+    t_ctx = L.orc_last_seconds(0) / F                            # per picture: camera motion + smoothing
+    t_out = L.orc_last_seconds(1) / n_out                        # per output picture: everything else
+    per_frame = t_a + t_ctx + t_out
+    return per_frame, {"stage_a_s": t_a, "context_s": t_ctx, "output_s": t_out, "wall_s": wall}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_out, ctx = 2, 14
+    times = []
+    for s in range(a.warmup + a.steps):
+        pf, det = cpu_sample(a, n_out, ctx, cores, seed=1234 + s)
+        if s >= a.warmup:
+            times.append(pf)
+    per_frame = float(np.mean(times))
+    val = 1.0 / per_frame
+    sample = (f"each step: {n_out} output pictures of the {a.width}x{a.height} workload after {ctx} context pictures "
+              f"(temporal window truncated to {ctx + 1} of {a.PS + a.PT - 1} pictures), oracle port of main.m RBF branch "
+              f"(oracle/cds_oracle.c) with a pthread parallel-for over {cores} threads; stage (a) port included")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": per_frame * 1e3 * n_out, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(a), "frames_per_step": n_out},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+class Cycle:
+    """A short synthetic clip that is replayed cyclically: picture poc uses entry poc % n."""
+
+    def __init__(self, cds, w, h, seed, n):
+        self.n = n
+        self.hdr, self.tok, self.base, self.byts = cds.ops.synth_clip(w, h, seed, n, first_poc=1)
+
+    def runs(self, poc, count):
+        """Split [poc, poc+count) into runs that are contiguous inside the cycle: (poc, index, length)."""
+        out = []
+        while count > 0:
+            i = poc % self.n
+            ln = min(count, self.n - i)
+            out.append((poc, i, ln)); poc += ln; count -= ln
+        return out
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import compressd_domain_saliencyprediction_b200 as cds
+    from compressd_domain_saliencyprediction_b200._lib import check
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        a.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = cds.lib()
+    if not cds.device_ok():
+        raise SystemExit("no usable B200: " + L.cds_last_error().decode())
+    w, h, B = a.width, a.height, a.batch
+    nctu = cds.ops.nctu(w, h)
+    SV, coef, rho, gamma, labels = synth_model(a.nsv)
+    model = cds.ops.SvmModel(SVs=SV, sv_coef=coef, rho=rho, gamma=gamma, Label=labels)
+    clip = cds.SaliencyClip(w, h, a.fps, model=model, meanVec=MEAN9, stdVec=STD9, use_rbf=True, max_batch=B)
+    cyc = Cycle(cds, w, h, 1234 + rank, 2 * B)
+
+    # ---- syntax resident in HBM (value) and in pinned host memory (e2e) ----
+    def pinned(x):
+        t = torch.from_numpy(x).pin_memory()
+        return t
+    h_hdr, h_tok, h_base, h_byts = pinned(cyc.hdr), pinned(cyc.tok), pinned(cyc.base), pinned(cyc.byts)
+    d_hdr, d_tok, d_base, d_byts = (t.to(dev) for t in (h_hdr, h_tok, h_base, h_byts))
+    d_maps = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+    h_maps = torch.empty((B, h, w), dtype=torch.float32).pin_memory()
+    h_cam = torch.zeros((B, 2), dtype=torch.int32)
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)       # a real (non-NULL) stream: the kernels, the events and the timing all sit on it
+    torch.cuda.set_stream(stream)
+    st = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
+    P = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+
+    def dev_step(poc, n, context=False):
+        for (p, i, ln) in cyc.runs(poc, n):
+            args = (clip.handle, p, ln, P(d_byts, i * nctu * 2), P(d_hdr, i * nctu * 16), P(d_tok), P(d_base, i * 8))
+            if context:
+                check(L.cds_clip_context_dev(*args, st), "cds_clip_context_dev")
+            else:
+                check(L.cds_clip_process_dev(*args, P(d_maps, (p - poc) * h * w * 4), None, st), "cds_clip_process_dev")
+
+    def host_step(poc, n, context=False):
+        for (p, i, ln) in cyc.runs(poc, n):
+            args = (clip.handle, p, ln, P(h_byts, i * nctu * 2), P(h_hdr, i * nctu * 16), P(h_tok), P(h_base, i * 8), cyc.tok.size)
+            if context:
+                check(L.cds_clip_context(*args), "cds_clip_context")
+            else:
+                check(L.cds_clip_process(*args, P(h_maps, (p - poc) * h * w * 4), P(h_cam, (p - poc) * 8)), "cds_clip_process")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    halo = -(-(a.PS + a.PT - 2) // B) * B           # fill the temporal window (untimed set-up, context stages only)
+    # ---- device-resident timing ----
+    clip.seek(0)
+    dev_step(0, halo, context=True)
+    poc = halo
+    for _ in range(a.warmup):
+        dev_step(poc, B); poc += B
+    barrier()
+    cds.take_launch_count()
+    clk = Clocks(local)
+    time.sleep(0.3)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        dev_step(poc, B); poc += B
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = cds.take_launch_count()
+    clocks = clk.stop()
+    frames = a.steps * B * world
+    value = frames / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI ----
+    clip.seek(0)
+    host_step(0, halo, context=True)
+    poc = halo
+    for _ in range(a.warmup):
+        host_step(poc, B); poc += B
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        host_step(poc, B); poc += B
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    tok_per_step = int(cyc.base[B] - cyc.base[0])
+    h2d = B * nctu * (2 + 16) + tok_per_step * 2 + (B + 1) * 8
+    d2h = B * h * w * 4 + B * 8 + 4
+    e2e = {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_s * 1e3 / a.steps, "api": "cds_clip_process (pinned host syntax in, FP32 maps out)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B, "PS": a.PS, "PT": a.PT, "parallelism": f"video-shard x{world}",
+                       "l2": "no explicit flush: one step streams >3 GB of intermediates (9 full-res maps x 32 pictures), far above the 126 MB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+
+    # ---- per-stage device times, roofline of the dominant kernel (rank 0) ----
+    if rank == 0:
+        names = L.cds_profile_stage_names().decode().split(",")
+        check(L.cds_profile_enable(clip.handle, 1), "profile")
+        nprof = 3
+        for _ in range(nprof):
+            dev_step(poc, B); poc += B
+        msv = (C.c_double * 16)(); calls = (C.c_long * 16)()
+        check(L.cds_profile_read(clip.handle, msv, calls, 16), "profile_read")
+        check(L.cds_profile_enable(clip.handle, 0), "profile")
+        stage_ms = {n: msv[i] / nprof for i, n in enumerate(names)}
+        tot = sum(stage_ms.values())
+        pk = (C.c_double * 3)()
+        check(L.cds_measure_peaks(C.byref(pk, 0), C.byref(pk, 8), C.byref(pk, 16)), "peaks")
+        pair_ips, ffma_ips, mufu_ips = pk[0], pk[1], pk[2]
+        pairs = contrast_pairs(w, h)
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))
+        roofs = []
+        # contrast: 2 FP32-pipe lane-instructions per pair (FADD + FFMA with |.| modifier) = 3 FLOP; peak = measured FADD+FFMA mix issue rate
+        for key in ("win48", "win24"):
+            t = stage_ms[f"contrast_{key}"] * 1e-3
+            roofs.append({"kernel": f"contrast_{key}", "bound": "fp32", "achieved": pairs[key] * B * 3 / t / 1e12, "peak": pair_ips * 1.5 / 1e12,
+                          "unit": "TFLOP/s", "frac": pairs[key] * B * 2 / t / pair_ips, "traffic": traffic.get(f"contrast_{key}"),
+                          "ms_per_launch": t * 1e3, "share_of_step": stage_ms[f"contrast_{key}"] / tot,
+                          "work": "3 FLOP (FADD+FFMA) per (cell, neighbour) pair; peak = measured FADD+FFMA issue rate x 1.5 FLOP/instr (cds_measure_peaks, this run)"})
+        # SVM: 19 FP32 lane-instructions (9 FADD + 10 FFMA = 29 FLOP) + 1 MUFU.EX2 per (instance, SV) pair
+        t = stage_ms["svm_rbf"] * 1e-3
+        sv_pairs = 40000.0 * a.nsv * B
+        roofs.append({"kernel": "svm_rbf", "bound": "fp32", "achieved": sv_pairs * 29 / t / 1e12, "peak": ffma_ips * 29 / 19 / 1e12, "unit": "TFLOP/s",
+                      "frac": sv_pairs * 19 / t / ffma_ips, "frac_mufu": sv_pairs / t / mufu_ips, "traffic": traffic.get("svm_rbf"),
+                      "ms_per_launch": t * 1e3, "share_of_step": stage_ms["svm_rbf"] / tot,
+                      "work": "19 FP32 instr (29 FLOP) + 1 MUFU.EX2 per (instance, SV) pair in libsvm's difference form; peak = measured FFMA issue rate"})
+        roofs.sort(key=lambda r: -r["share_of_step"])
+        line["roofline"] = roofs[0]
+        line["roofline_all"] = roofs[1:]
+        line["stage_ms_per_step"] = stage_ms
+        line["peaks_measured"] = {"fp32_fadd_ffma_lane_instr_per_s": pair_ips, "ffma_lane_instr_per_s": ffma_ips, "mufu_ex2_per_s": mufu_ips,
+                                  "hbm_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+                                  if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}
+    clip.close()
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ----
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cores = os.cpu_count() or 1
+        n_out, ctx = 4, 14
+        pf, det = cpu_sample(a, n_out, ctx, cores)
+        line["cpu_baseline"] = {"value": 1.0 / pf, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n_out} output pictures of the same 1080p workload after {ctx} context pictures, oracle/cds_oracle.c "
+                                          f"(port of main.m RBF branch + getFrame) with {cores} threads; per-picture s: {det}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--fps", type=float, default=50.0)
+    ap.add_argument("--nsv", type=int, default=4096)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    a.PS = int(np.floor(a.fps * 0.3 + 0.5)); a.PT = int(np.floor(a.PS * 7 + 0.5))
+    if a.impl == "reference":
+        return run_reference(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_b200(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
