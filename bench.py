@@ -315,13 +315,13 @@ def run_b200(a):
                           "unit": "TFLOP/s", "frac": pairs[key] * B * 2 / t / pair_ips, "traffic": traffic.get(f"contrast_{key}"),
                           "ms_per_launch": t * 1e3, "share_of_step": stage_ms[f"contrast_{key}"] / tot,
                           "work": "3 FLOP (FADD+FFMA) per (cell, neighbour) pair; peak = measured FADD+FFMA issue rate x 1.5 FLOP/instr (cds_measure_peaks, this run)"})
-        # SVM: 19 FP32 lane-instructions (9 FADD + 10 FFMA = 29 FLOP) + 1 MUFU.EX2 per (instance, SV) pair
+        # SVM: 11 FP32 lane-instructions (1 FADD + 10 FFMA = 21 FLOP) + 1 MUFU.EX2 per (instance, SV) pair (expanded form, svm.cu)
         t = stage_ms["svm_rbf"] * 1e-3
         sv_pairs = 40000.0 * a.nsv * B
-        roofs.append({"kernel": "svm_rbf", "bound": "fp32", "achieved": sv_pairs * 29 / t / 1e12, "peak": ffma_ips * 29 / 19 / 1e12, "unit": "TFLOP/s",
-                      "frac": sv_pairs * 19 / t / ffma_ips, "frac_mufu": sv_pairs / t / mufu_ips, "traffic": traffic.get("svm_rbf"),
+        roofs.append({"kernel": "svm_rbf", "bound": "fp32", "achieved": sv_pairs * 21 / t / 1e12, "peak": ffma_ips * 21 / 11 / 1e12, "unit": "TFLOP/s",
+                      "frac": sv_pairs * 11 / t / ffma_ips, "frac_mufu": sv_pairs / t / mufu_ips, "traffic": traffic.get("svm_rbf"),
                       "ms_per_launch": t * 1e3, "share_of_step": stage_ms["svm_rbf"] / tot,
-                      "work": "19 FP32 instr (29 FLOP) + 1 MUFU.EX2 per (instance, SV) pair in libsvm's difference form; peak = measured FFMA issue rate"})
+                      "work": "11 FP32 instr (1 FADD + 10 FFMA = 21 FLOP) + 1 MUFU.EX2 per (instance, SV) pair; peak = measured FFMA issue rate"})
         roofs.sort(key=lambda r: -r["share_of_step"])
         line["roofline"] = roofs[0]
         line["roofline_all"] = roofs[1:]
