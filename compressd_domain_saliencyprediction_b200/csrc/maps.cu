@@ -121,6 +121,11 @@ void banded_from_dense(const std::vector<double>& A, int n_out, int n_in, Banded
     out->start[i] = lo[i];
     for (int j = lo[i]; j <= hi[i]; j++) out->w[(size_t)i * nt + (j - lo[i])] = (float)A[(size_t)i * n_in + j];
   }
+  out->span4 = 0;
+  for (int i = 0; i < n_out; i++) {
+    if (i + 1 < n_out && out->start[i + 1] < out->start[i]) { out->span4 = -1; break; }
+    out->span4 = std::max(out->span4, out->start[std::min(i + 3, n_out - 1)] - out->start[i]);
+  }
 }
 
 int Banded::upload() {
@@ -459,38 +464,58 @@ int fullres_hpass_launch(const float* X, int nmaps, int h4, int w4, const Polyph
   return CDS_OK;
 }
 
-// vertical + reductions: Y[m][4r+ph][x] = sum_d G[ph][d] T[m][r+d][x]; thread = column x, CTA = 128 columns x VP_CELLS cell rows.
-constexpr int VP_CELLS = 8;
+// vertical + reductions: Y[m][4r+ph][x] = sum_d G[ph][d] T[m][r+d][x].
+// Register-tiled FIR: a thread owns 4 adjacent columns (one LDG.128 per input row) and VP_RPT consecutive cell rows
+// (= 4*VP_RPT output rows), so each loaded float4 feeds 16*VP_RPT FFMAs against VP_RPT broadcast LDS.128 of weights.
+// Taps run in ascending order for every output, like the straightforward loop; the zero-weight pad entries add exact zeros.
+constexpr int VP_RPT = 4;
 __global__ void __launch_bounds__(128)
 fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int nt, const float4* __restrict__ G,
                      float* __restrict__ Ystore, const int* __restrict__ store_index, float* __restrict__ partial) {
-  extern __shared__ float4 sGv[];               // nt float4
+  extern __shared__ float4 sGv[];               // nt + 2*(VP_RPT-1) float4: weights with VP_RPT-1 zero entries on both sides
   __shared__ float redf[4];
   __shared__ double redd[4];
-  const int m = blockIdx.z, x = blockIdx.x * 128 + threadIdx.x;
-  const int r0 = blockIdx.y * VP_CELLS;
-  for (int i = threadIdx.x; i < nt; i += 128) sGv[i] = G[i];
+  const int m = blockIdx.z, x4 = blockIdx.x * blockDim.x + threadIdx.x, W4 = W >> 2;
+  const int r0 = blockIdx.y * VP_RPT;
+  for (int i = threadIdx.x; i < nt + 2 * (VP_RPT - 1); i += blockDim.x) {
+    const int t = i - (VP_RPT - 1);
+    sGv[i] = (t >= 0 && t < nt) ? G[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
-  const float* __restrict__ Tm = T + (size_t)m * h4 * W;
+  const float4* __restrict__ Tm = reinterpret_cast<const float4*>(T + (size_t)m * h4 * W);
   const int sidx = store_index ? store_index[m] : -1;
-  float* __restrict__ Ys = sidx >= 0 ? Ystore + (size_t)sidx * (size_t)h4 * 4 * W : nullptr;
   float mn = INFINITY, mx = -INFINITY; double sum = 0;
-  if (x < W) {
-    for (int rc = 0; rc < VP_CELLS; rc++) {
-      const int r = r0 + rc;
-      if (r >= h4) break;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int t_lo = max(0, -(r + dmin)), t_hi = min(nt, h4 - (r + dmin));
-      for (int t = t_lo; t < t_hi; t++) {
-        const float v = __ldg(Tm + (size_t)(r + dmin + t) * W + x); const float4 g = sGv[t];
-        a.x = fmaf(g.x, v, a.x); a.y = fmaf(g.y, v, a.y); a.z = fmaf(g.z, v, a.z); a.w = fmaf(g.w, v, a.w);
+  if (x4 < W4) {
+    float4 acc[VP_RPT][4];                      // [cell row][phase] x 4 columns
+#pragma unroll
+    for (int k = 0; k < VP_RPT; k++)
+#pragma unroll
+      for (int ph = 0; ph < 4; ph++) acc[k][ph] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int i0 = r0 + dmin;
+    const int u_lo = max(0, -i0), u_hi = min(nt + VP_RPT - 1, h4 - i0);
+    for (int u = u_lo; u < u_hi; u++) {
+      const float4 v = __ldg(Tm + (size_t)(i0 + u) * W4 + x4);
+#pragma unroll
+      for (int k = 0; k < VP_RPT; k++) {
+        const float4 g = sGv[u - k + VP_RPT - 1];   // tap t = u - k of cell row r0 + k
+        acc[k][0].x = fmaf(g.x, v.x, acc[k][0].x); acc[k][0].y = fmaf(g.x, v.y, acc[k][0].y); acc[k][0].z = fmaf(g.x, v.z, acc[k][0].z); acc[k][0].w = fmaf(g.x, v.w, acc[k][0].w);
+        acc[k][1].x = fmaf(g.y, v.x, acc[k][1].x); acc[k][1].y = fmaf(g.y, v.y, acc[k][1].y); acc[k][1].z = fmaf(g.y, v.z, acc[k][1].z); acc[k][1].w = fmaf(g.y, v.w, acc[k][1].w);
+        acc[k][2].x = fmaf(g.z, v.x, acc[k][2].x); acc[k][2].y = fmaf(g.z, v.y, acc[k][2].y); acc[k][2].z = fmaf(g.z, v.z, acc[k][2].z); acc[k][2].w = fmaf(g.z, v.w, acc[k][2].w);
+        acc[k][3].x = fmaf(g.w, v.x, acc[k][3].x); acc[k][3].y = fmaf(g.w, v.y, acc[k][3].y); acc[k][3].z = fmaf(g.w, v.z, acc[k][3].z); acc[k][3].w = fmaf(g.w, v.w, acc[k][3].w);
       }
-      mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
-      mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
-      sum += (double)a.x + (double)a.y + (double)a.z + (double)a.w;
-      if (Ys) {
-        float* y = Ys + (size_t)(4 * r) * W + x;
-        y[0] = a.x; y[W] = a.y; y[2 * (size_t)W] = a.z; y[3 * (size_t)W] = a.w;
+    }
+    float4* __restrict__ Ys = sidx >= 0 ? reinterpret_cast<float4*>(Ystore + (size_t)sidx * (size_t)h4 * 4 * W) : nullptr;
+#pragma unroll
+    for (int k = 0; k < VP_RPT; k++) {
+      if (r0 + k < h4) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) {
+          const float4 a = acc[k][ph];
+          mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
+          mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+          sum += ((double)a.x + (double)a.y) + ((double)a.z + (double)a.w);
+          if (Ys) Ys[(size_t)(4 * (r0 + k) + ph) * W4 + x4] = a;
+        }
       }
     }
   }
@@ -504,11 +529,18 @@ fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int n
   }
 }
 
+int fir_threads(int W4) {                       // 96 or 128 threads, whichever wastes fewer columns
+  const int w96 = ceil_div(W4, 96) * 96 - W4, w128 = ceil_div(W4, 128) * 128 - W4;
+  return w96 < w128 ? 96 : 128;
+}
+int fullres_vpass_nblocks(int h4, int W) { return ceil_div(W / 4, fir_threads(W / 4)) * ceil_div(h4, VP_RPT); }
+
 int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polyphase& P, float* Ystore, const int* store_index,
                          float* partial, int* nblocks_out, cudaStream_t st) {
-  dim3 grid(ceil_div(W, 128), ceil_div(h4, VP_CELLS), nmaps);
-  fullres_vpass_kernel<<<grid, 128, (size_t)P.nt * 16, st>>>(T, h4, W, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g),
-                                                           Ystore, store_index, partial);
+  const int thr = fir_threads(W / 4);
+  dim3 grid(ceil_div(W / 4, thr), ceil_div(h4, VP_RPT), nmaps);
+  fullres_vpass_kernel<<<grid, thr, (size_t)(P.nt + 2 * (VP_RPT - 1)) * 16, st>>>(T, h4, W, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g),
+                                                                                  Ystore, store_index, partial);
   CDS_LAUNCH_CHECK();
   *nblocks_out = grid.x * grid.y;
   return CDS_OK;
@@ -537,10 +569,39 @@ int stats_finalize_launch(const float* partial, int nmaps, int nblocks, float* s
 // generic banded operators
 // =================================================================================================
 // out[m][i][x] = sum_t w[i][t] * f(in[m][start[i]+t][x]);  f = identity or min((v-a)*b, thr) per map.
+// A thread owns 4 adjacent columns (LDG.128 / STG.128); cols must be a multiple of 4.
+template <bool XF>
 __global__ void __launch_bounds__(128)
 banded_rows_kernel(const float* __restrict__ in, int in_rows, int cols, const float* __restrict__ w, const int* __restrict__ start,
                    int nt, int n_out, const float* __restrict__ xf, float* __restrict__ out) {
   extern __shared__ float sw[];                 // nt weights of this output row
+  const int i = blockIdx.y, m = blockIdx.z, C4 = cols >> 2;
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) sw[t] = w[(size_t)i * nt + t];
+  __syncthreads();
+  const int s0 = start[i];
+  const int t_hi = min(nt, in_rows - s0);
+  float a = 0.f, b = 1.f, thr = INFINITY;
+  if (XF) { a = xf[4 * m]; b = xf[4 * m + 1]; thr = xf[4 * m + 2]; }
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(in + (size_t)m * in_rows * cols);
+  float4* __restrict__ dst = reinterpret_cast<float4*>(out + ((size_t)m * n_out + i) * cols);
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < C4; x += gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int t = 0; t < t_hi; t++) {
+      float4 v = __ldg(src + (size_t)(s0 + t) * C4 + x);
+      if (XF) { v.x = fminf((v.x - a) * b, thr); v.y = fminf((v.y - a) * b, thr); v.z = fminf((v.z - a) * b, thr); v.w = fminf((v.w - a) * b, thr); }
+      const float g = sw[t];
+      acc.x = fmaf(g, v.x, acc.x); acc.y = fmaf(g, v.y, acc.y); acc.z = fmaf(g, v.z, acc.z); acc.w = fmaf(g, v.w, acc.w);
+    }
+    dst[x] = acc;
+  }
+}
+
+// scalar-column variant for widths that are not a multiple of 4 (cell grids of pictures whose width is 8 mod 16)
+__global__ void __launch_bounds__(128)
+banded_rows_scalar_kernel(const float* __restrict__ in, int in_rows, int cols, const float* __restrict__ w, const int* __restrict__ start,
+                          int nt, int n_out, const float* __restrict__ xf, float* __restrict__ out) {
+  extern __shared__ float sw[];
   const int i = blockIdx.y, m = blockIdx.z;
   for (int t = threadIdx.x; t < nt; t += 128) sw[t] = w[(size_t)i * nt + t];
   __syncthreads();
@@ -551,15 +612,26 @@ banded_rows_kernel(const float* __restrict__ in, int in_rows, int cols, const fl
   const float* __restrict__ src = in + (size_t)m * in_rows * cols;
   for (int x = blockIdx.x * 128 + threadIdx.x; x < cols; x += gridDim.x * 128) {
     float acc = 0.f;
-    if (xf) { for (int t = 0; t < t_hi; t++) acc = fmaf(sw[t], fminf((__ldg(src + (size_t)(s0 + t) * cols + x) - a) * b, thr), acc); }
-    else    { for (int t = 0; t < t_hi; t++) acc = fmaf(sw[t], __ldg(src + (size_t)(s0 + t) * cols + x), acc); }
+    for (int t = 0; t < t_hi; t++) {
+      float v = __ldg(src + (size_t)(s0 + t) * cols + x);
+      if (xf) v = fminf((v - a) * b, thr);
+      acc = fmaf(sw[t], v, acc);
+    }
     out[((size_t)m * n_out + i) * cols + x] = acc;
   }
 }
 
 int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const Banded& B, const float* xf, float* out, cudaStream_t st) {
-  dim3 grid(min(ceil_div(cols, 128), 64), B.n_out, nmaps);
-  banded_rows_kernel<<<grid, 128, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
+  if (cols % 4) {
+    dim3 grid(min(ceil_div(cols, 128), 64), B.n_out, nmaps);
+    banded_rows_scalar_kernel<<<grid, 128, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
+    CDS_LAUNCH_CHECK();
+    return CDS_OK;
+  }
+  const int thr = fir_threads(cols / 4);
+  dim3 grid(ceil_div(cols / 4, thr), B.n_out, nmaps);
+  if (xf) banded_rows_kernel<true><<<grid, thr, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
+  else    banded_rows_kernel<false><<<grid, thr, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }

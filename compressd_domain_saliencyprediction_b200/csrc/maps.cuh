@@ -11,6 +11,7 @@ namespace cds {
 // contiguous support).  Host copy + device copy.
 struct Banded {
   int n_out = 0, n_in = 0, nt = 0;
+  int span4 = 0;             // max over i of start[min(i+3, n_out-1)] - start[i]; -1 when start is not non-decreasing
   std::vector<float> w;      // [n_out][nt]
   std::vector<int> start;    // [n_out]  (start + nt may exceed n_in; weights there are 0 and reads are clamped)
   float* d_w = nullptr;
@@ -65,6 +66,8 @@ int contrast_post_mv_launch(const float* rawx, const float* rawy, const unsigned
 int fullres_hpass_launch(const float* X, int nmaps, int h4, int w4, const Polyphase& P, float* T, cudaStream_t st);
 int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polyphase& P, float* Ystore /*or null*/,
                          const int* store_index /*[nmaps] -> slot in Ystore or -1*/, float* partial, int* nblocks_out, cudaStream_t st);
+int fir_threads(int W4);                      // CTA width (96 or 128 threads of 4 columns) wasting the fewest columns
+int fullres_vpass_nblocks(int h4, int W);   // partial blocks per map written by fullres_vpass_launch
 int stats_finalize_launch(const float* partial, int nmaps, int nblocks, float* stats /*[nmaps][4] min,max,sum_lo,sum_hi*/, cudaStream_t st);
 // generic banded operators, batched over nmaps; xf (optional, [nmaps][4] = a,b,thr,unused): v = min((in - a) * b, thr)
 int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const Banded& B, const float* xf, float* out, cudaStream_t st);

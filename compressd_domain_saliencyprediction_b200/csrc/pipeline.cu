@@ -226,36 +226,70 @@ dec_minmax_norm_kernel(const float* __restrict__ dec, float* __restrict__ C) {
   for (int i = threadIdx.x; i < 40000; i += 1024) C[(size_t)f * 40000 + i] = (d[i] - m0) * inv;
 }
 
-// final map: Y = Bv * T2 (imfilter o imresize), times the centre prior, stored raw + min/max partials (main.m:300-304)
+// final map: Y = Bv * T2 (imfilter o imresize), times the centre prior, stored raw + min/max partials (main.m:300-304).
+// Register-tiled banded FIR: a thread owns 4 columns x 4 consecutive output rows; the CTA stages the four rows'
+// weights over their common input window as float4 (one broadcast LDS.128 per input row feeds 16 FFMAs).
+constexpr int FR_ROWS = 4;
 __global__ void __launch_bounds__(128)
 final_rows_kernel(const float* __restrict__ T2, int W, int H, const float* __restrict__ w, const int* __restrict__ start, int nt,
                   const float* __restrict__ dist, float* __restrict__ raw, float* __restrict__ partial) {
-  extern __shared__ float swf[];
+  extern __shared__ float4 swf4[];                // [window] x 4 rows
   __shared__ float redf[4];
-  const int y = blockIdx.y, f = blockIdx.z;
-  for (int t = threadIdx.x; t < nt; t += 128) swf[t] = w[(size_t)y * nt + t];
+  const int y0 = blockIdx.y * FR_ROWS, f = blockIdx.z, W4 = W >> 2;
+  const int ylast = min(y0 + FR_ROWS - 1, H - 1);
+  const int s_lo = start[y0], L = min(start[ylast] + nt, 200) - s_lo;
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    float g[FR_ROWS];
+#pragma unroll
+    for (int k = 0; k < FR_ROWS; k++) {
+      const int y = y0 + k;
+      const int t = y < H ? j + s_lo - start[min(y, H - 1)] : -1;
+      g[k] = (t >= 0 && t < nt) ? w[(size_t)y * nt + t] : 0.f;
+    }
+    swf4[j] = make_float4(g[0], g[1], g[2], g[3]);
+  }
   __syncthreads();
-  const int s0 = start[y], t_hi = min(nt, 200 - s0);
-  const float* __restrict__ src = T2 + (size_t)f * 200 * W;
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(T2 + (size_t)f * 200 * W);
   float mn = INFINITY, mx = -INFINITY;
-  for (int x = blockIdx.x * 128 + threadIdx.x; x < W; x += gridDim.x * 128) {
-    float acc = 0.f;
-    for (int t = 0; t < t_hi; t++) acc = fmaf(swf[t], __ldg(src + (size_t)(s0 + t) * W + x), acc);
-    acc *= dist[(size_t)y * W + x];
-    raw[((size_t)f * H + y) * W + x] = acc;
-    mn = fminf(mn, acc); mx = fmaxf(mx, acc);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < W4) {
+    float4 acc[FR_ROWS];
+#pragma unroll
+    for (int k = 0; k < FR_ROWS; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int j = 0; j < L; j++) {
+      const float4 v = __ldg(src + (size_t)(s_lo + j) * W4 + x);
+      const float4 g = swf4[j];
+      acc[0].x = fmaf(g.x, v.x, acc[0].x); acc[0].y = fmaf(g.x, v.y, acc[0].y); acc[0].z = fmaf(g.x, v.z, acc[0].z); acc[0].w = fmaf(g.x, v.w, acc[0].w);
+      acc[1].x = fmaf(g.y, v.x, acc[1].x); acc[1].y = fmaf(g.y, v.y, acc[1].y); acc[1].z = fmaf(g.y, v.z, acc[1].z); acc[1].w = fmaf(g.y, v.w, acc[1].w);
+      acc[2].x = fmaf(g.z, v.x, acc[2].x); acc[2].y = fmaf(g.z, v.y, acc[2].y); acc[2].z = fmaf(g.z, v.z, acc[2].z); acc[2].w = fmaf(g.z, v.w, acc[2].w);
+      acc[3].x = fmaf(g.w, v.x, acc[3].x); acc[3].y = fmaf(g.w, v.y, acc[3].y); acc[3].z = fmaf(g.w, v.z, acc[3].z); acc[3].w = fmaf(g.w, v.w, acc[3].w);
+    }
+#pragma unroll
+    for (int k = 0; k < FR_ROWS; k++) {
+      const int y = y0 + k;
+      if (y < H) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dist) + (size_t)y * W4 + x);
+        float4 a = acc[k];
+        a.x *= d.x; a.y *= d.y; a.z *= d.z; a.w *= d.w;
+        reinterpret_cast<float4*>(raw)[((size_t)f * H + y) * W4 + x] = a;
+        mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
+        mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+      }
+    }
   }
   mn = warp_min(mn); mx = warp_max(mx);
+  const int nw = (blockDim.x + 31) >> 5;
   if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mn;
   __syncthreads();
-  const float m0 = fminf(fminf(redf[0], redf[1]), fminf(redf[2], redf[3]));
+  float m0 = redf[0]; for (int i = 1; i < nw; i++) m0 = fminf(m0, redf[i]);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) redf[threadIdx.x >> 5] = mx;
   __syncthreads();
-  const float m1 = fmaxf(fmaxf(redf[0], redf[1]), fmaxf(redf[2], redf[3]));
+  float m1 = redf[0]; for (int i = 1; i < nw; i++) m1 = fmaxf(m1, redf[i]);
   if (threadIdx.x == 0) {
     const size_t nb = (size_t)gridDim.x * gridDim.y;
-    float* p = partial + ((size_t)f * nb + (size_t)y * gridDim.x + blockIdx.x) * 4;
+    float* p = partial + ((size_t)f * nb + (size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
     p[0] = m0; p[1] = m1; reinterpret_cast<double*>(p + 2)[0] = 0.0;
   }
 }
@@ -338,6 +372,7 @@ int build_operators(cds_ctx* c) {
     banded_from_dense(dense_mul(Gh, W, W, Uh, 200), W, 200, &c->Bh);
   }
   for (Banded* b : {&c->Av, &c->Ah, &c->Rv, &c->Rh, &c->Bv, &c->Bh}) if (int e = b->upload()) return e;
+  if (c->Bv.span4 < 0) { set_error("cds_create: final-map operator is not banded monotonically"); return CDS_EINVAL; }
   // centre prior, getdistMatrix.m:1-17
   {
     std::vector<float> dist((size_t)H * W);
@@ -412,9 +447,9 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   A(d_T, (size_t)9 * B * h4 * W);
   A(d_Y, (size_t)(p->use_rbf ? 3 : 9) * B * HW);
   A(d_store_index, (size_t)9 * B);
-  c->nblk = ((W + 127) / 128) * ((h4 + 7) / 8);
+  c->nblk = fullres_vpass_nblocks(h4, W);
   c->nblk2 = 64;
-  c->nblkf = p->use_rbf ? std::min((W + 127) / 128, 64) * H : 128;
+  c->nblkf = p->use_rbf ? ceil_div(W / 4, fir_threads(W / 4)) * ceil_div(H, FR_ROWS) : 128;
   A(d_partial, (size_t)9 * B * c->nblk * 4); A(d_stats9, (size_t)9 * B * 4);
   A(d_partial2, (size_t)3 * B * c->nblk2 * 4); A(d_xf, (size_t)3 * B * 4);
   A(d_A1, (size_t)9 * B * 200 * w4); A(d_F200, (size_t)9 * B * 40000);
@@ -579,8 +614,9 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     CDS_LAUNCH_CHECK();
     if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, st)) return e;
     {
-      dim3 grid(std::min(ceil_div(W, 128), 64), H, n);
-      final_rows_kernel<<<grid, 128, (size_t)c->Bv.nt * 4, st>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
+      const int thr = fir_threads(W / 4);
+      dim3 grid(ceil_div(W / 4, thr), ceil_div(H, FR_ROWS), n);
+      final_rows_kernel<<<grid, thr, (size_t)(c->Bv.nt + c->Bv.span4) * 16, st>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
       CDS_LAUNCH_CHECK();
       nbf = grid.x * grid.y;
     }
