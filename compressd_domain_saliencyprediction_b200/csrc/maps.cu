@@ -239,34 +239,59 @@ int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, 
 // temporal difference with accumulated camera motion (main.m:174-199, immove.m)
 // grid: x = picture in batch (fast, so the pictures that share ring data run together), y = cell tile
 // =================================================================================================
+constexpr int TMP_MAXJ = 1024;      // PT - 1 <= 7 * round(0.3 * 240) - 1 = 503
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __global__ void __launch_bounds__(256)
 temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float* __restrict__ mvx_s, const float* __restrict__ mvy_s,
                 const float* __restrict__ bit_s, const float* __restrict__ dep_s, const int* __restrict__ cam,
                 const float* __restrict__ wtab /*[PT][4]: exp(-j/26), exp(-j/46), exp(-j/46)*/, float* __restrict__ Xmaps) {
+  // per (picture, j): ring slot offset of picture poc-j and the accumulated camera shift, shared by every cell of the picture
+  extern __shared__ int4 s_tab[];                 // [jmax + 1] = {slot offset in cells, sx, sy, 0}
   const int f = blockIdx.x, n4 = h4 * w4;
+  const int poc = first_poc + f;
+  const int jmax = min(PT - 1, poc);
+  if (threadIdx.x < 32) {                         // warp 0: inclusive scan of x_cammov / y_cammov over j (main.m:189-190)
+    const int lane = threadIdx.x;
+    int cx = 0, cy = 0;
+    for (int j0 = 1; j0 <= jmax; j0 += 32) {
+      const int j = j0 + lane;
+      int vx = 0, vy = 0;
+      if (j <= jmax) { const int cs = ((poc - j + 1) % RL) * 2; vx = cam[cs]; vy = cam[cs + 1]; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
+        if (lane >= o) { vx += tx; vy += ty; }
+      }
+      const int camX = cx + vx, camY = cy + vy;
+      if (j <= jmax) {
+        const int sx = camX >= 0 ? (camX + 2) >> 2 : -((-camX + 2) >> 2);   // round(camX/4), half away from zero
+        const int sy = camY >= 0 ? (camY + 2) >> 2 : -((-camY + 2) >> 2);
+        s_tab[j] = make_int4(((poc - j) % RL) * n4, sx, sy, 0);
+      }
+      cx += __shfl_sync(0xffffffffu, vx, 31); cy += __shfl_sync(0xffffffffu, vy, 31);
+    }
+  }
+  __syncthreads();
   const int o = blockIdx.y * 256 + threadIdx.x;
   if (o >= n4) return;
   const int r = o / w4, c = o - r * w4;
-  const int poc = first_poc + f;
   const size_t cur = (size_t)(poc % RL) * n4 + o;
   const float rx = mvx_s[cur], ry = mvy_s[cur], rb = bit_s[cur], rd = dep_s[cur];
   float am = 0.f, ab = 0.f, ad = 0.f;
-  int camX = 0, camY = 0;
-  const int jmax = min(PT - 1, poc);
+  const float4* __restrict__ w4tab = reinterpret_cast<const float4*>(wtab);
+#pragma unroll 2
   for (int j = 1; j <= jmax; j++) {
-    const int cs = ((poc - j + 1) % RL) * 2;
-    camX += cam[cs]; camY += cam[cs + 1];                          // :189-190
-    const int sx = camX >= 0 ? (camX + 2) >> 2 : -((-camX + 2) >> 2);   // round(camX/4), half away from zero
-    const int sy = camY >= 0 ? (camY + 2) >> 2 : -((-camY + 2) >> 2);
-    const int sr = r - sy, sc = c - sx;                            // immove: +x moves content right, +y down, zero fill
+    const int4 t = s_tab[j];
+    const int sr = r - t.z, sc = c - t.y;                          // immove: +x moves content right, +y down, zero fill
     float tx = 0.f, ty = 0.f, tb = 0.f, td = 0.f;
-    if (sr >= 0 && sr < h4 && sc >= 0 && sc < w4) {
-      const size_t s = (size_t)((poc - j) % RL) * n4 + (size_t)sr * w4 + sc;
-      tx = mvx_s[s]; ty = mvy_s[s]; tb = bit_s[s]; td = dep_s[s];
+    if ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) {
+      const int s = t.x + sr * w4 + sc;
+      tx = __ldg(mvx_s + s); ty = __ldg(mvy_s + s); tb = __ldg(bit_s + s); td = __ldg(dep_s + s);
     }
-    const float4 wj = *reinterpret_cast<const float4*>(wtab + 4 * j);
+    const float4 wj = __ldg(w4tab + j);
     const float dx = rx - tx, dy = ry - ty;
-    am = fmaf(wj.x, sqrtf(fmaf(dx, dx, dy * dy)), am);            // :195
+    am = fmaf(wj.x, sqrt_approx(fmaf(dx, dx, dy * dy)), am);      // :195
     ab = fmaf(wj.y, fabsf(rb - tb), ab);                           // :196
     ad = fmaf(wj.z, fabsf(rd - td), ad);                           // :197
   }
@@ -277,7 +302,8 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float* __re
 int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float* mvx_s, const float* mvy_s,
                     const float* bit_s, const float* dep_s, const int* cam_ring, const float* wtab, float* Xmaps, cudaStream_t st) {
   dim3 grid(B, ceil_div(h4 * w4, 256));
-  temporal_kernel<<<grid, 256, 0, st>>>(h4, w4, PT, ring_len, first_poc, mvx_s, mvy_s, bit_s, dep_s, cam_ring, wtab, Xmaps);
+  if (PT > TMP_MAXJ) { set_error("temporal: PT %d exceeds %d", PT, TMP_MAXJ); return CDS_EINVAL; }
+  temporal_kernel<<<grid, 256, (size_t)PT * sizeof(int4), st>>>(h4, w4, PT, ring_len, first_poc, mvx_s, mvy_s, bit_s, dep_s, cam_ring, wtab, Xmaps);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
@@ -493,8 +519,7 @@ fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int n
       for (int ph = 0; ph < 4; ph++) acc[k][ph] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int i0 = r0 + dmin;
     const int u_lo = max(0, -i0), u_hi = min(nt + VP_RPT - 1, h4 - i0);
-    for (int u = u_lo; u < u_hi; u++) {
-      const float4 v = __ldg(Tm + (size_t)(i0 + u) * W4 + x4);
+    auto taps = [&](int u, const float4 v) {
 #pragma unroll
       for (int k = 0; k < VP_RPT; k++) {
         const float4 g = sGv[u - k + VP_RPT - 1];   // tap t = u - k of cell row r0 + k
@@ -503,7 +528,14 @@ fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int n
         acc[k][2].x = fmaf(g.z, v.x, acc[k][2].x); acc[k][2].y = fmaf(g.z, v.y, acc[k][2].y); acc[k][2].z = fmaf(g.z, v.z, acc[k][2].z); acc[k][2].w = fmaf(g.z, v.w, acc[k][2].w);
         acc[k][3].x = fmaf(g.w, v.x, acc[k][3].x); acc[k][3].y = fmaf(g.w, v.y, acc[k][3].y); acc[k][3].z = fmaf(g.w, v.z, acc[k][3].z); acc[k][3].w = fmaf(g.w, v.w, acc[k][3].w);
       }
+    };
+    const float4* __restrict__ tp = Tm + (size_t)(i0 + u_lo) * W4 + x4;
+    int u = u_lo;
+    for (; u + 4 <= u_hi; u += 4, tp += (size_t)4 * W4) {      // four independent LDG.128 in flight per thread
+      const float4 v0 = __ldg(tp), v1 = __ldg(tp + W4), v2 = __ldg(tp + 2 * (size_t)W4), v3 = __ldg(tp + 3 * (size_t)W4);
+      taps(u, v0); taps(u + 1, v1); taps(u + 2, v2); taps(u + 3, v3);
     }
+    for (; u < u_hi; u++, tp += W4) taps(u, __ldg(tp));
     float4* __restrict__ Ys = sidx >= 0 ? reinterpret_cast<float4*>(Ystore + (size_t)sidx * (size_t)h4 * 4 * W) : nullptr;
 #pragma unroll
     for (int k = 0; k < VP_RPT; k++) {

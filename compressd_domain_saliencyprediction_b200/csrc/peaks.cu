@@ -60,6 +60,85 @@ __global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, float seed, 
   if (s == 123.456f) out[0] = s;
 }
 
+
+// ---- instruction-mix probes (tools/mix_probe.py): how well FFMA / FFMA2 co-issue with MUFU.EX2 and LDS ----
+// which = 0: 11 FFMA : 1 MUFU.EX2 (the SVM pair), 8 independent chains
+//         1: pure FFMA2 (fma.rn.f32x2), 8 chains of 2 lanes
+//         2: 5 FFMA2 + 1 FFMA : 1 MUFU per pair-of-pairs equivalent (packed SVM inner product)
+//         3: 11 FFMA : 1 MUFU : 0.75 LDS.128 (adds the broadcast shared-memory loads)
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__global__ void __launch_bounds__(128) mix_probe_kernel(float* out, float seed, int iters, int which) {
+  __shared__ float4 sb[256];
+  for (int i = threadIdx.x; i < 256; i += 128) sb[i] = make_float4(seed * i, seed, -seed, 0.25f * seed);
+  __syncthreads();
+  float x[9], acc[8], e[8];
+#pragma unroll
+  for (int d = 0; d < 9; d++) x[d] = seed * (d + 1) * 1e-3f + threadIdx.x * 1e-7f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { acc[k] = 0.f; e[k] = -seed * k; }
+  if (which == 0 || which == 3) {
+    for (int it = 0; it < iters; it++) {
+      float4 a = make_float4(seed, seed * 0.5f, seed * 0.25f, seed * 0.125f), b = a, c = a;
+      if (which == 3) { a = sb[(it * 3) & 255]; b = sb[(it * 3 + 1) & 255]; c = sb[(it * 3 + 2) & 255]; }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        float t = c.y + e[k];
+        t = fmaf(x[0], a.x, t); t = fmaf(x[1], a.y, t); t = fmaf(x[2], a.z, t); t = fmaf(x[3], a.w, t);
+        t = fmaf(x[4], b.x, t); t = fmaf(x[5], b.y, t); t = fmaf(x[6], b.z, t); t = fmaf(x[7], b.w, t); t = fmaf(x[8], c.x, t);
+        acc[k] = fmaf(c.z, ex2f(t), acc[k]);
+        if (which == 3 && (k & 3) == 3) { a = sb[(it * 3 + k) & 255]; b = sb[(it * 3 + k + 1) & 255]; c = sb[(it * 3 + k + 2) & 255]; }
+      }
+    }
+  } else if (which == 1) {
+    unsigned long long A[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) A[k] = pk(seed * k, seed * (k + 1));
+    const unsigned long long m = pk(0.9999f, 0.9998f), b = pk(seed * 1e-3f, seed * 2e-3f);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 12; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) A[k] = ffma2(A[k], m, b);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = __uint_as_float((unsigned)A[k]) + __uint_as_float((unsigned)(A[k] >> 32));
+  } else {
+    // packed SVM pair: two instances (lo, hi) against one SV: e2 = (na + c.y) ; 9 FFMA2 ; 2 MUFU ; 1 FFMA2 (coef)
+    unsigned long long X[9], E[4], ACC[4];
+#pragma unroll
+    for (int d = 0; d < 9; d++) X[d] = pk(x[d], x[d] * 1.01f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { E[k] = pk(e[k], e[k + 4]); ACC[k] = pk(0.f, 0.f); }
+    for (int it = 0; it < iters; it++) {
+      const float s = seed + it * 1e-9f;
+      const unsigned long long a0 = pk(s, s), a1 = pk(s * 0.5f, s * 0.5f), a2 = pk(s * 0.25f, s * 0.25f), cz = pk(0.5f, 0.5f);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        unsigned long long t = E[k];
+        t = ffma2(X[0], a0, t); t = ffma2(X[1], a1, t); t = ffma2(X[2], a2, t); t = ffma2(X[3], a0, t); t = ffma2(X[4], a1, t);
+        t = ffma2(X[5], a2, t); t = ffma2(X[6], a0, t); t = ffma2(X[7], a1, t); t = ffma2(X[8], a2, t);
+        const float lo = ex2f(__uint_as_float((unsigned)t)), hi = ex2f(__uint_as_float((unsigned)(t >> 32)));
+        ACC[k] = ffma2(cz, pk(lo, hi), ACC[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { acc[k] = __uint_as_float((unsigned)ACC[k]); acc[k + 4] = __uint_as_float((unsigned)(ACC[k] >> 32)); }
+  }
+  float sres = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) sres += acc[k];
+  if (sres == 123.456f) out[0] = sres;
+}
+
 }  // namespace cds
 
 using namespace cds;
@@ -97,5 +176,38 @@ extern "C" int cds_measure_peaks(double* fp32_pair_ips, double* ffma_ips, double
   if (fp32_pair_ips) *fp32_pair_ips = best[0];
   if (ffma_ips) *ffma_ips = best[1];
   if (mufu_ips) *mufu_ips = best[2];
+  return CDS_OK;
+}
+
+// Probe: returns FP32 FMA lane-operations per second (an FFMA2 counts as 2) and MUFU per second for mix `which`
+// (see mix_probe_kernel).  ctas_per_sm CTAs of 128 threads per SM.
+extern "C" int cds_probe_mix(int which, int ctas_per_sm, double* fma_lane_ops_per_s, double* mufu_per_s) {
+  if (int e = ensure_device()) return e;
+  int dev = 0, sms = 0;
+  CDS_CUDA(cudaGetDevice(&dev));
+  CDS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float* d = nullptr;
+  CDS_CUDA(cudaMalloc(&d, 256));
+  cudaEvent_t e0, e1;
+  CDS_CUDA(cudaEventCreate(&e0)); CDS_CUDA(cudaEventCreate(&e1));
+  const int grid = sms * ctas_per_sm, iters = 4000;
+  double best = 1e30;
+  for (int r = 0; r < 4; r++) {
+    CDS_CUDA(cudaEventRecord(e0));
+    mix_probe_kernel<<<grid, 128>>>(d, 0.5f, iters, which);
+    CDS_LAUNCH_CHECK();
+    CDS_CUDA(cudaEventRecord(e1));
+    CDS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; CDS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  const double thr = (double)grid * 128;
+  double fma = 0, mufu = 0;
+  if (which == 0 || which == 3) { fma = (double)iters * 8 * 10; mufu = (double)iters * 8; }     // + 1 FADD per pair not counted
+  else if (which == 1) { fma = (double)iters * 12 * 8 * 2; }
+  else { fma = (double)iters * 4 * 10 * 2; mufu = (double)iters * 8; }
+  if (fma_lane_ops_per_s) *fma_lane_ops_per_s = fma * thr / (best * 1e-3);
+  if (mufu_per_s) *mufu_per_s = mufu * thr / (best * 1e-3);
   return CDS_OK;
 }
