@@ -23,6 +23,10 @@ struct cds_svm_model {
   float* d_rec = nullptr;        // F == 9 fast path: [nsv_pad][12] = 9 scaled feats, -||s'||^2/2, coef, 0
   float* d_sv = nullptr;         // generic path: [nsv][nfeat] unscaled
   float* d_coef = nullptr;       // generic path: [nsv]
+  // F == 9 tensor-core path (svm_rbf9_tc_kernel): SVs grouped by coefficient sign and packed as ready-made shared-memory
+  // images of 128-SV tiles, [tile][hi|lo][k chunk 0..3][128 SVs][4] TF32-rounded floats (16 KB per tile)
+  float* d_tiles = nullptr;
+  int ntiles = 0, ntiles_pos = 0;
 };
 
 namespace cds {
@@ -83,6 +87,204 @@ svm_rbf9_kernel(const float* __restrict__ X, long N, const float4* __restrict__ 
     if (base + i < N) dec[base + i] = acc[i] - rho;
 }
 
+// =================================================================================================
+// Tensor-core path (tcgen05 + TMEM): the exponent of every (instance, SV) pair as one TF32 GEMM.
+//
+//   log2(|coef| * K(x, s)) = x'.s' - |x'|^2/2 - |s'|^2/2 + log2|coef|  =  xa . sa   with the augmented K = 16 vectors
+//   xa = [x'0..x'8, 1, -|x'|^2/2, 0...],  sa = [s'0..s'8, -|s'|^2/2 + log2|coef|, 1, 0...]
+// TF32 keeps 11 mantissa bits, far short of the 1e-4 tolerance on exp(.), so both operands are split
+// hi + lo (each TF32-exact) and three MMAs are accumulated in FP32: lo*hi + hi*lo + hi*hi (the dropped
+// lo*lo term is 2^-22 relative).  A CTA owns 128 instances (A tile, built once in shared memory) and streams
+// all 128-SV tiles: a producer thread moves 16 KB tile images with cp.async.bulk onto an mbarrier ring, one
+// thread issues 6 tcgen05.mma (128x128x8) per tile into one of two 128-column TMEM accumulators, and the four
+// epilogue warps read the other accumulator with tcgen05.ld, apply MUFU.EX2 and add.  SVs are grouped by the
+// sign of coef, so a tile adds to a "positive" or a "negative" sum and no coefficient is read in the epilogue:
+// 1 MUFU + 1 FADD per pair; the kernel is MUFU-bound (16 ex2 / clk / SM), not FP32-issue-bound.
+// =================================================================================================
+namespace tc {
+constexpr int TM = 128, TN = 128, KPAD = 16, STAGES = 4;
+constexpr int TILE_FLOATS = 2 * KPAD * TN;                 // hi + lo
+constexpr int TILE_BYTES = TILE_FLOATS * 4;                // 16 KB
+constexpr int HALF_BYTES = KPAD * TN * 4;                  // hi -> lo offset (8 KB); also A hi -> A lo
+constexpr int KSTEP_BYTES = 2 * TN * 16;                   // two 16-byte k chunks of 128 rows = one K=8 MMA step
+constexpr int A_BYTES = 2 * KPAD * TM * 4;                 // 16 KB
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = A_BYTES + STAGES * TILE_BYTES + BAR_BYTES;
+constexpr int THREADS = 192;                               // warps 0-3 epilogue, warp 4 MMA + TMEM alloc, warp 5 producer
+constexpr uint32_t TMEM_COLS = 256;                        // two 128-column FP32 accumulators
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 24)) __trap();                    // a protocol bug must fault, never hang the device
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major, no swizzle (cute::UMMA::SmemDescriptor): 8-row x 16-byte core matrices stored contiguously (128 B);
+// SBO = distance between 8-row groups, LBO = distance between the two 16-byte k chunks of one K = 8 step.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u; }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+}  // namespace tc
+
+__global__ void __launch_bounds__(tc::THREADS, 2)
+svm_rbf9_tc_kernel(const float* __restrict__ X, long N, const float* __restrict__ tiles, int ntiles, int ntiles_pos,
+                   float xscale, float rho, float* __restrict__ dec) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                        // [hi|lo][k chunk][128 instances][4]
+  uint8_t* sB = smem + A_BYTES;                              // STAGES tile images
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + STAGES * TILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row0 = (long)blockIdx.x * TM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < TM) {                                    // one instance per thread: augmented, scaled, split hi/lo
+    const long n = row0 + threadIdx.x;
+    float xa[KPAD];
+    float s2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 9; d++) { const float v = (n < N) ? __ldg(X + n * 9 + d) * xscale : 0.f; xa[d] = v; s2 = fmaf(v, v, s2); }
+    xa[9] = 1.f; xa[10] = -0.5f * s2;
+#pragma unroll
+    for (int d = 11; d < KPAD; d++) xa[d] = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < 4; kc++) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { hi[j] = tf32_rna(xa[4 * kc + j]); lo[j] = tf32_rna(xa[4 * kc + j] - __uint_as_float(hi[j])); }
+      *reinterpret_cast<uint4*>(sA + (kc * TM + threadIdx.x) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sA + HALF_BYTES + (kc * TM + threadIdx.x) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor-core (async) proxy
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (lane == 0) {                                         // ---- producer: SV tile images, global -> shared ----
+      for (int t = 0; t < ntiles; t++) {
+        const int s = t % STAGES;
+        mbar_wait(empty(s), ((t / STAGES) & 1) ^ 1);
+        mbar_expect_tx(full(s), TILE_BYTES);
+        bulk_g2s(smem_u32(sB + s * TILE_BYTES), tiles + (size_t)t * TILE_FLOATS, TILE_BYTES, full(s));
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {                                         // ---- MMA issuer ----
+      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + HALF_BYTES;
+      for (int t = 0; t < ntiles; t++) {
+        const int s = t % STAGES, buf = t & 1;
+        mbar_wait(tempty(buf), ((t >> 1) & 1) ^ 1);
+        mbar_wait(full(s), (t / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t b_hi = smem_u32(sB + s * TILE_BYTES), b_lo = b_hi + HALF_BYTES;
+        const uint32_t d = tmem_base + (uint32_t)buf * TN;
+        const uint32_t LBO = TN * 16, SBO = 128;             // TM == TN
+#define CDS_DESC(base, ks) smem_desc((base) + (ks) * KSTEP_BYTES, LBO, SBO)
+        mma_tf32(d, CDS_DESC(a_lo, 0), CDS_DESC(b_hi, 0), 0u);   // small terms first
+        mma_tf32(d, CDS_DESC(a_lo, 1), CDS_DESC(b_hi, 1), 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_lo, 0), 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_lo, 1), 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_hi, 0), 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_hi, 1), 1u);
+#undef CDS_DESC
+        mma_commit(empty(s));                                // shared-memory stage free once these MMAs have read it
+        mma_commit(tfull(buf));                              // accumulator ready for the epilogue
+      }
+    }
+  } else {                                                   // ---- epilogue warps 0-3: TMEM lanes 32*warp .. +31 ----
+    float accp[4] = {0.f, 0.f, 0.f, 0.f}, accn[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < ntiles; t++) {
+      const int buf = t & 1;
+      mbar_wait(tfull(buf), (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * TN;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < TN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          a0 += ex2_approx(__uint_as_float(v[j])); a1 += ex2_approx(__uint_as_float(v[j + 1]));
+          a2 += ex2_approx(__uint_as_float(v[j + 2])); a3 += ex2_approx(__uint_as_float(v[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));               // this warp's quarter of the accumulator is drained
+      if (t < ntiles_pos) { accp[0] += a0; accp[1] += a1; accp[2] += a2; accp[3] += a3; }
+      else                { accn[0] += a0; accn[1] += a1; accn[2] += a2; accn[3] += a3; }
+    }
+    const long n = row0 + threadIdx.x;
+    if (n < N) dec[n] = ((accp[0] + accp[1]) + (accp[2] + accp[3])) - ((accn[0] + accn[1]) + (accn[2] + accn[3])) - rho;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // Generic feature count (<= 64): difference form in libsvm's own order, one instance per thread.
 __global__ void __launch_bounds__(128)
 svm_rbf_generic_kernel(const float* __restrict__ X, long N, int F, const float* __restrict__ SV,
@@ -124,7 +326,17 @@ __global__ void dec_f2d_label_kernel(const float* __restrict__ dec, double* __re
 
 int svm_predict_launch(const cds_svm_model* m, const float* X, long N, float* dec, cudaStream_t st) {
   const double g2 = m->gamma * 1.4426950408889634;   // gamma * log2(e)
-  if (m->nfeat == 9) {
+  static const int impl = [] { const char* e = getenv("CDS_SVM_IMPL"); return (e && !strcmp(e, "fp32")) ? 0 : 1; }();
+  if (m->nfeat == 9 && impl == 1 && m->d_tiles) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      CDS_CUDA(cudaFuncSetAttribute(svm_rbf9_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      attr_done = true;
+    }
+    const unsigned grid = (unsigned)((N + tc::TM - 1) / tc::TM);
+    svm_rbf9_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(X, N, m->d_tiles, m->ntiles, m->ntiles_pos, (float)sqrt(2 * g2),
+                                                                 (float)m->rho, dec);
+  } else if (m->nfeat == 9) {
     const long per_block = (long)SVM_THREADS * SVM_IPT;
     const unsigned grid = (unsigned)((N + per_block - 1) / per_block);
     svm_rbf9_kernel<<<grid, SVM_THREADS, 0, st>>>(X, N, reinterpret_cast<const float4*>(m->d_rec), m->nsv_pad,
@@ -160,6 +372,42 @@ static int model_upload(cds_svm_model* m, const double* SV, const double* coef) 
     for (int i = nsv; i < m->nsv_pad; i++) rec[(size_t)i * 12 + 9] = -1e30f;
     CDS_CUDA(cudaMalloc(&m->d_rec, rec.size() * 4));
     CDS_CUDA(cudaMemcpy(m->d_rec, rec.data(), rec.size() * 4, cudaMemcpyHostToDevice));
+    // tensor-core path: SVs grouped by sign(coef) (zero coefficients dropped), each group padded to whole 128-SV tiles
+    {
+      auto tf32 = [](float v) { uint32_t u; memcpy(&u, &v, 4); u += 0x1000u; u &= 0xffffe000u; memcpy(&v, &u, 4); return v; };   // cvt.rna.tf32
+      std::vector<int> order;
+      for (int i = 0; i < nsv; i++) if (coef[i] > 0) order.push_back(i);
+      const int npos = (int)order.size(), tpos = ceil_div(npos, tc::TN);
+      order.resize((size_t)tpos * tc::TN, -1);
+      for (int i = 0; i < nsv; i++) if (coef[i] < 0) order.push_back(i);
+      const int ttot = ceil_div((int)order.size(), tc::TN);
+      order.resize((size_t)ttot * tc::TN, -1);
+      std::vector<float> img((size_t)ttot * tc::TILE_FLOATS, 0.f);
+      for (int t = 0; t < ttot; t++)
+        for (int r = 0; r < tc::TN; r++) {
+          const int i = order[(size_t)t * tc::TN + r];
+          float sa[tc::KPAD] = {0};
+          if (i >= 0) {
+            double s2 = 0;
+            for (int d = 0; d < 9; d++) { sa[d] = (float)(SV[(size_t)i * 9 + d] * sc); s2 += (double)sa[d] * sa[d]; }
+            sa[9] = (float)(-0.5 * s2 + log2(fabs(coef[i])));
+          } else {
+            sa[9] = -1e30f;                                    // padding: 2^(-1e30) == 0
+          }
+          sa[10] = 1.f;
+          float* base = img.data() + (size_t)t * tc::TILE_FLOATS;
+          for (int k = 0; k < tc::KPAD; k++) {
+            const float hi = tf32(sa[k]), lo = tf32(sa[k] - hi);
+            const size_t o = ((size_t)(k / 4) * tc::TN + r) * 4 + (k % 4);
+            base[o] = hi; base[(size_t)tc::KPAD * tc::TN + o] = lo;
+          }
+        }
+      m->ntiles = ttot; m->ntiles_pos = tpos;
+      if (ttot > 0) {
+        CDS_CUDA(cudaMalloc(&m->d_tiles, img.size() * 4));
+        CDS_CUDA(cudaMemcpy(m->d_tiles, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+      }
+    }
   } else {
     std::vector<float> sv((size_t)nsv * F), cf(nsv);
     for (size_t i = 0; i < sv.size(); i++) sv[i] = (float)SV[i];
@@ -244,6 +492,7 @@ extern "C" void cds_svm_model_free(cds_svm_model* m) {
   if (m->d_rec) cudaFree(m->d_rec);
   if (m->d_sv) cudaFree(m->d_sv);
   if (m->d_coef) cudaFree(m->d_coef);
+  if (m->d_tiles) cudaFree(m->d_tiles);
   delete m;
 }
 extern "C" int cds_svm_model_nsv(const cds_svm_model* m) { return m ? m->nsv : 0; }
