@@ -315,13 +315,15 @@ def run_b200(a):
                           "unit": "TFLOP/s", "frac": pairs[key] * B * 2 / t / pair_ips, "traffic": traffic.get(f"contrast_{key}"),
                           "ms_per_launch": t * 1e3, "share_of_step": stage_ms[f"contrast_{key}"] / tot,
                           "work": "3 FLOP (FADD+FFMA) per (cell, neighbour) pair; peak = measured FADD+FFMA issue rate x 1.5 FLOP/instr (cds_measure_peaks, this run)"})
-        # SVM: 11 FP32 lane-instructions (1 FADD + 10 FFMA = 21 FLOP) + 1 MUFU.EX2 per (instance, SV) pair (expanded form, svm.cu)
+        # SVM (svm_rbf9_tc_kernel): exponents from a tcgen05 TF32x3 GEMM (K padded to 16, three MMAs), then 1 MUFU.EX2 + 1 FADD per
+        # (instance, SV) pair -> MUFU-bound; peak = measured MUFU.EX2 rate (cds_measure_peaks, this run)
         t = stage_ms["svm_rbf"] * 1e-3
         sv_pairs = 40000.0 * a.nsv * B
-        roofs.append({"kernel": "svm_rbf", "bound": "fp32", "achieved": sv_pairs * 21 / t / 1e12, "peak": ffma_ips * 21 / 11 / 1e12, "unit": "TFLOP/s",
-                      "frac": sv_pairs * 11 / t / ffma_ips, "frac_mufu": sv_pairs / t / mufu_ips, "traffic": traffic.get("svm_rbf"),
+        roofs.append({"kernel": "svm_rbf9_tc", "bound": "mufu", "achieved": sv_pairs / t / 1e12, "peak": mufu_ips / 1e12, "unit": "Tex2/s",
+                      "frac": sv_pairs / t / mufu_ips, "tensor_tflops_tf32": sv_pairs * 2 * 16 * 3 / t / 1e12, "traffic": traffic.get("svm_rbf"),
                       "ms_per_launch": t * 1e3, "share_of_step": stage_ms["svm_rbf"] / tot,
-                      "work": "11 FP32 instr (1 FADD + 10 FFMA = 21 FLOP) + 1 MUFU.EX2 per (instance, SV) pair; peak = measured FFMA issue rate"})
+                      "work": "1 MUFU.EX2 per (instance, SV) pair after a TF32x3 tensor-core distance GEMM (96 tensor FLOP per pair incl. K padding); "
+                              "peak = measured MUFU.EX2 issue rate"})
         roofs.sort(key=lambda r: -r["share_of_step"])
         line["roofline"] = roofs[0]
         line["roofline_all"] = roofs[1:]

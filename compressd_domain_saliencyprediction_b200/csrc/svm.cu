@@ -103,6 +103,7 @@ svm_rbf9_kernel(const float* __restrict__ X, long N, const float4* __restrict__ 
 // =================================================================================================
 namespace tc {
 constexpr int TM = 128, TN = 128, KPAD = 16, STAGES = 4;
+static_assert(TN == 128, "the epilogue below is unrolled for four 32-column TMEM loads");
 constexpr int TILE_FLOATS = 2 * KPAD * TN;                 // hi + lo
 constexpr int TILE_BYTES = TILE_FLOATS * 4;                // 16 KB
 constexpr int HALF_BYTES = KPAD * TN * 4;                  // hi -> lo offset (8 KB); also A hi -> A lo
@@ -257,20 +258,30 @@ svm_rbf9_tc_kernel(const float* __restrict__ X, long N, const float* __restrict_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * TN;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < TN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
+      auto consume = [&](const uint32_t (&v)[32]) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           a0 += ex2_approx(__uint_as_float(v[j])); a1 += ex2_approx(__uint_as_float(v[j + 1]));
           a2 += ex2_approx(__uint_as_float(v[j + 2])); a3 += ex2_approx(__uint_as_float(v[j + 3]));
         }
-      }
+      };
+      // register double buffering: the next 32 columns are in flight from TMEM while the MUFUs of the current ones issue
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 32, vb);
+      consume(va);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 64, va);
+      consume(vb);
+      tmem_ld_wait();
+      tmem_ld32(taddr + 96, vb);
+      consume(va);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(buf));               // this warp's quarter of the accumulator is drained
+      if (lane == 0) mbar_arrive(tempty(buf));               // this warp's quarter of the accumulator is drained (all loads waited on)
+      consume(vb);
       if (t < ntiles_pos) { accp[0] += a0; accp[1] += a1; accp[2] += a2; accp[3] += a3; }
       else                { accn[0] += a0; accn[1] += a1; accn[2] += a2; accn[3] += a3; }
     }
