@@ -460,103 +460,163 @@ int contrast_post_mv_launch(const float* rawx, const float* rawy, const unsigned
 // =================================================================================================
 // full-resolution replicate + Gaussian as a polyphase filter
 // =================================================================================================
-// horizontal: T[m][r][4c+ph] = sum_d G[ph][d] X[m][r][c+d].  One CTA per (row, map); the row sits in smem.
-__global__ void __launch_bounds__(256)
-fullres_hpass_kernel(const float* __restrict__ X, int h4, int w4, int dmin, int nt, const float4* __restrict__ G,
+// horizontal: T[m][r][4c+ph] = sum_d G[ph][d] X[m][r][c+d].  One CTA per (row, map); the zero-padded row sits in smem.
+// A thread owns HP_CPT = 4 adjacent cells (16 outputs) and slides a 4-value window along the row: per 4 taps one
+// conflict-free LDS.128 of inputs and four broadcast LDS.128 of weights feed 64 FFMAs.
+constexpr int HP_CPT = 4;
+__global__ void __launch_bounds__(128)
+fullres_hpass_kernel(const float* __restrict__ X, int h4, int w4, int dmin, int nt, int nt4, const float4* __restrict__ G,
                      float* __restrict__ T) {
-  extern __shared__ float srow[];               // [w4 + nt - 1] zero padded, then nt float4 weights
-  float4* sG = reinterpret_cast<float4*>(srow + ((w4 + nt - 1 + 3) / 4) * 4);
+  extern __shared__ __align__(16) float srow[];   // [w4p + nt4 + 4] inputs (zero padded), then nt4 float4 weights (zero padded to a multiple of 4 taps)
+  const int w4p = ceil_div(w4, HP_CPT) * HP_CPT;
+  const int nin = w4p + nt4 + 4;
+  float4* sG = reinterpret_cast<float4*>(srow + nin);
   const int r = blockIdx.x, m = blockIdx.y;
   const float* __restrict__ xr = X + ((size_t)m * h4 + r) * w4;
-  for (int i = threadIdx.x; i < w4 + nt - 1; i += 256) { const int c = i + dmin; srow[i] = (c >= 0 && c < w4) ? xr[c] : 0.f; }
-  for (int i = threadIdx.x; i < nt; i += 256) sG[i] = G[i];
+  for (int i = threadIdx.x; i < nin; i += blockDim.x) { const int c = i + dmin; srow[i] = (c >= 0 && c < w4) ? xr[c] : 0.f; }
+  for (int i = threadIdx.x; i < nt4; i += blockDim.x) sG[i] = i < nt ? G[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   float4* __restrict__ out = reinterpret_cast<float4*>(T + ((size_t)m * h4 + r) * (size_t)w4 * 4);
-  for (int c = threadIdx.x; c < w4; c += 256) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < nt; t++) {
-      const float x = srow[c + t]; const float4 g = sG[t];
-      a.x = fmaf(g.x, x, a.x); a.y = fmaf(g.y, x, a.y); a.z = fmaf(g.z, x, a.z); a.w = fmaf(g.w, x, a.w);
+  for (int c0 = threadIdx.x * HP_CPT; c0 < w4; c0 += blockDim.x * HP_CPT) {
+    float4 acc[HP_CPT];
+#pragma unroll
+    for (int k = 0; k < HP_CPT; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 w0 = *reinterpret_cast<const float4*>(srow + c0);          // x[c0 + t .. c0 + t + 3]
+    for (int t = 0; t < nt4; t += 4) {
+      const float4 w1 = *reinterpret_cast<const float4*>(srow + c0 + t + 4);
+      const float win[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int tt = 0; tt < 4; tt++) {
+        const float4 g = sG[t + tt];
+#pragma unroll
+        for (int k = 0; k < HP_CPT; k++) {
+          const float x = win[tt + k];
+          acc[k].x = fmaf(g.x, x, acc[k].x); acc[k].y = fmaf(g.y, x, acc[k].y); acc[k].z = fmaf(g.z, x, acc[k].z); acc[k].w = fmaf(g.w, x, acc[k].w);
+        }
+      }
+      w0 = w1;
     }
-    out[c] = a;
+#pragma unroll
+    for (int k = 0; k < HP_CPT; k++) if (c0 + k < w4) out[c0 + k] = acc[k];
   }
 }
 
 int fullres_hpass_launch(const float* X, int nmaps, int h4, int w4, const Polyphase& P, float* T, cudaStream_t st) {
   dim3 grid(h4, nmaps);
-  const size_t smem = (size_t)(((w4 + P.nt - 1 + 3) / 4) * 4) * 4 + (size_t)P.nt * 16;
-  fullres_hpass_kernel<<<grid, 256, smem, st>>>(X, h4, w4, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g), T);
+  const int nt4 = ceil_div(P.nt, 4) * 4, w4p = ceil_div(w4, HP_CPT) * HP_CPT;
+  const size_t smem = (size_t)(w4p + nt4 + 4) * 4 + (size_t)nt4 * 16;
+  const int thr = std::min(128, ceil_div(ceil_div(w4, HP_CPT), 32) * 32);
+  fullres_hpass_kernel<<<grid, thr, smem, st>>>(X, h4, w4, P.dmin, P.nt, nt4, reinterpret_cast<const float4*>(P.d_g), T);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
 
 // vertical + reductions: Y[m][4r+ph][x] = sum_d G[ph][d] T[m][r+d][x].
-// Register-tiled FIR: a thread owns 4 adjacent columns (one LDG.128 per input row) and VP_RPT consecutive cell rows
-// (= 4*VP_RPT output rows), so each loaded float4 feeds 16*VP_RPT FFMAs against VP_RPT broadcast LDS.128 of weights.
-// Taps run in ascending order for every output, like the straightforward loop; the zero-weight pad entries add exact zeros.
+// One CTA owns a 128-column strip of one map and walks down it in tiles of VP_ROWS cell rows.  The (VP_ROWS + nt + 2)
+// input rows of a tile are staged in shared memory with cp.async (out-of-picture rows zero-filled) into one of two
+// buffers, so the next tile streams in from L2 while the current one is computed; staging cuts the L2 re-read factor
+// from (nt+3)/4 to (VP_ROWS+nt)/VP_ROWS.  A thread owns 4 adjacent columns x VP_RPT consecutive cell rows (16 output
+// rows): one LDS.128 of inputs and one new broadcast LDS.128 of weights per tap feed 16*VP_RPT FFMAs.  Taps run in
+// ascending order for every output; the zero-weight pad entries add exact zeros.
 constexpr int VP_RPT = 4;
-__global__ void __launch_bounds__(128)
+constexpr int VP_ROWS = 32;                     // cell rows per tile
+constexpr int VP_COLS4 = 32;                    // float4 columns per CTA
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__global__ void __launch_bounds__(256, 2)
 fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int nt, const float4* __restrict__ G,
                      float* __restrict__ Ystore, const int* __restrict__ store_index, float* __restrict__ partial) {
-  extern __shared__ float4 sGv[];               // nt + 2*(VP_RPT-1) float4: weights with VP_RPT-1 zero entries on both sides
-  __shared__ float redf[4];
-  __shared__ double redd[4];
-  const int m = blockIdx.z, x4 = blockIdx.x * blockDim.x + threadIdx.x, W4 = W >> 2;
-  const int r0 = blockIdx.y * VP_RPT;
-  for (int i = threadIdx.x; i < nt + 2 * (VP_RPT - 1); i += blockDim.x) {
+  extern __shared__ float4 sm4[];               // weights [nt + 2*(VP_RPT-1)], then two input tiles [nin][VP_COLS4]
+  __shared__ float redf[8];
+  __shared__ double redd[8];
+  const int ngw = nt + 2 * (VP_RPT - 1);
+  const int nin = VP_ROWS + nt + VP_RPT - 2;    // input rows R0 + dmin .. R0 + dmin + nin - 1 of a tile
+  float4* sGv = sm4;
+  float4* tiles = sm4 + ngw;
+  const int m = blockIdx.y, W4 = W >> 2;
+  const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int x4 = blockIdx.x * VP_COLS4 + cg;
+  const float4* __restrict__ Tm = reinterpret_cast<const float4*>(T + (size_t)m * h4 * W);
+  auto stage = [&](int tile_idx, int buf) {     // warp rg copies whole 512-byte row segments
+    float4* dst = tiles + (size_t)buf * nin * VP_COLS4;
+    const int R0 = tile_idx * VP_ROWS;
+    for (int i = rg; i < nin; i += 8) {
+      const int gr = R0 + dmin + i;
+      const bool ok = gr >= 0 && gr < h4 && x4 < W4;
+      cp_async16_zfill(dst + i * VP_COLS4 + cg, ok ? (const void*)(Tm + (size_t)gr * W4 + x4) : (const void*)Tm, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int ntiles = ceil_div(h4, VP_ROWS);
+  stage(0, 0);
+  for (int i = threadIdx.x; i < ngw; i += 256) {
     const int t = i - (VP_RPT - 1);
     sGv[i] = (t >= 0 && t < nt) ? G[t] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __syncthreads();
-  const float4* __restrict__ Tm = reinterpret_cast<const float4*>(T + (size_t)m * h4 * W);
   const int sidx = store_index ? store_index[m] : -1;
+  float4* __restrict__ Ys = sidx >= 0 ? reinterpret_cast<float4*>(Ystore + (size_t)sidx * (size_t)h4 * 4 * W) : nullptr;
   float mn = INFINITY, mx = -INFINITY; double sum = 0;
-  if (x4 < W4) {
-    float4 acc[VP_RPT][4];                      // [cell row][phase] x 4 columns
+  for (int ti = 0; ti < ntiles; ti++) {
+    if (ti + 1 < ntiles) { stage(ti + 1, (ti + 1) & 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                            // tile ti has landed for every thread
+    const int r0 = ti * VP_ROWS + rg * VP_RPT;
+    if (x4 < W4 && r0 < h4) {
+      float4 acc[VP_RPT][4];                    // [cell row][phase] x 4 columns
 #pragma unroll
-    for (int k = 0; k < VP_RPT; k++)
+      for (int k = 0; k < VP_RPT; k++)
 #pragma unroll
-      for (int ph = 0; ph < 4; ph++) acc[k][ph] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int i0 = r0 + dmin;
-    const int u_lo = max(0, -i0), u_hi = min(nt + VP_RPT - 1, h4 - i0);
-    auto taps = [&](int u, const float4 v) {
+        for (int ph = 0; ph < 4; ph++) acc[k][ph] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* __restrict__ tp = tiles + (size_t)(ti & 1) * nin * VP_COLS4 + (rg * VP_RPT) * VP_COLS4 + cg;   // local input row of tap u of cell row r0
+      float4 g[VP_RPT];                         // g[k] = weights of tap u - k, i.e. sGv[u - k + VP_RPT - 1]
+#pragma unroll
+      for (int k = 1; k < VP_RPT; k++) g[k] = sGv[VP_RPT - 1 - k];
+      auto step = [&](int u) {
+        g[0] = sGv[u + VP_RPT - 1];
+        const float4 v = tp[u * VP_COLS4];
+#pragma unroll
+        for (int k = 0; k < VP_RPT; k++) {
+          acc[k][0].x = fmaf(g[k].x, v.x, acc[k][0].x); acc[k][0].y = fmaf(g[k].x, v.y, acc[k][0].y); acc[k][0].z = fmaf(g[k].x, v.z, acc[k][0].z); acc[k][0].w = fmaf(g[k].x, v.w, acc[k][0].w);
+          acc[k][1].x = fmaf(g[k].y, v.x, acc[k][1].x); acc[k][1].y = fmaf(g[k].y, v.y, acc[k][1].y); acc[k][1].z = fmaf(g[k].y, v.z, acc[k][1].z); acc[k][1].w = fmaf(g[k].y, v.w, acc[k][1].w);
+          acc[k][2].x = fmaf(g[k].z, v.x, acc[k][2].x); acc[k][2].y = fmaf(g[k].z, v.y, acc[k][2].y); acc[k][2].z = fmaf(g[k].z, v.z, acc[k][2].z); acc[k][2].w = fmaf(g[k].z, v.w, acc[k][2].w);
+          acc[k][3].x = fmaf(g[k].w, v.x, acc[k][3].x); acc[k][3].y = fmaf(g[k].w, v.y, acc[k][3].y); acc[k][3].z = fmaf(g[k].w, v.z, acc[k][3].z); acc[k][3].w = fmaf(g[k].w, v.w, acc[k][3].w);
+        }
+#pragma unroll
+        for (int k = VP_RPT - 1; k > 0; k--) g[k] = g[k - 1];      // renamed away when the caller unrolls by VP_RPT
+      };
+      const int nu = nt + VP_RPT - 1;
+      int u = 0;
+      for (; u + VP_RPT <= nu; u += VP_RPT) {
+#pragma unroll
+        for (int q = 0; q < VP_RPT; q++) step(u + q);
+      }
+      for (; u < nu; u++) step(u);
+      float tsum = 0.f;                        // 64 outputs of this tile in FP32 (the FIR itself is FP32), then FP64 across tiles / threads
 #pragma unroll
       for (int k = 0; k < VP_RPT; k++) {
-        const float4 g = sGv[u - k + VP_RPT - 1];   // tap t = u - k of cell row r0 + k
-        acc[k][0].x = fmaf(g.x, v.x, acc[k][0].x); acc[k][0].y = fmaf(g.x, v.y, acc[k][0].y); acc[k][0].z = fmaf(g.x, v.z, acc[k][0].z); acc[k][0].w = fmaf(g.x, v.w, acc[k][0].w);
-        acc[k][1].x = fmaf(g.y, v.x, acc[k][1].x); acc[k][1].y = fmaf(g.y, v.y, acc[k][1].y); acc[k][1].z = fmaf(g.y, v.z, acc[k][1].z); acc[k][1].w = fmaf(g.y, v.w, acc[k][1].w);
-        acc[k][2].x = fmaf(g.z, v.x, acc[k][2].x); acc[k][2].y = fmaf(g.z, v.y, acc[k][2].y); acc[k][2].z = fmaf(g.z, v.z, acc[k][2].z); acc[k][2].w = fmaf(g.z, v.w, acc[k][2].w);
-        acc[k][3].x = fmaf(g.w, v.x, acc[k][3].x); acc[k][3].y = fmaf(g.w, v.y, acc[k][3].y); acc[k][3].z = fmaf(g.w, v.z, acc[k][3].z); acc[k][3].w = fmaf(g.w, v.w, acc[k][3].w);
-      }
-    };
-    const float4* __restrict__ tp = Tm + (size_t)(i0 + u_lo) * W4 + x4;
-    int u = u_lo;
-    for (; u + 4 <= u_hi; u += 4, tp += (size_t)4 * W4) {      // four independent LDG.128 in flight per thread
-      const float4 v0 = __ldg(tp), v1 = __ldg(tp + W4), v2 = __ldg(tp + 2 * (size_t)W4), v3 = __ldg(tp + 3 * (size_t)W4);
-      taps(u, v0); taps(u + 1, v1); taps(u + 2, v2); taps(u + 3, v3);
-    }
-    for (; u < u_hi; u++, tp += W4) taps(u, __ldg(tp));
-    float4* __restrict__ Ys = sidx >= 0 ? reinterpret_cast<float4*>(Ystore + (size_t)sidx * (size_t)h4 * 4 * W) : nullptr;
+        if (r0 + k < h4) {
 #pragma unroll
-    for (int k = 0; k < VP_RPT; k++) {
-      if (r0 + k < h4) {
-#pragma unroll
-        for (int ph = 0; ph < 4; ph++) {
-          const float4 a = acc[k][ph];
-          mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
-          mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
-          sum += ((double)a.x + (double)a.y) + ((double)a.z + (double)a.w);
-          if (Ys) Ys[(size_t)(4 * (r0 + k) + ph) * W4 + x4] = a;
+          for (int ph = 0; ph < 4; ph++) {
+            const float4 a = acc[k][ph];
+            mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
+            mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+            tsum += (a.x + a.y) + (a.z + a.w);
+            if (Ys) Ys[(size_t)(4 * (r0 + k) + ph) * W4 + x4] = a;
+          }
         }
       }
+      sum += (double)tsum;
     }
+    __syncthreads();                            // everyone is done with buffer ti & 1 before tile ti + 2 is staged into it
   }
   mn = block_reduce(mn, redf, OpMin());
   mx = block_reduce(mx, redf, OpMax());
   sum = block_reduce(sum, redd, OpAddD());
   if (threadIdx.x == 0) {
-    const size_t nb = (size_t)gridDim.x * gridDim.y;
-    float* p = partial + ((size_t)m * nb + (size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+    float* p = partial + ((size_t)m * gridDim.x + blockIdx.x) * 4;
     p[0] = mn; p[1] = mx; reinterpret_cast<double*>(p + 2)[0] = sum;
   }
 }
@@ -565,16 +625,20 @@ int fir_threads(int W4) {                       // 96 or 128 threads, whichever 
   const int w96 = ceil_div(W4, 96) * 96 - W4, w128 = ceil_div(W4, 128) * 128 - W4;
   return w96 < w128 ? 96 : 128;
 }
-int fullres_vpass_nblocks(int h4, int W) { return ceil_div(W / 4, fir_threads(W / 4)) * ceil_div(h4, VP_RPT); }
+int fullres_vpass_nblocks(int h4, int W) { (void)h4; return ceil_div(W / 4, VP_COLS4); }
 
 int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polyphase& P, float* Ystore, const int* store_index,
                          float* partial, int* nblocks_out, cudaStream_t st) {
-  const int thr = fir_threads(W / 4);
-  dim3 grid(ceil_div(W / 4, thr), ceil_div(h4, VP_RPT), nmaps);
-  fullres_vpass_kernel<<<grid, thr, (size_t)(P.nt + 2 * (VP_RPT - 1)) * 16, st>>>(T, h4, W, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g),
-                                                                                  Ystore, store_index, partial);
+  dim3 grid(ceil_div(W / 4, VP_COLS4), nmaps);
+  const size_t smem = (size_t)(P.nt + 2 * (VP_RPT - 1)) * 16 + (size_t)2 * (VP_ROWS + P.nt + VP_RPT - 2) * VP_COLS4 * 16;
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    CDS_CUDA(cudaFuncSetAttribute(fullres_vpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  fullres_vpass_kernel<<<grid, 256, smem, st>>>(T, h4, W, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g), Ystore, store_index, partial);
   CDS_LAUNCH_CHECK();
-  *nblocks_out = grid.x * grid.y;
+  *nblocks_out = grid.x;
   return CDS_OK;
 }
 

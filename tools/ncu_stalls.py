@@ -10,7 +10,12 @@ def main():
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hi]
-    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    data = []
+    for r in rows[hi + 1:]:                      # first kernel instance only
+        if r and r[0] in ("Kernel Name", "Address"):
+            break
+        if len(r) == len(hdr):
+            data.append(r)
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     si = hdr.index("# Samples"); ie = hdr.index("Instructions Executed")
     tot = sum(int(r[si]) for r in data)
