@@ -36,9 +36,9 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
-        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "cds_common.cuh")),
-                os.path.getmtime(os.path.join(HERE, "..", "include", "cds.h"))):
+        hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+        hdrs.append(os.path.join(HERE, "..", "include", "cds.h"))
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max([os.path.getmtime(src)] + [os.path.getmtime(x) for x in hdrs]):
             continue
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -133,9 +133,16 @@ int Banded::upload() {
   CDS_CUDA(cudaMalloc(&d_start, start.size() * 4));
   CDS_CUDA(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
   CDS_CUDA(cudaMemcpy(d_start, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<float> wT(w.size());
+  for (int i = 0; i < n_out; i++) for (int t = 0; t < nt; t++) wT[(size_t)t * n_out + i] = w[(size_t)i * nt + t];
+  CDS_CUDA(cudaMalloc(&d_wT, wT.size() * 4));
+  CDS_CUDA(cudaMemcpy(d_wT, wT.data(), wT.size() * 4, cudaMemcpyHostToDevice));
   return CDS_OK;
 }
-void Banded::release() { if (d_w) cudaFree(d_w); if (d_start) cudaFree(d_start); d_w = nullptr; d_start = nullptr; }
+void Banded::release() {
+  if (d_w) cudaFree(d_w); if (d_start) cudaFree(d_start); if (d_wT) cudaFree(d_wT);
+  d_w = nullptr; d_start = nullptr; d_wT = nullptr;
+}
 int Polyphase::upload() {
   CDS_CUDA(cudaMalloc(&d_g, g.size() * 4));
   CDS_CUDA(cudaMemcpy(d_g, g.data(), g.size() * 4, cudaMemcpyHostToDevice));
@@ -732,27 +739,45 @@ int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const 
   return CDS_OK;
 }
 
-// out[m][r][j] = sum_t w[j][t] * in[m][r][start[j]+t].  One CTA per (row, map): the input row sits in smem.
+// out[m][r][j] = sum_t w[j][t] * in[m][r][start[j]+t].  One CTA per (group of BC_ROWS rows, map): the input rows sit in
+// smem, a thread owns output column j for all BC_ROWS rows, so each (transposed, coalesced) weight load feeds BC_ROWS FFMAs.
+constexpr int BC_ROWS = 8;
 __global__ void __launch_bounds__(256)
-banded_cols_kernel(const float* __restrict__ in, int rows, int in_cols, const float* __restrict__ w, const int* __restrict__ start,
+banded_cols_kernel(const float* __restrict__ in, int rows, int in_cols, const float* __restrict__ wT, const int* __restrict__ start,
                    int nt, int n_out, float* __restrict__ out) {
-  extern __shared__ float srow2[];              // in_cols
-  const int r = blockIdx.x, m = blockIdx.y;
-  const float* __restrict__ src = in + ((size_t)m * rows + r) * in_cols;
-  for (int i = threadIdx.x; i < in_cols; i += 256) srow2[i] = src[i];
+  extern __shared__ float srow2[];              // [BC_ROWS][in_cols + 1]
+  const int r0 = blockIdx.x * BC_ROWS, m = blockIdx.y, pitch = in_cols + 1;
+  const int nr = min(BC_ROWS, rows - r0);
+  const float* __restrict__ src = in + ((size_t)m * rows + r0) * in_cols;
+  for (int i = threadIdx.x; i < BC_ROWS * in_cols; i += 256) {
+    const int r = i / in_cols, c = i - r * in_cols;
+    srow2[r * pitch + c] = r < nr ? src[i] : 0.f;
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < n_out; j += 256) {
     const int s0 = start[j], t_hi = min(nt, in_cols - s0);
-    const float* __restrict__ wj = w + (size_t)j * nt;
-    float acc = 0.f;
-    for (int t = 0; t < t_hi; t++) acc = fmaf(__ldg(wj + t), srow2[s0 + t], acc);
-    out[((size_t)m * rows + r) * n_out + j] = acc;
+    float acc[BC_ROWS];
+#pragma unroll
+    for (int r = 0; r < BC_ROWS; r++) acc[r] = 0.f;
+    for (int t = 0; t < t_hi; t++) {
+      const float wv = __ldg(wT + (size_t)t * n_out + j);
+#pragma unroll
+      for (int r = 0; r < BC_ROWS; r++) acc[r] = fmaf(wv, srow2[r * pitch + s0 + t], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < BC_ROWS; r++) if (r < nr) out[((size_t)m * rows + r0 + r) * n_out + j] = acc[r];
   }
 }
 
 int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st) {
-  dim3 grid(rows, nmaps);
-  banded_cols_kernel<<<grid, 256, (size_t)in_cols * 4, st>>>(in, rows, in_cols, B.d_w, B.d_start, B.nt, B.n_out, out);
+  dim3 grid(ceil_div(rows, BC_ROWS), nmaps);
+  const size_t smem = (size_t)BC_ROWS * (in_cols + 1) * 4;
+  static size_t attr_set = 48 * 1024;
+  if (smem > attr_set) {
+    CDS_CUDA(cudaFuncSetAttribute(banded_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  banded_cols_kernel<<<grid, 256, smem, st>>>(in, rows, in_cols, B.d_wT, B.d_start, B.nt, B.n_out, out);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }

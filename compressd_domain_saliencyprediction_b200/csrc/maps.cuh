@@ -15,6 +15,7 @@ struct Banded {
   std::vector<float> w;      // [n_out][nt]
   std::vector<int> start;    // [n_out]  (start + nt may exceed n_in; weights there are 0 and reads are clamped)
   float* d_w = nullptr;
+  float* d_wT = nullptr;     // [nt][n_out] transposed copy (coalesced reads when a thread owns an output column)
   int* d_start = nullptr;
   int upload();
   void release();

@@ -12,6 +12,8 @@
 //     two-level radix select on shared-memory histograms (no sort), exact in int64;
 //   * x_ave = S/8/count is one double division -> identical to MATLAB's sum(...)/n.
 #include "cds_common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include <math.h>
 #include <mutex>
 #include <vector>
@@ -122,18 +124,54 @@ __device__ __forceinline__ void find_pivot(const unsigned* hist, int nbins, int 
   *bin_out = b < nbins ? b : nbins - 1; *below_out = cum;
 }
 
-// grid: one CTA per picture f (slot given by slot_of[f] into the ring outputs)
+// warp-parallel radix-select pivot search (same result as find_pivot): executed by one full warp
+__device__ __forceinline__ void find_pivot_warp(const unsigned* hist, int nbins, int rank, int* bin_out, int* below_out) {
+  const int lane = threadIdx.x & 31, per = nbins >> 5;          // nbins is 512 or 256
+  int mine = 0;
+  for (int i = 0; i < per; i++) mine += (int)hist[lane * per + i];
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const int excl = incl - mine;
+  const unsigned holds = __ballot_sync(0xffffffffu, excl <= rank && rank < incl);
+  if (holds == 0) { if (lane == 0) { *bin_out = nbins - 1; *below_out = __shfl_sync(0xffffffffu, incl, 31); } return; }
+  const int owner = __ffs(holds) - 1;
+  if (lane == owner) {
+    int cum = excl, b = lane * per;
+    for (; b < lane * per + per; b++) { if (cum + (int)hist[b] > rank) break; cum += hist[b]; }
+    *bin_out = b; *below_out = cum;
+  }
+}
+
+struct CmCluster {                 // cluster-wide accumulators: the copy in the rank-0 CTA is the one everybody adds to / reads
+  int hist[16];
+  unsigned hx[512], hy[512];       // level-1 radix-select histograms
+  unsigned hx2[256], hy2[256];     // level-2
+  int dmax, N, T;
+  int xmin, xmax, ymin, ymax;
+  unsigned long long sumx_all, sumy_all, sumx_less, sumy_less;   // two's-complement sums
+  int pivx_hi, pivy_hi, belowx, belowy, pivx, pivy, lessx, lessy;
+  unsigned vmax_bits;
+};
+
+// grid: CM_CLUSTER CTAs (one thread-block cluster) per picture f; the CTAs split the cells, partial results meet in the
+// rank-0 CTA's shared memory through distributed-shared-memory atomics, and every CTA derives the (identical) decisions.
 // VT = double for the clip pipeline: the smoothed mv maps feed Sudoku_contrastcpp5's `p != 0` test after a
 // pm_norm, so ties at the map minimum must round exactly as the reference's double arithmetic does.
+constexpr int CM_CLUSTER = 8;
 template <typename VT>
-__global__ void __launch_bounds__(CM_THREADS)
+__global__ void __cluster_dims__(CM_CLUSTER, 1, 1) __launch_bounds__(CM_THREADS)
 camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const int16_t* __restrict__ mvy_all,
                      const uint16_t* __restrict__ bytes_all, const uint8_t* __restrict__ depth_all,
                      VT* __restrict__ Vx_ring, VT* __restrict__ Vy_ring, float* __restrict__ mvn_ring,
                      float* __restrict__ bitn_ring, float* __restrict__ depn_ring, int* __restrict__ cam_ring,
                      double* __restrict__ ave_out, int* __restrict__ flag_out, int first_slot, int ring_len) {
-  __shared__ CmShared S;
-  const int f = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ CmShared S;           // CTA-local scratch (reductions, local histograms in S.hx / S.hy)
+  __shared__ CmCluster Csm;
+  CmCluster* C0 = cluster.map_shared_rank(&Csm, 0);
+  const int crank = (int)cluster.block_rank();
+  const int f = blockIdx.x / CM_CLUSTER;
   const int h4 = h >> 2, w4 = w >> 2, ncol = (w + 63) >> 6, nctu = ncol * ((h + 63) >> 6);
   const int n4 = h4 * w4;
   const int16_t* __restrict__ mvx = mvx_all + (size_t)f * n4;
@@ -144,23 +182,34 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
   VT* Vx = Vx_ring + (size_t)slot * n4; VT* Vy = Vy_ring + (size_t)slot * n4;
   float* mvn = mvn_ring + (size_t)slot * n4; float* bitn = bitn_ring + (size_t)slot * n4; float* depn = depn_ring + (size_t)slot * n4;
   const int tid = threadIdx.x, lane = tid & 31;
+  const int chunk = (n4 + CM_CLUSTER - 1) / CM_CLUSTER;
+  const int o_lo = min(n4, crank * chunk), o_hi = min(n4, o_lo + chunk);      // this CTA's cells
 
-  // ---- bytes min/max over CTUs, depth max over cells ----
+  // ---- zero the accumulators (only rank 0's copy is used, every CTA clears its own) ----
+  if (tid < 16) Csm.hist[tid] = 0;
+  for (int i = tid; i < 512; i += CM_THREADS) { Csm.hx[i] = 0; Csm.hy[i] = 0; }
+  for (int i = tid; i < 256; i += CM_THREADS) { Csm.hx2[i] = 0; Csm.hy2[i] = 0; }
+  if (tid == 0) {
+    Csm.dmax = 0; Csm.N = 0; Csm.T = 0;
+    Csm.xmin = 1 << 30; Csm.xmax = -(1 << 30); Csm.ymin = 1 << 30; Csm.ymax = -(1 << 30);
+    Csm.sumx_all = 0; Csm.sumy_all = 0; Csm.sumx_less = 0; Csm.sumy_less = 0; Csm.vmax_bits = 0;
+  }
+  cluster.sync();
+
+  // ---- bytes min/max over CTUs (tiny: every CTA does all of it), depth max over this CTA's cells ----
   int bmn = 1 << 30, bmx = 0, dmx = 0;
   for (int i = tid; i < nctu; i += CM_THREADS) { const int b = byts[i]; bmn = min(bmn, b); bmx = max(bmx, b); }
-  for (int i = tid; i < n4; i += CM_THREADS) dmx = max(dmx, (int)dep[i]);
+  for (int i = o_lo + tid; i < o_hi; i += CM_THREADS) dmx = max(dmx, (int)dep[i]);
   bmn = block_reduce_min_i(bmn, S.red_i);
   bmx = block_reduce_max_i(bmx, S.red_i);
   dmx = block_reduce_max_i(dmx, S.red_i);
-  if (tid < 16) S.hist[tid] = 0;
-  __syncthreads();
 
   // ---- pass 1: background count N, static count T, direction histogram ----
   int N = 0, T = 0, hacc = 0;
-  for (int o0 = 0; o0 < n4; o0 += CM_THREADS) {
+  for (int o0 = o_lo; o0 < o_hi; o0 += CM_THREADS) {
     const int o = o0 + tid;
     bool eff = false; int bin = -1;
-    if (o < n4) {
+    if (o < o_hi) {
       const CmCell c = cm_cell(mvx, mvy, byts, h4, w4, ncol, bmn, o);
       eff = c.eff;
       if (eff) {
@@ -175,25 +224,32 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
       if (lane == b) hacc += __popc(m);
     }
   }
-  if (lane < 16 && hacc) atomicAdd(&S.hist[lane], hacc);
+  if (lane < 16 && hacc) atomicAdd(&C0->hist[lane], hacc);
   N = block_reduce_sum_i(N, S.red_i);
   T = block_reduce_sum_i(T, S.red_i);
+  if (tid == 0) { atomicAdd(&C0->N, N); atomicAdd(&C0->T, T); atomicMax(&C0->dmax, dmx); }
+  cluster.sync();
   if (tid == 0) {
+    N = C0->N; T = C0->T;
+    S.dmax = C0->dmax;
     S.flag = !(2 * (long long)T > N);                                         // cm_judge.m:8-12 (T > 0.5*N -> static)
+    int hv[16];
+    for (int k = 0; k < 16; k++) hv[k] = C0->hist[k];
     int best = 0;
-    for (int k = 1; k < 16; k++) if (S.hist[k] > S.hist[best]) best = k;      // first maximum
-    S.best = best; S.x_ave = 0; S.y_ave = 0;
+    for (int k = 1; k < 16; k++) if (hv[k] > hv[best]) best = k;              // first maximum
+    S.best = best; S.N = hv[best]; S.x_ave = 0; S.y_ave = 0;
   }
   __syncthreads();
-  const int flag = S.flag, best = S.best, Len = S.hist[best];
+  const int flag = S.flag, best = S.best, Len = S.N;
+  dmx = S.dmax;
 
-  if (flag && Len > 0) {
+  if (flag && Len > 0) {                                                      // uniform over the cluster
     // ---- pass 2: level-1 histograms (high 9 bits of key+65536), min/max, total sums ----
     for (int i = tid; i < 512; i += CM_THREADS) { S.hx[i] = 0; S.hy[i] = 0; }
     __syncthreads();
     int xmn = 1 << 30, xmx = -(1 << 30), ymn = 1 << 30, ymx = -(1 << 30);
     long long sx = 0, sy = 0;
-    for (int o = tid; o < n4; o += CM_THREADS) {
+    for (int o = o_lo + tid; o < o_hi; o += CM_THREADS) {
       const CmCell c = cm_cell(mvx, mvy, byts, h4, w4, ncol, bmn, o);
       if (c.eff && dir_bin16(c.kx, c.ky) == best) {
         xmn = min(xmn, c.kx); xmx = max(xmx, c.kx); ymn = min(ymn, c.ky); ymx = max(ymx, c.ky);
@@ -205,22 +261,32 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
     xmn = block_reduce_min_i(xmn, S.red_i); xmx = block_reduce_max_i(xmx, S.red_i);
     ymn = block_reduce_min_i(ymn, S.red_i); ymx = block_reduce_max_i(ymx, S.red_i);
     sx = block_reduce_sum_ll(sx, S.red_ll); sy = block_reduce_sum_ll(sy, S.red_ll);
+    __syncthreads();
+    for (int i = tid; i < 512; i += CM_THREADS) {
+      if (S.hx[i]) atomicAdd(&C0->hx[i], S.hx[i]);
+      if (S.hy[i]) atomicAdd(&C0->hy[i], S.hy[i]);
+    }
+    if (tid == 0) {
+      atomicMin(&C0->xmin, xmn); atomicMax(&C0->xmax, xmx); atomicMin(&C0->ymin, ymn); atomicMax(&C0->ymax, ymx);
+      atomicAdd(&C0->sumx_all, (unsigned long long)sx); atomicAdd(&C0->sumy_all, (unsigned long long)sy);
+    }
+    cluster.sync();
+    xmn = C0->xmin; xmx = C0->xmax; ymn = C0->ymin; ymx = C0->ymax;
+    sx = (long long)C0->sumx_all; sy = (long long)C0->sumy_all;
     // number of smallest keys to sum: direction_cluster.m:40-50
     const int Lencut = Len / 2;
     const bool topx = abs(xmn) > abs(xmx), topy = abs(ymn) > abs(ymx);
     const int mx_ = topx ? Lencut - 1 : Lencut, my_ = topy ? Lencut - 1 : Lencut;    // sum of the m smallest
-    if (tid == 0) {
-      S.sumx_all = sx; S.sumy_all = sy;
-      if (mx_ > 0) find_pivot(S.hx, 512, mx_ - 1, &S.pivx_hi, &S.belowx); else { S.pivx_hi = -1; S.belowx = 0; }
-      if (my_ > 0) find_pivot(S.hy, 512, my_ - 1, &S.pivy_hi, &S.belowy); else { S.pivy_hi = -1; S.belowy = 0; }
+    if (crank == 0 && tid < 32) {
+      if (mx_ > 0) find_pivot_warp(Csm.hx, 512, mx_ - 1, &Csm.pivx_hi, &Csm.belowx); else if (tid == 0) { Csm.pivx_hi = -1; Csm.belowx = 0; }
+      if (my_ > 0) find_pivot_warp(Csm.hy, 512, my_ - 1, &Csm.pivy_hi, &Csm.belowy); else if (tid == 0) { Csm.pivy_hi = -1; Csm.belowy = 0; }
     }
-    __syncthreads();
-    const int phx = S.pivx_hi, phy = S.pivy_hi;
+    cluster.sync();
+    const int phx = C0->pivx_hi, phy = C0->pivy_hi;
     // ---- pass 3: level-2 histograms (low 8 bits) inside the pivot bins ----
-    __syncthreads();
     for (int i = tid; i < 256; i += CM_THREADS) { S.hx[i] = 0; S.hy[i] = 0; }
     __syncthreads();
-    for (int o = tid; o < n4; o += CM_THREADS) {
+    for (int o = o_lo + tid; o < o_hi; o += CM_THREADS) {
       const CmCell c = cm_cell(mvx, mvy, byts, h4, w4, ncol, bmn, o);
       if (c.eff && dir_bin16(c.kx, c.ky) == best) {
         const int ux = c.kx + 65536, uy = c.ky + 65536;
@@ -229,18 +295,24 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      int b, below;
-      if (phx >= 0) { find_pivot(S.hx, 256, mx_ - 1 - S.belowx, &b, &below); S.pivx = (phx << 8) | b; S.lessx = S.belowx + below; }
-      else { S.pivx = 0; S.lessx = 0; }
-      if (phy >= 0) { find_pivot(S.hy, 256, my_ - 1 - S.belowy, &b, &below); S.pivy = (phy << 8) | b; S.lessy = S.belowy + below; }
-      else { S.pivy = 0; S.lessy = 0; }
+    for (int i = tid; i < 256; i += CM_THREADS) {
+      if (S.hx[i]) atomicAdd(&C0->hx2[i], S.hx[i]);
+      if (S.hy[i]) atomicAdd(&C0->hy2[i], S.hy[i]);
     }
-    __syncthreads();
-    const int pvx = S.pivx, pvy = S.pivy;
+    cluster.sync();
+    if (crank == 0 && tid < 32) {
+      int b = 0, below = 0;
+      if (phx >= 0) { find_pivot_warp(Csm.hx2, 256, mx_ - 1 - Csm.belowx, &S.pivx, &S.lessx); __syncwarp(); if (tid == 0) { b = S.pivx; below = S.lessx; Csm.pivx = (phx << 8) | b; Csm.lessx = Csm.belowx + below; } }
+      else if (tid == 0) { Csm.pivx = 0; Csm.lessx = 0; }
+      __syncwarp();
+      if (phy >= 0) { find_pivot_warp(Csm.hy2, 256, my_ - 1 - Csm.belowy, &S.pivy, &S.lessy); __syncwarp(); if (tid == 0) { b = S.pivy; below = S.lessy; Csm.pivy = (phy << 8) | b; Csm.lessy = Csm.belowy + below; } }
+      else if (tid == 0) { Csm.pivy = 0; Csm.lessy = 0; }
+    }
+    cluster.sync();
+    const int pvx = C0->pivx, pvy = C0->pivy, lessx = C0->lessx, lessy = C0->lessy;
     // ---- pass 4: exact sums of the keys strictly below the pivots ----
     long long lx = 0, ly = 0;
-    for (int o = tid; o < n4; o += CM_THREADS) {
+    for (int o = o_lo + tid; o < o_hi; o += CM_THREADS) {
       const CmCell c = cm_cell(mvx, mvy, byts, h4, w4, ncol, bmn, o);
       if (c.eff && dir_bin16(c.kx, c.ky) == best) {
         if (c.kx + 65536 < pvx) lx += c.kx;
@@ -248,10 +320,13 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
       }
     }
     lx = block_reduce_sum_ll(lx, S.red_ll); ly = block_reduce_sum_ll(ly, S.red_ll);
+    if (tid == 0) { atomicAdd(&C0->sumx_less, (unsigned long long)lx); atomicAdd(&C0->sumy_less, (unsigned long long)ly); }
+    cluster.sync();
     if (tid == 0) {
+      lx = (long long)C0->sumx_less; ly = (long long)C0->sumy_less;
       // sum of the m smallest = (keys < pivot) + (m - #less) copies of the pivot
-      const long long smx = mx_ > 0 ? lx + (long long)(mx_ - S.lessx) * (pvx - 65536) : 0;
-      const long long smy = my_ > 0 ? ly + (long long)(my_ - S.lessy) * (pvy - 65536) : 0;
+      const long long smx = mx_ > 0 ? lx + (long long)(mx_ - lessx) * (pvx - 65536) : 0;
+      const long long smy = my_ > 0 ? ly + (long long)(my_ - lessy) * (pvy - 65536) : 0;
       double xa, ya;
       if (Len < 2) { xa = (double)sx / 8.0; ya = (double)sy / 8.0; }          // reference undefined (index 0 / 0-division): the value itself
       else {
@@ -266,7 +341,7 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
 
   // ---- pass 5: compensated field, |V| max ----
   float vmax = 0.f;
-  for (int o = tid; o < n4; o += CM_THREADS) {
+  for (int o = o_lo + tid; o < o_hi; o += CM_THREADS) {
     double dvx, dvy;
     if (flag) {
       const CmCell c = cm_cell(mvx, mvy, byts, h4, w4, ncol, bmn, o);
@@ -281,27 +356,31 @@ camera_motion_kernel(int w, int h, const int16_t* __restrict__ mvx_all, const in
     vmax = fmaxf(vmax, m);
   }
   vmax = block_reduce_max_f(vmax, S.red_f);
+  if (tid == 0) atomicMax(&C0->vmax_bits, __float_as_uint(vmax));              // vmax >= 0: bit patterns order like the values
+  cluster.sync();
+  vmax = __uint_as_float(C0->vmax_bits);
   const float eps = 2.220446049250313e-16f;
   const float inv_b = 1.f / ((float)bmx + eps), inv_d = 1.f / ((float)dmx + eps);
-  for (int o = tid; o < n4; o += CM_THREADS) {
+  for (int o = o_lo + tid; o < o_hi; o += CM_THREADS) {
     const int r = o / w4, c = o - r * w4;
     mvn[o] = mvn[o] / (vmax + eps);                                            // main.m:102
     bitn[o] = (float)byts[(r >> 4) * ncol + (c >> 4)] * inv_b;                // main.m:103
     depn[o] = (float)dep[o] * inv_d;                                           // main.m:104
   }
-  if (tid == 0) {
+  if (crank == 0 && tid == 0) {
     // round() half away from zero (main.m:98-99)
     cam_ring[2 * slot + 0] = (int)(x_ave < 0 ? -floor(-x_ave + 0.5) : floor(x_ave + 0.5));
     cam_ring[2 * slot + 1] = (int)(y_ave < 0 ? -floor(-y_ave + 0.5) : floor(y_ave + 0.5));
     if (ave_out) { ave_out[2 * f] = x_ave; ave_out[2 * f + 1] = y_ave; }
     if (flag_out) flag_out[f] = flag;
   }
+  cluster.sync();                  // rank 0's shared memory must outlive every remote access
 }
 
 int camera_motion_launch(int w, int h, int nframes, const int16_t* mvx, const int16_t* mvy, const uint16_t* byts,
                          const uint8_t* depth, float* Vx, float* Vy, float* mvn, float* bitn, float* depn, int* cam,
                          double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st) {
-  camera_motion_kernel<float><<<nframes, CM_THREADS, 0, st>>>(w, h, mvx, mvy, byts, depth, Vx, Vy, mvn, bitn, depn, cam, ave,
+  camera_motion_kernel<float><<<nframes * CM_CLUSTER, CM_THREADS, 0, st>>>(w, h, mvx, mvy, byts, depth, Vx, Vy, mvn, bitn, depn, cam, ave,
                                                               flag, first_slot, ring_len);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
@@ -309,7 +388,7 @@ int camera_motion_launch(int w, int h, int nframes, const int16_t* mvx, const in
 int camera_motion_launch_f64(int w, int h, int nframes, const int16_t* mvx, const int16_t* mvy, const uint16_t* byts,
                              const uint8_t* depth, double* Vx, double* Vy, float* mvn, float* bitn, float* depn, int* cam,
                              double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st) {
-  camera_motion_kernel<double><<<nframes, CM_THREADS, 0, st>>>(w, h, mvx, mvy, byts, depth, Vx, Vy, mvn, bitn, depn, cam, ave,
+  camera_motion_kernel<double><<<nframes * CM_CLUSTER, CM_THREADS, 0, st>>>(w, h, mvx, mvy, byts, depth, Vx, Vy, mvn, bitn, depn, cam, ave,
                                                                flag, first_slot, ring_len);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
