@@ -72,7 +72,12 @@ struct cds_ctx {
   float *d_fparam = nullptr, *d_C = nullptr;         // [9][4] mean, 1/std, weight; [B][200][200]
   float *d_T2 = nullptr, *d_raw = nullptr;           // [B][200][W], [B][H][W]
   float *d_fpartial = nullptr, *d_fstats = nullptr;  // final min/max
-  void* d_out = nullptr;               // [B][H][W] f32 or u8 (hook API)
+  void* d_out[2] = {nullptr, nullptr};   // two [B][H][W] f32 or u8 output buffers: batch i+1 renders while batch i drains to the host
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  int last_buf = 0, out_flip = 0;
+  int* d_cam_stage = nullptr;            // [2][B][2] camera motion of the batch in each output buffer
+  int* h_cam_pin = nullptr; size_t h_cam_cap = 0;   // pinned staging: a device->host copy into pageable memory would block the host and serialise the pipeline
   // staging for host-buffer entry points
   uint16_t* d_bytes = nullptr; int32_t* d_hdr = nullptr; int16_t* d_tok = nullptr; int64_t* d_tokbase = nullptr;
   size_t tok_cap = 0;
@@ -125,6 +130,11 @@ double mround(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); }
 __global__ void fill_u32_kernel(unsigned* p, size_t n, unsigned v0, unsigned v1) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = (i & 1) ? v1 : v0;
+}
+
+__global__ void gather_cam_kernel(const int* __restrict__ ring, int RL, int first_poc, int n, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * n) out[i] = ring[2 * ((first_poc + (i >> 1)) % RL) + (i & 1)];
 }
 
 __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v0, unsigned long long v1) {
@@ -456,11 +466,17 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   A(d_R1, (size_t)3 * B * 200 * W); A(d_Ft, (size_t)3 * B * 40000);
   A(d_xsvm, (size_t)B * 40000 * 9); A(d_dec, (size_t)B * 40000); A(d_C, (size_t)B * 40000);
   A(d_T2, (size_t)B * 200 * W); A(d_raw, (size_t)B * HW);
-  A(d_fpartial, (size_t)B * c->nblkf * 4); A(d_fstats, (size_t)B * 4);
+  A(d_fpartial, (size_t)B * c->nblkf * 4); A(d_fstats, (size_t)B * 4); A(d_cam_stage, (size_t)4 * B);
   A(d_bytes, (size_t)B * c->nctu); A(d_hdr, (size_t)B * c->nctu * 4); A(d_tokbase, (size_t)B + 1);
   c->tok_cap = (size_t)B * c->nctu * 160;
   A(d_tok, c->tok_cap);
-  if (!e) { void* q = nullptr; ce = cudaMalloc(&q, (size_t)B * HW * (p->out_u8 ? 1 : 4) + 256); if (ce != cudaSuccess) { set_error("cudaMalloc out"); e = CDS_ENOMEM; } else { c->allocs.push_back(q); c->d_out = q; } }
+  for (int b = 0; b < 2 && !e; b++) {
+    void* q = nullptr; ce = cudaMalloc(&q, (size_t)B * HW * (p->out_u8 ? 1 : 4) + 256);
+    if (ce != cudaSuccess) { set_error("cudaMalloc out"); e = CDS_ENOMEM; } else { c->allocs.push_back(q); c->d_out[b] = q; }
+    if (!e && (cudaEventCreateWithFlags(&c->ev_done[b], cudaEventDisableTiming) != cudaSuccess ||
+               cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming) != cudaSuccess)) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
+  }
+  if (!e && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate copy"); e = CDS_ECUDA; }
 #undef A
   float* d_fparam = nullptr;
   if (!e) e = dalloc(c, &d_fparam, 36);
@@ -488,6 +504,9 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
 extern "C" void cds_destroy(cds_ctx* c) {
   if (!c) return;
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (int b = 0; b < 2; b++) { if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); }
+  if (c->h_cam_pin) cudaFreeHost(c->h_cam_pin);
   for (void* q : c->allocs) cudaFree(q);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   c->poly.release();
@@ -674,45 +693,74 @@ extern "C" int cds_clip_process_dev(cds_ctx* c, int first_poc, int nframes, cons
   return CDS_OK;
 }
 
-// host buffers in, results rendered into c->d_out batch by batch and copied to host_out when given
+// host buffers in; batch i renders into d_out[i & 1] on the compute stream while batch i-1 drains to host_out on the copy
+// stream (events order the two), so the device->host copy of the maps overlaps the next batch's kernels.
 static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* ctu_bytes, const int32_t* hdr,
                         const int16_t* tok, const int64_t* tok_base, size_t ntok, void* host_out, int* cam_out,
                         bool context_only = false) {
-  cudaStream_t st = c->stream;
+  cudaStream_t st = c->stream, cs = c->copy_stream;
   const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
+  const int nb = (nframes + c->B - 1) / c->B;
+  // validate the token ranges and size the staging buffer once (worst case 1237 tokens per CTU)
+  size_t need = 0;
   for (int done = 0; done < nframes; done += c->B) {
     const int n = std::min(c->B, nframes - done);
     const int64_t t0 = tok_base[done], t1 = tok_base[done + n];
     if (t0 < 0 || t1 < t0 || (size_t)t1 > ntok) { set_error("cds_clip_process: tok_base out of range"); return CDS_EFORMAT; }
-    if ((size_t)(t1 - t0) > c->tok_cap) {        // grow the token staging buffer (worst case 1237 tokens per CTU)
-      CDS_CUDA(cudaStreamSynchronize(st));
-      const size_t want = (size_t)(t1 - t0) + (size_t)(t1 - t0) / 4;
-      void* q = nullptr;
-      if (cudaMalloc(&q, want * 2 + 256) != cudaSuccess) { set_error("cds_clip_process: cannot stage %zu tokens", want); return CDS_ENOMEM; }
-      for (void*& a : c->allocs) if (a == (void*)c->d_tok) { cudaFree(a); a = q; }
-      c->d_tok = reinterpret_cast<int16_t*>(q); c->tok_cap = want;
-    }
-    std::vector<int64_t> base(n + 1);
-    for (int i = 0; i <= n; i++) base[i] = tok_base[done + i] - t0;
+    need = std::max(need, (size_t)(t1 - t0));
+  }
+  if (need > c->tok_cap) {
+    CDS_CUDA(cudaStreamSynchronize(st));
+    const size_t want = need + need / 4;
+    void* q = nullptr;
+    if (cudaMalloc(&q, want * 2 + 256) != cudaSuccess) { set_error("cds_clip_process: cannot stage %zu tokens", want); return CDS_ENOMEM; }
+    for (void*& a : c->allocs) if (a == (void*)c->d_tok) { cudaFree(a); a = q; }
+    c->d_tok = reinterpret_cast<int16_t*>(q); c->tok_cap = want;
+  }
+  std::vector<int64_t> base((size_t)nb * (c->B + 1));       // lives until the final synchronisation below
+  if (cam_out && !context_only && (size_t)2 * nframes > c->h_cam_cap) {
+    if (c->h_cam_pin) cudaFreeHost(c->h_cam_pin);
+    c->h_cam_pin = nullptr; c->h_cam_cap = 0;
+    CDS_CUDA(cudaHostAlloc((void**)&c->h_cam_pin, (size_t)2 * nframes * sizeof(int), cudaHostAllocDefault));
+    c->h_cam_cap = (size_t)2 * nframes;
+  }
+  int bi = 0;
+  for (int done = 0; done < nframes; done += c->B, bi++) {
+    const int n = std::min(c->B, nframes - done);
+    const int64_t t0 = tok_base[done], t1 = tok_base[done + n];
+    int64_t* bs = base.data() + (size_t)bi * (c->B + 1);
+    for (int i = 0; i <= n; i++) bs[i] = tok_base[done + i] - t0;
     CDS_CUDA(cudaMemcpyAsync(c->d_bytes, ctu_bytes + (size_t)done * c->nctu, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, st));
     CDS_CUDA(cudaMemcpyAsync(c->d_hdr, hdr + (size_t)done * c->nctu * 4, (size_t)n * c->nctu * 16, cudaMemcpyHostToDevice, st));
     CDS_CUDA(cudaMemcpyAsync(c->d_tok, tok + t0, (size_t)(t1 - t0) * 2, cudaMemcpyHostToDevice, st));
-    CDS_CUDA(cudaMemcpyAsync(c->d_tokbase, base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-    CDS_CUDA(cudaStreamSynchronize(st));   // `base` is a host temporary
+    CDS_CUDA(cudaMemcpyAsync(c->d_tokbase, bs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     if (context_only) {
       if (int e = run_context_stages(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, st)) return e;
-    } else {
-      if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out, nullptr, st)) return e;
+      continue;
     }
-    if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)done * px, c->d_out, (size_t)n * px, cudaMemcpyDeviceToHost, st));
+    const int buf = c->out_flip; c->out_flip ^= 1;
+    CDS_CUDA(cudaStreamWaitEvent(st, c->ev_copied[buf], 0));   // the copy that last read this buffer has finished (no-op if never recorded)
+    if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out[buf], nullptr, st)) return e;
+    if (cam_out) {
+      gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, c->RL, first_poc + done, n, c->d_cam_stage + (size_t)buf * 2 * c->B);
+      CDS_LAUNCH_CHECK();
+    }
+    CDS_CUDA(cudaEventRecord(c->ev_done[buf], st));
+    CDS_CUDA(cudaStreamWaitEvent(cs, c->ev_done[buf], 0));
+    if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)done * px, c->d_out[buf], (size_t)n * px, cudaMemcpyDeviceToHost, cs));
     if (cam_out)
-      for (int f = 0; f < n; f++)
-        CDS_CUDA(cudaMemcpyAsync(cam_out + 2 * (done + f), c->r_cam + 2 * ((first_poc + done + f) % c->RL), 8, cudaMemcpyDeviceToHost, st));
-    int herr = 0;
-    CDS_CUDA(cudaMemcpyAsync(&herr, c->d_err, 4, cudaMemcpyDeviceToHost, st));
-    CDS_CUDA(cudaStreamSynchronize(st));
-    if (herr) { CDS_CUDA(cudaMemset(c->d_err, 0, 4)); set_error("cds_clip_process: malformed CU token stream in pictures %d..%d", first_poc + done, first_poc + done + n - 1); return CDS_EFORMAT; }
-    if (!context_only) { c->last_first = first_poc + done; c->last_n = n; }
+      CDS_CUDA(cudaMemcpyAsync(c->h_cam_pin + 2 * done, c->d_cam_stage + (size_t)buf * 2 * c->B, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
+    CDS_CUDA(cudaEventRecord(c->ev_copied[buf], cs));
+    c->last_first = first_poc + done; c->last_n = n; c->last_buf = buf;
+  }
+  int herr = 0;
+  CDS_CUDA(cudaMemcpyAsync(&herr, c->d_err, 4, cudaMemcpyDeviceToHost, st));
+  CDS_CUDA(cudaStreamSynchronize(st));
+  CDS_CUDA(cudaStreamSynchronize(cs));
+  if (cam_out && !context_only) memcpy(cam_out, c->h_cam_pin, (size_t)2 * nframes * sizeof(int));
+  if (herr) {
+    CDS_CUDA(cudaMemset(c->d_err, 0, 4));
+    set_error("cds_clip_process: malformed CU token stream in pictures %d..%d", first_poc, first_poc + nframes - 1); return CDS_EFORMAT;
   }
   c->next_poc = first_poc + nframes;
   return CDS_OK;
@@ -784,7 +832,7 @@ extern "C" int cds_get_map(cds_ctx* c, int poc, void* dst, int* cam_xy) {
     set_error("cds_get_map: picture %d is not in the most recent batch [%d, %d)", poc, c->last_first, c->last_first + c->last_n); return CDS_EINVAL;
   }
   const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
-  CDS_CUDA(cudaMemcpy(dst, (char*)c->d_out + (size_t)(poc - c->last_first) * px, px, cudaMemcpyDeviceToHost));
+  CDS_CUDA(cudaMemcpy(dst, (char*)c->d_out[c->last_buf] + (size_t)(poc - c->last_first) * px, px, cudaMemcpyDeviceToHost));
   if (cam_xy) CDS_CUDA(cudaMemcpy(cam_xy, c->r_cam + 2 * (poc % c->RL), 8, cudaMemcpyDeviceToHost));
   return CDS_OK;
 }
