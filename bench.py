@@ -164,6 +164,10 @@ def run_b200(a):
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: anything libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != a.gpus and world > 1:
         a.gpus = world
     torch.cuda.set_device(local)
@@ -346,11 +350,14 @@ def run_b200(a):
         line["cpu_baseline"] = {"value": 1.0 / pf, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{n_out} output pictures of the same 1080p workload after {ctx} context pictures, oracle/cds_oracle.c "
                                           f"(port of main.m RBF branch + getFrame) with {cores} threads; per-picture s: {det}"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     return 0
 
 

@@ -120,6 +120,25 @@ def test_frame_range_shard_with_halo_is_bytewise_identical(cds):
     one.close(); sh.close()
 
 
+def test_shard_planner_two_ranks_reproduce_single_context(cds):
+    """plan_frame_ranges + process_frame_range for world = 2 (ranks run one after the other here) == one context."""
+    w, h, F, fps = 416, 240, 33, 10.0
+    packed, _ = _clip(cds, w, h, 21, F)
+    hdr, tok, base, byts = packed
+    mdl, gm = _model(cds, 64)
+    one = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=8)
+    full, fcam = one.process(0, *packed)
+    one.close()
+    plan = cds.shard.plan_frame_ranges(F, 2, cds.shard.halo_frames(fps))
+    parts = []
+    for p in plan:
+        c = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=8)
+        parts.append(cds.shard.process_frame_range(c, p, hdr, tok, base, byts))
+        c.close()
+    assert np.array_equal(np.concatenate([m for m, _ in parts]), full)
+    assert np.array_equal(np.concatenate([c for _, c in parts]), fcam)
+
+
 def test_u8_output(cds):
     w, h, F, fps = 416, 240, 5, 10.0
     packed, _ = _clip(cds, w, h, 3, F)
