@@ -346,9 +346,9 @@ __global__ void __launch_bounds__(256)
 normalize_out_kernel(const float* __restrict__ raw, long HW, const float* __restrict__ fstats, OutT* __restrict__ out) {
   const int f = blockIdx.y;
   const float mn = fstats[(size_t)f * 4], mx = fstats[(size_t)f * 4 + 1];
-  const float inv = mx > mn ? 1.f / (mx - mn) : 0.f;                        // pm_norm (main.m:304)
+  const float den = mx - mn;                                                // pm_norm (main.m:304): a true division, so the maximum maps to exactly 1
   for (long p = blockIdx.x * 256L + threadIdx.x; p < HW; p += (long)gridDim.x * 256) {
-    const float v = (raw[(size_t)f * HW + p] - mn) * inv;
+    const float v = den > 0.f ? (raw[(size_t)f * HW + p] - mn) / den : 0.f;
     if (sizeof(OutT) == 1) out[(size_t)f * HW + p] = (OutT)__float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * 255.f);
     else out[(size_t)f * HW + p] = (OutT)v;
   }

@@ -1,0 +1,111 @@
+"""GPU parity at BASELINE.json's full sizes.  The oracle is too slow for long clips at these sizes, so:
+  * a few pictures per resolution are compared directly (oracle: seconds per picture on the host cores),
+  * the rest goes through size-independent properties: determinism (two runs are bytewise identical),
+    frame-range sharding == single context, batch-size independence, and the integer stages bit-exact
+    against the oracle on every picture."""
+import numpy as np
+import pytest
+
+import _oracle as o
+
+pytestmark = pytest.mark.gpu
+MEAN9 = np.full(9, 0.3)
+STD9 = np.full(9, 0.2)
+
+
+@pytest.fixture(scope="module")
+def cds():
+    import compressd_domain_saliencyprediction_b200 as pkg
+    assert pkg.device_ok(), pkg.lib().cds_last_error()
+    return pkg
+
+
+def _model(cds, nsv):
+    SV, coef, rho, gamma, labels = o.synth_model(nsv)
+    SV = SV * 0.5 + 1.0
+    return (SV, coef, rho, gamma, labels), cds.ops.SvmModel(SVs=SV, sv_coef=coef, rho=rho, gamma=gamma, Label=labels)
+
+
+@pytest.mark.parametrize("wh", [(832, 480), (1920, 1080)])
+def test_clip_maps_vs_oracle_full_resolution(cds, wh):
+    w, h = wh
+    F, fps = 4, 10.0                                  # PS 3: smoothing window reached, short temporal window
+    o.oracle().orc_set_threads(16)
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 4321, F)
+    ints = [o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    mvx = np.stack([m[0] for m in ints]); mvy = np.stack([m[1] for m in ints]); dep = np.stack([m[2] for m in ints])
+    mdl, gm = _model(cds, 256)
+    want, wcam, _ = o.orc_process_clip(w, h, fps, mvx, mvy, dep, byts, mdl, MEAN9, STD9, first_out=F - 2, use_rbf=1)
+    clip = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=4)
+    got, cam = clip.process(0, hdr, tok, base, byts)
+    clip.close()
+    assert np.array_equal(cam, wcam)
+    for k in range(2):
+        err = np.max(np.abs(got[F - 2 + k] - np.nan_to_num(want[k])))
+        assert err <= 1e-4, (k, err)                  # north_star: saliency maps within 1e-4 (maps are pm_norm'ed to [0, 1])
+
+
+@pytest.mark.parametrize("wh", [(1920, 1080), (2560, 1600), (3840, 2160)])
+def test_integer_stages_bit_exact_at_full_size(cds, wh):
+    """Stage (a) maps and stage (c) votes on every picture of a short clip, bit-exact vs the oracle."""
+    w, h = wh
+    F = 3
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 77, F, first_poc=1)
+    for f in range(F):
+        t = tok[base[f]:base[f + 1]]
+        got = cds.ops.getframe(w, h, hdr[f], t)
+        want = o.orc_getframe(w, h, hdr[f], t)
+        assert all(np.array_equal(g, x) for g, x in zip(got, want))
+        r = cds.ops.camera_motion(w, h, want[0], want[1], byts[f], want[2])
+        wouts, wcam, wave, wflag = o.orc_camera_motion(w, h, want[0], want[1], byts[f], want[2])
+        assert np.array_equal(r["cam"], wcam) and r["flag"] == wflag and np.array_equal(r["ave"], wave)
+
+
+def test_determinism_batch_independence_and_sharding_1080p(cds):
+    """1080p, 50 fps geometry shortened in time (fps 10 -> PS 3, PT 21): two runs are bytewise identical, the result does
+    not depend on the batch size, and a two-rank frame-range plan reproduces it."""
+    w, h, F, fps = 1920, 1080, 30, 10.0
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 2024, F)
+    mdl, gm = _model(cds, 128)
+
+    def run(batch):
+        c = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=batch)
+        r = c.process(0, hdr, tok, base, byts)
+        c.close()
+        return r
+    a, acam = run(8)
+    b, bcam = run(8)
+    assert np.array_equal(a, b) and np.array_equal(acam, bcam)
+    c, ccam = run(5)
+    assert np.array_equal(a, c) and np.array_equal(acam, ccam)
+    assert np.all(np.isfinite(a)) and a.min() >= 0.0 and a.max() <= 1.0
+    for f in range(F):
+        assert a[f].max() == 1.0 or a[f].max() == 0.0      # pm_norm: every non-flat map spans [0, 1] exactly
+    plan = cds.shard.plan_frame_ranges(F, 2, cds.shard.halo_frames(fps))
+    parts = []
+    for p in plan:
+        cl = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=8)
+        parts.append(cds.shard.process_frame_range(cl, p, hdr, tok, base, byts))
+        cl.close()
+    assert np.array_equal(np.concatenate([m for m, _ in parts]), a)
+
+
+def test_contrast_1080p_map_vs_reference_kernel(cds):
+    """One 270x480 mv map, 48x48 window (the dominant contrast shape) against the oracle's computecontrast5."""
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((270, 480)) * 2
+    a[rng.random(a.shape) < 0.05] = a.min()            # ties at the minimum: exercises the p == 0 skip
+    pad, W, ln, win = o.sudoku_inputs(a, 11.0, 1, 48)
+    got = cds.ops.computecontrast5(pad, W, ln, win, 270, 480)
+    want = o.orc_computecontrast5(pad, W, ln, win, 270, 480)
+    assert np.max(np.abs(got - want)) <= 1e-4 * np.max(np.abs(want))
+
+
+def test_svm_full_frame_vs_oracle(cds):
+    """40 000 instances (one picture's 200x200 features) against 4096 support vectors."""
+    SV, coef, rho, gamma, labels = o.synth_model(4096)
+    X = np.random.default_rng(9).standard_normal((40000, 9)) * 1.2
+    m = cds.ops.SvmModel(SVs=SV, sv_coef=coef, rho=rho, gamma=gamma, Label=labels)
+    dec, _ = m.decision_values(X)
+    want, _ = o.orc_svm_predict(SV, coef, rho, gamma, labels, X)
+    assert np.max(np.abs(dec - want)) <= 1e-4 * (np.max(np.abs(want + rho)) + abs(rho))
