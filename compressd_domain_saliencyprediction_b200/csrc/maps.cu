@@ -178,7 +178,7 @@ struct OpAddI { __device__ int operator()(int a, int b) const { return a + b; } 
 __global__ void __launch_bounds__(256)
 smooth_kernel(int n4, int PS, int RL, int first_poc, const double* __restrict__ Vx, const double* __restrict__ Vy,
               const float* __restrict__ mvn, const float* __restrict__ bitn, const float* __restrict__ depn,
-              float* __restrict__ mvx_s, float* __restrict__ mvy_s, float* __restrict__ bit_s, float* __restrict__ dep_s,
+              float4* __restrict__ sm4 /*ring [RL][n4]: {mvx, mvy, bit, depth} smoothed*/,
               float* __restrict__ mv_s, double* __restrict__ cxy, int B) {
   const int o = blockIdx.x * 256 + threadIdx.x, f = blockIdx.y;
   if (o >= n4) return;
@@ -193,15 +193,16 @@ smooth_kernel(int n4, int PS, int RL, int first_poc, const double* __restrict__ 
   const float fc = (float)cnt;
   b /= (double)cnt; c /= (double)cnt;
   const size_t so = (size_t)(poc % RL) * n4 + o;
-  mv_s[(size_t)f * n4 + o] = a / fc; mvx_s[so] = (float)b; mvy_s[so] = (float)c; bit_s[so] = d / fc; dep_s[so] = e / fc;
+  mv_s[(size_t)f * n4 + o] = a / fc;
+  sm4[so] = make_float4((float)b, (float)c, d / fc, e / fc);
   if (cxy) { cxy[(size_t)f * n4 + o] = b; cxy[((size_t)B + f) * n4 + o] = c; }     // [mvx: B maps | mvy: B maps]
 }
 
 int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const double* Vx, const double* Vy, const float* mvn,
-                  const float* bitn, const float* depn, float* mvx_s, float* mvy_s, float* bit_s, float* dep_s, float* mv_s,
+                  const float* bitn, const float* depn, float4* sm4, float* mv_s,
                   double* cxy, cudaStream_t st) {
   dim3 grid(ceil_div(n4, 256), B);
-  smooth_kernel<<<grid, 256, 0, st>>>(n4, PS, ring_len, first_poc, Vx, Vy, mvn, bitn, depn, mvx_s, mvy_s, bit_s, dep_s, mv_s, cxy, B);
+  smooth_kernel<<<grid, 256, 0, st>>>(n4, PS, ring_len, first_poc, Vx, Vy, mvn, bitn, depn, sm4, mv_s, cxy, B);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
@@ -211,33 +212,35 @@ int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const doub
 // =================================================================================================
 __global__ void __launch_bounds__(1024)
 myst_small_kernel(int n4, double inv_hw, int RL, int first_poc, const float* __restrict__ mv_s,
-                  const float* __restrict__ bit_ring, const float* __restrict__ dep_ring, float* __restrict__ Xmaps) {
+                  const float4* __restrict__ sm4, float* __restrict__ Xmaps) {
   __shared__ float redf[32];
   __shared__ double redd[32];
   __shared__ int redi[32];
   const int f = blockIdx.x, which = blockIdx.y;       // 0 mv, 1 bit, 2 depth
   const size_t slot = (size_t)((first_poc + f) % RL) * n4;
-  const float* __restrict__ src = which == 0 ? mv_s + (size_t)f * n4 : which == 1 ? bit_ring + slot : dep_ring + slot;
+  // which == 0: the batch's smoothed mv_norm (stride 1); 1 / 2: components z / w of the interleaved ring (stride 4)
+  const float* __restrict__ src = which == 0 ? mv_s + (size_t)f * n4 : reinterpret_cast<const float*>(sm4 + slot) + (which + 1);
+  const int sst = which == 0 ? 1 : 4;
   float* __restrict__ dst = Xmaps + ((size_t)f * 9 + which * 3) * n4;
   double s = 0; float mx = -INFINITY;
-  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[o]; s += v; mx = fmaxf(mx, v); }
+  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[(size_t)o * sst]; s += v; mx = fmaxf(mx, v); }
   s = block_reduce(s, redd, OpAddD());
   mx = block_reduce(mx, redf, OpMax());
   const float lim = mx - (float)(s * inv_hw);                     // max - ave, ave over im_height*im_width (:3-4)
   double sb = 0; int nb = 0;
-  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[o]; if (v > lim) { sb += v; nb++; } }
+  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[(size_t)o * sst]; if (v > lim) { sb += v; nb++; } }
   sb = block_reduce(sb, redd, OpAddD());
   nb = block_reduce(nb, redi, OpAddI());
   const float thresh = nb > 0 ? (float)(sb / nb) : NAN;           // :5
   const float M = nb > 0 ? fminf(thresh, mx) : mx;                // max after the clamp
   const float inv = 1.f / (M + 0.000001f);                        // :7
-  for (int o = threadIdx.x; o < n4; o += 1024) { float v = src[o]; if (v > thresh) v = thresh; dst[o] = v * inv; }
+  for (int o = threadIdx.x; o < n4; o += 1024) { float v = src[(size_t)o * sst]; if (v > thresh) v = thresh; dst[o] = v * inv; }
 }
 
-int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float* bit_s_ring,
-                      const float* dep_s_ring, float* Xmaps, cudaStream_t st) {
+int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float4* sm4,
+                      float* Xmaps, cudaStream_t st) {
   dim3 grid(B, 3);
-  myst_small_kernel<<<grid, 1024, 0, st>>>(n4, 1.0 / ((double)H * W), ring_len, first_poc, mv_s, bit_s_ring, dep_s_ring, Xmaps);
+  myst_small_kernel<<<grid, 1024, 0, st>>>(n4, 1.0 / ((double)H * W), ring_len, first_poc, mv_s, sm4, Xmaps);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
@@ -250,8 +253,8 @@ constexpr int TMP_MAXJ = 1024;      // PT - 1 <= 7 * round(0.3 * 240) - 1 = 503
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __global__ void __launch_bounds__(256)
-temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float* __restrict__ mvx_s, const float* __restrict__ mvy_s,
-                const float* __restrict__ bit_s, const float* __restrict__ dep_s, const int* __restrict__ cam,
+temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __restrict__ sm4 /*{mvx, mvy, bit, depth} smoothed*/,
+                const int* __restrict__ cam,
                 const float* __restrict__ wtab /*[PT][4]: exp(-j/26), exp(-j/46), exp(-j/46)*/, float* __restrict__ Xmaps) {
   // per (picture, j): ring slot offset of picture poc-j and the accumulated camera shift, shared by every cell of the picture
   extern __shared__ int4 s_tab[];                 // [jmax + 1] = {slot offset in cells, sx, sy, 0}
@@ -284,33 +287,31 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float* __re
   if (o >= n4) return;
   const int r = o / w4, c = o - r * w4;
   const size_t cur = (size_t)(poc % RL) * n4 + o;
-  const float rx = mvx_s[cur], ry = mvy_s[cur], rb = bit_s[cur], rd = dep_s[cur];
+  const float4 ref = sm4[cur];
+  const float rx = ref.x, ry = ref.y, rb = ref.z, rd = ref.w;
   float am = 0.f, ab = 0.f, ad = 0.f;
   const float4* __restrict__ w4tab = reinterpret_cast<const float4*>(wtab);
 #pragma unroll 2
   for (int j = 1; j <= jmax; j++) {
     const int4 t = s_tab[j];
     const int sr = r - t.z, sc = c - t.y;                          // immove: +x moves content right, +y down, zero fill
-    float tx = 0.f, ty = 0.f, tb = 0.f, td = 0.f;
-    if ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) {
-      const int s = t.x + sr * w4 + sc;
-      tx = __ldg(mvx_s + s); ty = __ldg(mvy_s + s); tb = __ldg(bit_s + s); td = __ldg(dep_s + s);
-    }
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) p = __ldg(sm4 + (t.x + sr * w4 + sc));   // one LDG.128 for the four maps
     const float4 wj = __ldg(w4tab + j);
-    const float dx = rx - tx, dy = ry - ty;
+    const float dx = rx - p.x, dy = ry - p.y;
     am = fmaf(wj.x, sqrt_approx(fmaf(dx, dx, dy * dy)), am);      // :195
-    ab = fmaf(wj.y, fabsf(rb - tb), ab);                           // :196
-    ad = fmaf(wj.z, fabsf(rd - td), ad);                           // :197
+    ab = fmaf(wj.y, fabsf(rb - p.z), ab);                          // :196
+    ad = fmaf(wj.z, fabsf(rd - p.w), ad);                          // :197
   }
   float* X = Xmaps + (size_t)f * 9 * n4 + o;
   X[(size_t)1 * n4] = am; X[(size_t)4 * n4] = ab; X[(size_t)7 * n4] = ad;
 }
 
-int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float* mvx_s, const float* mvy_s,
-                    const float* bit_s, const float* dep_s, const int* cam_ring, const float* wtab, float* Xmaps, cudaStream_t st) {
+int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float4* sm4, const int* cam_ring,
+                    const float* wtab, float* Xmaps, cudaStream_t st) {
   dim3 grid(B, ceil_div(h4 * w4, 256));
   if (PT > TMP_MAXJ) { set_error("temporal: PT %d exceeds %d", PT, TMP_MAXJ); return CDS_EINVAL; }
-  temporal_kernel<<<grid, 256, (size_t)PT * sizeof(int4), st>>>(h4, w4, PT, ring_len, first_poc, mvx_s, mvy_s, bit_s, dep_s, cam_ring, wtab, Xmaps);
+  temporal_kernel<<<grid, 256, (size_t)PT * sizeof(int4), st>>>(h4, w4, PT, ring_len, first_poc, sm4, cam_ring, wtab, Xmaps);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
@@ -700,6 +701,48 @@ banded_rows_kernel(const float* __restrict__ in, int in_rows, int cols, const fl
   }
 }
 
+// Four consecutive output rows per CTA (operators whose rows overlap heavily, e.g. resize o gaussian): the rows' weights
+// are staged over their common input window as float4, so one LDG.128 of inputs + one broadcast LDS.128 feed 16 FFMAs
+// and each input row is fetched once per 4 output rows.  Taps stay in ascending order; pad weights add exact zeros.
+constexpr int BR_ROWS = 4;
+__global__ void __launch_bounds__(128)
+banded_rows4_kernel(const float* __restrict__ in, int in_rows, int cols, const float* __restrict__ w, const int* __restrict__ start,
+                    int nt, int n_out, float* __restrict__ out) {
+  extern __shared__ float4 sw4[];               // [window] x 4 rows
+  const int i0 = blockIdx.y * BR_ROWS, m = blockIdx.z, C4 = cols >> 2;
+  const int ilast = min(i0 + BR_ROWS - 1, n_out - 1);
+  const int s_lo = start[i0], L = min(start[ilast] + nt, in_rows) - s_lo;
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    float g[BR_ROWS];
+#pragma unroll
+    for (int k = 0; k < BR_ROWS; k++) {
+      const int i = i0 + k;
+      const int t = i < n_out ? j + s_lo - start[min(i, n_out - 1)] : -1;
+      g[k] = (t >= 0 && t < nt) ? w[(size_t)i * nt + t] : 0.f;
+    }
+    sw4[j] = make_float4(g[0], g[1], g[2], g[3]);
+  }
+  __syncthreads();
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(in + (size_t)m * in_rows * cols);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= C4) return;
+  float4 acc[BR_ROWS];
+#pragma unroll
+  for (int k = 0; k < BR_ROWS; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int j = 0; j < L; j++) {
+    const float4 v = __ldg(src + (size_t)(s_lo + j) * C4 + x);
+    const float4 g = sw4[j];
+    acc[0].x = fmaf(g.x, v.x, acc[0].x); acc[0].y = fmaf(g.x, v.y, acc[0].y); acc[0].z = fmaf(g.x, v.z, acc[0].z); acc[0].w = fmaf(g.x, v.w, acc[0].w);
+    acc[1].x = fmaf(g.y, v.x, acc[1].x); acc[1].y = fmaf(g.y, v.y, acc[1].y); acc[1].z = fmaf(g.y, v.z, acc[1].z); acc[1].w = fmaf(g.y, v.w, acc[1].w);
+    acc[2].x = fmaf(g.z, v.x, acc[2].x); acc[2].y = fmaf(g.z, v.y, acc[2].y); acc[2].z = fmaf(g.z, v.z, acc[2].z); acc[2].w = fmaf(g.z, v.w, acc[2].w);
+    acc[3].x = fmaf(g.w, v.x, acc[3].x); acc[3].y = fmaf(g.w, v.y, acc[3].y); acc[3].z = fmaf(g.w, v.z, acc[3].z); acc[3].w = fmaf(g.w, v.w, acc[3].w);
+  }
+#pragma unroll
+  for (int k = 0; k < BR_ROWS; k++)
+    if (i0 + k < n_out) reinterpret_cast<float4*>(out + ((size_t)m * n_out + i0 + k) * cols)[x] = acc[k];
+}
+
 // scalar-column variant for widths that are not a multiple of 4 (cell grids of pictures whose width is 8 mod 16)
 __global__ void __launch_bounds__(128)
 banded_rows_scalar_kernel(const float* __restrict__ in, int in_rows, int cols, const float* __restrict__ w, const int* __restrict__ start,
@@ -732,6 +775,12 @@ int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const 
     return CDS_OK;
   }
   const int thr = fir_threads(cols / 4);
+  if (!xf && B.span4 >= 0 && B.span4 <= B.nt / 2) {           // heavily overlapping rows: 4 output rows per CTA
+    dim3 grid4(ceil_div(cols / 4, thr), ceil_div(B.n_out, BR_ROWS), nmaps);
+    banded_rows4_kernel<<<grid4, thr, (size_t)(B.nt + B.span4) * 16, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, out);
+    CDS_LAUNCH_CHECK();
+    return CDS_OK;
+  }
   dim3 grid(ceil_div(cols / 4, thr), B.n_out, nmaps);
   if (xf) banded_rows_kernel<true><<<grid, thr, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
   else    banded_rows_kernel<false><<<grid, thr, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);

@@ -43,16 +43,16 @@ void banded_from_dense(const std::vector<double>& A, int n_out, int n_in, Banded
 // Vx / Vy rings are double (the reference's mv_x / mv_y cell arrays); cxy (optional) receives the smoothed
 // mvx_crop | mvy_crop of this batch in double, [2][B][n4], for contrast_prep_f64_launch
 int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const double* Vx, const double* Vy, const float* mvn,
-                  const float* bitn, const float* depn, float* mvx_s, float* mvy_s, float* bit_s, float* dep_s, float* mv_s,
+                  const float* bitn, const float* depn, float4* sm4 /*ring [RL][n4] {mvx, mvy, bit, depth} smoothed*/, float* mv_s,
                   double* cxy, cudaStream_t st);
 // Sudoku :18-34 for the signed mv maps in double -> padded FP32 maps; keys [nmaps][2] preset to {~0ull, 0}
 int contrast_prep_f64_launch(const double* src, int nmaps, int rows, int cols, int len, unsigned long long* keys, float* pad,
                              cudaStream_t st);
 // mysterythrehold on the three smoothed h4 x w4 maps -> Xmaps slots 0,3,6
-int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float* bit_s_ring,
-                      const float* dep_s_ring, float* Xmaps, cudaStream_t st);
-int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float* mvx_s, const float* mvy_s,
-                    const float* bit_s, const float* dep_s, const int* cam_ring, const float* wtab, float* Xmaps, cudaStream_t st);
+int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float4* sm4,
+                      float* Xmaps, cudaStream_t st);
+int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float4* sm4, const int* cam_ring,
+                    const float* wtab, float* Xmaps, cudaStream_t st);
 // block-mean downsample (cusize) + 1e-8 + min/max of one map type; src_stride/src_off select the map inside a batch buffer
 int contrast_sub_launch(const float* src, long src_frame_stride, int ring_len, int first_slot, int B, int rows, int cols,
                         int cusize, float* sub, unsigned* minmax_keys, cudaStream_t st);

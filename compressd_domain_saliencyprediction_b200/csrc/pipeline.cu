@@ -51,7 +51,7 @@ struct cds_ctx {
   // rings [RL][n4]
   double *r_Vx = nullptr, *r_Vy = nullptr;            // mv_x / mv_y stay double up to the contrast's pm_norm (zero-test ties)
   float *r_mvn = nullptr, *r_bitn = nullptr, *r_depn = nullptr;
-  float *r_mvx_s = nullptr, *r_mvy_s = nullptr, *r_bit_s = nullptr, *r_dep_s = nullptr;
+  float4* r_sm4 = nullptr;             // smoothed {mvx, mvy, bit, depth} interleaved: the temporal pass reads all four with one LDG.128
   int* r_cam = nullptr;                // [RL][2]
   // batch buffers
   float *d_mv_s = nullptr, *d_X = nullptr;           // [B][n4], [B][9][n4]
@@ -446,8 +446,7 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   A(d_mvx, (size_t)B * n4); A(d_mvy, (size_t)B * n4); A(d_dep, (size_t)B * n4); A(d_err, 4);
   if (!e && cudaMemset(c->d_err, 0, 16) != cudaSuccess) { set_error("cudaMemset d_err"); e = CDS_ECUDA; }
   A(r_Vx, (size_t)c->RL * n4); A(r_Vy, (size_t)c->RL * n4); A(r_mvn, (size_t)c->RL * n4); A(r_bitn, (size_t)c->RL * n4);
-  A(r_depn, (size_t)c->RL * n4); A(r_mvx_s, (size_t)c->RL * n4); A(r_mvy_s, (size_t)c->RL * n4); A(r_bit_s, (size_t)c->RL * n4);
-  A(r_dep_s, (size_t)c->RL * n4); A(r_cam, (size_t)c->RL * 2);
+  A(r_depn, (size_t)c->RL * n4); A(r_sm4, (size_t)c->RL * n4); A(r_cam, (size_t)c->RL * 2);
   A(d_mv_s, (size_t)B * n4); A(d_X, (size_t)B * 9 * n4); A(d_cxy, (size_t)2 * B * n4); A(d_keys64, (size_t)4 * B);
   const int sbR = (h4 + 15) / 16, sbC = (w4 + 15) / 16, sdR = (h4 + 1) / 2, sdC = (w4 + 1) / 2;
   A(d_subB, (size_t)B * sbR * sbC); A(d_padB, (size_t)B * (sbR + 4) * (sbC + 4)); A(d_rawB, (size_t)B * sbR * sbC);
@@ -518,8 +517,9 @@ extern "C" int cds_seek(cds_ctx* c, int poc) {
   if (!c || poc < 0) { set_error("cds_seek: bad arguments"); return CDS_EINVAL; }
   cudaStreamSynchronize(c->stream);
   const size_t rb = (size_t)c->RL * c->n4 * 4;
-  for (float* r : {c->r_mvn, c->r_bitn, c->r_depn, c->r_mvx_s, c->r_mvy_s, c->r_bit_s, c->r_dep_s})
+  for (float* r : {c->r_mvn, c->r_bitn, c->r_depn})
     CDS_CUDA(cudaMemset(r, 0, rb));
+  CDS_CUDA(cudaMemset(c->r_sm4, 0, 4 * rb));
   for (double* r : {c->r_Vx, c->r_Vy}) CDS_CUDA(cudaMemset(r, 0, 2 * rb));
   CDS_CUDA(cudaMemset(c->r_cam, 0, (size_t)c->RL * 8));
   c->next_poc = poc; c->pending = 0; c->pending_first = poc; c->last_first = -1; c->last_n = 0;
@@ -539,8 +539,8 @@ int run_context_stages(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, 
   if (int e = camera_motion_launch_f64(c->w, c->h, n, c->d_mvx, c->d_mvy, bytes, c->d_dep, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn,
                                        c->r_depn, c->r_cam, nullptr, nullptr, first_poc % c->RL, c->RL, st)) return e;
   prof_mark(c, ST_SMOOTH, st);
-  return smooth_launch(c->n4, c->PS, c->RL, first_poc, n, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn, c->r_depn, c->r_mvx_s, c->r_mvy_s,
-                       c->r_bit_s, c->r_dep_s, c->d_mv_s, c->d_cxy, st);
+  return smooth_launch(c->n4, c->PS, c->RL, first_poc, n, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn, c->r_depn, c->r_sm4,
+                       c->d_mv_s, c->d_cxy, st);
 }
 
 template <typename OutT>
@@ -558,8 +558,8 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, st)) return e;
   // ---- thresholded smoothed maps and temporal features -> X slots 0,3,6 / 1,4,7 ----
   prof_mark(c, ST_THRESH_TEMPORAL, st);
-  if (int e = myst_small_launch(n4, H, W, RL, first_poc, n, c->d_mv_s, c->r_bit_s, c->r_dep_s, c->d_X, st)) return e;
-  if (int e = temporal_launch(h4, w4, c->PT, RL, first_poc, n, c->r_mvx_s, c->r_mvy_s, c->r_bit_s, c->r_dep_s, c->r_cam, c->d_wtab,
+  if (int e = myst_small_launch(n4, H, W, RL, first_poc, n, c->d_mv_s, c->r_sm4, c->d_X, st)) return e;
+  if (int e = temporal_launch(h4, w4, c->PT, RL, first_poc, n, c->r_sm4, c->r_cam, c->d_wtab,
                               c->d_X, st)) return e;
   // ---- (b) contrast: bit (cusize 16, delta 3, win 5), depth (2, 13, 24), mvx / mvy (1, 11, 48)  main.m:226-235 ----
   {
