@@ -1,6 +1,8 @@
 """CPU-only: pin the oracle (oracle/cds_oracle.c) against the reference's golden vectors and, where
 oracle/_ref exists (the reference's own sources compiled in the build container), against the
 reference code itself."""
+import os
+
 import numpy as np
 import pytest
 
@@ -105,3 +107,21 @@ def test_svm_heart_scale_known_answer():
     assert d["SV"].shape[0] == 130
     assert int((lab == d["y"]).sum()) == 234
     assert np.array_equal(dec, d["dec_ref"])
+
+
+@pytest.mark.parametrize("name", ["BasketballDrill", "BasketballDrive"])
+def test_oracle_getframe_on_consecutive_real_pictures_vs_authors_golden(name):
+    """tests/golden/real_*.npz: consecutive pictures of the bundled streams with the authors' .mat maps."""
+    d = np.load(os.path.join(o.ROOT, "tests", "golden", f"real_{name}.npz"))
+    w, h = int(d["w"]), int(d["h"])
+    for f in range(len(d["pocs"])):
+        got = o.orc_getframe(w, h, d["hdr"][f], d["tok"][d["tok_base"][f]:d["tok_base"][f + 1]])
+        assert np.array_equal(got[0], d["mvx"][f]) and np.array_equal(got[1], d["mvy"][f]) and np.array_equal(got[2], d["depth"][f]), f
+
+
+def test_oracle_camera_motion_fires_on_basketballdrive_pan():
+    d = np.load(os.path.join(o.ROOT, "tests", "golden", "real_BasketballDrive.npz"))
+    w, h = int(d["w"]), int(d["h"])
+    for f in range(4):
+        outs, cam, ave, flag = o.orc_camera_motion(w, h, d["mvx"][f], d["mvy"][f], d["ctu_bytes"][f], d["depth"][f])
+        assert flag == 1 and cam[0] >= 6 and cam[1] == 0
