@@ -51,7 +51,28 @@ extern Bool g_md5_mismatch;
 static Void calcAndPrintHashStatus(TComPicYuv& pic, const SEIDecodedPictureHash* pictureHashSEI);
 '''
 
+# --mode cds: the same decoder with the saliency block replaced by this repo's binding (include/cds_hm_hook.h):
+# the hooks hand packed syntax to libcds_b200.so (dlopen'ed from $CDS_LIB) and write the maps to $CDS_OUT.
+CDS_BLOCK = r'''
+  /* ---- B200 saliency path (replaces the reference's OpenCV saliency block) ---- */
+  {
+    CdsHmHook& s_cds_hook = CdsHmHook::get();
+    TComSPS* sps = pcSlice->getSPS();
+    Window& cw = sps->getConformanceWindow();
+    const int cw_w = (int)sps->getPicWidthInLumaSamples() - cw.getWindowLeftOffset() - cw.getWindowRightOffset();
+    const int cw_h = (int)sps->getPicHeightInLumaSamples() - cw.getWindowTopOffset() - cw.getWindowBottomOffset();
+    s_cds_hook.onSlice(pcSlice->getPOC(), cw_w, cw_h, (int)rpcPic->getNumCUsInFrame(), TDecCu::bits, &TDecCu::MV[0][0],
+                       &TDecCu::Pred[0][0], &TDecCu::CUPU[0][0]);
+  }
+}
+'''
+
+
 def main():
+    mode = "cds" if "--mode" in sys.argv and sys.argv[sys.argv.index("--mode") + 1] == "cds" else "dump"
+    global WORK
+    if mode == "cds":
+        WORK = WORK + "_cds"
     if not os.path.isdir(REF):
         print("reference tree absent; nothing to build"); return 0
     if os.path.isdir(WORK): shutil.rmtree(WORK)
@@ -81,15 +102,21 @@ def main():
            and "MergeSort" not in l and "Merge(" not in l and "MeanArry" not in l
            and "int max(int" not in l and "g_md5_mismatch" not in l
            and not l.startswith("static Void calcAndPrintHashStatus")]
-    out = "\n".join(head) + "\n#include <math.h>\n" + STATICS + "\n".join(mid) + DUMP + "\n".join(tail) + "\n"
+    block, extra = DUMP, ""
+    if mode == "cds":
+        block, extra = CDS_BLOCK, '#include "cds_hm_hook.h"\n'
+        for hname in ("cds.h", "cds_hm_hook.h"):          # this repo's own headers into the scratch tree
+            shutil.copy(os.path.join(HERE, "..", "..", "include", hname), os.path.join(WORK, "source/Lib/TLibDecoder", hname))
+    out = "\n".join(head) + "\n#include <math.h>\n" + extra + STATICS + "\n".join(mid) + block + "\n".join(tail) + "\n"
     open(p, "w", encoding="latin-1").write(out)
     env = dict(os.environ)
     for lib in ("TLibVideoIO", "TLibCommon", "TLibDecoder", "TAppCommon"):
         subprocess.check_call(["make", "-j8", "-C", os.path.join(WORK, "build/linux/lib", lib), "release"], env=env)
     subprocess.check_call(["make", "-C", os.path.join(WORK, "build/linux/app/TAppDecoder"), "release"], env=env)
     os.makedirs(OUT, exist_ok=True)
-    shutil.copy(os.path.join(WORK, "bin/TAppDecoderStatic"), os.path.join(OUT, "hm_syntax_dump"))
-    print("built", os.path.join(OUT, "hm_syntax_dump"))
+    name = "hm_cds_decoder" if mode == "cds" else "hm_syntax_dump"
+    shutil.copy(os.path.join(WORK, "bin/TAppDecoderStatic"), os.path.join(OUT, name))
+    print("built", os.path.join(OUT, name))
     return 0
 
 if __name__ == "__main__":

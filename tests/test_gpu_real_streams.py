@@ -58,3 +58,44 @@ def test_real_stream_clip_vs_oracle(cds, name, fps, nout):
     for k in range(F - first):
         err = np.max(np.abs(got[first + k] - np.nan_to_num(want[k])))
         assert err <= 1e-4, (name, first + k, err)
+
+
+def _write_libsvm_model(path, SV, coef, rho, gamma):
+    """svm_save_model text format (svm.cpp:2756)."""
+    npos = int(np.sum(coef > 0))
+    with open(path, "w") as f:
+        f.write(f"svm_type c_svc\nkernel_type rbf\ngamma {gamma:.17g}\nnr_class 2\ntotal_sv {len(coef)}\nrho {rho:.17g}\n"
+                f"label 1 -1\nnr_sv {npos} {len(coef) - npos}\nSV\n")
+        for c, s in zip(coef, SV):
+            f.write(f"{c:.17g} " + " ".join(f"{i + 1}:{v:.17g}" for i, v in enumerate(s)) + " \n")
+
+
+def test_hm_decoder_with_cds_hook_end_to_end(cds, tmp_path):
+    """The reference's HM-16.0 decoder, rebuilt with include/cds_hm_hook.h in place of its OpenCV block
+    (oracle/_ref/hm_cds_decoder, built by oracle/hm_dump/build_hm_dump.py --mode cds), decodes a bundled bitstream:
+    CABAC parse on the host, hooks -> packed syntax -> libcds_b200.so -> maps.  The maps of the first pictures must be
+    bytewise identical to the library fed with the same pictures' syntax from the fixture."""
+    import subprocess
+    dec = os.path.join(o.ROOT, "oracle", "_ref", "hm_cds_decoder")
+    stream = os.path.join(o.ROOT, "oracle", "_ref", "streams", "BasketballPass.bin")
+    if not (os.path.exists(dec) and os.path.exists(stream)):
+        pytest.skip("hooked HM decoder / bitstream not built (needs the reference tree at build time)")
+    SV, coef, rho, gamma, labels = o.synth_model(64)
+    SV = SV * 0.5 + 1.0
+    mpath = str(tmp_path / "standin.model")
+    _write_libsvm_model(mpath, SV, coef, rho, gamma)
+    out = str(tmp_path / "maps.f32")
+    env = dict(os.environ, CDS_LIB=cds.lib_path(), CDS_OUT=out, CDS_FPS="50", CDS_SVM_MODEL=mpath, CDS_BATCH="16",
+               CDS_MEAN=",".join(["0.3"] * 9), CDS_STD=",".join(["0.2"] * 9))
+    r = subprocess.run([dec, "-b", stream], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "[cds hook] 500 pictures" in r.stderr, r.stderr[-2000:]
+    print(r.stderr.strip().splitlines()[-1])
+    maps = np.fromfile(out, np.float32).reshape(-1, 240, 416)
+    assert maps.shape[0] == 500 and np.all(np.isfinite(maps))
+    d, w, h, F = _load("BasketballPass")
+    gm = cds.ops.SvmModel(path=mpath)
+    clip = cds.SaliencyClip(w, h, 50.0, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=16)
+    got, _ = clip.process(0, d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"])
+    clip.close()
+    assert np.array_equal(maps[:F], got)
