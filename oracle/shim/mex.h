@@ -17,4 +17,14 @@ static inline mxArray* mxCreateDoubleMatrix(size_t m, size_t n, int) {
   return a;
 }
 static inline void mxDestroyArray(mxArray* a) { if (a) { free(a->pr); free(a); } }
+/* mexErrMsgIdAndTxt aborts the mex call in MATLAB; the stand-in records the message (tests read it back). */
+#include <stdarg.h>
+#include <stdio.h>
+static char g_mex_shim_error[512];
+static inline void mexErrMsgIdAndTxt(const char* id, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  int n = snprintf(g_mex_shim_error, sizeof(g_mex_shim_error), "%s: ", id);
+  vsnprintf(g_mex_shim_error + n, sizeof(g_mex_shim_error) - n, fmt, ap);
+  va_end(ap);
+}
 #endif
