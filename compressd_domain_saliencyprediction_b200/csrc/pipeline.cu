@@ -93,14 +93,14 @@ struct cds_ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<std::pair<int, cudaEvent_t>> ev_marks;     // (stage id that STARTS here, event); id -1 closes a batch
-  double prof_ms[16] = {0};
-  long prof_calls[16] = {0};
+  double prof_ms[24] = {0};
+  long prof_calls[24] = {0};
 };
 
-enum Stage { ST_GETFRAME = 0, ST_VOTE, ST_SMOOTH, ST_THRESH_TEMPORAL, ST_CONTRAST_PREP, ST_CONTRAST_W5, ST_CONTRAST_W24,
-             ST_CONTRAST_W48, ST_FULLRES, ST_RESIZE200, ST_SVM, ST_FINAL, ST_COUNT };
-static const char* kStageNames = "getframe,vote,smooth,thresh_temporal,contrast_prep,contrast_win5,contrast_win24,contrast_win48,"
-                                 "fullres_gauss,resize200,svm_rbf,final_map";
+enum Stage { ST_GETFRAME = 0, ST_VOTE, ST_SMOOTH, ST_THRESH, ST_TEMPORAL, ST_CONTRAST_PREP, ST_CONTRAST_W5, ST_CONTRAST_W24,
+             ST_CONTRAST_W48, ST_CONTRAST_POST, ST_FULLRES_H, ST_FULLRES_V, ST_TEMPORAL_STATS, ST_RESIZE200, ST_SVM, ST_FINAL, ST_COUNT };
+static const char* kStageNames = "getframe,vote,smooth,thresh_small,temporal,contrast_prep,contrast_win5,contrast_win24,contrast_win48,"
+                                 "contrast_post,fullres_hpass,fullres_vpass,temporal_stats,resize200,svm_rbf,final_map";
 
 static void prof_mark(cds_ctx* c, int stage, cudaStream_t st) {
   if (!c->prof_on) return;
@@ -557,8 +557,9 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   const float* fparam = c->d_fparam;
   if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, st)) return e;
   // ---- thresholded smoothed maps and temporal features -> X slots 0,3,6 / 1,4,7 ----
-  prof_mark(c, ST_THRESH_TEMPORAL, st);
+  prof_mark(c, ST_THRESH, st);
   if (int e = myst_small_launch(n4, H, W, RL, first_poc, n, c->d_mv_s, c->r_sm4, c->d_X, st)) return e;
+  prof_mark(c, ST_TEMPORAL, st);
   if (int e = temporal_launch(h4, w4, c->PT, RL, first_poc, n, c->r_sm4, c->r_cam, c->d_wtab,
                               c->d_X, st)) return e;
   // ---- (b) contrast: bit (cusize 16, delta 3, win 5), depth (2, 13, 24), mvx / mvy (1, 11, 48)  main.m:226-235 ----
@@ -595,15 +596,18 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     prof_mark(c, ST_CONTRAST_W48, st);
     gaussian_factor(48, 11.0, g);
     if (int e = contrast_sep_launch(c->d_padM, c->d_rawM, mX, 2 * n, h4, w4, 48, g, g, nullptr, st)) return e;   // mX,mY contiguous
-    prof_mark(c, ST_FULLRES, st);
+    prof_mark(c, ST_CONTRAST_POST, st);
     if (int e = contrast_post_launch(c->d_rawB, mB, n, sbR, sbC, 16, h4, w4, c->d_X, 5, st)) return e;
     if (int e = contrast_post_launch(c->d_rawD, mD, n, sdR, sdC, 2, h4, w4, c->d_X, 8, st)) return e;
     if (int e = contrast_post_mv_launch(c->d_rawM, c->d_rawM + (size_t)n * n4, mX, mY, n, h4, w4, c->d_X, 2, st)) return e;
   }
   // ---- fourX2 + imfilter(gaussian) at full resolution: statistics (and the temporal maps themselves) ----
   int nb = 0;
+  prof_mark(c, ST_FULLRES_H, st);
   if (int e = fullres_hpass_launch(c->d_X, 9 * n, h4, w4, c->poly, c->d_T, st)) return e;
+  prof_mark(c, ST_FULLRES_V, st);
   if (int e = fullres_vpass_launch(c->d_T, 9 * n, h4, W, c->poly, c->d_Y, c->d_store_index, c->d_partial, &nb, st)) return e;
+  prof_mark(c, ST_TEMPORAL_STATS, st);
   if (int e = stats_finalize_launch(c->d_partial, 9 * n, nb, c->d_stats9, st)) return e;
   {
     dim3 grid(c->nblk2, 3 * n);
@@ -844,7 +848,7 @@ extern "C" int cds_profile_enable(cds_ctx* c, int on) {
   if (!c) { set_error("cds_profile_enable: null context"); return CDS_EINVAL; }
   CDS_CUDA(cudaStreamSynchronize(c->stream));
   c->prof_on = on != 0; c->ev_used = 0; c->ev_marks.clear();
-  for (int i = 0; i < 16; i++) { c->prof_ms[i] = 0; c->prof_calls[i] = 0; }
+  for (int i = 0; i < 24; i++) { c->prof_ms[i] = 0; c->prof_calls[i] = 0; }
   return CDS_OK;
 }
 
