@@ -529,6 +529,14 @@ int fullres_hpass_launch(const float* X, int nmaps, int h4, int w4, const Polyph
 constexpr int VP_RPT = 4;
 constexpr int VP_ROWS = 32;                     // cell rows per tile
 constexpr int VP_COLS4 = 32;                    // float4 columns per CTA
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int n = valid ? 16 : 0;
@@ -573,27 +581,32 @@ fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int n
     __syncthreads();                            // tile ti has landed for every thread
     const int r0 = ti * VP_ROWS + rg * VP_RPT;
     if (x4 < W4 && r0 < h4) {
-      float4 acc[VP_RPT][4];                    // [cell row][phase] x 4 columns
+      // Packed FP32 (FFMA2, sm_100): an accumulator pair (x,y) / (z,w) of one phase is one 64-bit register pair and one
+      // fma.rn.f32x2 does two IEEE FP32 FMAs, so the 64 FMAs per tap take 32 issue slots and leave the rest for the LDS.
+      unsigned long long acc2[VP_RPT][4][2];    // [cell row][phase][xy | zw]
 #pragma unroll
       for (int k = 0; k < VP_RPT; k++)
 #pragma unroll
-        for (int ph = 0; ph < 4; ph++) acc[k][ph] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ph = 0; ph < 4; ph++) { acc2[k][ph][0] = 0ull; acc2[k][ph][1] = 0ull; }
       const float4* __restrict__ tp = tiles + (size_t)(ti & 1) * nin * VP_COLS4 + (rg * VP_RPT) * VP_COLS4 + cg;   // local input row of tap u of cell row r0
-      float4 g[VP_RPT];                         // g[k] = weights of tap u - k, i.e. sGv[u - k + VP_RPT - 1]
+      unsigned long long gd[VP_RPT][4];         // gd[k][ph] = (w, w) with w = weight of tap u - k, phase ph
 #pragma unroll
-      for (int k = 1; k < VP_RPT; k++) g[k] = sGv[VP_RPT - 1 - k];
+      for (int k = 1; k < VP_RPT; k++) { const float4 w = sGv[VP_RPT - 1 - k]; gd[k][0] = pack2(w.x, w.x); gd[k][1] = pack2(w.y, w.y); gd[k][2] = pack2(w.z, w.z); gd[k][3] = pack2(w.w, w.w); }
       auto step = [&](int u) {
-        g[0] = sGv[u + VP_RPT - 1];
+        { const float4 w = sGv[u + VP_RPT - 1]; gd[0][0] = pack2(w.x, w.x); gd[0][1] = pack2(w.y, w.y); gd[0][2] = pack2(w.z, w.z); gd[0][3] = pack2(w.w, w.w); }
         const float4 v = tp[u * VP_COLS4];
+        const unsigned long long vxy = pack2(v.x, v.y), vzw = pack2(v.z, v.w);
 #pragma unroll
-        for (int k = 0; k < VP_RPT; k++) {
-          acc[k][0].x = fmaf(g[k].x, v.x, acc[k][0].x); acc[k][0].y = fmaf(g[k].x, v.y, acc[k][0].y); acc[k][0].z = fmaf(g[k].x, v.z, acc[k][0].z); acc[k][0].w = fmaf(g[k].x, v.w, acc[k][0].w);
-          acc[k][1].x = fmaf(g[k].y, v.x, acc[k][1].x); acc[k][1].y = fmaf(g[k].y, v.y, acc[k][1].y); acc[k][1].z = fmaf(g[k].y, v.z, acc[k][1].z); acc[k][1].w = fmaf(g[k].y, v.w, acc[k][1].w);
-          acc[k][2].x = fmaf(g[k].z, v.x, acc[k][2].x); acc[k][2].y = fmaf(g[k].z, v.y, acc[k][2].y); acc[k][2].z = fmaf(g[k].z, v.z, acc[k][2].z); acc[k][2].w = fmaf(g[k].z, v.w, acc[k][2].w);
-          acc[k][3].x = fmaf(g[k].w, v.x, acc[k][3].x); acc[k][3].y = fmaf(g[k].w, v.y, acc[k][3].y); acc[k][3].z = fmaf(g[k].w, v.z, acc[k][3].z); acc[k][3].w = fmaf(g[k].w, v.w, acc[k][3].w);
-        }
+        for (int k = 0; k < VP_RPT; k++)
 #pragma unroll
-        for (int k = VP_RPT - 1; k > 0; k--) g[k] = g[k - 1];      // renamed away when the caller unrolls by VP_RPT
+          for (int ph = 0; ph < 4; ph++) {
+            acc2[k][ph][0] = ffma2(gd[k][ph], vxy, acc2[k][ph][0]);
+            acc2[k][ph][1] = ffma2(gd[k][ph], vzw, acc2[k][ph][1]);
+          }
+#pragma unroll
+        for (int k = VP_RPT - 1; k > 0; k--)
+#pragma unroll
+          for (int ph = 0; ph < 4; ph++) gd[k][ph] = gd[k - 1][ph];      // renamed away when the caller unrolls by VP_RPT
       };
       const int nu = nt + VP_RPT - 1;
       int u = 0;
@@ -602,6 +615,14 @@ fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int n
         for (int q = 0; q < VP_RPT; q++) step(u + q);
       }
       for (; u < nu; u++) step(u);
+      float4 acc[VP_RPT][4];
+#pragma unroll
+      for (int k = 0; k < VP_RPT; k++)
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) {
+          acc[k][ph].x = lo2(acc2[k][ph][0]); acc[k][ph].y = hi2(acc2[k][ph][0]);
+          acc[k][ph].z = lo2(acc2[k][ph][1]); acc[k][ph].w = hi2(acc2[k][ph][1]);
+        }
       float tsum = 0.f;                        // 64 outputs of this tile in FP32 (the FIR itself is FP32), then FP64 across tiles / threads
 #pragma unroll
       for (int k = 0; k < VP_RPT; k++) {
