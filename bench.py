@@ -170,6 +170,7 @@ def run_b200(a):
     os.dup2(2, 1)
     if world != a.gpus and world > 1:
         a.gpus = world
+    numa_cpus = cds.shard.bind_to_gpu_numa(local) if world > 1 else None     # before any pinned allocation (first touch)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -274,17 +275,20 @@ def run_b200(a):
         return {"value": frames / sec, "unit": UNIT, "h2d_bytes_per_step": int(B * nctu * (2 + 16) + tok_per_step * 2 + (B + 1) * 8),
                 "d2h_bytes_per_step": int(B * h * w * bytes_per_px + B * 8 + 4), "ms_per_step": sec * 1e3 / a.steps}
 
-    e2e = e2e_leg(clip, h_maps, 4)
-    e2e["api"] = f"cds_clip_process (pinned host syntax in, FP32 maps out to pinned host memory), {E2E_CHUNK} steps per call"
-    # the same leg with 8-bit maps (what the reference's hook writes as PNG, TDecGop.cpp:327-332): 4x less device->host traffic
+    # Primary e2e leg: 8-bit maps, the output format of the reference-facing hook (TDecGop.cpp:327-332 converts the map to CV_8U
+    # and imwrite()s it; main.m:312-320 writes the same 8-bit video).  The FP32 variant (the maps the parity tests compare at
+    # 1e-4) is reported beside it: at N >= 4 its 8.3 MB per picture saturate the host's ingest bandwidth, not the GPUs.
     clip8 = cds.SaliencyClip(w, h, a.fps, model=model, meanVec=MEAN9, stdVec=STD9, use_rbf=True, max_batch=B, out_u8=True)
-    e2e_u8 = e2e_leg(clip8, h_maps, 1)
+    e2e = e2e_leg(clip8, h_maps, 1)
     clip8.close()
+    e2e["api"] = f"cds_clip_process (pinned host syntax in, 8-bit maps out to pinned host memory, as the reference hook writes them), {E2E_CHUNK} steps per call"
+    e2e_f32 = e2e_leg(clip, h_maps, 4)
+    e2e_f32["api"] = f"cds_clip_process (pinned host syntax in, FP32 maps out to pinned host memory), {E2E_CHUNK} steps per call"
     # host link: device->host copy rate of the output buffer alone (explains the FP32 e2e number)
     torch.cuda.synchronize()
     big = torch.empty_like(h_maps, device=dev)
     t0 = time.perf_counter(); h_maps.copy_(big, non_blocking=True); torch.cuda.synchronize()
-    e2e["d2h_link_gbs"] = big.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    e2e_f32["d2h_link_gbs"] = big.numel() * 4 / (time.perf_counter() - t0) / 1e9
     del big
     clip.seek((a.warmup + a.steps) * B)          # refill the temporal window for the per-stage profile pass below
     dev_step((a.warmup + a.steps) * B, halo, context=True)
@@ -292,9 +296,9 @@ def run_b200(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B, "PS": a.PS, "PT": a.PT, "parallelism": f"video-shard x{world}",
+            "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B, "PS": a.PS, "PT": a.PT, "parallelism": f"video-shard x{world}", "numa_bound_cores": (len(numa_cpus) if numa_cpus else None),
                        "l2": "no explicit flush: one step streams >3 GB of intermediates (9 full-res maps x 32 pictures), far above the 126 MB L2"},
-            "clocks": clocks, "e2e": e2e, "e2e_u8_maps": e2e_u8, "gpu_launches": int(launches)}
+            "clocks": clocks, "e2e": e2e, "e2e_f32_maps": e2e_f32, "gpu_launches": int(launches)}
 
     # ---- per-stage device times, roofline of the dominant kernel (rank 0) ----
     if rank == 0:

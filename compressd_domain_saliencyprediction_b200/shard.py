@@ -75,3 +75,38 @@ def gather_to_rank0(local, dist=None, group=None):
     if rank != 0:
         return None
     return np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)], axis=0)
+
+
+def bind_to_gpu_numa(gpu_index):
+    """Pin this process to the CPU cores local to `gpu_index` (from `nvidia-smi topo -m`), BEFORE pinned host buffers are
+    allocated: first-touch then places them on the GPU's NUMA node, which keeps the device->host map copies of several
+    ranks from funnelling through one socket.  Returns the core list, or None when the topology cannot be read."""
+    import os
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    header = None
+    for line in out.splitlines():
+        cols = re.split(r"\t+|\s{2,}", line.strip())
+        if header is None and any("CPU Affinity" in c for c in cols):
+            header = [c.strip() for c in cols]
+            continue
+        if header is not None and cols and cols[0] == f"GPU{gpu_index}":
+            # the row has one more leading cell (its own name) than the header has GPU/NIC columns
+            for cell in cols[1:]:
+                if re.fullmatch(r"[0-9,\-]+", cell) and ("-" in cell or "," in cell):
+                    cpus = set()
+                    for part in cell.split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+                    avail = os.sched_getaffinity(0)
+                    cpus &= avail
+                    if cpus:
+                        os.sched_setaffinity(0, cpus)
+                        return sorted(cpus)
+                    return None
+    return None
