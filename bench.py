@@ -36,6 +36,14 @@ MEAN9 = np.full(NINE, 0.3)      # placeholders for svmRBFmodel_all.mat's meanVec
 STD9 = np.full(NINE, 0.2)
 
 
+KIND_TEXT = {
+    "reference": "the reference's own getFrame (code_mat_h.h), computecontrast5 mexFunction and libsvm-3.17 svm_predict_values compiled "
+                 "from /root/reference (oracle/_ref), run in bands / chunks over the thread pool, with the MATLAB glue of main.m restated in C "
+                 "(oracle/cds_oracle.c)",
+    "port": "oracle/cds_oracle.c, the C restatement of main.m (RBF branch) + getFrame (oracle/_ref absent)",
+}
+
+
 def synth_model(nsv, seed=7):
     """Stand-in for svmRBFmodel_all.mat:model: gamma 1/9, SV ~ N(0,1), coef ~ +-U(0,1), rho 0.1."""
     rng = np.random.default_rng(seed)
@@ -102,27 +110,44 @@ class Clocks:
 # CPU arm: the oracle port of main.m (RBF branch) on the host cores
 # ----------------------------------------------------------------------------------------------
 def cpu_sample(a, n_out, ctx_frames, threads, seed=1234):
-    """Times n_out output pictures after ctx_frames pictures of temporal context.  Returns (seconds, detail)."""
+    """Times n_out output pictures after ctx_frames pictures of temporal context on `threads` host threads.
+    Where oracle/_ref exists (the reference's own sources compiled in the build container) the three C/C++ kernels of the
+    path are the REFERENCE'S code: verbatim getFrame (code_mat_h.h), the computecontrast5 mexFunction and libsvm-3.17's
+    svm_predict_values, cut into bands / chunks over the thread pool; the MATLAB glue around them is the oracle port.
+    Returns (seconds per picture, detail, kind)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as o                                         # checker / CPU baseline only
     import compressd_domain_saliencyprediction_b200 as cds
+    from concurrent.futures import ThreadPoolExecutor
     L = o.oracle()
     L.orc_last_seconds.restype = C.c_double
     L.orc_set_threads(int(threads))
     F = ctx_frames + n_out
     hdr, tok, base, byts = cds.ops.synth_clip(a.width, a.height, seed, F, first_poc=1)   # poc 0 is all-intra: skip it
-    t0 = time.perf_counter()
-    maps = [o.orc_getframe(a.width, a.height, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
-    t_a = (time.perf_counter() - t0) / F
-    mvx = np.stack([m[0] for m in maps]); mvy = np.stack([m[1] for m in maps]); dep = np.stack([m[2] for m in maps])
     model = synth_model(a.nsv)
+    use_ref = o.use_reference_kernels(model) and o.ref(f"getframe_{a.width}x{a.height}") is not None
+    if not use_ref:
+        o.use_reference_kernels(None)
     t0 = time.perf_counter()
-    o.orc_process_clip(a.width, a.height, a.fps, mvx, mvy, dep, byts, model, MEAN9, STD9, first_out=ctx_frames, use_rbf=1)
+    if use_ref:                                                  # verbatim getFrame, one picture per thread (ctypes drops the GIL)
+        with ThreadPoolExecutor(int(threads)) as ex:
+            maps = list(ex.map(lambda f: o.ref_getframe(a.width, a.height, hdr[f], tok[base[f]:base[f + 1]]), range(F)))
+    else:
+        maps = [o.orc_getframe(a.width, a.height, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    t_a = (time.perf_counter() - t0) / F
+    mvx = np.stack([m[0] for m in maps]).astype(np.int16); mvy = np.stack([m[1] for m in maps]).astype(np.int16)
+    dep = np.stack([m[2] for m in maps]).astype(np.uint8)
+    t0 = time.perf_counter()
+    try:
+        o.orc_process_clip(a.width, a.height, a.fps, mvx, mvy, dep, byts, model, MEAN9, STD9, first_out=ctx_frames, use_rbf=1)
+    finally:
+        o.use_reference_kernels(None)
     wall = time.perf_counter() - t0
     t_ctx = L.orc_last_seconds(0) / F                            # per picture: camera motion + smoothing
     t_out = L.orc_last_seconds(1) / n_out                        # per output picture: everything else
     per_frame = t_a + t_ctx + t_out
-    return per_frame, {"stage_a_s": t_a, "context_s": t_ctx, "output_s": t_out, "wall_s": wall}
+    return per_frame, {"stage_a_s": round(t_a, 5), "context_s": round(t_ctx, 5), "output_s": round(t_out, 4), "wall_s": round(wall, 3)}, \
+        ("reference" if use_ref else "port")
 
 
 def run_reference(a):
@@ -132,19 +157,19 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     n_out, ctx = 2, 14
     times = []
+    kind = "port"
     for s in range(a.warmup + a.steps):
-        pf, det = cpu_sample(a, n_out, ctx, cores, seed=1234 + s)
+        pf, det, kind = cpu_sample(a, n_out, ctx, cores, seed=1234 + s)
         if s >= a.warmup:
             times.append(pf)
     per_frame = float(np.mean(times))
     val = 1.0 / per_frame
     sample = (f"each step: {n_out} output pictures of the {a.width}x{a.height} workload after {ctx} context pictures "
-              f"(temporal window truncated to {ctx + 1} of {a.PS + a.PT - 1} pictures), oracle port of main.m RBF branch "
-              f"(oracle/cds_oracle.c) with a pthread parallel-for over {cores} threads; stage (a) port included")
+              f"(temporal window truncated to {ctx + 1} of {a.PS + a.PT - 1} pictures) on {cores} threads; " + KIND_TEXT[kind])
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": per_frame * 1e3 * n_out, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": workload_name(a), "frames_per_step": n_out},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
@@ -368,10 +393,10 @@ def run_b200(a):
     if rank == 0 and world == 1 and not a.no_cpu:
         cores = os.cpu_count() or 1
         n_out, ctx = 4, 14
-        pf, det = cpu_sample(a, n_out, ctx, cores)
-        line["cpu_baseline"] = {"value": 1.0 / pf, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{n_out} output pictures of the same 1080p workload after {ctx} context pictures, oracle/cds_oracle.c "
-                                          f"(port of main.m RBF branch + getFrame) with {cores} threads; per-picture s: {det}"}
+        pf, det, kind = cpu_sample(a, n_out, ctx, cores)
+        line["cpu_baseline"] = {"value": 1.0 / pf, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{n_out} output pictures of the same workload after {ctx} context pictures on {cores} threads; "
+                                          f"{KIND_TEXT[kind]}; per-picture s: {det}"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -242,10 +242,32 @@ static void orc_cc5_rows(long lo, long hi, void* vp) {
     }
   }
 }
+/* CPU-baseline option (bench.py --impl reference): route the two heavy kernels through the REFERENCE'S OWN code compiled
+ * under oracle/_ref (verbatim computecontrast5.cpp mexFunction, libsvm-3.17 svm_predict_values).  They are single-threaded,
+ * so the work is cut into independent bands / chunks that run on the pthread pool; the results are those of the
+ * reference code itself.  Unset (the default), the restatements in this file are used. */
+static orc_ref_contrast_fn g_ref_contrast = 0;
+static orc_ref_svm_fn g_ref_svm = 0;
+static void* g_ref_svm_model = 0;
+void orc_use_reference_kernels(orc_ref_contrast_fn contrast, orc_ref_svm_fn svm, void* svm_model) {
+  g_ref_contrast = contrast; g_ref_svm = svm; g_ref_svm_model = svm_model;
+}
+static void orc_cc5_ref_bands(long lo, long hi, void* vp) {
+  orc_cc5_ctx* a = (orc_cc5_ctx*)vp;
+  const int m1 = a->m1, len = a->len, win = a->win, m = a->m, n = a->n, n1 = n + 2 * len;
+  const int bm = (int)(hi - lo), bm1 = bm + 2 * len;           /* output rows lo..hi-1 need padded rows lo..hi-1+2*len */
+  if (bm <= 0) return;
+  double* sub = (double*)malloc(sizeof(double) * (size_t)bm1 * n1);
+  double* so = (double*)malloc(sizeof(double) * (size_t)bm * n);
+  for (int c = 0; c < n1; c++) memcpy(sub + (size_t)c * bm1, a->pad + (size_t)c * m1 + lo, sizeof(double) * bm1);
+  g_ref_contrast(sub, bm1, n1, a->W, len, win, bm, n, so);
+  for (int c = 0; c < n; c++) memcpy(a->out + (size_t)c * m + lo, so + (size_t)c * bm, sizeof(double) * bm);
+  free(sub); free(so);
+}
 void orc_computecontrast5(const double* pad, int m1, int n1, const double* W, int len, int win,
                           int m, int n, double* out) {
-  (void)n1;
   orc_cc5_ctx a = {pad, m1, W, len, win, m, n, out};
+  if (g_ref_contrast && m1 == m + 2 * len && n1 == n + 2 * len) { orc_parallel_for(m, orc_cc5_ref_bands, &a); return; }
   orc_parallel_for(m, orc_cc5_rows, &a);
 }
 
@@ -344,10 +366,20 @@ static void orc_svm_rows(long lo, long hi, void* vp) {
     label[n] = sum > 0 ? label0 : label1;                                          /* :2556-2559 */
   }
 }
+static void orc_svm_ref_chunks(long lo, long hi, void* vp) {      /* libsvm's svm_predict_values on a chunk of instances */
+  orc_svm_ctx* a = (orc_svm_ctx*)vp;
+  const int cn = (int)(hi - lo), F = a->nfeat, N = a->N;
+  if (cn <= 0) return;
+  double* sx = (double*)malloc(sizeof(double) * (size_t)cn * F);
+  for (int j = 0; j < F; j++) memcpy(sx + (size_t)j * cn, a->X + (size_t)j * N + lo, sizeof(double) * cn);
+  g_ref_svm(g_ref_svm_model, sx, cn, F, a->dec + lo, a->label + lo);
+  free(sx);
+}
 void orc_svm_rbf_predict(int nsv, int nfeat, const double* SV, const double* coef, double rho,
                          double gamma, int label0, int label1, const double* X, int N,
                          double* dec, double* label) {
   orc_svm_ctx a = {nsv, nfeat, SV, coef, rho, gamma, label0, label1, X, N, dec, label};
+  if (g_ref_svm && g_ref_svm_model) { orc_parallel_for(N, orc_svm_ref_chunks, &a); return; }
   orc_parallel_for(N, orc_svm_rows, &a);
 }
 

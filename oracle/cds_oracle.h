@@ -89,6 +89,12 @@ int orc_process_clip(const orc_clip_params* p, const int16_t* mvx, const int16_t
                      const uint8_t* depth, const uint16_t* bitmap, int first_out,
                      double* out, int* cam, double* feat200);
 
+/* CPU-baseline option: run the two heavy kernels through the reference's own code (oracle/_ref: ref_computecontrast5 =
+ * the verbatim mexFunction, ref_svm_predict = libsvm-3.17) in bands / chunks on the thread pool.  NULLs restore the port. */
+typedef void (*orc_ref_contrast_fn)(const double* pad, int m1, int n1, const double* W, int len, int win, int m, int n, double* out);
+typedef void (*orc_ref_svm_fn)(void* model, const double* X, int N, int F, double* dec, double* label);
+void orc_use_reference_kernels(orc_ref_contrast_fn contrast, orc_ref_svm_fn svm, void* svm_model);
+
 /* timing of the last orc_process_clip (CPU-baseline bookkeeping): which = 0 -> seconds in pass 1 +
  * smoothing over all frames, 1 -> seconds in the per-output-frame work.  orc_threads() = worker threads in use. */
 double orc_last_seconds(int which);

@@ -192,3 +192,27 @@ def orc_process_clip(w, h, fps, mvx, mvy, depth, bitmap, model, mean_vec, std_ve
                                    _ptr(feat) if feat is not None else None)
     assert rc == 0, rc
     return out, cam, feat
+
+
+# ---------------------------------------------------------------------------- CPU baseline with the reference's own kernels
+_REF_KEEP = []
+
+
+def use_reference_kernels(model=None):
+    """Route the oracle's contrast and SVM calls through oracle/_ref (the reference's verbatim computecontrast5 mexFunction
+    and libsvm-3.17).  model = (SV, coef, rho, gamma, labels) builds the libsvm model; None restores the restatements.
+    Returns True when the reference kernels are in use."""
+    L = oracle()
+    L.orc_use_reference_kernels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    if model is None or ref("contrast") is None or ref("svm") is None:
+        L.orc_use_reference_kernels(None, None, None)
+        return False
+    SV, coef, rho, gamma, labels = model
+    Ls = ref("svm")
+    Ls.ref_svm_build.restype = C.c_void_p
+    SV = np.ascontiguousarray(SV, np.float64); coef = np.ascontiguousarray(coef, np.float64)
+    m = Ls.ref_svm_build(SV.shape[0], SV.shape[1], _ptr(SV), _ptr(coef), C.c_double(rho), C.c_double(gamma),
+                         int(labels[0]), int(labels[1]), int(np.sum(coef > 0)))
+    _REF_KEEP.append((SV, coef))
+    L.orc_use_reference_kernels(C.cast(ref("contrast").ref_computecontrast5, C.c_void_p), C.cast(Ls.ref_svm_predict, C.c_void_p), C.c_void_p(m))
+    return True

@@ -125,3 +125,28 @@ def test_oracle_camera_motion_fires_on_basketballdrive_pan():
     for f in range(4):
         outs, cam, ave, flag = o.orc_camera_motion(w, h, d["mvx"][f], d["mvy"][f], d["ctu_bytes"][f], d["depth"][f])
         assert flag == 1 and cam[0] >= 6 and cam[1] == 0
+
+
+def test_clip_through_reference_kernels_matches_the_port():
+    """bench.py --impl reference routes contrast and SVM through the reference's own compiled code (oracle/_ref); the maps
+    must agree with the restatements (same algorithm, same double arithmetic up to summation order)."""
+    import compressd_domain_saliencyprediction_b200 as cds
+    if o.ref("contrast") is None or o.ref("svm") is None:
+        pytest.skip("oracle/_ref not built")
+    w, h, F, fps = 416, 240, 4, 10.0
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 31, F)
+    ints = [o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    mvx = np.stack([m[0] for m in ints]); mvy = np.stack([m[1] for m in ints]); dep = np.stack([m[2] for m in ints])
+    SV, coef, rho, gamma, labels = o.synth_model(64)
+    SV = SV * 0.5 + 1.0
+    mdl = (SV, coef, rho, gamma, labels)
+    mean9, std9 = np.full(9, 0.3), np.full(9, 0.2)
+    o.oracle().orc_set_threads(4)
+    a, acam, _ = o.orc_process_clip(w, h, fps, mvx, mvy, dep, byts, mdl, mean9, std9, first_out=F - 1)
+    assert o.use_reference_kernels(mdl)
+    try:
+        b, bcam, _ = o.orc_process_clip(w, h, fps, mvx, mvy, dep, byts, mdl, mean9, std9, first_out=F - 1)
+    finally:
+        o.use_reference_kernels(None)
+    assert np.array_equal(acam, bcam)
+    assert np.max(np.abs(np.nan_to_num(a) - np.nan_to_num(b))) <= 1e-9
