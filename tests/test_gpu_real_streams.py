@@ -99,3 +99,31 @@ def test_hm_decoder_with_cds_hook_end_to_end(cds, tmp_path):
     got, _ = clip.process(0, d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"])
     clip.close()
     assert np.array_equal(maps[:F], got)
+
+
+@pytest.mark.parametrize("name", ["BasketballPass", "BasketballDrill", "BasketballDrive"])
+def test_auc_nss_match_the_oracle_to_three_decimals(cds, name):
+    """north_star: "AUC/NSS matching to 3 decimals".  The reference's eye-tracking fixations for these pictures
+    (tests/golden/fixations_*.npz, from video_database.mat per main.m:325-346) score the GPU maps and the oracle maps
+    with the same AUC-Judd / NSS code."""
+    d, w, h, F = _load(name)
+    fx = np.load(os.path.join(GOLD, f"fixations_{name}.npz"))
+    hdr, tok, base, byts = d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"]
+    o.oracle().orc_set_threads(16)
+    ints = [o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    mvx = np.stack([m[0] for m in ints]); mvy = np.stack([m[1] for m in ints]); dep = np.stack([m[2] for m in ints])
+    SV, coef, rho, gamma, labels = o.synth_model(256)
+    SV = SV * 0.5 + 1.0
+    gm = cds.ops.SvmModel(SVs=SV, sv_coef=coef, rho=rho, gamma=gamma, Label=labels)
+    first = max(0, F - (6 if w > 1000 else 14))
+    want, _, _ = o.orc_process_clip(w, h, 10.0, mvx, mvy, dep, byts, (SV, coef, rho, gamma, labels), MEAN9, STD9, first_out=first, use_rbf=1)
+    clip = cds.SaliencyClip(w, h, 10.0, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=8)
+    got, _ = clip.process(0, hdr, tok, base, byts)
+    clip.close()
+    off = fx["offsets"][first:] - fx["offsets"][first]
+    xy = fx["xy"][fx["offsets"][first]:]
+    auc_g, nss_g, n_g = cds.metrics.evaluate_clip(got[first:], xy, off)
+    auc_o, nss_o, n_o = cds.metrics.evaluate_clip(np.nan_to_num(want), xy, off)
+    print(f"{name}: AUC-Judd {auc_g:.4f} (oracle {auc_o:.4f}), NSS {nss_g:.4f} (oracle {nss_o:.4f}) over {n_g} pictures (stand-in SVM model)")
+    assert n_g == n_o and n_g >= 6
+    assert abs(auc_g - auc_o) < 5e-4 and abs(nss_g - nss_o) < 5e-4
