@@ -177,10 +177,11 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.69314694f); p = fmaf(p, f, 1.0000001f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(fi) << 23));
 }
-constexpr int POLY_OF_8 = 2;                                 // of every 8 exponentials, this many go to the FMA pipe
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace tc
 
+// POLY_OF_8: of every 8 exponentials, this many are computed on the FMA pipe (ex2_poly) instead of MUFU.EX2
+template <int POLY_OF_8>
 __global__ void __launch_bounds__(tc::THREADS, 2)
 svm_rbf9_tc_kernel(const float* __restrict__ X, long N, const float* __restrict__ tiles, int ntiles, int ntiles_pos,
                    float xscale, float rho, float* __restrict__ dec) {
@@ -357,14 +358,17 @@ int svm_predict_launch(const cds_svm_model* m, const float* X, long N, float* de
   const double g2 = m->gamma * 1.4426950408889634;   // gamma * log2(e)
   static const int impl = [] { const char* e = getenv("CDS_SVM_IMPL"); return (e && !strcmp(e, "fp32")) ? 0 : 1; }();
   if (m->nfeat == 9 && impl == 1 && m->d_tiles) {
+    // share of exponentials on the FMA pipe; measured at nSV 4096: 0/8 1.40 ms, 1/8 1.28, 2/8 1.17, 3/8 1.22, 4/8 1.44 (CDS_SVM_POLY overrides)
+    static const int poly = [] { const char* e = getenv("CDS_SVM_POLY"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : v > 4 ? 4 : v; }();
+    auto kern = poly == 0 ? svm_rbf9_tc_kernel<0> : poly == 1 ? svm_rbf9_tc_kernel<1> : poly == 2 ? svm_rbf9_tc_kernel<2>
+              : poly == 3 ? svm_rbf9_tc_kernel<3> : svm_rbf9_tc_kernel<4>;
     static bool attr_done = false;
     if (!attr_done) {
-      CDS_CUDA(cudaFuncSetAttribute(svm_rbf9_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      CDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
       attr_done = true;
     }
     const unsigned grid = (unsigned)((N + tc::TM - 1) / tc::TM);
-    svm_rbf9_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(X, N, m->d_tiles, m->ntiles, m->ntiles_pos, (float)sqrt(2 * g2),
-                                                                 (float)m->rho, dec);
+    kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(X, N, m->d_tiles, m->ntiles, m->ntiles_pos, (float)sqrt(2 * g2), (float)m->rho, dec);
   } else if (m->nfeat == 9) {
     const long per_block = (long)SVM_THREADS * SVM_IPT;
     const unsigned grid = (unsigned)((N + per_block - 1) / per_block);
