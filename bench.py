@@ -6,7 +6,7 @@ stage (a) scatter -> (c) camera-motion vote -> (e) smoothing / temporal / Gaussi
     python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (default N=1, K=10, W=3)
     python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port on the host cores
 
-A "step" is one batch of B (default 32) consecutive pictures of a synthetic 1920x1080, 50 fps clip
+A "step" is one batch of B (default 64) consecutive pictures of a synthetic 1920x1080, 50 fps clip
 (seeded syntax buffers) through the clip context, at steady state (temporal window
 full).  `value` is measured with the syntax resident in HBM (cds_clip_process_dev, CUDA events on
 the launching stream, max over ranks); `e2e` goes through the host-buffer C-ABI call
@@ -178,7 +178,7 @@ def run_reference(a):
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
-E2E_CHUNK = 5        # batches handed to cds_clip_process per call on the e2e leg (bounds the pinned output buffer)
+E2E_CHUNK = 3        # batches handed to cds_clip_process per call on the e2e leg (bounds the pinned output buffer)
 
 
 def run_b200(a):
@@ -322,7 +322,7 @@ def run_b200(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B, "PS": a.PS, "PT": a.PT, "parallelism": f"video-shard x{world}", "numa_bound_cores": (len(numa_cpus) if numa_cpus else None),
-                       "l2": "no explicit flush: one step streams >3 GB of intermediates (9 full-res maps x 32 pictures), far above the 126 MB L2"},
+                       "l2": "no explicit flush: one step streams several GB of intermediates (9 maps x B pictures at h/4 x W, 3 at full resolution), far above the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "e2e_f32_maps": e2e_f32, "gpu_launches": int(launches)}
 
     # ---- per-stage device times, roofline of the dominant kernel (rank 0) ----
@@ -418,7 +418,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--fps", type=float, default=50.0)
     ap.add_argument("--nsv", type=int, default=4096)
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
