@@ -15,6 +15,10 @@
 //     deterministic finalize, so results do not depend on scheduling.
 // All of these passes are bandwidth/latency class (HBM / L2), not FLOP class.
 #include "maps.cuh"
+#include "tc_common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <math.h>
 #include <algorithm>
 
@@ -148,7 +152,7 @@ int Polyphase::upload() {
   CDS_CUDA(cudaMemcpy(d_g, g.data(), g.size() * 4, cudaMemcpyHostToDevice));
   return CDS_OK;
 }
-void Polyphase::release() { if (d_g) cudaFree(d_g); d_g = nullptr; }
+void Polyphase::release() { if (d_g) cudaFree(d_g); if (d_aimg) cudaFree(d_aimg); d_g = nullptr; d_aimg = nullptr; }
 
 // =================================================================================================
 // block reductions (deterministic: fixed tree)
@@ -650,6 +654,260 @@ fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int n
   }
 }
 
+// =================================================================================================
+// Vertical pass on the tensor cores (tcgen05 + TMEM).
+//
+// Y[4r+ph][x] = sum_t G[ph][t] T[r + dmin + t][x] is a banded GEMM: for a tile of 32 cell rows (128 output rows) the
+// 128 x KP weight matrix A[m][k] = G[m % 4][k - m / 4] (KP = 32 + nt - 1 rounded up to 8) is THE SAME for every tile,
+// strip and map, so it sits in shared memory for the life of the CTA (copied once with cp.async.bulk), and the input
+// rows stream through as the B operand, 8 rows (one K step) at a time.  TF32 keeps 11 mantissa bits, so both operands
+// are split hi + lo and three MMAs per K step accumulate lo*hi + hi*lo + hi*hi in FP32 (error ~2^-22, like the SVM
+// kernel).  A CTA owns a 256-column strip of one map and walks down its row tiles: four staging warps load 8 x 256
+// inputs per step, split them and transpose them into the K-major core-matrix layout the MMA reads; one thread issues the MMAs into
+// one of two 256-column TMEM accumulators; four epilogue warps drain the other one (min / max / sum, and the store for
+// the three temporal maps).  The FIR costs 3 x 72 x 2 tensor flops per output instead of 37 FFMA issue slots, which
+// turns the pass from FP32-issue-bound into HBM-bound.
+// =================================================================================================
+namespace vtc {
+using namespace tc;
+constexpr int TM = 128, TN = 256, CELLS = TM / 4;       // N = 256: a tcgen05.mma with K = 8 has a ~140-cycle floor, smaller N only wastes it
+constexpr int MAX_STAGES = 4;                     // operand ring (hi + lo of one K = 8 step per stage); 7 stages measured the same (shared-memory bandwidth bound)
+constexpr int HALF_STAGE = 8 * TN * 4;            // one K = 8 step of hi (or lo): 8 rows x 128 columns
+constexpr int STAGE_BYTES = 2 * HALF_STAGE;
+constexpr int NCONV = 8;                          // converter warps: WPS per K step (2 k chunks x WPS/2 column parts), four steps in flight
+constexpr int WPS = NCONV / 4;                    // measured: 8 warps 1.46 ms, 16 warps 1.66 ms per 64 pictures (shared-memory bandwidth is the wall)
+constexpr int CBLK = 32 / (WPS / 2);              // 8-column blocks per converter warp
+constexpr int THREADS = (6 + NCONV) * 32;         // warps 0-3 epilogue, warp 4 MMA + TMEM alloc, then NCONV converter warps, then the producer warp
+constexpr int RSTAGES = 4;                        // raw FP32 input ring filled by TMA; == number of converter groups, so a group sees every phase of its stage
+constexpr int RAW_PITCH = TN * 4;                 // dense TMA box
+constexpr int RAW_STAGE = 8 * RAW_PITCH;
+constexpr int BAR_BYTES = 1024;
+constexpr uint32_t TMEM_COLS = 512;               // two 256-column FP32 accumulators
+constexpr uint32_t IDESC = idesc_tf32(TM, TN, 0, 0);   // both operands K-major
+}  // namespace vtc
+
+__global__ void __launch_bounds__(vtc::THREADS, 1)
+fullres_vpass_tc_kernel(const __grid_constant__ CUtensorMap tmap /*T as [maps][h4][W] FP32, box [1][8][256]*/, int nmaps, int h4, int W, int dmin,
+                        int kp, int nstages, const float* __restrict__ aimg, float* __restrict__ Ystore, const int* __restrict__ store_index,
+                        float* __restrict__ partial) {
+  using namespace vtc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int a_half = kp * TM * 4;                 // bytes of A hi (then A lo)
+  uint8_t* sA = smem;                             // [hi|lo][k chunk of 4][128 rows][4]   (K-major, no swizzle)
+  uint8_t* sB = smem + 2 * a_half;                // STAGES x [hi|lo][k chunk of 4][256 columns][4]   (K-major, no swizzle)
+  uint8_t* sR = sB + nstages * STAGE_BYTES;       // RSTAGES x [8 rows][128] raw FP32 inputs (TMA boxes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + RSTAGES * RAW_STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+  float* red = reinterpret_cast<float*>(bars + 52);     // [4 warps][4]: min, max, sum as double
+  const uint32_t bar0 = smem_u32(bars);
+  constexpr int STAGES = MAX_STAGES;              // barrier slots; the ring itself uses `nstages` of them
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t abar = bar0 + 8u * (2 * STAGES + 4);
+  auto rfull = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + s); };
+  auto rempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + RSTAGES + s); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = 4 * h4;
+  const int ntile = (H + TM - 1) / TM, ksteps = kp >> 3, total = ntile * ksteps;   // per work item
+  const int nstrips = (W + TN - 1) / TN, nitems = nstrips * nmaps;
+  // Persistent CTA (one per SM): work item = (column strip, map).  The weight matrix, the TMEM allocation and the barrier
+  // phases live across items, so the pipeline never drains between items: every role walks the same item sequence with
+  // global step / tile counters.
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; s++) { mbar_init(full(s), WPS); mbar_init(empty(s), 1); }   // WPS converter warps fill one stage
+    for (int b = 0; b < 2; b++) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 4); }
+    mbar_init(abar, 1);
+    for (int r = 0; r < RSTAGES; r++) { mbar_init(rfull(r), 1); mbar_init(rempty(r), WPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(abar, 2u * a_half);
+    bulk_g2s(smem_u32(sA), aimg, 2u * a_half, abar);
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5 + NCONV) {
+    if (lane == 0) {                                // ---- producer: one TMA box (8 rows x 256 columns) per K step; rows / columns outside the map arrive as zeros ----
+      int g = 0;
+      for (int wi = blockIdx.x; wi < nitems; wi += gridDim.x) {
+        const int m = wi / nstrips, x0 = (wi - m * nstrips) * TN;
+        for (int it = 0; it < total; it++, g++) {
+          const int t = it / ksteps, ks = it - t * ksteps, rs = g % RSTAGES;
+          mbar_wait(rempty(rs), ((g / RSTAGES) & 1) ^ 1);
+          mbar_expect_tx(rfull(rs), (uint32_t)RAW_STAGE);
+          const int r0 = CELLS * t + dmin + ks * 8;
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                       ::"r"(smem_u32(sR + rs * RAW_STAGE)), "l"(&tmap), "r"(x0), "r"(r0), "r"(m), "r"(rfull(rs)) : "memory");
+        }
+      }
+    }
+  } else if (warp >= 5) {                           // ---- converter warps: raw FP32 -> split hi / lo -> UMMA K-major layout ----
+    // Four groups of WPS warps take the K steps round-robin; a warp converts one 4-row k chunk of one column part.
+    // Lane (kk, c) handles k = kk of the chunk and column c of an 8-column block.
+    const int cw = warp - 5, pr = cw / WPS, kc = cw & 1, ch = (cw % WPS) >> 1;   // group pr converts steps g = pr, pr + 4, ...; a warp does one k chunk of one column part
+    const int kk = lane & 3, c = lane >> 2;
+    int nsteps = 0;
+    for (int wi = blockIdx.x; wi < nitems; wi += gridDim.x) nsteps += total;
+    for (int g = pr; g < nsteps; g += 4) {
+      const int rs = g % RSTAGES, s = g % nstages;
+      mbar_wait(rfull(rs), (g / RSTAGES) & 1);
+      mbar_wait(empty(s), ((g / nstages) & 1) ^ 1);
+      const uint8_t* raw = sR + rs * RAW_STAGE;
+      const float* __restrict__ src = reinterpret_cast<const float*>(raw + (kc * 4 + kk) * RAW_PITCH) + ch * (CBLK * 8) + c;
+      uint8_t* dst = sB + s * STAGE_BYTES + kc * (TN * 16) + (ch * (CBLK * 8) + c) * 16 + kk * 4;   // [k chunk][column][4 k]: this lane fills word kk of its column
+      // The four kk lanes of a column read rows 1024 B apart (same bank), so each lane starts kk column blocks further
+      // on: lanes then cover 32 different banks in the LDS and still 32 different banks in the transposing STS.
+      float v[CBLK];                                // all loads first: the compiler will not hoist LDS above the STS below on its own
+#pragma unroll
+      for (int b8 = 0; b8 < CBLK; b8++) v[b8] = src[((b8 + kk) & (CBLK - 1)) * 8];
+#pragma unroll
+      for (int b8 = 0; b8 < CBLK; b8++) {
+        const int nb = ((b8 + kk) & (CBLK - 1)) * 128;   // byte offset of column block (b8 + kk) % CBLK in the operand stage
+        const uint32_t hi = tf32_rna(v[b8]);
+        *reinterpret_cast<uint32_t*>(dst + nb) = hi;
+        *reinterpret_cast<uint32_t*>(dst + HALF_STAGE + nb) = tf32_rna(v[b8] - __uint_as_float(hi));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(full(s)); mbar_arrive(rempty(rs)); }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {                                // ---- MMA issuer ----
+      mbar_wait(abar, 0);
+      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + a_half;
+      int g = 0, tg = 0;
+      for (int wi = blockIdx.x; wi < nitems; wi += gridDim.x) {
+        for (int t = 0; t < ntile; t++, tg++) {
+          const int buf = tg & 1;
+          mbar_wait(tempty(buf), ((tg >> 1) & 1) ^ 1);
+          const uint32_t d = tmem_base + (uint32_t)buf * TN;
+          for (int ks = 0; ks < ksteps; ks++, g++) {
+            const int s = g % nstages;
+            mbar_wait(full(s), (g / nstages) & 1);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(sB + s * STAGE_BYTES), b_lo = b_hi + HALF_STAGE;
+            // A: K-major, LBO = distance between the two 16-byte k chunks of this step (128 rows x 16 B), SBO = 8-row groups
+            const uint64_t ah = smem_desc(a_hi + ks * 2 * (TM * 16), TM * 16, 128), al = smem_desc(a_lo + ks * 2 * (TM * 16), TM * 16, 128);
+            // B: K-major as well (the converter warps transpose on the fly; MN-major TF32 without swizzle gives zeros, tools/umma_probe.py)
+            const uint64_t bh = smem_desc(b_hi, TN * 16, 128), bl = smem_desc(b_lo, TN * 16, 128);
+            mma_tf32(d, al, bh, IDESC, ks > 0 ? 1u : 0u);
+            mma_tf32(d, ah, bl, IDESC, 1u);
+            mma_tf32(d, ah, bh, IDESC, 1u);
+            mma_commit(empty(s));
+          }
+          mma_commit(tfull(buf));
+        }
+      }
+    }
+  } else {                                          // ---- epilogue warps 0-3: TMEM lanes 32*warp .. +31 = output rows of the tile ----
+    int tg = 0;
+    for (int wi = blockIdx.x; wi < nitems; wi += gridDim.x) {
+      const int m = wi / nstrips, x0 = (wi - m * nstrips) * TN;
+      const int sidx = store_index ? store_index[m] : -1;
+      float* __restrict__ Ys = sidx >= 0 ? Ystore + (size_t)sidx * (size_t)H * W : nullptr;
+      float mn = INFINITY, mx = -INFINITY; double sum = 0;
+      for (int t = 0; t < ntile; t++, tg++) {
+        const int buf = tg & 1;
+        mbar_wait(tfull(buf), (tg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * TN;
+        const int y = t * TM + warp * 32 + lane;
+        float tsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < TN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          if (y < H) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int x = x0 + c + j;
+              if (x < W) {
+                const float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
+                mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+                tsum += (a.x + a.y) + (a.z + a.w);
+                if (Ys) *reinterpret_cast<float4*>(Ys + (size_t)y * W + x) = a;
+              }
+            }
+          }
+        }
+        sum += (double)tsum;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));
+      }
+      // per-item statistics: the four epilogue warps meet on a named barrier (the other roles keep running)
+      mn = warp_min(mn); mx = warp_max(mx); sum = warp_sum(sum);
+      if (lane == 0) { red[warp * 4] = mn; red[warp * 4 + 1] = mx; reinterpret_cast<double*>(red + warp * 4 + 2)[0] = sum; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        float m0 = red[0], m1 = red[1]; double sm = reinterpret_cast<double*>(red + 2)[0];
+        for (int i = 1; i < 4; i++) { m0 = fminf(m0, red[i * 4]); m1 = fmaxf(m1, red[i * 4 + 1]); sm += reinterpret_cast<double*>(red + i * 4 + 2)[0]; }
+        float* p = partial + (size_t)wi * 4;        // wi = m * nstrips + strip
+        p[0] = m0; p[1] = m1; reinterpret_cast<double*>(p + 2)[0] = sm;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(vtc::TMEM_COLS) : "memory");
+  }
+}
+
+// host: TMA descriptor of the T buffer viewed as [maps][h4][W] FP32 with an 8-row x 256-column box (zero fill outside)
+static int vpass_tc_tensor_map(const float* T, int nmaps, int h4, int W, CUtensorMap* out) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    CDS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return CDS_ECUDA; }
+    encode = (encode_fn)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)h4, (cuuint64_t)nmaps};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)h4 * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)vtc::TN, 8, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(T), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for %d maps of %d x %d", (int)r, nmaps, h4, W); return CDS_ECUDA; }
+  return CDS_OK;
+}
+
+// host: the 128 x KP banded weight matrix of one tile, split hi / lo, as the shared-memory image the kernel bulk-copies
+static int vpass_tc_prepare(const Polyphase& P, int* kp_out, const float** img_out) {
+  Polyphase& PP = const_cast<Polyphase&>(P);
+  const int kp = ceil_div(vtc::CELLS + P.nt - 1, 8) * 8;
+  if (!PP.d_aimg) {
+    auto tf32 = [](float v) { uint32_t u; memcpy(&u, &v, 4); u += 0x1000u; u &= 0xffffe000u; memcpy(&v, &u, 4); return v; };
+    std::vector<float> img((size_t)2 * kp * vtc::TM, 0.f);
+    for (int mrow = 0; mrow < vtc::TM; mrow++)
+      for (int k = 0; k < kp; k++) {
+        const int tap = k - mrow / 4;
+        const float wv = (tap >= 0 && tap < P.nt) ? P.g[(size_t)tap * 4 + (mrow % 4)] : 0.f;
+        const float hi = tf32(wv), lo = tf32(wv - hi);
+        const size_t o = ((size_t)(k / 4) * vtc::TM + mrow) * 4 + (k % 4);
+        img[o] = hi; img[(size_t)kp * vtc::TM + o] = lo;
+      }
+    CDS_CUDA(cudaMalloc(&PP.d_aimg, img.size() * 4));
+    CDS_CUDA(cudaMemcpy(PP.d_aimg, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+  }
+  *kp_out = kp; *img_out = PP.d_aimg;
+  return CDS_OK;
+}
+
 int fir_threads(int W4) {                       // 96 or 128 threads, whichever wastes fewer columns
   const int w96 = ceil_div(W4, 96) * 96 - W4, w128 = ceil_div(W4, 128) * 128 - W4;
   return w96 < w128 ? 96 : 128;
@@ -658,6 +916,31 @@ int fullres_vpass_nblocks(int h4, int W) { (void)h4; return ceil_div(W / 4, VP_C
 
 int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polyphase& P, float* Ystore, const int* store_index,
                          float* partial, int* nblocks_out, cudaStream_t st) {
+  static const int impl = [] { const char* e = getenv("CDS_VPASS_IMPL"); return (e && !strcmp(e, "fp32")) ? 0 : 1; }();
+  if (impl == 1) {
+    int kp = 0; const float* img = nullptr;
+    if (int e = vpass_tc_prepare(P, &kp, &img)) return e;
+    const size_t fixed = (size_t)2 * kp * vtc::TM * 4 + (size_t)vtc::RSTAGES * vtc::RAW_STAGE + vtc::BAR_BYTES;
+    const int nstages = (int)std::min<size_t>(vtc::MAX_STAGES, fixed < 220 * 1024 ? (220 * 1024 - fixed) / vtc::STAGE_BYTES : 0);
+    const size_t smem = fixed + (size_t)nstages * vtc::STAGE_BYTES;
+    if (nstages >= 4) {
+      static size_t attr_set = 0;
+      if (smem > attr_set) {
+        CDS_CUDA(cudaFuncSetAttribute(fullres_vpass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+      }
+      const int nstrips = ceil_div(W, vtc::TN);
+      CUtensorMap tmap;
+      if (int e = vpass_tc_tensor_map(T, nmaps, h4, W, &tmap)) return e;
+      static int sms = 0;
+      if (!sms) { int dev = 0; CDS_CUDA(cudaGetDevice(&dev)); CDS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+      dim3 grid(std::min(sms, nstrips * nmaps));
+fullres_vpass_tc_kernel<<<grid, vtc::THREADS, smem, st>>>(tmap, nmaps, h4, W, P.dmin, kp, nstages, img, Ystore, store_index, partial);
+      CDS_LAUNCH_CHECK();
+      *nblocks_out = nstrips;
+      return CDS_OK;
+    }
+  }
   dim3 grid(ceil_div(W / 4, VP_COLS4), nmaps);
   const size_t smem = (size_t)(P.nt + 2 * (VP_RPT - 1)) * 16 + (size_t)2 * (VP_ROWS + P.nt + VP_RPT - 2) * VP_COLS4 * 16;
   static size_t attr_set = 0;

@@ -27,6 +27,7 @@ struct Polyphase {
   int dmin = 0, nt = 0;
   std::vector<float> g;      // [nt][4]  (tap-major so one float4 holds the 4 phases of a tap)
   float* d_g = nullptr;
+  float* d_aimg = nullptr;   // tensor-core V pass: banded 128 x KP weight matrix, hi | lo, shared-memory image (built on first use)
   int upload();
   void release();
 };

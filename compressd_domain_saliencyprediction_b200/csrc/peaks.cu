@@ -2,6 +2,7 @@
 // library runs on.  MEASURED_PEAKS.json only has HBM and bf16-tensor numbers; the contrast and SVM
 // kernels are FP32/MUFU bound, so bench.py measures their roofline denominators live with these.
 #include "cds_common.cuh"
+#include "tc_common.cuh"
 
 namespace cds {
 
@@ -209,5 +210,57 @@ extern "C" int cds_probe_mix(int which, int ctas_per_sm, double* fma_lane_ops_pe
   else { fma = (double)iters * 4 * 10 * 2; mufu = (double)iters * 8; }
   if (fma_lane_ops_per_s) *fma_lane_ops_per_s = fma * thr / (best * 1e-3);
   if (mufu_per_s) *mufu_per_s = mufu * thr / (best * 1e-3);
+  return CDS_OK;
+}
+
+// ---- UMMA layout probe (tools/umma_probe.py): one tcgen05.mma.kind::tf32 128 x 256 x 8 with caller-supplied shared-memory
+// images and descriptor strides, so operand layouts can be checked against numpy without recompiling ----
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const float* __restrict__ a_img, int a_bytes, const float* __restrict__ b_img, int b_bytes, unsigned a_lbo, unsigned a_sbo,
+                  unsigned b_lbo, unsigned b_sbo, unsigned idesc, float* __restrict__ D) {
+  using namespace cds::tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* sA = smem; uint8_t* sB = smem + 16384;
+  for (int i = threadIdx.x; i < a_bytes / 4; i += 128) reinterpret_cast<float*>(sA)[i] = a_img[i];
+  for (int i = threadIdx.x; i < b_bytes / 4; i += 128) reinterpret_cast<float*>(sB)[i] = b_img[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tb = tmem_slot;
+  if (threadIdx.x == 0) {
+    mma_tf32(tb, smem_desc(smem_u32(sA), a_lbo, a_sbo), smem_desc(smem_u32(sB), b_lbo, b_sbo), idesc, 0u);
+    mma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = 0; c < 256; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; j++) D[(size_t)(warp * 32 + lane) * 256 + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(256u) : "memory"); }
+}
+
+// a_img / b_img: host float arrays (<= 16 KB each) copied verbatim into shared memory; D: host [128][256].
+extern "C" int cds_probe_umma(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo, unsigned a_sbo,
+                              unsigned b_lbo, unsigned b_sbo, int a_mn_major, int b_mn_major, float* D) {
+  if (int e = ensure_device()) return e;
+  if (a_bytes > 16384 || b_bytes > 16384) { set_error("cds_probe_umma: images are limited to 16 KB"); return CDS_EINVAL; }
+  float *da = nullptr, *db = nullptr, *dd = nullptr;
+  CDS_CUDA(cudaMalloc(&da, 16384)); CDS_CUDA(cudaMalloc(&db, 16384)); CDS_CUDA(cudaMalloc(&dd, 128 * 256 * 4));
+  CDS_CUDA(cudaMemcpy(da, a_img, a_bytes, cudaMemcpyHostToDevice)); CDS_CUDA(cudaMemcpy(db, b_img, b_bytes, cudaMemcpyHostToDevice));
+  umma_probe_kernel<<<1, 128, 32768>>>(da, a_bytes, db, b_bytes, a_lbo, a_sbo, b_lbo, b_sbo, cds::tc::idesc_tf32(128, 256, a_mn_major, b_mn_major), dd);
+  CDS_LAUNCH_CHECK();
+  CDS_CUDA(cudaMemcpy(D, dd, 128 * 256 * 4, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dd);
   return CDS_OK;
 }

@@ -880,6 +880,7 @@ extern "C" int cds_debug_copy(cds_ctx* c, const char* which, int frame_in_batch,
   else if (!strcmp(which, "xf")) { src = c->d_xf + (size_t)f * 12; n = 12 * 4; }
   else if (!strcmp(which, "xsvm")) { src = c->d_xsvm + (size_t)f * 40000 * 9; n = (size_t)40000 * 9 * 4; }
   else if (!strcmp(which, "dec")) { src = c->d_dec + (size_t)f * 40000; n = (size_t)40000 * 4; }
+  else if (!strcmp(which, "ymaps")) { src = c->d_Y + (size_t)f * (c->p.use_rbf ? 3 : 9) * c->HW; n = (size_t)(c->p.use_rbf ? 3 : 9) * c->HW * 4; }
   else if (!strcmp(which, "raw")) { src = c->d_raw + (size_t)f * c->HW; n = (size_t)c->HW * 4; }
   else { set_error("cds_debug_copy: unknown intermediate %s", which); return CDS_EINVAL; }
   if (bytes < n) { set_error("cds_debug_copy: %s needs %zu bytes", which, n); return CDS_EINVAL; }

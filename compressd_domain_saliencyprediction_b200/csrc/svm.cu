@@ -9,6 +9,7 @@
 // so one pair costs 1 FADD + 9 FFMA + 1 MUFU.EX2 + 1 FFMA.  Each thread keeps IPT instances in
 // registers; SVs stream through shared memory in 48-byte records read as three broadcast LDS.128.
 #include "cds_common.cuh"
+#include "tc_common.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -115,56 +116,8 @@ constexpr int THREADS = 192;                               // warps 0-3 epilogue
 constexpr uint32_t TMEM_COLS = 256;                        // two 128-column FP32 accumulators
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
 // both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC = idesc_tf32(TM, TN, 0, 0);
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) break;
-    if (++spins > (1u << 24)) __trap();                    // a protocol bug must fault, never hang the device
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// K-major, no swizzle (cute::UMMA::SmemDescriptor): 8-row x 16-byte core matrices stored contiguously (128 B);
-// SBO = distance between 8-row groups, LBO = distance between the two 16-byte k chunks of one K = 8 step.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ uint32_t tf32_rna(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u; }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-}
 // 2^x on the FMA pipe (round-to-nearest split, degree-5 minimax polynomial on [-0.5, 0.5], exponent patched in with an
 // integer add): max relative error 2.3e-7, the same as MUFU.EX2's 2^-22.  The epilogue is MUFU-bound (16 ex2 / clk / SM)
 // while the FMA pipe idles, so a fixed share of the exponentials is computed here instead.
@@ -177,7 +130,6 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.69314694f); p = fmaf(p, f, 1.0000001f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(fi) << 23));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace tc
 
 // POLY_OF_8: of every 8 exponentials, this many are computed on the FMA pipe (ex2_poly) instead of MUFU.EX2
@@ -253,12 +205,12 @@ svm_rbf9_tc_kernel(const float* __restrict__ X, long N, const float* __restrict_
         const uint32_t d = tmem_base + (uint32_t)buf * TN;
         const uint32_t LBO = TN * 16, SBO = 128;             // TM == TN
 #define CDS_DESC(base, ks) smem_desc((base) + (ks) * KSTEP_BYTES, LBO, SBO)
-        mma_tf32(d, CDS_DESC(a_lo, 0), CDS_DESC(b_hi, 0), 0u);   // small terms first
-        mma_tf32(d, CDS_DESC(a_lo, 1), CDS_DESC(b_hi, 1), 1u);
-        mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_lo, 0), 1u);
-        mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_lo, 1), 1u);
-        mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_hi, 0), 1u);
-        mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_hi, 1), 1u);
+        mma_tf32(d, CDS_DESC(a_lo, 0), CDS_DESC(b_hi, 0), IDESC, 0u);   // small terms first
+        mma_tf32(d, CDS_DESC(a_lo, 1), CDS_DESC(b_hi, 1), IDESC, 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_lo, 0), IDESC, 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_lo, 1), IDESC, 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_hi, 0), IDESC, 1u);
+        mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_hi, 1), IDESC, 1u);
 #undef CDS_DESC
         mma_commit(empty(s));                                // shared-memory stage free once these MMAs have read it
         mma_commit(tfull(buf));                              // accumulator ready for the epilogue
