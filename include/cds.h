@@ -185,6 +185,11 @@ int cds_profile_read(cds_ctx* ctx, double* ms, long* calls, int n);
  * contrast kernel's FADD+FFMA pair mix, pure FFMA, and MUFU.EX2.  Used as roofline denominators
  * for the FP32/MUFU-bound kernels (MEASURED_PEAKS.json has only HBM and bf16 tensor numbers). */
 int cds_measure_peaks(double* fp32_pair_ips, double* ffma_ips, double* mufu_ips);
+/* Development probes (tools/mix_probe.py, tools/umma_probe.py): instruction-mix throughput and one tcgen05.mma with
+ * caller-supplied shared-memory operand images / descriptor strides.  Not part of the drop-in surface. */
+int cds_probe_mix(int which, int ctas_per_sm, double* fma_lane_ops_per_s, double* mufu_per_s);
+int cds_probe_umma(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo, unsigned a_sbo,
+                   unsigned b_lbo, unsigned b_sbo, int a_mn_major, int b_mn_major, float* D);
 /* Number of kernel launches issued by this library since the last call (bench bookkeeping). */
 long cds_take_launch_count(void);
 
