@@ -220,7 +220,7 @@ def run_b200(a):
         return t
     h_hdr, h_tok, h_base, h_byts = pinned(c_hdr), pinned(c_tok), pinned(c_base), pinned(c_byts)
     d_hdr, d_tok, d_base, d_byts = (t.to(dev) for t in (h_hdr, h_tok, h_base, h_byts))
-    d_maps = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+    d_maps = torch.empty((max(a.steps, a.warmup, nprof) * B, h, w), dtype=torch.float32, device=dev)
     h_maps = torch.empty((E2E_CHUNK * B, h, w), dtype=torch.float32).pin_memory()
     h_cam = torch.zeros((E2E_CHUNK * B, 2), dtype=torch.int32)
     torch.cuda.synchronize()
@@ -254,16 +254,16 @@ def run_b200(a):
     clip.seek(0)
     dev_step(0, halo, context=True)
     poc = halo
-    for _ in range(a.warmup):
-        dev_step(poc, B); poc += B
+    # one API call per leg: K steps = K batches handed over together, so the library may overlap the MUFU-bound back half
+    # (SVM -> map) of batch i with the FP32-bound front half of batch i+1 on its second stream
+    dev_step(poc, a.warmup * B); poc += a.warmup * B
     barrier()
     cds.take_launch_count()
     clk = Clocks(local)
     time.sleep(0.3)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(a.steps):
-        dev_step(poc, B); poc += B
+    dev_step(poc, a.steps * B); poc += a.steps * B
     e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))

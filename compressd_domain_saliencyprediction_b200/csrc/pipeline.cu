@@ -69,6 +69,10 @@ struct cds_ctx {
   float *d_A1 = nullptr, *d_F200 = nullptr;          // [9B][200][w4], [9B][200][200]
   float *d_R1 = nullptr, *d_Ft = nullptr;            // [3B][200][W], [3B][200][200]
   float *d_xsvm = nullptr, *d_dec = nullptr;         // [B][40000][9], [B][40000]
+  float* d_xsvm2[2] = {nullptr, nullptr};            // d_xsvm and a second copy: the back half of batch i (SVM -> map) overlaps the front half of batch i+1
+  cudaStream_t back_stream = nullptr;
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr};
+  int xs_flip = 0, last_xs = 0; bool overlap = true;
   float *d_fparam = nullptr, *d_C = nullptr;         // [9][4] mean, 1/std, weight; [B][200][200]
   float *d_T2 = nullptr, *d_raw = nullptr;           // [B][200][W], [B][H][W]
   float *d_fpartial = nullptr, *d_fstats = nullptr;  // final min/max
@@ -464,6 +468,8 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   A(d_A1, (size_t)9 * B * 200 * w4); A(d_F200, (size_t)9 * B * 40000);
   A(d_R1, (size_t)3 * B * 200 * W); A(d_Ft, (size_t)3 * B * 40000);
   A(d_xsvm, (size_t)B * 40000 * 9); A(d_dec, (size_t)B * 40000); A(d_C, (size_t)B * 40000);
+  if (p->use_rbf) { A(d_xsvm2[1], (size_t)B * 40000 * 9); }
+  c->d_xsvm2[0] = c->d_xsvm;
   A(d_T2, (size_t)B * 200 * W); A(d_raw, (size_t)B * HW);
   A(d_fpartial, (size_t)B * c->nblkf * 4); A(d_fstats, (size_t)B * 4); A(d_cam_stage, (size_t)4 * B);
   A(d_bytes, (size_t)B * c->nctu); A(d_hdr, (size_t)B * c->nctu * 4); A(d_tokbase, (size_t)B + 1);
@@ -476,6 +482,10 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
                cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming) != cudaSuccess)) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
   }
   if (!e && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate copy"); e = CDS_ECUDA; }
+  if (!e && cudaStreamCreateWithFlags(&c->back_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate back"); e = CDS_ECUDA; }
+  for (int b = 0; b < 2 && !e; b++)
+    if (cudaEventCreateWithFlags(&c->ev_front[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_back[b], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
+  { const char* ov = getenv("CDS_OVERLAP"); c->overlap = !(ov && ov[0] == '0') && p->use_rbf; }
 #undef A
   float* d_fparam = nullptr;
   if (!e) e = dalloc(c, &d_fparam, 36);
@@ -504,6 +514,8 @@ extern "C" void cds_destroy(cds_ctx* c) {
   if (!c) return;
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->back_stream) { cudaStreamSynchronize(c->back_stream); cudaStreamDestroy(c->back_stream); }
+  for (int b = 0; b < 2; b++) { if (c->ev_front[b]) cudaEventDestroy(c->ev_front[b]); if (c->ev_back[b]) cudaEventDestroy(c->ev_back[b]); }
   for (int b = 0; b < 2; b++) { if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); }
   if (c->h_cam_pin) cudaFreeHost(c->h_cam_pin);
   for (void* q : c->allocs) cudaFree(q);
@@ -551,8 +563,21 @@ int launch_normalize(cds_ctx* c, int n, void* out, cudaStream_t st) {
   return CDS_OK;
 }
 
+// The batch has a front half (stages a, c, e, b and the 200x200 features; FP32-pipe bound) and a back half (SVM -> final map;
+// MUFU / tensor bound).  With `overlap` the back half runs on the context's back stream, so it shares the SMs with the front
+// half of the next batch; xsvm is double buffered and events order the halves.  `before_back` (optional) must have happened
+// before the back half writes maps_out.  Returns the event that marks the end of the batch in *done_ev (nullptr: on `st`).
 int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
-              const int64_t* tok_base, void* maps_out, int* cam_out, cudaStream_t st) {
+              const int64_t* tok_base, void* maps_out, int* cam_out, cudaStream_t st, cudaEvent_t before_back = nullptr,
+              cudaEvent_t* done_ev = nullptr) {
+  const bool ov = c->overlap && c->p.use_rbf && !c->prof_on;
+  const int slot = ov ? c->xs_flip : 0;
+  if (ov) c->xs_flip ^= 1;
+  c->last_xs = slot;
+  float* xsvm = c->d_xsvm2[slot];
+  cudaStream_t sb = ov ? c->back_stream : st;
+  if (done_ev) *done_ev = nullptr;
+  if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));      // the back half of batch i-2 has finished reading xsvm[slot]
   const int h4 = c->h4, w4 = c->w4, n4 = c->n4, H = c->h, W = c->w, RL = c->RL;
   const float* fparam = c->d_fparam;
   if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, st)) return e;
@@ -626,40 +651,60 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     if (int e = banded_cols_launch(c->d_R1, 3 * n, 200, W, c->Rh, c->d_Ft, st)) return e;
     {
       dim3 grid(ceil_div(40000, 256), n);
-      assemble_features_kernel<<<grid, 256, 0, st>>>(c->d_F200, c->d_Ft, c->d_stats9, c->d_xf, fparam, c->d_xsvm);
+      assemble_features_kernel<<<grid, 256, 0, st>>>(c->d_F200, c->d_Ft, c->d_stats9, c->d_xf, fparam, xsvm);
       CDS_LAUNCH_CHECK();
     }
     // ---- (d) RBF-SVM, then pm_norm -> imresize -> imfilter -> centre prior (main.m:297-304) ----
+    if (cam_out) {      // cam_out is a DEVICE pointer here: gather the ring slots of this batch (front half: it reads the ring)
+      gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, RL, first_poc, n, cam_out);
+      CDS_LAUNCH_CHECK();
+    }
+    if (ov) {
+      CDS_CUDA(cudaEventRecord(c->ev_front[slot], st));
+      CDS_CUDA(cudaStreamWaitEvent(sb, c->ev_front[slot], 0));
+    }
+    if (before_back) CDS_CUDA(cudaStreamWaitEvent(sb, before_back, 0));
     prof_mark(c, ST_SVM, st);
-    if (int e = svm_predict_launch(c->p.model, c->d_xsvm, (long)n * 40000, c->d_dec, st)) return e;
+    if (int e = svm_predict_launch(c->p.model, xsvm, (long)n * 40000, c->d_dec, sb)) return e;
     prof_mark(c, ST_FINAL, st);
-    dec_minmax_norm_kernel<<<n, 1024, 0, st>>>(c->d_dec, c->d_C);
+    dec_minmax_norm_kernel<<<n, 1024, 0, sb>>>(c->d_dec, c->d_C);
     CDS_LAUNCH_CHECK();
-    if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, st)) return e;
+    if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, sb)) return e;
     {
       const int thr = fir_threads(W / 4);
       dim3 grid(ceil_div(W / 4, thr), ceil_div(H, FR_ROWS), n);
-      final_rows_kernel<<<grid, thr, (size_t)(c->Bv.nt + c->Bv.span4) * 16, st>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
+      final_rows_kernel<<<grid, thr, (size_t)(c->Bv.nt + c->Bv.span4) * 16, sb>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
       CDS_LAUNCH_CHECK();
       nbf = grid.x * grid.y;
     }
   } else {
+    if (cam_out) {
+      gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, RL, first_poc, n, cam_out);
+      CDS_LAUNCH_CHECK();
+    }
+    if (before_back) CDS_CUDA(cudaStreamWaitEvent(sb, before_back, 0));
     prof_mark(c, ST_FINAL, st);
     dim3 grid(128, n);
     linear_comb_kernel<<<grid, 256, 0, st>>>(c->d_Y, c->HW, c->d_stats9, c->d_xf, fparam, c->d_dist, c->d_raw, c->d_fpartial);
     CDS_LAUNCH_CHECK();
     nbf = 128;
   }
-  if (int e = stats_finalize_launch(c->d_fpartial, n, nbf, c->d_fstats, st)) return e;
+  if (int e = stats_finalize_launch(c->d_fpartial, n, nbf, c->d_fstats, sb)) return e;
   if (maps_out) {
-    if (int e = c->p.out_u8 ? launch_normalize<uint8_t>(c, n, maps_out, st) : launch_normalize<float>(c, n, maps_out, st)) return e;
+    if (int e = c->p.out_u8 ? launch_normalize<uint8_t>(c, n, maps_out, sb) : launch_normalize<float>(c, n, maps_out, sb)) return e;
   }
-  if (cam_out) {
-    // cam_out is a DEVICE pointer here: gather the ring slots of this batch
-    for (int f = 0; f < n; f++)
-      CDS_CUDA(cudaMemcpyAsync(cam_out + 2 * f, c->r_cam + 2 * ((first_poc + f) % RL), 8, cudaMemcpyDeviceToDevice, st));
+  if (ov) {
+    CDS_CUDA(cudaEventRecord(c->ev_back[slot], sb));
+    if (done_ev) *done_ev = c->ev_back[slot];
   }
   prof_mark(c, -1, st);
+  return CDS_OK;
+}
+
+// make `st` wait for every back half still in flight (end of an API call: the caller's stream then covers all the work)
+int join_back(cds_ctx* c, cudaStream_t st) {
+  if (c->overlap && c->p.use_rbf)
+    for (int b = 0; b < 2; b++) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[b], 0));
   return CDS_OK;
 }
 
@@ -693,6 +738,7 @@ extern "C" int cds_clip_process_dev(cds_ctx* c, int first_poc, int nframes, cons
                           tok_base + done, maps_out ? (char*)maps_out + (size_t)done * px : nullptr,
                           cam_out ? cam_out + 2 * done : nullptr, st)) return e;
   }
+  if (int e = join_back(c, st)) return e;
   c->next_poc = first_poc + nframes;
   return CDS_OK;
 }
@@ -743,13 +789,13 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
       continue;
     }
     const int buf = c->out_flip; c->out_flip ^= 1;
-    CDS_CUDA(cudaStreamWaitEvent(st, c->ev_copied[buf], 0));   // the copy that last read this buffer has finished (no-op if never recorded)
-    if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out[buf], nullptr, st)) return e;
-    if (cam_out) {
-      gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, c->RL, first_poc + done, n, c->d_cam_stage + (size_t)buf * 2 * c->B);
-      CDS_LAUNCH_CHECK();
-    }
-    CDS_CUDA(cudaEventRecord(c->ev_done[buf], st));
+    // before_back = the copy that last read d_out[buf] has finished (a never-recorded event is a no-op)
+    cudaEvent_t done_ev = nullptr;
+    if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out[buf],
+                          cam_out ? c->d_cam_stage + (size_t)buf * 2 * c->B : nullptr, st, c->ev_copied[buf], &done_ev)) return e;
+    if (!done_ev) { CDS_CUDA(cudaEventRecord(c->ev_done[buf], st)); done_ev = c->ev_done[buf]; }
+    else CDS_CUDA(cudaEventRecord(c->ev_done[buf], st));          // front half (incl. the camera-motion gather) done
+    CDS_CUDA(cudaStreamWaitEvent(cs, done_ev, 0));
     CDS_CUDA(cudaStreamWaitEvent(cs, c->ev_done[buf], 0));
     if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)done * px, c->d_out[buf], (size_t)n * px, cudaMemcpyDeviceToHost, cs));
     if (cam_out)
@@ -758,6 +804,7 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
     c->last_first = first_poc + done; c->last_n = n; c->last_buf = buf;
   }
   int herr = 0;
+  if (int e = join_back(c, st)) return e;
   CDS_CUDA(cudaMemcpyAsync(&herr, c->d_err, 4, cudaMemcpyDeviceToHost, st));
   CDS_CUDA(cudaStreamSynchronize(st));
   CDS_CUDA(cudaStreamSynchronize(cs));
@@ -878,13 +925,14 @@ extern "C" int cds_debug_copy(cds_ctx* c, const char* which, int frame_in_batch,
   else if (!strcmp(which, "feat200")) { src = c->d_F200 + (size_t)f * 9 * 40000; n = (size_t)9 * 40000 * 4; }
   else if (!strcmp(which, "ft")) { src = c->d_Ft + (size_t)f * 3 * 40000; n = (size_t)3 * 40000 * 4; }
   else if (!strcmp(which, "xf")) { src = c->d_xf + (size_t)f * 12; n = 12 * 4; }
-  else if (!strcmp(which, "xsvm")) { src = c->d_xsvm + (size_t)f * 40000 * 9; n = (size_t)40000 * 9 * 4; }
+  else if (!strcmp(which, "xsvm")) { src = c->d_xsvm2[c->last_xs] + (size_t)f * 40000 * 9; n = (size_t)40000 * 9 * 4; }
   else if (!strcmp(which, "dec")) { src = c->d_dec + (size_t)f * 40000; n = (size_t)40000 * 4; }
   else if (!strcmp(which, "ymaps")) { src = c->d_Y + (size_t)f * (c->p.use_rbf ? 3 : 9) * c->HW; n = (size_t)(c->p.use_rbf ? 3 : 9) * c->HW * 4; }
   else if (!strcmp(which, "raw")) { src = c->d_raw + (size_t)f * c->HW; n = (size_t)c->HW * 4; }
   else { set_error("cds_debug_copy: unknown intermediate %s", which); return CDS_EINVAL; }
   if (bytes < n) { set_error("cds_debug_copy: %s needs %zu bytes", which, n); return CDS_EINVAL; }
   CDS_CUDA(cudaStreamSynchronize(c->stream));
+  CDS_CUDA(cudaStreamSynchronize(c->back_stream));
   CDS_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost));
   return CDS_OK;
 }
