@@ -211,8 +211,19 @@ def run_b200(a):
     halo = -(-(a.PS + a.PT - 2) // B) * B           # fill the temporal window (untimed set-up, context stages only)
     nprof = 3
     total = halo + (a.warmup + a.steps + nprof) * B
-    # one synthetic clip per rank (its own seed = its own video); picture poc uses entry poc
-    c_hdr, c_tok, c_base, c_byts = cds.ops.synth_clip(w, h, 1234 + rank, total, first_poc=1)
+    # one synthetic clip per rank (its own seed = its own video); picture poc uses entry poc % clip_len (long runs replay the
+    # clip: bounded host / device memory whatever --steps is)
+    clip_len = min(total, 16 * B + halo)
+    c_hdr, c_tok, c_base, c_byts = cds.ops.synth_clip(w, h, 1234 + rank, clip_len, first_poc=1)
+
+    def runs(poc, n, max_batches):
+        """[poc, poc+n) cut into calls of at most max_batches batches that are contiguous inside the replayed clip."""
+        out = []
+        while n > 0:
+            i = poc % clip_len
+            ln = min(n, clip_len - i, max_batches * B)
+            out.append((poc, i, ln)); poc += ln; n -= ln
+        return out
 
     # ---- syntax resident in HBM (value) and in pinned host memory (e2e) ----
     def pinned(x):
@@ -220,7 +231,8 @@ def run_b200(a):
         return t
     h_hdr, h_tok, h_base, h_byts = pinned(c_hdr), pinned(c_tok), pinned(c_base), pinned(c_byts)
     d_hdr, d_tok, d_base, d_byts = (t.to(dev) for t in (h_hdr, h_tok, h_base, h_byts))
-    d_maps = torch.empty((max(a.steps, a.warmup, nprof) * B, h, w), dtype=torch.float32, device=dev)
+    DEV_CHUNK = 8                                  # batches per device-resident call (bounds the output buffer)
+    d_maps = torch.empty((min(max(a.steps, a.warmup, nprof), DEV_CHUNK) * B, h, w), dtype=torch.float32, device=dev)
     h_maps = torch.empty((E2E_CHUNK * B, h, w), dtype=torch.float32).pin_memory()
     h_cam = torch.zeros((E2E_CHUNK * B, 2), dtype=torch.int32)
     torch.cuda.synchronize()
@@ -231,11 +243,12 @@ def run_b200(a):
     P = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
 
     def dev_step(poc, n, context=False):
-        args = (clip.handle, poc, n, P(d_byts, poc * nctu * 2), P(d_hdr, poc * nctu * 16), P(d_tok), P(d_base, poc * 8))
-        if context:
-            check(L.cds_clip_context_dev(*args, st), "cds_clip_context_dev")
-        else:
-            check(L.cds_clip_process_dev(*args, P(d_maps), None, st), "cds_clip_process_dev")
+        for (p, i, ln) in runs(poc, n, DEV_CHUNK):
+            args = (clip.handle, p, ln, P(d_byts, i * nctu * 2), P(d_hdr, i * nctu * 16), P(d_tok), P(d_base, i * 8))
+            if context:
+                check(L.cds_clip_context_dev(*args, st), "cds_clip_context_dev")
+            else:
+                check(L.cds_clip_process_dev(*args, P(d_maps), None, st), "cds_clip_process_dev")
 
     def barrier():
         torch.cuda.synchronize()
@@ -276,11 +289,12 @@ def run_b200(a):
     #      device->host copy of batch i with the kernels of batch i+1; every step's copies are inside the timed region ----
     def e2e_leg(cl, out_buf, bytes_per_px):
         def hstep(poc, n, context=False):
-            args = (cl.handle, poc, n, P(h_byts, poc * nctu * 2), P(h_hdr, poc * nctu * 16), P(h_tok), P(h_base, poc * 8), c_tok.size)
-            if context:
-                check(L.cds_clip_context(*args), "cds_clip_context")
-            else:
-                check(L.cds_clip_process(*args, P(out_buf), P(h_cam)), "cds_clip_process")
+            for (p, i, ln) in runs(poc, n, E2E_CHUNK):
+                args = (cl.handle, p, ln, P(h_byts, i * nctu * 2), P(h_hdr, i * nctu * 16), P(h_tok), P(h_base, i * 8), c_tok.size)
+                if context:
+                    check(L.cds_clip_context(*args), "cds_clip_context")
+                else:
+                    check(L.cds_clip_process(*args, P(out_buf), P(h_cam)), "cds_clip_process")
         cl.seek(0)
         hstep(0, halo, context=True)
         poc = halo
