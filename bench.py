@@ -359,7 +359,7 @@ def run_b200(a):
         traffic = {}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp))
+            traffic = {k: v * B for k, v in json.load(open(tp)).items() if not k.startswith("_")}   # stored per picture
         roofs = []
         # contrast: 2 FP32-pipe lane-instructions per pair (FADD + FFMA with |.| modifier) = 3 FLOP; peak = measured FADD+FFMA mix issue rate
         for key in ("win48", "win24"):
