@@ -127,3 +127,17 @@ def test_auc_nss_match_the_oracle_to_three_decimals(cds, name):
     print(f"{name}: AUC-Judd {auc_g:.4f} (oracle {auc_o:.4f}), NSS {nss_g:.4f} (oracle {nss_o:.4f}) over {n_g} pictures (stand-in SVM model)")
     assert n_g == n_o and n_g >= 6
     assert abs(auc_g - auc_o) < 5e-4 and abs(nss_g - nss_o) < 5e-4
+
+
+def test_stage_a_bit_exact_on_every_bundled_stream(cds):
+    """Two pictures of each of the 24 bundled streams the reference handles (416x240 ... 1920x1080, incl. 1024x768 and 1280x800):
+    the CUDA scatter against the maps of the reference's own getFrame (tests/golden/all_streams.npz)."""
+    d = np.load(os.path.join(GOLD, "all_streams.npz"))
+    sizes = set()
+    for k, name in enumerate(d["names"]):
+        w, h = int(d[f"w{k}"]), int(d[f"h{k}"])
+        sizes.add((w, h))
+        for i in range(2):
+            got = cds.ops.getframe(w, h, d[f"hdr{k}"][i], d[f"tok{k}"][d[f"base{k}"][i]:d[f"base{k}"][i + 1]])
+            assert np.array_equal(got[0], d[f"mvx{k}"][i]) and np.array_equal(got[1], d[f"mvy{k}"][i]) and np.array_equal(got[2], d[f"dep{k}"][i]), (name, i)
+    assert len(d["names"]) == 24 and len(sizes) >= 5

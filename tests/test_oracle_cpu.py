@@ -150,3 +150,15 @@ def test_clip_through_reference_kernels_matches_the_port():
         o.use_reference_kernels(None)
     assert np.array_equal(acam, bcam)
     assert np.max(np.abs(np.nan_to_num(a) - np.nan_to_num(b))) <= 1e-9
+
+
+def test_oracle_getframe_on_every_bundled_stream_vs_reference_getframe():
+    """tests/golden/all_streams.npz: two pictures of each of the 24 bundled HM16.0 streams whose geometry the reference handles
+    (the 1280x720 clips are excluded: its CTU-row formula is wrong there), with the maps of the verbatim reference getFrame."""
+    d = np.load(os.path.join(o.ROOT, "tests", "golden", "all_streams.npz"))
+    assert len(d["names"]) == 24
+    for k, name in enumerate(d["names"]):
+        w, h = int(d[f"w{k}"]), int(d[f"h{k}"])
+        for i in range(2):
+            got = o.orc_getframe(w, h, d[f"hdr{k}"][i], d[f"tok{k}"][d[f"base{k}"][i]:d[f"base{k}"][i + 1]])
+            assert np.array_equal(got[0], d[f"mvx{k}"][i]) and np.array_equal(got[1], d[f"mvy{k}"][i]) and np.array_equal(got[2], d[f"dep{k}"][i]), (name, i)
