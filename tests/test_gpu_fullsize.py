@@ -109,3 +109,22 @@ def test_svm_full_frame_vs_oracle(cds):
     dec, _ = m.decision_values(X)
     want, _ = o.orc_svm_predict(SV, coef, rho, gamma, labels, X)
     assert np.max(np.abs(dec - want)) <= 1e-4 * (np.max(np.abs(want + rho)) + abs(rho))
+
+
+def test_full_temporal_window_at_50fps_vs_oracle(cds):
+    """50 fps geometry of the benchmark (PS 15, PT 105): the pictures after the window has filled (119 pictures of history)
+    against the oracle, which only has to produce the last two maps."""
+    w, h, fps, F = 832, 480, 50.0, 122
+    o.oracle().orc_set_threads(16)
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 50, F)
+    ints = [o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    mvx = np.stack([m[0] for m in ints]); mvy = np.stack([m[1] for m in ints]); dep = np.stack([m[2] for m in ints])
+    mdl, gm = _model(cds, 256)
+    want, wcam, _ = o.orc_process_clip(w, h, fps, mvx, mvy, dep, byts, mdl, MEAN9, STD9, first_out=F - 2, use_rbf=1)
+    clip = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=32)
+    got, cam = clip.process(0, hdr, tok, base, byts)
+    clip.close()
+    assert np.array_equal(cam, wcam)
+    for k in range(2):
+        err = np.max(np.abs(got[F - 2 + k] - np.nan_to_num(want[k])))
+        assert err <= 1e-4, (k, err)
