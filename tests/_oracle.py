@@ -145,6 +145,27 @@ def synth_model(nsv, nfeat=9, seed=7):
     return SV, coef, 0.1, 1.0 / nfeat, (1, -1)
 
 
+def load_libsvm_model(path):
+    """Parse the text written by svm_save_model (svm.cpp:2756) for a 2-class C-SVC / RBF model -> (SV, coef, rho, gamma, labels)."""
+    hdr = {}
+    with open(path) as f:
+        for line in f:
+            k = line.split()
+            if k[0] == "SV":
+                break
+            hdr[k[0]] = k[1:]
+        rows = [l.split() for l in f if l.strip()]
+    assert hdr["svm_type"] == ["c_svc"] and hdr["kernel_type"] == ["rbf"] and hdr["nr_class"] == ["2"]
+    nfeat = max(int(t.split(":")[0]) for r in rows for t in r[1:])
+    SV = np.zeros((len(rows), nfeat)); coef = np.zeros(len(rows))
+    for i, r in enumerate(rows):
+        coef[i] = float(r[0])
+        for t in r[1:]:
+            j, v = t.split(":"); SV[i, int(j) - 1] = float(v)
+    assert len(rows) == int(hdr["total_sv"][0])
+    return SV, coef, float(hdr["rho"][0]), float(hdr["gamma"][0]), (int(hdr["label"][0]), int(hdr["label"][1]))
+
+
 # ---------------------------------------------------------------------------- stage (c) / clip
 def orc_camera_motion(w, h, mvx, mvy, bitmap, depth):
     h4, w4 = h // 4, w // 4

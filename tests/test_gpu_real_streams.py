@@ -129,6 +129,40 @@ def test_auc_nss_match_the_oracle_to_three_decimals(cds, name):
     assert abs(auc_g - auc_o) < 5e-4 and abs(nss_g - nss_o) < 5e-4
 
 
+@pytest.mark.parametrize("name", ["BasketballPass", "BasketballDrill", "BasketballDrive"])
+def test_trained_standin_model_on_real_clips(cds, name):
+    """the RBF model is missing from the reference checkout; tests/golden/standin_svmRBFmodel.model is a stand-in
+    trained by the reference's own svm-train (libsvm-3.17) on the nine features of these pictures against the reference's
+    fixations (make_golden_standin_model.py).  The library loads the libsvm text file (cds_svm_model_load), the maps match the
+    oracle within 1e-4, AUC / NSS to 3 decimals, and the learnt model scores the fixations well above chance."""
+    d, w, h, F = _load(name)
+    fx = np.load(os.path.join(GOLD, f"fixations_{name}.npz"))
+    st = np.load(os.path.join(GOLD, "standin_svmRBFmodel.npz"))
+    path = os.path.join(GOLD, "standin_svmRBFmodel.model")
+    hdr, tok, base, byts = d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"]
+    o.oracle().orc_set_threads(16)
+    ints = [o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    mvx = np.stack([m[0] for m in ints]); mvy = np.stack([m[1] for m in ints]); dep = np.stack([m[2] for m in ints])
+    gm = cds.ops.SvmModel(path=path)
+    mdl = o.load_libsvm_model(path)
+    assert gm.totalSV == mdl[0].shape[0] and gm.nfeat == 9
+    first = max(0, F - (6 if w > 1000 else 12))
+    want, _, _ = o.orc_process_clip(w, h, 10.0, mvx, mvy, dep, byts, mdl, st["meanVec"], st["stdVec"], first_out=first, use_rbf=1)
+    want = np.nan_to_num(want)
+    clip = cds.SaliencyClip(w, h, 10.0, model=gm, meanVec=st["meanVec"], stdVec=st["stdVec"], max_batch=8)
+    got, _ = clip.process(0, hdr, tok, base, byts)
+    clip.close()
+    err = float(np.max(np.abs(got[first:] - want)))
+    off = fx["offsets"][first:] - fx["offsets"][first]
+    xy = fx["xy"][fx["offsets"][first]:]
+    auc_g, nss_g, n_g = cds.metrics.evaluate_clip(got[first:], xy, off)
+    auc_o, nss_o, _ = cds.metrics.evaluate_clip(want, xy, off)
+    print(f"{name}: trained stand-in model ({gm.totalSV} SVs): max |err| {err:.2e}, AUC-Judd {auc_g:.4f} (oracle {auc_o:.4f}), NSS {nss_g:.4f} (oracle {nss_o:.4f}), {n_g} pictures")
+    assert err <= 1e-4
+    assert abs(auc_g - auc_o) < 5e-4 and abs(nss_g - nss_o) < 5e-4
+    assert auc_g > 0.65 and nss_g > 0.3
+
+
 def test_stage_a_bit_exact_on_every_bundled_stream(cds):
     """Two pictures of each of the 24 bundled streams the reference handles (416x240 ... 1920x1080, incl. 1024x768 and 1280x800):
     the CUDA scatter against the maps of the reference's own getFrame (tests/golden/all_streams.npz)."""

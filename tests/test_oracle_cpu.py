@@ -162,3 +162,20 @@ def test_oracle_getframe_on_every_bundled_stream_vs_reference_getframe():
         for i in range(2):
             got = o.orc_getframe(w, h, d[f"hdr{k}"][i], d[f"tok{k}"][d[f"base{k}"][i]:d[f"base{k}"][i + 1]])
             assert np.array_equal(got[0], d[f"mvx{k}"][i]) and np.array_equal(got[1], d[f"mvy{k}"][i]) and np.array_equal(got[2], d[f"dep{k}"][i]), (name, i)
+
+
+def test_standin_trained_model_fixture_loads_and_matches_reference_libsvm():
+    """tests/golden/standin_svmRBFmodel.model: trained by the reference's own svm-train on the reference's fixations
+    (make_golden_standin_model.py).  The text parser, the oracle's decision values and libsvm-3.17's agree."""
+    g = os.path.join(o.ROOT, "tests", "golden")
+    SV, coef, rho, gamma, labels = o.load_libsvm_model(os.path.join(g, "standin_svmRBFmodel.model"))
+    st = np.load(os.path.join(g, "standin_svmRBFmodel.npz"))
+    assert SV.shape[1] == 9 and SV.shape[0] > 100 and abs(gamma - 1 / 9) < 1e-5 and labels == (1, -1)
+    assert st["meanVec"].shape == (9,) and np.all(st["stdVec"] > 0)
+    assert np.all(np.abs(coef) <= 1.0 + 1e-12)                       # C = 1 box constraint
+    X = np.random.default_rng(5).standard_normal((400, 9))
+    dec, lab = o.orc_svm_predict(SV, coef, rho, gamma, labels, X)
+    assert 0 < int((lab > 0).sum()) < 400
+    r = o.ref_svm_predict(SV, coef, rho, gamma, labels, X, nsv0=int((coef > 0).sum()))
+    if r is not None:
+        assert np.array_equal(dec, r[0]) and np.array_equal(lab, r[1])
