@@ -13,6 +13,8 @@
  *                                 (oracle/_ref/libref_svm.so, heart_scale known answer).
  *   stages (c),(e), MATLAB glue : PARITY UNPINNED — restated from the .m text; the reference
  *                                 ships no outputs for them and MATLAB is not available.
+ *   fast version orc_fast_*     : pinned — the reference's 39 golden PNGs (bin/HMdata/0..38.png),
+ *                                 see cds_oracle_fast.c and tests/test_oracle_fast_cpu.py.
  *
  * Conventions: maps are row-major [rows][cols] doubles unless a function says "col-major"
  * (the two mex drop-ins keep MATLAB's column-major layout).
@@ -100,6 +102,22 @@ void orc_use_reference_kernels(orc_ref_contrast_fn contrast, orc_ref_svm_fn svm,
 double orc_last_seconds(int which);
 void orc_set_threads(int n);   /* pthread parallel-for width (default 1; results do not depend on it) */
 int orc_threads(void);
+
+/* ---------- the reference's FAST version (cds_oracle_fast.c): TDecGop.cpp:225-333,486-656 + salmat.cpp, float32 ----------
+ * Pinned by the 39 golden PNGs HM_16.0_features/bin/HMdata/0..38.png (tests/golden/fast_BasketballDrill.npz). */
+typedef struct orc_fast orc_fast;
+orc_fast* orc_fast_create(int w, int h, double fps);          /* NULL unless w, h are positive multiples of 4 */
+void orc_fast_destroy(orc_fast* o);
+int orc_fast_PS(const orc_fast* o);
+int orc_fast_PT(const orc_fast* o);
+/* One picture (FrameIndex = pictures fed so far): stage-(a) maps h/4 x w/4, bytes per CTU.  out_u8: h x w (what imwrite
+ * stores); out_f32 (may be NULL): the normalised map before x255; cam[2] (may be NULL); feat9 (may be NULL): 9 x h x w in the
+ * order of FeatureWeight (TDecGop.cpp:319). */
+int orc_fast_frame(orc_fast* o, const int16_t* mvx, const int16_t* mvy, const uint8_t* depth, const uint16_t* ctu_bytes,
+                   uint8_t* out_u8, float* out_f32, int* cam, float* feat9);
+/* cv::getGaussianKernel(n, sigma, CV_32F) and cv::GaussianBlur(CV_32F, BORDER_CONSTANT) as OpenCV 2.4.9 evaluates them */
+void orc_cv_gaussian_kernel(int n, double sigma, float* k);
+void orc_cv_gaussian_blur(const float* src, int rows, int cols, int ksize, double sigma, float* dst, float* tmp);
 
 #ifdef __cplusplus
 }

@@ -237,3 +237,38 @@ def use_reference_kernels(model=None):
     _REF_KEEP.append((SV, coef))
     L.orc_use_reference_kernels(C.cast(ref("contrast").ref_computecontrast5, C.c_void_p), C.cast(Ls.ref_svm_predict, C.c_void_p), C.c_void_p(m))
     return True
+
+
+# ---------------------------------------------------------------------------- fast version (cds_oracle_fast.c)
+class FastOracle:
+    """The reference's fast version (TDecGop.cpp:225-333 + salmat.cpp), one picture at a time."""
+
+    def __init__(self, w, h, fps):
+        L = oracle()
+        L.orc_fast_create.restype = C.c_void_p
+        L.orc_fast_create.argtypes = [C.c_int, C.c_int, C.c_double]
+        L.orc_fast_destroy.argtypes = [C.c_void_p]
+        L.orc_fast_frame.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.orc_fast_PS.argtypes = [C.c_void_p]; L.orc_fast_PT.argtypes = [C.c_void_p]
+        self.L, self.w, self.h = L, w, h
+        self.o = L.orc_fast_create(w, h, float(fps))
+        assert self.o, "orc_fast_create failed"
+        self.PS, self.PT = L.orc_fast_PS(self.o), L.orc_fast_PT(self.o)
+
+    def frame(self, mvx, mvy, depth, ctu_bytes, want_feat=False):
+        """-> (u8 map [h][w], f32 map [h][w], cam (2,), feat9 [9][h][w] or None)"""
+        mvx = np.ascontiguousarray(mvx, np.int16); mvy = np.ascontiguousarray(mvy, np.int16)
+        depth = np.ascontiguousarray(depth, np.uint8); byts = np.ascontiguousarray(ctu_bytes, np.uint16)
+        u8 = np.zeros((self.h, self.w), np.uint8); f32 = np.zeros((self.h, self.w), np.float32); cam = np.zeros(2, np.int32)
+        feat = np.zeros((9, self.h, self.w), np.float32) if want_feat else None
+        rc = self.L.orc_fast_frame(self.o, _ptr(mvx), _ptr(mvy), _ptr(depth), _ptr(byts), _ptr(u8), _ptr(f32), _ptr(cam),
+                                   _ptr(feat) if want_feat else None)
+        assert rc == 0
+        return u8, f32, cam, feat
+
+    def close(self):
+        if self.o:
+            self.L.orc_fast_destroy(self.o); self.o = None
+
+    def __del__(self):
+        self.close()
