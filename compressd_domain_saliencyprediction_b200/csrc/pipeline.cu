@@ -7,6 +7,7 @@
 // cds_clip_process_dev.  Stages: (a) getframe.cu, (c) vote.cu, (e) maps.cu, (b) contrast.cu,
 // (d) svm.cu, final map below.
 #include "maps.cuh"
+#include "fast.cuh"
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -36,6 +37,7 @@ static const float kFeatureWeight[9] = {0.058f, 0.171f, -0.095f, 0.068f, -0.01f,
 
 struct cds_ctx {
   cds_params p;
+  FastState* fast = nullptr;           // use_rbf == CDS_FUSION_FAST: the reference's fast version (fast.cu) replaces stages (c)-(e), (b), (d)
   int w, h, h4, w4, n4, ncol, nrow, nctu, B, RL, PS, PT, gk;
   double gs;
   int next_poc = 0;
@@ -426,10 +428,12 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
     set_error("cds_create: %dx%d unsupported (multiples of 8, 64..8192)", p->w, p->h); return CDS_EINVAL;
   }
   if (!(p->fps >= 4) || p->fps > 240) { set_error("cds_create: fps %.3f out of range", p->fps); return CDS_EINVAL; }
-  if (p->use_rbf && (!p->model || cds_svm_model_nfeat(p->model) != 9)) {
+  if (p->use_rbf < 0 || p->use_rbf > CDS_FUSION_FAST) { set_error("cds_create: use_rbf %d unknown", p->use_rbf); return CDS_EINVAL; }
+  const bool fm = p->use_rbf == CDS_FUSION_FAST;
+  if (p->use_rbf == CDS_FUSION_RBF && (!p->model || cds_svm_model_nfeat(p->model) != 9)) {
     set_error("cds_create: use_rbf needs a 9-feature RBF model (svmRBFmodel_all.mat stand-in)"); return CDS_EINVAL;
   }
-  for (int i = 0; i < 9; i++) if (!(p->std_vec[i] != 0)) { set_error("cds_create: std_vec[%d] is zero", i); return CDS_EINVAL; }
+  for (int i = 0; i < 9 && !fm; i++) if (!(p->std_vec[i] != 0)) { set_error("cds_create: std_vec[%d] is zero", i); return CDS_EINVAL; }
   cds_ctx* c = new cds_ctx();
   c->p = *p;
   c->w = p->w; c->h = p->h; c->h4 = p->h / 4; c->w4 = p->w / 4; c->n4 = c->h4 * c->w4;
@@ -449,6 +453,12 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
 #define A(ptr, count) if (!e) e = dalloc(c, &c->ptr, (size_t)(count))
   A(d_mvx, (size_t)B * n4); A(d_mvy, (size_t)B * n4); A(d_dep, (size_t)B * n4); A(d_err, 4);
   if (!e && cudaMemset(c->d_err, 0, 16) != cudaSuccess) { set_error("cudaMemset d_err"); e = CDS_ECUDA; }
+  if (fm) {
+    if (!e) e = fast_create(p->w, p->h, p->fps, B, &c->fast);
+    if (!e) { c->PS = fast_halo(c->fast) + 2; c->PT = 0; }
+  }
+#undef A
+#define A(ptr, count) if (!e && !fm) e = dalloc(c, &c->ptr, (size_t)(count))
   A(r_Vx, (size_t)c->RL * n4); A(r_Vy, (size_t)c->RL * n4); A(r_mvn, (size_t)c->RL * n4); A(r_bitn, (size_t)c->RL * n4);
   A(r_depn, (size_t)c->RL * n4); A(r_sm4, (size_t)c->RL * n4); A(r_cam, (size_t)c->RL * 2);
   A(d_mv_s, (size_t)B * n4); A(d_X, (size_t)B * 9 * n4); A(d_cxy, (size_t)2 * B * n4); A(d_keys64, (size_t)4 * B);
@@ -471,7 +481,10 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   if (p->use_rbf) { A(d_xsvm2[1], (size_t)B * 40000 * 9); }
   c->d_xsvm2[0] = c->d_xsvm;
   A(d_T2, (size_t)B * 200 * W); A(d_raw, (size_t)B * HW);
-  A(d_fpartial, (size_t)B * c->nblkf * 4); A(d_fstats, (size_t)B * 4); A(d_cam_stage, (size_t)4 * B);
+  A(d_fpartial, (size_t)B * c->nblkf * 4); A(d_fstats, (size_t)B * 4);
+#undef A
+#define A(ptr, count) if (!e) e = dalloc(c, &c->ptr, (size_t)(count))
+  A(d_cam_stage, (size_t)4 * B);
   A(d_bytes, (size_t)B * c->nctu); A(d_hdr, (size_t)B * c->nctu * 4); A(d_tokbase, (size_t)B + 1);
   c->tok_cap = (size_t)B * c->nctu * 160;
   A(d_tok, c->tok_cap);
@@ -485,18 +498,18 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   if (!e && cudaStreamCreateWithFlags(&c->back_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate back"); e = CDS_ECUDA; }
   for (int b = 0; b < 2 && !e; b++)
     if (cudaEventCreateWithFlags(&c->ev_front[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_back[b], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
-  { const char* ov = getenv("CDS_OVERLAP"); c->overlap = !(ov && ov[0] == '0') && p->use_rbf; }
+  { const char* ov = getenv("CDS_OVERLAP"); c->overlap = !(ov && ov[0] == '0') && p->use_rbf == CDS_FUSION_RBF; }
 #undef A
   float* d_fparam = nullptr;
-  if (!e) e = dalloc(c, &d_fparam, 36);
-  if (!e) {
+  if (!e && !fm) e = dalloc(c, &d_fparam, 36);
+  if (!e && !fm) {
     float fp[36];
     for (int i = 0; i < 9; i++) { fp[4 * i] = (float)p->mean_vec[i]; fp[4 * i + 1] = (float)(1.0 / p->std_vec[i]); fp[4 * i + 2] = kFeatureWeight[i]; fp[4 * i + 3] = 0.f; }
     if (cudaMemcpy(d_fparam, fp, sizeof(fp), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("cudaMemcpy fparam"); e = CDS_ECUDA; }
     c->d_fparam = d_fparam;
   }
-  if (!e) e = build_operators(c);
-  if (!e) {
+  if (!e && !fm) e = build_operators(c);
+  if (!e && !fm) {
     std::vector<int> si((size_t)9 * B);
     for (int f = 0; f < B; f++) for (int i = 0; i < 9; i++)
       si[(size_t)f * 9 + i] = p->use_rbf ? ((i % 3 == 1) ? f * 3 + i / 3 : -1) : f * 9 + i;
@@ -518,6 +531,7 @@ extern "C" void cds_destroy(cds_ctx* c) {
   for (int b = 0; b < 2; b++) { if (c->ev_front[b]) cudaEventDestroy(c->ev_front[b]); if (c->ev_back[b]) cudaEventDestroy(c->ev_back[b]); }
   for (int b = 0; b < 2; b++) { if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); }
   if (c->h_cam_pin) cudaFreeHost(c->h_cam_pin);
+  fast_destroy(c->fast);
   for (void* q : c->allocs) cudaFree(q);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   c->poly.release();
@@ -528,6 +542,13 @@ extern "C" void cds_destroy(cds_ctx* c) {
 extern "C" int cds_seek(cds_ctx* c, int poc) {
   if (!c || poc < 0) { set_error("cds_seek: bad arguments"); return CDS_EINVAL; }
   cudaStreamSynchronize(c->stream);
+  if (c->fast) {
+    if (int e = fast_clear(c->fast, c->stream)) return e;
+    cudaStreamSynchronize(c->stream);
+    c->next_poc = poc; c->pending = 0; c->pending_first = poc; c->last_first = -1; c->last_n = 0;
+    c->h_tok.clear();
+    return CDS_OK;
+  }
   const size_t rb = (size_t)c->RL * c->n4 * 4;
   for (float* r : {c->r_mvn, c->r_bitn, c->r_depn})
     CDS_CUDA(cudaMemset(r, 0, rb));
@@ -547,6 +568,7 @@ int run_context_stages(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, 
                        const int64_t* tok_base, cudaStream_t st) {
   prof_mark(c, ST_GETFRAME, st);
   if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
+  if (c->fast) return fast_run_batch(c->fast, first_poc, n, c->d_mvx, c->d_mvy, c->d_dep, bytes, nullptr, 0, nullptr, st);
   prof_mark(c, ST_VOTE, st);
   if (int e = camera_motion_launch_f64(c->w, c->h, n, c->d_mvx, c->d_mvy, bytes, c->d_dep, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn,
                                        c->r_depn, c->r_cam, nullptr, nullptr, first_poc % c->RL, c->RL, st)) return e;
@@ -570,6 +592,16 @@ int launch_normalize(cds_ctx* c, int n, void* out, cudaStream_t st) {
 int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
               const int64_t* tok_base, void* maps_out, int* cam_out, cudaStream_t st, cudaEvent_t before_back = nullptr,
               cudaEvent_t* done_ev = nullptr) {
+  if (c->fast) {          // TDecGop.cpp:270-332 for n pictures: stage (a), then the fast version's kernels (fast.cu)
+    if (done_ev) *done_ev = nullptr;
+    prof_mark(c, ST_GETFRAME, st);
+    if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
+    prof_mark(c, ST_FINAL, st);
+    if (before_back) CDS_CUDA(cudaStreamWaitEvent(st, before_back, 0));
+    if (int e = fast_run_batch(c->fast, first_poc, n, c->d_mvx, c->d_mvy, c->d_dep, bytes, maps_out, c->p.out_u8, cam_out, st)) return e;
+    prof_mark(c, -1, st);
+    return CDS_OK;
+  }
   const bool ov = c->overlap && c->p.use_rbf && !c->prof_on;
   const int slot = ov ? c->xs_flip : 0;
   if (ov) c->xs_flip ^= 1;
@@ -884,6 +916,7 @@ extern "C" int cds_get_map(cds_ctx* c, int poc, void* dst, int* cam_xy) {
   }
   const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
   CDS_CUDA(cudaMemcpy(dst, (char*)c->d_out[c->last_buf] + (size_t)(poc - c->last_first) * px, px, cudaMemcpyDeviceToHost));
+  if (cam_xy && c->fast) return fast_get_cam(c->fast, poc, cam_xy);
   if (cam_xy) CDS_CUDA(cudaMemcpy(cam_xy, c->r_cam + 2 * (poc % c->RL), 8, cudaMemcpyDeviceToHost));
   return CDS_OK;
 }
@@ -920,6 +953,7 @@ extern "C" int cds_profile_read(cds_ctx* c, double* ms, long* calls, int n) {
 extern "C" int cds_debug_copy(cds_ctx* c, const char* which, int frame_in_batch, void* dst, size_t bytes) {
   if (!c || !which || !dst || frame_in_batch < 0 || frame_in_batch >= c->B) { set_error("cds_debug_copy: bad arguments"); return CDS_EINVAL; }
   const int f = frame_in_batch; const void* src = nullptr; size_t n = 0;
+  if (c->fast) return fast_debug_copy(c->fast, which, f, dst, bytes, c->stream);
   if (!strcmp(which, "xmaps")) { src = c->d_X + (size_t)f * 9 * c->n4; n = (size_t)9 * c->n4 * 4; }
   else if (!strcmp(which, "stats")) { src = c->d_stats9 + (size_t)f * 36; n = 36 * 4; }
   else if (!strcmp(which, "feat200")) { src = c->d_F200 + (size_t)f * 9 * 40000; n = (size_t)9 * 40000 * 4; }

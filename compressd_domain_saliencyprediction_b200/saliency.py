@@ -23,12 +23,15 @@ class SaliencyClip:
     model / meanVec / stdVec are the contents of svmRBFmodel_all.mat (main.m:113); the file is absent
     from the reference checkout, so callers pass a stand-in."""
 
-    def __init__(self, w, h, fps, model=None, meanVec=None, stdVec=None, use_rbf=True, max_batch=32, out_u8=False):
+    def __init__(self, w, h, fps, model=None, meanVec=None, stdVec=None, use_rbf=True, max_batch=32, out_u8=False, fast=False):
+        """fast=True selects the reference's FAST version (TDecGop.cpp:225-333 + salmat.cpp; no model needed), whose 8-bit maps
+        are what its decoder writes to ../HMdata/<POC>.png."""
         self.w, self.h, self.fps = int(w), int(h), float(fps)
         self.out_u8 = bool(out_u8)
         self.model = model
+        self.fast = bool(fast)
         p = _Params()
-        p.w, p.h, p.fps, p.use_rbf = self.w, self.h, self.fps, int(bool(use_rbf))
+        p.w, p.h, p.fps, p.use_rbf = self.w, self.h, self.fps, (2 if fast else int(bool(use_rbf)))
         p.model = model.handle if model is not None else None
         mv = np.zeros(9) if meanVec is None else np.asarray(meanVec, np.float64).reshape(9)
         sv = np.ones(9) if stdVec is None else np.asarray(stdVec, np.float64).reshape(9)
@@ -38,7 +41,10 @@ class SaliencyClip:
         self._h = C.c_void_p()
         check(lib().cds_create(C.byref(p), C.byref(self._h)), "cds_create")
         self.max_batch = int(max_batch)
-        self.PS = int(np.floor(self.fps * 0.3 + 0.5)); self.PT = int(np.floor(self.PS * 7 + 0.5))
+        if fast:      # cvRound (half to even), salmat.cpp:18-19
+            self.PS = max(1, int(np.rint(self.fps * 0.3))); self.PT = max(1, int(np.rint(self.fps * 0.7)))
+        else:         # main.m:119,129
+            self.PS = int(np.floor(self.fps * 0.3 + 0.5)); self.PT = int(np.floor(self.PS * 7 + 0.5))
 
     @property
     def handle(self):

@@ -126,10 +126,16 @@ int cds_magnitude_vote(const double* value, int n, double* v_ave);
  * whole path: per-clip context (main.m:113-305 with the RBF-SVM branch; TDecGop.cpp:225-333 hook)
  * ------------------------------------------------------------------------------------------ */
 typedef struct cds_ctx cds_ctx;
+#define CDS_FUSION_LINEAR 0
+#define CDS_FUSION_RBF 1
+#define CDS_FUSION_FAST 2
 typedef struct {
   int w, h;            /* luma size; multiples of 8 */
   double fps;          /* PreframSmooth = round(0.3 fps), PreframTemporal = round(7 PS) (main.m:119,129) */
-  int use_rbf;         /* 1: RBF-SVM fusion (main.m:273-301); 0: linear fusion (main.m:258-272) */
+  int use_rbf;         /* CDS_FUSION_RBF 1: RBF-SVM fusion (main.m:273-301); CDS_FUSION_LINEAR 0: linear fusion (main.m:258-272);
+                        * CDS_FUSION_FAST 2: the FAST version's arithmetic (TDecGop.cpp:225-333, 486-656 + salmat.cpp: float32,
+                        * CameraDect / Umean vote, PS = cvRound(0.3 fps), PT = cvRound(0.7 fps), coarse-grid contrast, fixed feature
+                        * weights, cv::GaussianBlur, 8-bit map) — reproduces the decoder's ../HMdata/<POC>.png; width % 16 == 0 */
   const cds_svm_model* model;   /* stand-in for svmRBFmodel_all.mat:model (required when use_rbf) */
   double mean_vec[9], std_vec[9];   /* svmRBFmodel_all.mat: meanVec, stdVec */
   int max_batch;       /* pictures processed per launch group (0 = default 32) */
