@@ -1,0 +1,110 @@
+"""The reference's FAST version (TDecGop.cpp:225-333, 486-656 + salmat.cpp) on the GPU (use_rbf = CDS_FUSION_FAST) against
+  * the reference's own golden outputs bin/HMdata/0..38.png (tests/golden/fast_BasketballDrill.npz), and
+  * the fast-version oracle (oracle/cds_oracle_fast.c), which is pinned by the same PNGs.
+The kernels reproduce the reference's float32 operation order, so the bar against the oracle is bit-exact: the 8-bit maps, the
+FP32 maps before x255 and the camera-motion votes must be identical, not merely within 1e-4."""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as o
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(o.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def cds():
+    import compressd_domain_saliencyprediction_b200 as pkg
+    assert pkg.device_ok(), pkg.lib().cds_last_error()
+    return pkg
+
+
+def _oracle_clip(w, h, fps, hdr, tok, base, byts, frames=None):
+    fo = o.FastOracle(w, h, fps)
+    u8s, f32s, cams = [], [], []
+    for f in range(hdr.shape[0] if frames is None else frames):
+        mvx, mvy, dep = o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]])
+        u8, f32, cam, _ = fo.frame(mvx, mvy, dep, byts[f])
+        u8s.append(u8); f32s.append(f32); cams.append(cam.copy())
+    fo.close()
+    return np.stack(u8s), np.stack(f32s), np.stack(cams)
+
+
+def test_fast_version_reproduces_the_reference_golden_pngs(cds):
+    d = np.load(os.path.join(GOLD, "fast_BasketballDrill.npz"))
+    w, h, fps = int(d["w"]), int(d["h"]), float(d["fps"])
+    clip = cds.SaliencyClip(w, h, fps, fast=True, out_u8=True, max_batch=16)
+    got, cam = clip.process(0, d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"])
+    clip.close()
+    diff = np.abs(got.astype(np.int16) - d["png"].astype(np.int16))
+    per = (diff > 0).reshape(len(got), -1).sum(1)
+    print(f"GPU fast version vs the reference's PNGs: {int((per == 0).sum())} of {len(got)} pictures byte-identical, "
+          f"{int(per.sum())} pixels differ in total (max |diff| {int(diff.max())})")
+    assert diff.max() <= 1 and per.max() <= 1 and per.sum() <= 3 and (per == 0).sum() >= 36
+    assert not cam.any()
+    want, _, _ = _oracle_clip(w, h, fps, d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name,batch", [("BasketballDrive", 5), ("BasketballPass", 32)])
+def test_fast_version_bit_exact_vs_oracle_on_real_clips(cds, name, batch):
+    """BasketballDrive 126..137 pans: CameraDect fires on every picture (vote_alg + Umean + translateTransform shifts)."""
+    d = np.load(os.path.join(GOLD, f"real_{name}.npz"))
+    w, h, fps = int(d["w"]), int(d["h"]), 50.0
+    hdr, tok, base, byts = d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"]
+    want_u8, want_f32, want_cam = _oracle_clip(w, h, fps, hdr, tok, base, byts)
+    for u8 in (True, False):
+        clip = cds.SaliencyClip(w, h, fps, fast=True, out_u8=u8, max_batch=batch)
+        got, cam = clip.process(0, hdr, tok, base, byts)
+        clip.close()
+        assert np.array_equal(cam, want_cam)
+        assert np.array_equal(got, want_u8 if u8 else want_f32)
+    if name == "BasketballDrive":
+        assert np.all(np.abs(want_cam).sum(1) > 0), want_cam
+
+
+@pytest.mark.parametrize("w,h,fps,F,seed", [(416, 240, 50.0, 60, 5), (832, 480, 24.0, 30, 9), (1024, 768, 30.0, 12, 2)])
+def test_fast_version_bit_exact_vs_oracle_on_synthetic_pans(cds, w, h, fps, F, seed):
+    """Synthetic syntax with a global pan per picture: the camera branch fires, the clip runs past PS + PT pictures (ring wrap),
+    and batches of 7 split the clip at positions unrelated to PS / PT."""
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, seed, F)
+    want_u8, want_f32, want_cam = _oracle_clip(w, h, fps, hdr, tok, base, byts)
+    clip = cds.SaliencyClip(w, h, fps, fast=True, out_u8=False, max_batch=7)
+    got, cam = clip.process(0, hdr, tok, base, byts)
+    clip.close()
+    assert np.array_equal(cam, want_cam)
+    assert np.abs(want_cam).sum() > 0
+    bad = [f for f in range(F) if not np.array_equal(got[f], want_f32[f])]
+    assert not bad, (bad, float(np.max(np.abs(got - want_f32))))
+
+
+def test_fast_version_hook_surface_and_frame_range_halo(cds):
+    """cds_submit_frame / cds_get_map (the decoder hook's calls) and a frame-range shard with halo give the same bytes."""
+    w, h, fps, F = 416, 240, 30.0, 48
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 11, F)
+    ref = cds.SaliencyClip(w, h, fps, fast=True, out_u8=True, max_batch=16)
+    want, wcam = ref.process(0, hdr, tok, base, byts)
+    hook = cds.SaliencyClip(w, h, fps, fast=True, out_u8=True, max_batch=4)
+    for f in range(10):
+        hook.submit_frame(f, byts[f], hdr[f], tok[base[f]:base[f + 1]])
+    hook.flush()
+    m, cam = hook.get_map(9)
+    assert np.array_equal(m, want[9]) and np.array_equal(cam, wcam[9])
+    hook.close()
+    first = 40
+    halo = ref.PS + ref.PT - 2
+    shard = cds.SaliencyClip(w, h, fps, fast=True, out_u8=True, max_batch=16)
+    shard.seek(first - halo)
+    sl = slice(first - halo, first)
+    shard.context(first - halo, hdr[sl], tok[base[first - halo]:base[first]], base[first - halo:first + 1] - base[first - halo], byts[sl])
+    sl = slice(first, F)
+    got, cam = shard.process(first, hdr[sl], tok[base[first]:base[F]], base[first:F + 1] - base[first], byts[sl])
+    assert np.array_equal(got, want[first:]) and np.array_equal(cam, wcam[first:])
+    ref.close(); shard.close()
+
+
+def test_fast_version_rejects_unsupported_sizes(cds):
+    with pytest.raises(cds.CdsError):
+        cds.SaliencyClip(424, 240, 30.0, fast=True)          # width not a multiple of 16
