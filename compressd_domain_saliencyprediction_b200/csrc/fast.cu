@@ -31,7 +31,12 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double PI_REF = 3.1415926;   // TDecGop.cpp:59
 
+// per-phase cycle counts of block (0,0) of the latency-bound kernels (read with cds_debug_copy "fast_prof"); development aid
+__device__ long long g_fast_prof[32];
+#define FPROF(slot) do { if (blockIdx.x == P.prof_x && blockIdx.y == 0 && threadIdx.x == 0) { const long long _t = clock64(); g_fast_prof[slot] = _t - t_prof; t_prof = _t; } } while (0)
+
 struct FastP {
+  int prof_x;
   int w, h, h4, w4, n4, lw, lh, nctu, gw32, gh32, g32, B, PS, PT, RL;
   int ksize, half, hq, nq_h, nq_v;
   int16_t *r_mvx, *r_mvy; uint8_t* r_dep; uint16_t* r_bytes; float* r_sc; int* r_cam;
@@ -239,6 +244,7 @@ fast_camera_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, cons
   __shared__ __align__(16) float s_list[2][144];
   __shared__ int s_best, s_len; __shared__ float s_mean[2], s_v[2];
 
+  long long t_prof = clock64();
   // bytes: min / max; depth: max; copy this picture into the raw ring
   int mn = 65535, mxb = 0, mxd = 0;
   for (int i = tid; i < P.nctu; i += CAM_T) { const int v = by[i]; mn = min(mn, v); mxb = max(mxb, v); rb[i] = (uint16_t)v; }
@@ -264,6 +270,7 @@ fast_camera_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, cons
   back = block_reduce(back, OpAddI(), s_i); stat = block_reduce(stat, OpAddI(), s_i);
   const bool moving = stat <= back / 2;
   float vx = 0.f, vy = 0.f;
+  FPROF(0);
   if (moving) {
     // 16-bin direction histogram of the background cells (vote_alg :580-592)
     int mycount = 0;
@@ -280,6 +287,7 @@ fast_camera_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, cons
     }
     if (lane < 16) s_hist[wid][lane] = mycount;
     __syncthreads();
+    FPROF(1);
     if (tid == 0) {
       int best = 0, bc = -1;
       for (int j = 0; j < 16; j++) { int c = 0; for (int w = 0; w < CAM_T / 32; w++) c += s_hist[w][j]; if (c > bc) { bc = c; best = j; } }   // :600 first maximum
@@ -303,6 +311,7 @@ fast_camera_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, cons
     }
     __syncthreads();
     vx = s_v[0]; vy = s_v[1];
+    FPROF(2);
   }
   const float nx = moving ? -vx : -0.0f, ny = moving ? -vy : -0.0f;
   // m_norm (CalDist :552) of the compensated field: its maximum feeds MatrixNorm (TDecGop.cpp:294)
@@ -312,6 +321,7 @@ fast_camera_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, cons
     mxn = fmaxf(mxn, __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));
   }
   mxn = block_reduce(mxn, OpMaxF(), s_f);
+  FPROF(3);
   if (tid == 0) {
     float* sc = P.r_sc + (size_t)slot * 8;
     sc[0] = nx; sc[1] = ny;
@@ -375,6 +385,7 @@ __global__ void __launch_bounds__(256) fast_thr_kernel(FastP P) {
   const float* bs = P.d_smbit + (size_t)b * P.nctu;
   const float* v = P.d_sm + ((size_t)b * 4 + (map > 0 ? map - 1 : 0)) * n4;
   float mx = -INFINITY; double sum = 0.0;
+  long long t_prof = clock64();
   if (map == 0) {
     for (int i = tid; i < P.nctu; i += 256) {
       const float x = bs[i];
@@ -394,13 +405,16 @@ __global__ void __launch_bounds__(256) fast_thr_kernel(FastP P) {
   const double t = (double)mx - mean;
   int mode = !(t == 0.0 || t >= (double)mx);
   float tp = 0.f;
+  FPROF(8);
   if (mode && tid < 32) {
     int count = 0;
     const float S = map == 0 ? warp_select_sum_runs(bs, P.lh, P.lw, P.h4, P.w4, 16, t, s_rv, s_rn, &count)
                              : warp_select_sum(v, n4, t, s_list, &count);
     tp = __fdiv_rn(S, (float)count);
     if (tp == 0.f) mode = 0;
+    if (blockIdx.x == P.prof_x && blockIdx.y == 0 && tid == 0) g_fast_prof[10] = count;
   }
+  FPROF(9);
   if (tid == 0) {
     float* o = P.d_thr + ((size_t)b * 5 + map) * 4;
     const float mt = thr_apply(mx, tp, mode);
@@ -735,6 +749,7 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
   p.lw = (w + 63) / 64; p.lh = (h + 63) / 64; p.nctu = p.lw * p.lh;
   p.gw32 = (w + 31) / 32; p.gh32 = (h + 31) / 32; p.g32 = p.gw32 * p.gh32;
   p.B = B;
+  { const char* e = getenv("CDS_FAST_PROF"); p.prof_x = e ? atoi(e) : -1; }
   p.PS = std::max(1, cv_round_host(fps * 0.3)); p.PT = std::max(1, cv_round_host(fps * 0.7));     // salmat.cpp:18-19
   p.RL = B + p.PS + p.PT;
   p.ksize = cv_round_host((double)(h / 15)); if (p.ksize % 2 == 0) p.ksize++;                    // TDecGop.cpp:320-322
@@ -855,6 +870,12 @@ int fast_debug_copy(FastState* s, const char* which, int f, void* dst, size_t by
   else if (wname == "fast_tval") { src = p.d_tval + (size_t)f * 3 * p.g32; have = (size_t)3 * p.g32 * 4; }
   else if (wname == "fast_sval") { src = p.d_sval + (size_t)f * 3 * p.g32; have = (size_t)3 * p.g32 * 4; }
   else if (wname == "fast_comb") { src = p.d_comb + (size_t)f * p.n4; have = (size_t)p.n4 * 4; }
+  else if (wname == "fast_prof") {
+    if (bytes > sizeof(long long) * 32) { set_error("fast_debug_copy: fast_prof is 256 bytes"); return CDS_EINVAL; }
+    CDS_CUDA(cudaStreamSynchronize(st));
+    CDS_CUDA(cudaMemcpyFromSymbol(dst, g_fast_prof, bytes));
+    return CDS_OK;
+  }
   else if (wname == "fast_blur") { src = p.d_blur + (size_t)f * p.h * p.w; have = (size_t)p.h * p.w * 4; }
   else { set_error("fast_debug_copy: unknown '%s'", which); return CDS_EINVAL; }
   if (bytes > have) { set_error("fast_debug_copy: %zu > %zu bytes", bytes, have); return CDS_EINVAL; }

@@ -18,7 +18,9 @@
  *   CDS_SVM_MODEL  libsvm text model with 9 features            (default: none -> linear fusion, main.m:258-272)
  *   CDS_MEAN, CDS_STD  nine comma-separated values (meanVec / stdVec of svmRBFmodel_all.mat; default 0 / 1)
  *   CDS_BATCH      pictures per GPU batch                       (default 32)
- *   CDS_U8         1: 8-bit maps like the reference's imwrite (TDecGop.cpp:327-332), 0: FP32 (default 0)
+ *   CDS_U8         1: 8-bit maps like the reference's imwrite (TDecGop.cpp:327-332), 0: FP32 (default 0; 1 with CDS_MODE=fast)
+ *   CDS_MODE       "fast": the fast version's arithmetic, i.e. what this decoder's removed OpenCV block computed
+ *                  (TDecGop.cpp:225-333 + salmat.cpp); no SVM model needed; the 8-bit maps equal its ../HMdata/<POC>.png
  */
 #ifndef CDS_HM_HOOK_H
 #define CDS_HM_HOOK_H
@@ -100,8 +102,10 @@ class CdsHmHook {
       if (load_(getenv("CDS_SVM_MODEL"), &model_) != CDS_OK) { fail("cds_svm_model_load"); return false; }
       p.use_rbf = 1; p.model = model_;
     }
+    const bool fast = getenv("CDS_MODE") && !strcmp(getenv("CDS_MODE"), "fast");
+    if (fast) p.use_rbf = CDS_FUSION_FAST;     // the arithmetic this decoder's own OpenCV block had (TDecGop.cpp:225-333, salmat.cpp)
     batch_ = getenv("CDS_BATCH") ? atoi(getenv("CDS_BATCH")) : 32;
-    p.max_batch = batch_; p.out_u8 = getenv("CDS_U8") ? atoi(getenv("CDS_U8")) : 0;
+    p.max_batch = batch_; p.out_u8 = getenv("CDS_U8") ? atoi(getenv("CDS_U8")) : (fast ? 1 : 0);
     if (create_(&p, &ctx_) != CDS_OK) { fail("cds_create"); ctx_ = NULL; return false; }
     px_ = (size_t)w * h * (p.out_u8 ? 1 : 4);
     map_.resize(px_);
