@@ -42,7 +42,7 @@ struct FastP {
   int16_t *r_mvx, *r_mvy; uint8_t* r_dep; uint16_t* r_bytes; float* r_sc; int* r_cam;
   float *r_t64, *r_t32;
   uint8_t* d_bin; float *d_sm, *d_smbit, *d_thr, *d_tacc, *d_tval, *d_sval, *d_sraw, *d_comb, *d_hrow, *d_blur;
-  unsigned* d_mm;
+  unsigned* d_mm; int* d_cami;
   float *d_kh, *d_kv, *d_wt, *d_wm;
 };
 
@@ -102,91 +102,131 @@ __device__ float seq_add_run(float S, float v, int n) {
   return S;
 }
 
-// lane 0 adds the `total` floats of list (zero padded to a multiple of 16) to S in order
-__device__ __forceinline__ float lane0_add_list(float S, const float* list, int total) {
-  const float4* l4 = reinterpret_cast<const float4*>(list);
-  for (int i = 0; i < total; i += 16) {
-    const float4 a = l4[i >> 2], b = l4[(i >> 2) + 1], c = l4[(i >> 2) + 2], d = l4[(i >> 2) + 3];
-    S = __fadd_rn(S, a.x); S = __fadd_rn(S, a.y); S = __fadd_rn(S, a.z); S = __fadd_rn(S, a.w);
-    S = __fadd_rn(S, b.x); S = __fadd_rn(S, b.y); S = __fadd_rn(S, b.z); S = __fadd_rn(S, b.w);
-    S = __fadd_rn(S, c.x); S = __fadd_rn(S, c.y); S = __fadd_rn(S, c.z); S = __fadd_rn(S, c.w);
-    S = __fadd_rn(S, d.x); S = __fadd_rn(S, d.y); S = __fadd_rn(S, d.z); S = __fadd_rn(S, d.w);
-  }
-  return S;
+// ---- exact emulation of a sequential float sum S = S + t_i (raster order) without walking it one term at a time ------------
+// Inside one binade of S every addition moves S by a whole number of ulps that does not depend on S: fl(S + v) = S + rn_u(v),
+// rn_u = round to the binade's grid u (ties excepted: they depend on the parity of S).  A piece of the sequence can therefore be
+// applied as an INTEGER sum of increments, in any order, provided (a) no term is a tie on this grid, (b) every partial sum stays
+// inside the binade (bounded by the sums of the positive and of the negative increments), (c) every |v| < 2^(e-1), so that the
+// probe below is valid.  Pieces that fail are added one float at a time by one thread — that is where S crosses into the next
+// binade — and the rest is re-evaluated on the new grid.  The result is bit-identical to the sequential loop.
+
+// increment (in ulps of binade eb) of one term; probe C = 1.5 * 2^e has an even mantissa, C + ulp an odd one: they disagree on ties
+__device__ __forceinline__ bool term_increment(float v, unsigned Cb, float lim, int* q) {
+  if (!(fabsf(v) < lim)) return false;
+  const int q0 = (int)(__float_as_uint(__fadd_rn(__uint_as_float(Cb), v)) - Cb);
+  const int q1 = (int)(__float_as_uint(__fadd_rn(__uint_as_float(Cb + 1u), v)) - (Cb + 1u));
+  *q = q0;
+  return q0 == q1;
 }
 
-// One warp: compacts up to 4 selected terms per lane (in lane order = raster order) into list, lane 0 adds them.
-__device__ __forceinline__ float warp_ordered_add(float S, unsigned sel, float t0, float t1, float t2, float t3, float* list, int* count) {
-  const int lane = threadIdx.x & 31;
-  const int nsel = __popc(sel);
-  int inc = nsel;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
-  const int total = __shfl_sync(FULL, inc, 31);
-  if (total == 0) return S;
-  int p = inc - nsel;
-  if (sel & 1) list[p++] = t0;
-  if (sel & 2) list[p++] = t1;
-  if (sel & 4) list[p++] = t2;
-  if (sel & 8) list[p++] = t3;
-  const int padded = (total + 15) & ~15;
-  for (int i = total + lane; i < padded; i += 32) list[i] = 0.f;    // S + 0 == S
-  __syncwarp();
-  if (lane == 0) S = lane0_add_list(S, list, total);
-  __syncwarp();
-  *count += total;
-  return S;
-}
+template <int T>
+struct SeqSumSmem {
+  float terms[T * 4];
+  unsigned char sel[T];
+  int wqp[T / 32], wqn[T / 32], wflag[T / 32];
+  float S; int restart;
+};
 
-// Umean's loops (TDecGop.cpp:622-640) over the members of the winning direction bin, raster order.  a = m * 0.25f.
-// clamp = 0: sum of a;  clamp = 1: sum of ((flag && a < mean) || (!flag && a > mean)) ? a : mean.
-__device__ float warp_member_sum(const uint8_t* __restrict__ bin, int best, const int16_t* __restrict__ m, int n4, int clamp,
-                                 float mean, float* list) {
-  const int lane = threadIdx.x & 31;
-  const bool flag = mean > 0.f;
-  float S = 0.f; int cnt = 0;
-  for (int base = 0; base < n4; base += 128) {
-    const int k = base + lane * 4;
-    unsigned sel = 0; float t[4] = {0.f, 0.f, 0.f, 0.f};
-    if (k < n4) {
-      const uchar4 bb = *reinterpret_cast<const uchar4*>(bin + k);
-      const short4 mm = *reinterpret_cast<const short4*>(m + k);
-      const unsigned char bs[4] = {bb.x, bb.y, bb.z, bb.w};
-      const short ms[4] = {mm.x, mm.y, mm.z, mm.w};
+// The whole CTA (T threads) sums ngroups groups of 4 consecutive cells; load(g) fetches the raw words of group g, eval(raw, t)
+// returns its selection bits and four terms.  Returns the sum to every thread; *count_out = number of selected terms.
+template <int T, typename LoadFn, typename EvalFn>
+__device__ float block_seq_sum(int ngroups, LoadFn load, EvalFn eval, SeqSumSmem<T>& sm, int* count_out) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = T / 32;
+  int cnt = 0;
+  __syncthreads();
+  if (tid == 0) sm.S = 0.f;
+  auto raw_n = load(min(tid, ngroups - 1));              // raw words of the next chunk stay in registers until they are needed
+  for (int g0 = 0; g0 < ngroups; g0 += T) {
+    float tn[4];
+    const unsigned sel = g0 + tid < ngroups ? eval(raw_n, tn) : 0u;
+    const float t0 = tn[0], t1 = tn[1], t2 = tn[2], t3 = tn[3];
+    raw_n = load(min(g0 + T + tid, ngroups - 1));        // prefetch
+    cnt += __popc(sel);
+    __syncthreads();                                   // the previous chunk's reads of sm.terms are over
+    *reinterpret_cast<float4*>(&sm.terms[tid * 4]) = make_float4(t0, t1, t2, t3);
+    sm.sel[tid] = (unsigned char)sel;
+    int first = 0;
+    while (true) {
+      __syncthreads();
+      const unsigned Sb = __float_as_uint(sm.S);
+      const unsigned eb = (Sb >> 23) & 0xffu; const bool neg = (Sb >> 31) != 0u;
+      const bool bad = eb < 2u || eb >= 0xfeu;
+      const unsigned Cb = (eb << 23) | 0x400000u;
+      const float lim = __uint_as_float((eb - 1u) << 23);
+      int qp = 0, qn = 0, flag = bad ? 1 : 0;
+      if (wid >= first && !bad) {
+        const float tt[4] = {t0, t1, t2, t3};
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (bs[j] == best) {
-          const float a = __fmul_rn((float)ms[j], 0.25f);
-          t[j] = clamp ? (((flag && a < mean) || (!flag && a > mean)) ? a : mean) : a;
-          sel |= 1u << j;
+        for (int j = 0; j < 4; j++)
+          if ((sel >> j) & 1u) {
+            int q;
+            if (!term_increment(neg ? -tt[j] : tt[j], Cb, lim, &q)) flag = 1;
+            else if (q > 0) qp += q; else qn -= q;
+          }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { qp += __shfl_xor_sync(FULL, qp, o); qn += __shfl_xor_sync(FULL, qn, o); flag |= __shfl_xor_sync(FULL, flag, o); }
+      const unsigned anysel = __ballot_sync(FULL, sel != 0u);
+      if (lane == 0) { sm.wqp[wid] = qp; sm.wqn[wid] = qn; sm.wflag[wid] = anysel ? flag : -1; }      // -1: nothing selected in this piece
+      __syncthreads();
+      if (tid == 0) {
+        float S = sm.S; int restart = NW;
+        // the whole chunk at once when it is valid as one piece
+        unsigned tp = 0, tq = 0; int tf = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) if (w >= first && sm.wflag[w] >= 0) { tp += (unsigned)sm.wqp[w]; tq += (unsigned)sm.wqn[w]; tf |= sm.wflag[w]; }
+        {
+          const unsigned sb = __float_as_uint(S), ab = sb & 0x7fffffffu;
+          const unsigned m = (ab & 0x7fffffu) | 0x800000u;
+          if (!tf && m + tp <= 0xffffffu && (tq == 0u || m >= 0x800001u + tq)) {
+            S = __uint_as_float((sb & 0x80000000u) | (ab + tp - tq));
+            first = NW;
+          }
         }
+        for (int w = first; w < NW; w++) {
+          if (sm.wflag[w] < 0) continue;
+          const unsigned sb = __float_as_uint(S), ab = sb & 0x7fffffffu;
+          const unsigned m = (ab & 0x7fffffu) | 0x800000u;
+          const unsigned wp = (unsigned)sm.wqp[w], wn = (unsigned)sm.wqn[w];
+          if (!sm.wflag[w] && m + wp <= 0xffffffu && (wn == 0u || m >= 0x800001u + wn)) {
+            S = __uint_as_float((sb & 0x80000000u) | (ab + wp - wn));
+          } else {
+            for (int i = w * 32; i < w * 32 + 32; i++) {
+              const unsigned sl = sm.sel[i];
+              if (sl & 1u) S = __fadd_rn(S, sm.terms[i * 4]);
+              if (sl & 2u) S = __fadd_rn(S, sm.terms[i * 4 + 1]);
+              if (sl & 4u) S = __fadd_rn(S, sm.terms[i * 4 + 2]);
+              if (sl & 8u) S = __fadd_rn(S, sm.terms[i * 4 + 3]);
+            }
+            const unsigned nb = __float_as_uint(S);
+            if (((nb >> 23) & 0xffu) != eb || (nb >> 31) != (Sb >> 31)) { restart = w + 1; break; }
+          }
+        }
+        sm.S = S; sm.restart = restart;
+      }
+      __syncthreads();
+      first = sm.restart;
+      if (first >= NW) break;
     }
-    S = warp_ordered_add(S, sel, t[0], t[1], t[2], t[3], list, &cnt);
   }
-  return __shfl_sync(FULL, S, 0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+  __syncthreads();
+  if (lane == 0) sm.wqp[wid] = cnt;
+  __syncthreads();
+  int total = 0;
+  for (int w = 0; w < NW; w++) total += sm.wqp[w];
+  *count_out = total;
+  return sm.S;
 }
 
-// MapThreshold's first loop (salmat.cpp:155-162) on a dense float map: sum (float, raster order) and count of v > t
-__device__ float warp_select_sum(const float* __restrict__ v, int n, double t, float* list, int* count) {
-  const int lane = threadIdx.x & 31;
-  float S = 0.f; int cnt = 0;
-  for (int base = 0; base < n; base += 128) {
-    const int k = base + lane * 4;
-    unsigned sel = 0; float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k < n) {
-      q = *reinterpret_cast<const float4*>(v + k);
-      sel = ((double)q.x > t ? 1u : 0u) | ((double)q.y > t ? 2u : 0u) | ((double)q.z > t ? 4u : 0u) | ((double)q.w > t ? 8u : 0u);
-    }
-    S = warp_ordered_add(S, sel, q.x, q.y, q.z, q.w, list, &cnt);
-  }
-  *count = __shfl_sync(FULL, cnt, 0);
-  return __shfl_sync(FULL, S, 0);
-}
-
-// The same loop on a map of replicated blocks: block (i, j) of a gh x gw grid covers min(ms, rows - ms*i) x min(ms, cols - ms*j)
-// elements of a rows x cols raster.  Lanes pick the selected blocks of a block row, lane 0 walks the element rows.
+// MapThreshold's first loop (salmat.cpp:155-162) on a map of replicated blocks: block (i, j) of a gh x gw grid covers
+// min(ms, rows - ms*i) x min(ms, cols - ms*j) elements of a rows x cols raster, so an element row of block row i is a sequence of
+// runs "add v_e n_e times".  One warp: inside a binade a whole element row adds Q = sum n_e * q_e ulps, and k rows add k * Q; the run
+// in which S leaves the binade (found with a prefix scan), ties and terms too large for the probe go through seq_add_run.
 __device__ float warp_select_sum_runs(const float* vals, int gh, int gw, int rows, int cols, int ms, double t, float* rv, int* rn,
-                                      int* count) {
+                                      int* rq, int* count) {
   const int lane = threadIdx.x & 31;
   float S = 0.f; int cnt = 0;
   for (int i = 0; i < gh; i++) {
@@ -200,130 +240,212 @@ __device__ float warp_select_sum_runs(const float* vals, int gh, int gw, int row
       L += __popc(bal);
     }
     __syncwarp();
-    if (L > 0 && lane == 0) {
-      const int nr = min(ms, rows - ms * i);
-      int per_row = 0;
-      for (int e = 0; e < L; e++) per_row += rn[e];
-      for (int y = 0; y < nr; y++)
-        for (int e = 0; e < L; e++) S = seq_add_run(S, rv[e], rn[e]);
-      cnt += nr * per_row;
+    if (L == 0) continue;
+    const int nr = min(ms, rows - ms * i);
+    int per_row = 0;
+    for (int e = lane; e < L; e += 32) per_row += rn[e];
+    per_row = warp_sum(per_row);
+    cnt += nr * per_row;
+    int rows_left = nr, pos = 0;
+    while (rows_left > 0) {
+      const unsigned Sb = __float_as_uint(S), eb = (Sb >> 23) & 0xffu;
+      const bool bad = eb < 2u || eb >= 0xfeu;
+      const unsigned Cb = (eb << 23) | 0x400000u;
+      const float lim = __uint_as_float((eb - 1u) << 23);
+      const unsigned m = (Sb & 0x7fffffu) | 0x800000u;
+      int qsum = 0, anyflag = bad ? 1 : 0;
+      for (int e = lane; e < L; e += 32) {
+        int q = 0;
+        const bool ok = !bad && term_increment(rv[e], Cb, lim, &q);
+        const int qr = q > 0x1000000 / rn[e] ? 0x1000000 : q * rn[e];      // >= 2^24 ulps leaves the binade whatever S is
+        rq[e] = ok ? qr : -1;
+        if (ok) qsum += qr; else anyflag = 1;
+      }
+      __syncwarp();
+      qsum = warp_sum(qsum); anyflag = __any_sync(FULL, anyflag);           // at most 128 runs x 2^24: fits
+      if (pos == 0 && !anyflag) {
+        if (qsum == 0) break;                                   // every remaining addition leaves S unchanged
+        const unsigned k = min((unsigned)rows_left, (0xffffffu - m) / (unsigned)qsum);
+        S = __uint_as_float(Sb + k * (unsigned)qsum);
+        rows_left -= (int)k;
+        if (rows_left == 0) break;
+        if (k > 0) continue;                                    // S moved: recompute the bounds before walking the crossing row
+      }
+      // walk the current element row from run `pos`: everything before the first run that is flagged or leaves the binade is applied at once
+      unsigned running = 0; int found = -1; unsigned before = 0;
+      for (int e0 = 0; e0 < L && found < 0; e0 += 32) {
+        const int e = e0 + lane;
+        const bool act = e >= pos && e < L;
+        const int rqe = act ? rq[e] : 0;
+        unsigned pref = rqe > 0 ? (unsigned)rqe : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, pref, o); if (lane >= o) pref += u; }
+        const bool cross = act && (rqe < 0 || m + running + pref > 0xffffffu);
+        const unsigned bal = __ballot_sync(FULL, cross);
+        if (bal) {
+          const int l = __ffs(bal) - 1;
+          found = e0 + l;
+          const unsigned incl = __shfl_sync(FULL, pref, l);
+          const int own = __shfl_sync(FULL, rqe, l);
+          before = running + incl - (own > 0 ? (unsigned)own : 0u);
+        } else running += __shfl_sync(FULL, pref, 31);
+      }
+      if (found < 0) { S = __uint_as_float(__float_as_uint(S) + running); pos = 0; rows_left--; continue; }
+      S = __uint_as_float(__float_as_uint(S) + before);
+      S = seq_add_run(S, rv[found], rn[found]);
+      pos = found + 1;
+      if (pos == L) { pos = 0; rows_left--; }
     }
     __syncwarp();
   }
-  *count = __shfl_sync(FULL, cnt, 0);
-  return __shfl_sync(FULL, S, 0);
+  *count = cnt;
+  return S;
 }
 
 // ------------------------------------------------------------------------------------------------ K1: CameraDect + vote_alg + Umean
-constexpr int CAM_T = 512;
-
 __device__ __forceinline__ int direction_bin(float y, float x) {          // TDecGop.cpp:584-587
   // index = ((atan2f(y, x) / PI) + 1) * 8.0 truncated; only values next to a bin edge need the exactly rounded float atan2
-  const float af = atan2f(y, x);
-  double tt = ((double)af / PI_REF + 1.0) * 8.0;
-  if (fabs(tt - rint(tt)) < 1e-3) {
-    const float a = __double2float_rn(atan2((double)y, (double)x));
-    tt = ((double)a / PI_REF + 1.0) * 8.0;
-  }
-  int idx = (int)tt;
+  const float tf = (atan2f(y, x) * 0.318309886f + 1.0f) * 8.0f;
+  if (fabsf(tf - rintf(tf)) >= 1e-3f) return (int)tf;
+  const float a = __double2float_rn(atan2((double)y, (double)x));
+  const int idx = (int)(((double)a / PI_REF + 1.0) * 8.0);
   return idx == 16 ? 15 : idx;
 }
 
-__global__ void __launch_bounds__(CAM_T)
-fast_camera_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, const int16_t* __restrict__ mvy,
-                   const uint8_t* __restrict__ dep, const uint16_t* __restrict__ bytes, int* __restrict__ cam_out) {
-  const int b = blockIdx.x, F = first_poc + b, slot = F % P.RL, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+// K1a, grid (chunks of 1024 cells, pictures): copy the picture into the raw ring, background mask, BackNum / StaticNum
+// (TDecGop.cpp:509-519), direction bin of every background cell (vote_alg :580-592) and the 16-bin histogram.
+// d_cami[b]: {BackNum, StaticNum, hist[16], max depth}
+__global__ void __launch_bounds__(256)
+fast_cam_scan_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, const int16_t* __restrict__ mvy,
+                     const uint8_t* __restrict__ dep, const uint16_t* __restrict__ bytes) {
+  const int b = blockIdx.y, F = first_poc + b, slot = F % P.RL, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n4 = P.n4, w4 = P.w4, lw = P.lw;
-  const int16_t* mx = mvx + (size_t)b * n4; const int16_t* my = mvy + (size_t)b * n4;
-  const uint8_t* dp = dep + (size_t)b * n4; const uint16_t* by = bytes + (size_t)b * P.nctu;
-  int16_t* rx = P.r_mvx + (size_t)slot * n4; int16_t* ry = P.r_mvy + (size_t)slot * n4;
-  uint8_t* rd = P.r_dep + (size_t)slot * n4; uint16_t* rb = P.r_bytes + (size_t)slot * P.nctu;
-  uint8_t* bin = P.d_bin + (size_t)b * n4;
-  __shared__ int s_i[32]; __shared__ float s_f[32]; __shared__ long long s_l[32];
-  __shared__ int s_hist[CAM_T / 32][16];
-  __shared__ __align__(16) float s_list[2][144];
-  __shared__ int s_best, s_len; __shared__ float s_mean[2], s_v[2];
-
-  long long t_prof = clock64();
-  // bytes: min / max; depth: max; copy this picture into the raw ring
-  int mn = 65535, mxb = 0, mxd = 0;
-  for (int i = tid; i < P.nctu; i += CAM_T) { const int v = by[i]; mn = min(mn, v); mxb = max(mxb, v); rb[i] = (uint16_t)v; }
-  for (int i = tid; i < n4 / 4; i += CAM_T) {
-    reinterpret_cast<int2*>(rx)[i] = reinterpret_cast<const int2*>(mx)[i];
-    reinterpret_cast<int2*>(ry)[i] = reinterpret_cast<const int2*>(my)[i];
-    const uchar4 d = reinterpret_cast<const uchar4*>(dp)[i];
-    reinterpret_cast<uchar4*>(rd)[i] = d;
-    mxd = max(mxd, max(max((int)d.x, (int)d.y), max((int)d.z, (int)d.w)));
+  const uint16_t* by = bytes + (size_t)b * P.nctu;
+  __shared__ int s_i[32]; __shared__ int s_hist[8][16];
+  int mn = 65535;
+  for (int i = tid; i < P.nctu; i += 256) mn = min(mn, (int)by[i]);
+  mn = block_reduce(mn, OpMinI(), s_i);
+  if (blockIdx.x == 0) {
+    uint16_t* rb = P.r_bytes + (size_t)slot * P.nctu;
+    for (int i = tid; i < P.nctu; i += 256) rb[i] = by[i];
   }
-  mn = block_reduce(mn, OpMinI(), s_i); mxb = block_reduce(mxb, OpMaxI(), s_i); mxd = block_reduce(mxd, OpMaxI(), s_i);
-
-  // background mask, BackNum, StaticNum (TDecGop.cpp:509-519): mvx^2 + mvy^2 <= 2 in pixels == <= 32 in quarter-pel units
-  int back = 0, stat = 0;
-  for (int k = tid; k < n4; k += CAM_T) {
-    const int r = k / w4, c = k - r * w4;
+  const int k = (blockIdx.x * 256 + tid) * 4;
+  int back = 0, stat = 0, mxd = 0; int bi[4] = {255, 255, 255, 255};
+  if (k < n4) {
+    const size_t o = (size_t)b * n4 + k, ro = (size_t)slot * n4 + k;
+    const short4 mx = *reinterpret_cast<const short4*>(mvx + o), my = *reinterpret_cast<const short4*>(mvy + o);
+    const uchar4 d = *reinterpret_cast<const uchar4*>(dep + o);
+    *reinterpret_cast<short4*>(P.r_mvx + ro) = mx; *reinterpret_cast<short4*>(P.r_mvy + ro) = my;
+    *reinterpret_cast<uchar4*>(P.r_dep + ro) = d;
+    mxd = max(max((int)d.x, (int)d.y), max((int)d.z, (int)d.w));
+    const int r = k / w4, c = k - r * w4;                   // the 4 cells share a row (w4 % 4 == 0) and a CTU column (c % 4 == 0)
     if ((int)by[(r >> 4) * lw + (c >> 4)] < mn + 20) {
-      back++;
-      const int x = mx[k], y = my[k];
-      if (x * x + y * y <= 32) stat++;
-    }
-  }
-  back = block_reduce(back, OpAddI(), s_i); stat = block_reduce(stat, OpAddI(), s_i);
-  const bool moving = stat <= back / 2;
-  float vx = 0.f, vy = 0.f;
-  FPROF(0);
-  if (moving) {
-    // 16-bin direction histogram of the background cells (vote_alg :580-592)
-    int mycount = 0;
-    for (int k0 = wid * 32; k0 < n4; k0 += CAM_T) {
-      const int k = k0 + lane;
-      int bi = 255;
-      if (k < n4) {
-        const int r = k / w4, c = k - r * w4;
-        if ((int)by[(r >> 4) * lw + (c >> 4)] < mn + 20) bi = direction_bin(__fmul_rn((float)my[k], 0.25f), __fmul_rn((float)mx[k], 0.25f));
-        bin[k] = (uint8_t)bi;
-      }
+      const short xs[4] = {mx.x, mx.y, mx.z, mx.w}, ys[4] = {my.x, my.y, my.z, my.w};
 #pragma unroll
-      for (int j = 0; j < 16; j++) { const unsigned m = __ballot_sync(FULL, bi == j); if (lane == j) mycount += __popc(m); }
+      for (int j = 0; j < 4; j++) {
+        back++;
+        if ((int)xs[j] * xs[j] + (int)ys[j] * ys[j] <= 32) stat++;       // mvx^2 + mvy^2 <= 2 pixels^2, in quarter-pel units
+        bi[j] = direction_bin(__fmul_rn((float)ys[j], 0.25f), __fmul_rn((float)xs[j], 0.25f));
+      }
     }
-    if (lane < 16) s_hist[wid][lane] = mycount;
-    __syncthreads();
-    FPROF(1);
-    if (tid == 0) {
-      int best = 0, bc = -1;
-      for (int j = 0; j < 16; j++) { int c = 0; for (int w = 0; w < CAM_T / 32; w++) c += s_hist[w][j]; if (c > bc) { bc = c; best = j; } }   // :600 first maximum
-      s_best = best; s_len = bc;
-    }
-    __syncthreads();
-    const int best = s_best, len = s_len;
+    *reinterpret_cast<uchar4*>(P.d_bin + o) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1], (unsigned char)bi[2], (unsigned char)bi[3]);
+  }
+  int mycount = 0;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const int c = __popc(__ballot_sync(FULL, bi[0] == j)) + __popc(__ballot_sync(FULL, bi[1] == j)) +
+                  __popc(__ballot_sync(FULL, bi[2] == j)) + __popc(__ballot_sync(FULL, bi[3] == j));
+    if (lane == j) mycount = c;
+  }
+  if (lane < 16) s_hist[wid][lane] = mycount;
+  back = block_reduce(back, OpAddI(), s_i); stat = block_reduce(stat, OpAddI(), s_i); mxd = block_reduce(mxd, OpMaxI(), s_i);
+  int* ci = P.d_cami + b * 24;
+  if (tid == 0) { if (back) atomicAdd(ci, back); if (stat) atomicAdd(ci + 1, stat); atomicMax(ci + 18, mxd); }
+  if (tid < 16) { int c = 0; for (int w = 0; w < 8; w++) c += s_hist[w][tid]; if (c) atomicAdd(ci + 2 + tid, c); }
+}
+
+// K1b, one CTA per picture: static / moving decision, winning bin (:600 first maximum), Umean of its members (exact sequential
+// float sums), compensation offsets, cvRound'ed camera motion, and the maximum of the compensated m_norm.
+constexpr int CAM_T = 512;
+
+__global__ void __launch_bounds__(CAM_T)
+fast_cam_vote_kernel(FastP P, int first_poc, int* __restrict__ cam_out) {
+  const int b = blockIdx.x, F = first_poc + b, slot = F % P.RL, tid = threadIdx.x;
+  const int n4 = P.n4;
+  const int16_t* mx = P.r_mvx + (size_t)slot * n4; const int16_t* my = P.r_mvy + (size_t)slot * n4;
+  const uint8_t* bin = P.d_bin + (size_t)b * n4;
+  const uint16_t* rb = P.r_bytes + (size_t)slot * P.nctu;
+  const int* ci = P.d_cami + b * 24;
+  __shared__ int s_i[32]; __shared__ float s_f[32]; __shared__ long long s_l[32];
+  __shared__ SeqSumSmem<CAM_T> s_seq;
+  long long t_prof = clock64();
+  const int back = ci[0], stat = ci[1];
+  const bool moving = stat <= back / 2;
+  int mxb = 0;
+  for (int i = tid; i < P.nctu; i += CAM_T) mxb = max(mxb, (int)rb[i]);
+  mxb = block_reduce(mxb, OpMaxI(), s_i);
+  float vx = 0.f, vy = 0.f;
+  if (moving) {
+    int best = 0, bc = -1;
+    for (int j = 0; j < 16; j++) if (ci[2 + j] > bc) { bc = ci[2 + j]; best = j; }
+    const int len = bc;
     // first loop of Umean: exact in float whenever every partial sum is (sum of |m| < 2^24 quarter-pels)
     long long sx = 0, sy = 0, ax = 0, ay = 0;
-    for (int k = tid; k < n4; k += CAM_T)
-      if (bin[k] == best) { const int x = mx[k], y = my[k]; sx += x; sy += y; ax += abs(x); ay += abs(y); }
+    for (int g = tid; g < n4 / 4; g += CAM_T) {
+      const uchar4 bb = reinterpret_cast<const uchar4*>(bin)[g];
+      if (bb.x == best || bb.y == best || bb.z == best || bb.w == best) {
+        const short4 x4 = reinterpret_cast<const short4*>(mx)[g], y4 = reinterpret_cast<const short4*>(my)[g];
+        if (bb.x == best) { sx += x4.x; sy += y4.x; ax += abs((int)x4.x); ay += abs((int)y4.x); }
+        if (bb.y == best) { sx += x4.y; sy += y4.y; ax += abs((int)x4.y); ay += abs((int)y4.y); }
+        if (bb.z == best) { sx += x4.z; sy += y4.z; ax += abs((int)x4.z); ay += abs((int)y4.z); }
+        if (bb.w == best) { sx += x4.w; sy += y4.w; ax += abs((int)x4.w); ay += abs((int)y4.w); }
+      }
+    }
     sx = block_reduce(sx, OpAddL(), s_l); sy = block_reduce(sy, OpAddL(), s_l);
     ax = block_reduce(ax, OpAddL(), s_l); ay = block_reduce(ay, OpAddL(), s_l);
-    if (wid < 2) {
-      const int16_t* m = wid == 0 ? mx : my;
-      const long long s = wid == 0 ? sx : sy, a = wid == 0 ? ax : ay;
-      float sum = (a < (1ll << 24)) ? __fmul_rn((float)s, 0.25f) : warp_member_sum(bin, best, m, n4, 0, 0.f, s_list[wid]);
-      const float mean = __fdiv_rn(sum, (float)len);
-      sum = warp_member_sum(bin, best, m, n4, 1, mean, s_list[wid]);
-      if (lane == 0) s_v[wid] = __fdiv_rn(sum, (float)len);
+    FPROF(0);
+    for (int comp = 0; comp < 2; comp++) {
+      const int16_t* m = comp == 0 ? mx : my;
+      const long long s = comp == 0 ? sx : sy, a = comp == 0 ? ax : ay;
+      int cnt;
+      struct Raw { uchar4 b; short4 m; };
+      auto load = [&](int g) -> Raw { return Raw{reinterpret_cast<const uchar4*>(bin)[g], reinterpret_cast<const short4*>(m)[g]}; };
+      auto plain = [&](const Raw& r, float* t) -> unsigned {
+        t[0] = __fmul_rn((float)r.m.x, 0.25f); t[1] = __fmul_rn((float)r.m.y, 0.25f); t[2] = __fmul_rn((float)r.m.z, 0.25f); t[3] = __fmul_rn((float)r.m.w, 0.25f);
+        return (r.b.x == best ? 1u : 0u) | (r.b.y == best ? 2u : 0u) | (r.b.z == best ? 4u : 0u) | (r.b.w == best ? 8u : 0u);
+      };
+      const float sum1 = (a < (1ll << 24)) ? __fmul_rn((float)s, 0.25f) : block_seq_sum<CAM_T>(n4 / 4, load, plain, s_seq, &cnt);
+      const float mean = __fdiv_rn(sum1, (float)len);
+      const bool flag = mean > 0.f;
+      auto clamped = [&](const Raw& r, float* t) -> unsigned {          // TDecGop.cpp:633-639
+        const unsigned sel = plain(r, t);
+#pragma unroll
+        for (int j = 0; j < 4; j++) t[j] = ((flag && t[j] < mean) || (!flag && t[j] > mean)) ? t[j] : mean;
+        return sel;
+      };
+      const float sum2 = block_seq_sum<CAM_T>(n4 / 4, load, clamped, s_seq, &cnt);
+      const float v = __fdiv_rn(sum2, (float)len);
+      if (comp == 0) vx = v; else vy = v;
     }
-    __syncthreads();
-    vx = s_v[0]; vy = s_v[1];
     FPROF(2);
   }
   const float nx = moving ? -vx : -0.0f, ny = moving ? -vy : -0.0f;
   // m_norm (CalDist :552) of the compensated field: its maximum feeds MatrixNorm (TDecGop.cpp:294)
   float mxn = 0.f;
-  for (int k = tid; k < n4; k += CAM_T) {
-    const float x = __fadd_rn(__fmul_rn((float)mx[k], 0.25f), nx), y = __fadd_rn(__fmul_rn((float)my[k], 0.25f), ny);
-    mxn = fmaxf(mxn, __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));
+  for (int g = tid; g < n4 / 4; g += CAM_T) {
+    const short4 x4 = reinterpret_cast<const short4*>(mx)[g], y4 = reinterpret_cast<const short4*>(my)[g];
+    const short xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float x = __fadd_rn(__fmul_rn((float)xs[j], 0.25f), nx), y = __fadd_rn(__fmul_rn((float)ys[j], 0.25f), ny);
+      mxn = fmaxf(mxn, __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));
+    }
   }
   mxn = block_reduce(mxn, OpMaxF(), s_f);
   FPROF(3);
   if (tid == 0) {
     float* sc = P.r_sc + (size_t)slot * 8;
+    const int mxd = ci[18];
     sc[0] = nx; sc[1] = ny;
     sc[2] = mxb > 0 ? rcp_scale((float)mxb) : 1.f;
     sc[3] = mxd > 0 ? rcp_scale((float)mxd) : 1.f;
@@ -335,43 +457,66 @@ fast_camera_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, cons
 }
 
 // ------------------------------------------------------------------------------------------------ K2: ForwardFilter (salmat.cpp:39-55)
-// tempmat = tempmat + SmoothFrame[i] / cnt for ring slots i = 0.. in SLOT order: fl(fl(x * (float)(1./cnt)) + acc)
-__global__ void __launch_bounds__(256) fast_smooth_kernel(FastP P, int first_poc) {
-  const int b = blockIdx.y, F = first_poc + b, k = blockIdx.x * 256 + threadIdx.x;
-  const int n4 = P.n4, PS = P.PS;
-  if (k >= n4 + P.nctu) return;
+// tempmat = tempmat + SmoothFrame[i] / cnt for ring slots i = 0.. in SLOT order: fl(fl(x * (float)(1./cnt)) + acc).
+// A CTA owns 128 cells x SM_G consecutive pictures: the raw values of the SM_G + PS - 1 ring pictures they read are converted
+// once (compensated mv, its norm, normalised depth) into shared memory, then each thread walks its picture's slots.
+constexpr int SM_G = 4;
+
+__global__ void __launch_bounds__(128 * SM_G) fast_smooth_kernel(FastP P, int first_poc, int n) {
+  extern __shared__ float4 s_raw[];                      // [SM_G + PS - 1][128] {depth, norm, x, y}
+  const int c = threadIdx.x, g = threadIdx.y, tid = g * 128 + c;
+  const int k = blockIdx.x * 128 + c, b0 = blockIdx.y * SM_G, F0 = first_poc + b0;
+  const int n4 = P.n4, PS = P.PS, nf = SM_G + PS - 1;
+  const int fbase = F0 - (PS - 1);                       // picture held by tile row 0
+  for (int i = tid; i < nf * 128; i += 128 * SM_G) {
+    const int fr = i >> 7, cc = i & 127, f = fbase + fr, kk = blockIdx.x * 128 + cc;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f >= 0 && kk < n4 && f < first_poc + n) {
+      const int slot = f % P.RL;
+      const float* sc = P.r_sc + (size_t)slot * 8;
+      const size_t o = (size_t)slot * n4 + kk;
+      const float x = __fadd_rn(__fmul_rn((float)P.r_mvx[o], 0.25f), sc[0]), y = __fadd_rn(__fmul_rn((float)P.r_mvy[o], 0.25f), sc[1]);
+      v.x = __fmul_rn((float)P.r_dep[o], sc[3]);
+      v.y = __fmul_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))), sc[4]);
+      v.z = x; v.w = y;
+    }
+    s_raw[i] = v;
+  }
+  __syncthreads();
+  const int b = b0 + g, F = F0 + g;
+  if (b >= n || k >= n4) return;
   const int cnt = F < PS ? F + 1 : PS;
   const float rc = __double2float_rn(__ddiv_rn(1.0, (double)cnt));
   float ad = 0.f, an = 0.f, ax = 0.f, ay = 0.f;
   for (int i = 0; i < cnt; i++) {
     const int f = F < PS ? i : F - ((F - i) % PS);        // the picture held by ring slot i
-    const int slot = f % P.RL;
-    const float* sc = P.r_sc + (size_t)slot * 8;
-    if (k < n4) {
-      const size_t o = (size_t)slot * n4 + k;
-      const float x = __fadd_rn(__fmul_rn((float)P.r_mvx[o], 0.25f), sc[0]), y = __fadd_rn(__fmul_rn((float)P.r_mvy[o], 0.25f), sc[1]);
-      const float nr = __fmul_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))), sc[4]);
-      const float d = __fmul_rn((float)P.r_dep[o], sc[3]);
-      ad = __fadd_rn(__fmul_rn(d, rc), ad); an = __fadd_rn(__fmul_rn(nr, rc), an);
-      ax = __fadd_rn(__fmul_rn(x, rc), ax); ay = __fadd_rn(__fmul_rn(y, rc), ay);
-    } else {
-      const float v = __fmul_rn((float)P.r_bytes[(size_t)slot * P.nctu + (k - n4)], sc[2]);
-      ad = __fadd_rn(__fmul_rn(v, rc), ad);
-    }
+    const float4 v = s_raw[(f - fbase) * 128 + c];
+    ad = __fadd_rn(__fmul_rn(v.x, rc), ad); an = __fadd_rn(__fmul_rn(v.y, rc), an);
+    ax = __fadd_rn(__fmul_rn(v.z, rc), ax); ay = __fadd_rn(__fmul_rn(v.w, rc), ay);
   }
-  const int ts = F % P.RL;
-  if (k < n4) {
-    float* sm = P.d_sm + (size_t)b * 4 * n4;
-    sm[k] = ad; sm[n4 + k] = an; sm[2 * (size_t)n4 + k] = ax; sm[3 * (size_t)n4 + k] = ay;
-    const int r = k / P.w4, c = k - r * P.w4;
-    if (!(r & 7) && !(c & 7)) {                           // MapDownSample by MinSize/4 = 8 (salmat.cpp:205)
-      float* t = P.r_t32 + (size_t)ts * 3 * P.g32 + (r >> 3) * P.gw32 + (c >> 3);
-      t[0] = ad; t[P.g32] = ax; t[2 * P.g32] = ay;
-    }
-  } else {
-    P.d_smbit[(size_t)b * P.nctu + (k - n4)] = ad;
-    P.r_t64[(size_t)ts * P.nctu + (k - n4)] = ad;
+  float* sm = P.d_sm + (size_t)b * 4 * n4;
+  sm[k] = ad; sm[n4 + k] = an; sm[2 * (size_t)n4 + k] = ax; sm[3 * (size_t)n4 + k] = ay;
+  const int r = k / P.w4, cc = k - r * P.w4;
+  if (!(r & 7) && !(cc & 7)) {                            // MapDownSample by MinSize/4 = 8 (salmat.cpp:205)
+    float* t = P.r_t32 + (size_t)(F % P.RL) * 3 * P.g32 + (r >> 3) * P.gw32 + (cc >> 3);
+    t[0] = ad; t[P.g32] = ax; t[2 * P.g32] = ay;
   }
+}
+
+// the bit map lives on the CTU grid (the x16 replication commutes with the elementwise filter)
+__global__ void __launch_bounds__(128) fast_smooth_bit_kernel(FastP P, int first_poc) {
+  const int b = blockIdx.y, F = first_poc + b, k = blockIdx.x * 128 + threadIdx.x;
+  if (k >= P.nctu) return;
+  const int PS = P.PS, cnt = F < PS ? F + 1 : PS;
+  const float rc = __double2float_rn(__ddiv_rn(1.0, (double)cnt));
+  float acc = 0.f;
+  for (int i = 0; i < cnt; i++) {
+    const int f = F < PS ? i : F - ((F - i) % PS), slot = f % P.RL;
+    const float v = __fmul_rn((float)P.r_bytes[(size_t)slot * P.nctu + k], P.r_sc[(size_t)slot * 8 + 2]);
+    acc = __fadd_rn(__fmul_rn(v, rc), acc);
+  }
+  P.d_smbit[(size_t)b * P.nctu + k] = acc;
+  P.r_t64[(size_t)(F % P.RL) * P.nctu + k] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ K3: MapThreshold parameters
@@ -381,7 +526,8 @@ __global__ void __launch_bounds__(256) fast_thr_kernel(FastP P) {
   const int map = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int n4 = P.n4;
   __shared__ double s_d[32]; __shared__ float s_f[32];
-  __shared__ __align__(16) float s_list[144]; __shared__ float s_rv[128]; __shared__ int s_rn[128];
+  __shared__ float s_rv[128]; __shared__ int s_rn[128], s_rq[128];
+  __shared__ SeqSumSmem<256> s_seq;
   const float* bs = P.d_smbit + (size_t)b * P.nctu;
   const float* v = P.d_sm + ((size_t)b * 4 + (map > 0 ? map - 1 : 0)) * n4;
   float mx = -INFINITY; double sum = 0.0;
@@ -394,10 +540,17 @@ __global__ void __launch_bounds__(256) fast_thr_kernel(FastP P) {
       mx = fmaxf(mx, x);
     }
   } else {
-    for (int i = tid; i < n4 / 4; i += 256) {
-      const float4 q = reinterpret_cast<const float4*>(v)[i];
-      sum += (double)sum4(q.x, q.y, q.z, q.w);
-      mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    for (int i0 = 0; i0 < n4 / 4; i0 += 1024) {                 // 4 independent loads in flight per thread
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int i = i0 + u * 256 + tid; q[u] = i < n4 / 4 ? v4[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (i0 + u * 256 + tid < n4 / 4) {
+          sum += (double)sum4(q[u].x, q[u].y, q[u].z, q[u].w);
+          mx = fmaxf(mx, fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w)));
+        }
     }
   }
   sum = block_reduce(sum, OpAddD(), s_d); mx = block_reduce(mx, OpMaxF(), s_f);
@@ -406,10 +559,18 @@ __global__ void __launch_bounds__(256) fast_thr_kernel(FastP P) {
   int mode = !(t == 0.0 || t >= (double)mx);
   float tp = 0.f;
   FPROF(8);
-  if (mode && tid < 32) {
-    int count = 0;
-    const float S = map == 0 ? warp_select_sum_runs(bs, P.lh, P.lw, P.h4, P.w4, 16, t, s_rv, s_rn, &count)
-                             : warp_select_sum(v, n4, t, s_list, &count);
+  if (mode) {
+    int count = 0; float S = 0.f;
+    if (map == 0) {
+      if (tid < 32) S = warp_select_sum_runs(bs, P.lh, P.lw, P.h4, P.w4, 16, t, s_rv, s_rn, s_rq, &count);
+    } else {
+      auto load = [&](int g) -> float4 { return reinterpret_cast<const float4*>(v)[g]; };
+      auto sel_gt = [&](const float4& q, float* tt) -> unsigned {
+        tt[0] = q.x; tt[1] = q.y; tt[2] = q.z; tt[3] = q.w;
+        return ((double)q.x > t ? 1u : 0u) | ((double)q.y > t ? 2u : 0u) | ((double)q.z > t ? 4u : 0u) | ((double)q.w > t ? 8u : 0u);
+      };
+      S = block_seq_sum<256>(n4 / 4, load, sel_gt, s_seq, &count);
+    }
     tp = __fdiv_rn(S, (float)count);
     if (tp == 0.f) mode = 0;
     if (blockIdx.x == P.prof_x && blockIdx.y == 0 && tid == 0) g_fast_prof[10] = count;
@@ -463,7 +624,7 @@ __global__ void __launch_bounds__(128) fast_tthr_kernel(FastP P) {
   const int map = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int gw = map == 0 ? P.lw : P.gw32, gh = map == 0 ? P.lh : P.gh32, ms = map == 0 ? 64 : 32, g = gw * gh;
   extern __shared__ float s_v1[];
-  __shared__ double s_d[32]; __shared__ float s_f[32]; __shared__ float s_rv[128]; __shared__ int s_rn[128];
+  __shared__ double s_d[32]; __shared__ float s_f[32]; __shared__ float s_rv[128]; __shared__ int s_rn[128], s_rq[128];
   const float* acc = P.d_tacc + ((size_t)b * 3 + map) * P.g32;
   float mxa = 0.f;
   for (int i = tid; i < g; i += 128) mxa = fmaxf(mxa, acc[i]);
@@ -484,7 +645,7 @@ __global__ void __launch_bounds__(128) fast_tthr_kernel(FastP P) {
   float tp = 0.f;
   if (mode && tid < 32) {
     int count = 0;
-    const float S = warp_select_sum_runs(s_v1, gh, gw, P.h, P.w, ms, t, s_rv, s_rn, &count);
+    const float S = warp_select_sum_runs(s_v1, gh, gw, P.h, P.w, ms, t, s_rv, s_rn, s_rq, &count);
     tp = __fdiv_rn(S, (float)count);
     if (tp == 0.f) mode = 0;
   }
@@ -496,8 +657,10 @@ __global__ void __launch_bounds__(128) fast_tthr_kernel(FastP P) {
 }
 
 // ------------------------------------------------------------------------------------------------ K7: GenerateSpatialMap (salmat.cpp:299-400)
-// job (kind, picture): kind 0 bit (5x5, delta 3, CTU grid), 1 depth (12x12, delta 13), 2 mv x and y (12x12, delta 11) + _mv2
-__global__ void __launch_bounds__(256) fast_spatial_kernel(FastP P) {
+// job (kind, picture): kind 0 bit (5x5, delta 3, CTU grid), 1 depth (12x12, delta 13), 2 / 3 mv x / y (12x12, delta 11)
+constexpr int SP_T = 512;
+
+__global__ void __launch_bounds__(SP_T) fast_spatial_kernel(FastP P) {
   const int kind = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int W = kind == 0 ? 5 : 12, len = W / 2, ms4 = kind == 0 ? 16 : 8;
   const int rn = kind == 0 ? P.lh : P.gh32, cn = kind == 0 ? P.lw : P.gw32, g = rn * cn;
@@ -506,80 +669,79 @@ __global__ void __launch_bounds__(256) fast_spatial_kernel(FastP P) {
   float* s_w = s_P + pr * pc;
   __shared__ float s_f[32];
   const float* wm = P.d_wm + (kind == 0 ? 0 : kind == 1 ? 25 : 25 + 144);
-  for (int i = tid; i < W * W; i += 256) s_w[i] = wm[i];
-  float* raw = P.d_sraw + ((size_t)b * 4 + (kind == 2 ? 2 : kind)) * P.g32;     // [b][bit | depth | mv x | mv y]
-  for (int comp = 0; comp < (kind == 2 ? 2 : 1); comp++) {
-    const int map = kind == 0 ? 0 : kind == 1 ? 1 : 3 + comp;
-    const float* th = P.d_thr + ((size_t)b * 5 + map) * 4;
-    const float tp = th[0]; const int mode = (int)th[1];
-    const float* cur = kind == 0 ? P.d_smbit + (size_t)b * P.nctu : P.d_sm + ((size_t)b * 4 + map - 1) * P.n4;
-    // S = down(thr(cur)); zero pad; MatrixNorm2 of the padded map
-    float mn = 0.f, mx = 0.f;                            // the zero border takes part in the min / max
-    __syncthreads();
-    for (int i = tid; i < pr * pc; i += 256) s_P[i] = 0.f;
-    __syncthreads();
-    for (int i = tid; i < g; i += 256) {
-      const int r = i / cn, c = i - r * cn;
-      const float v = thr_apply(kind == 0 ? cur[i] : cur[(size_t)(r * ms4) * P.w4 + c * ms4], tp, mode);
-      s_P[(r + len) * pc + c + len] = v;
-      mn = fminf(mn, v); mx = fmaxf(mx, v);
-    }
-    mn = block_reduce(mn, OpMinF(), s_f); mx = block_reduce(mx, OpMaxF(), s_f);
-    const float neg = -mn;                               // dst = src - min  ->  fl(src + (float)(-min))
-    const float mx2 = __fadd_rn(mx, neg);                // max of the shifted map (the shift is monotonic)
-    const float s = mx2 > 0.f ? rcp_scale(mx2) : 1.f;
-    for (int i = tid; i < pr * pc; i += 256) { const float x = __fadd_rn(s_P[i], neg); s_P[i] = mx2 > 0.f ? __fmul_rn(x, s) : x; }
-    __syncthreads();
-    // out(i,j) = sum(|window - centre| .* WeightMap): float products, cv::sum order (4 floats in float, groups in double)
-    float omax = 0.f;
-    for (int i = tid; i < g; i += 256) {
-      const int r = i / cn, c = i - r * cn;
-      const float ctr = s_P[(r + len) * pc + c + len];
-      double acc = 0.0; float grp = 0.f; int q = 0;
-      const int nfull = (W * W) & ~3;
-      for (int e = 0; e < W * W; e++) {
-        const int u = e / W, v = e - u * W;
-        const float p = __fmul_rn(fabsf(__fsub_rn(s_P[(r + u) * pc + c + v], ctr)), s_w[e]);
+  for (int i = tid; i < W * W; i += SP_T) s_w[i] = wm[i];
+  const int map = kind == 0 ? 0 : kind == 1 ? 1 : kind + 1;          // thr job of this map (mv x: 3, mv y: 4)
+  const float* th = P.d_thr + ((size_t)b * 5 + map) * 4;
+  const float tp = th[0]; const int mode = (int)th[1];
+  const float* cur = kind == 0 ? P.d_smbit + (size_t)b * P.nctu : P.d_sm + ((size_t)b * 4 + map - 1) * P.n4;
+  // S = down(thr(cur)); zero pad; MatrixNorm2 of the padded map
+  float mn = 0.f, mx = 0.f;                              // the zero border takes part in the min / max
+  for (int i = tid; i < pr * pc; i += SP_T) s_P[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < g; i += SP_T) {
+    const int r = i / cn, c = i - r * cn;
+    const float v = thr_apply(kind == 0 ? cur[i] : cur[(size_t)(r * ms4) * P.w4 + c * ms4], tp, mode);
+    s_P[(r + len) * pc + c + len] = v;
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+  mn = block_reduce(mn, OpMinF(), s_f); mx = block_reduce(mx, OpMaxF(), s_f);
+  const float neg = -mn;                                 // dst = src - min  ->  fl(src + (float)(-min))
+  const float mx2 = __fadd_rn(mx, neg);                  // max of the shifted map (the shift is monotonic)
+  const float s = mx2 > 0.f ? rcp_scale(mx2) : 1.f;
+  for (int i = tid; i < pr * pc; i += SP_T) { const float x = __fadd_rn(s_P[i], neg); s_P[i] = mx2 > 0.f ? __fmul_rn(x, s) : x; }
+  __syncthreads();
+  // out(i,j) = sum(|window - centre| .* WeightMap): float products, cv::sum order (4 floats in float, groups in double)
+  float* raw = P.d_sraw + ((size_t)b * 4 + kind) * P.g32;
+  float omax = 0.f;
+  const int nfull = (W * W) & ~3;
+  for (int i = tid; i < g; i += SP_T) {
+    const int r = i / cn, c = i - r * cn;
+    const float ctr = s_P[(r + len) * pc + c + len];
+    double acc = 0.0; float grp = 0.f; int q = 0, e = 0;
+    for (int u = 0; u < W; u++) {
+      const float* row = s_P + (r + u) * pc + c;
+      for (int v = 0; v < W; v++, e++) {
+        const float p = __fmul_rn(fabsf(__fsub_rn(row[v], ctr)), s_w[e]);
         if (e < nfull) {
           grp = q == 0 ? p : __fadd_rn(grp, p);
           if (++q == 4) { acc += (double)grp; q = 0; }
         } else acc += (double)p;
       }
-      const float o = __double2float_rn(acc);
-      raw[(size_t)comp * P.g32 + i] = o;
-      omax = fmaxf(omax, o);
     }
-    omax = block_reduce(omax, OpMaxF(), s_f);
-    const float s1 = omax > 0.f ? rcp_scale(omax) : 1.f;                 // MatrixNorm(TempOut)
-    if (kind < 2) {
-      const float m2 = omax > 0.f ? __fmul_rn(omax, s1) : omax;          // MatrixNorm(TempmatL, SpatialMap) after the replication
-      const float s2 = m2 > 0.f ? rcp_scale(m2) : 1.f;
-      float* out = P.d_sval + ((size_t)b * 3 + (kind == 0 ? 1 : 2)) * P.g32;
-      for (int i = tid; i < g; i += 256) {
-        float o = raw[i];
-        if (omax > 0.f) o = __fmul_rn(o, s1);
-        if (m2 > 0.f) o = __fmul_rn(o, s2);
-        out[i] = o;
-      }
-    } else {
-      for (int i = tid; i < g; i += 256) if (omax > 0.f) raw[(size_t)comp * P.g32 + i] = __fmul_rn(raw[(size_t)comp * P.g32 + i], s1);
-    }
+    const float o = __double2float_rn(acc);
+    raw[i] = o;
+    omax = fmaxf(omax, o);
   }
-  if (kind == 2) {                                       // GenerateSpatialMap_mv2: MatrixNorm(sqrt(x.^2 + y.^2))
-    __syncthreads();
-    float hm = 0.f;
-    for (int i = tid; i < g; i += 256) {
-      const float x = raw[i], y = raw[P.g32 + i];
-      hm = fmaxf(hm, __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));
+  omax = block_reduce(omax, OpMaxF(), s_f);
+  const float s1 = omax > 0.f ? rcp_scale(omax) : 1.f;                   // MatrixNorm(TempOut)
+  if (kind < 2) {
+    const float m2 = omax > 0.f ? __fmul_rn(omax, s1) : omax;            // MatrixNorm(TempmatL, SpatialMap) after the replication
+    const float s2 = m2 > 0.f ? rcp_scale(m2) : 1.f;
+    float* out = P.d_sval + ((size_t)b * 3 + (kind == 0 ? 1 : 2)) * P.g32;
+    for (int i = tid; i < g; i += SP_T) {
+      float o = raw[i];
+      if (omax > 0.f) o = __fmul_rn(o, s1);
+      if (m2 > 0.f) o = __fmul_rn(o, s2);
+      out[i] = o;
     }
-    hm = block_reduce(hm, OpMaxF(), s_f);
-    const float s = hm > 0.f ? rcp_scale(hm) : 1.f;
-    float* out = P.d_sval + (size_t)b * 3 * P.g32;
-    for (int i = tid; i < g; i += 256) {
-      const float x = raw[i], y = raw[P.g32 + i];
-      const float hv = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
-      out[i] = hm > 0.f ? __fmul_rn(hv, s) : hv;
-    }
+  } else if (omax > 0.f) {
+    for (int i = tid; i < g; i += SP_T) raw[i] = __fmul_rn(raw[i], s1);
+  }
+}
+
+// GenerateSpatialMap_mv2 (salmat.cpp:402): MatrixNorm(sqrt(x.^2 + y.^2)) on the 32-pixel grid
+__global__ void __launch_bounds__(256) fast_mvs_kernel(FastP P) {
+  const int b = blockIdx.x, tid = threadIdx.x, g = P.g32;
+  __shared__ float s_f[32];
+  const float* rx = P.d_sraw + ((size_t)b * 4 + 2) * g; const float* ry = rx + g;
+  float hm = 0.f;
+  for (int i = tid; i < g; i += 256) hm = fmaxf(hm, __fsqrt_rn(__fadd_rn(__fmul_rn(rx[i], rx[i]), __fmul_rn(ry[i], ry[i]))));
+  hm = block_reduce(hm, OpMaxF(), s_f);
+  const float s = hm > 0.f ? rcp_scale(hm) : 1.f;
+  float* out = P.d_sval + (size_t)b * 3 * g;
+  for (int i = tid; i < g; i += 256) {
+    const float hv = __fsqrt_rn(__fadd_rn(__fmul_rn(rx[i], rx[i]), __fmul_rn(ry[i], ry[i])));
+    out[i] = hm > 0.f ? __fmul_rn(hv, s) : hv;
   }
 }
 
@@ -643,22 +805,34 @@ __global__ void __launch_bounds__(256) fast_blur_h_kernel(FastP P) {
 
 // Column pass (filter.cpp SymmColumnFilter): s = fl(x[0] * k[0]); s = fl(s + fl(fl(x[+t] + x[-t]) * k[t])), t = 1..half.  The row-pass
 // output is constant over the 4 pixel rows of a cell row; a thread computes the 4 pixel rows of one cell row q for one column.
-__global__ void __launch_bounds__(128) fast_blur_v_kernel(FastP P) {
-  const int x = blockIdx.x * 128 + threadIdx.x, q = blockIdx.y, b = blockIdx.z;
-  const int W = P.w, h4 = P.h4;
+// A CTA stages BV_Q cell rows plus the nq_v + 1 rows above and below of a 128-column strip in shared memory.
+constexpr int BV_Q = 8;
+
+__global__ void __launch_bounds__(256) fast_blur_v_kernel(FastP P) {
+  extern __shared__ float s_t[];                          // [BV_Q + 2 * (nq_v + 1)][128] cell rows, then the taps
+  const int x0 = blockIdx.x * 128, q0 = blockIdx.y * BV_Q, b = blockIdx.z;
+  const int W = P.w, h4 = P.h4, nq = P.nq_v, nr = BV_Q + 2 * (nq + 1);
+  float* s_k = s_t + nr * 128;
   __shared__ float s_f[32];
+  const float* hr = P.d_hrow + (size_t)b * h4 * W;
+  for (int i = threadIdx.x; i < nr * 128; i += 256) {
+    const int rr = i >> 7, cc = i & 127, q = q0 - (nq + 1) + rr, x = x0 + cc;
+    s_t[i] = (q >= 0 && q < h4 && x < W) ? hr[(size_t)q * W + x] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 4 + 4 * nq; i += 256) s_k[i] = P.d_kv[i];
+  __syncthreads();
   float lo = INFINITY, hi = -INFINITY;
-  if (x < W) {
-    const float* hr = P.d_hrow + (size_t)b * h4 * W + x;
-    const float4* k4 = reinterpret_cast<const float4*>(P.d_kv + 4);
-    const float ctr = hr[(size_t)q * W];
-    const float k0 = __ldg(P.d_kv);
-    float s0 = __fmul_rn(ctr, k0), s1 = s0, s2 = s0, s3 = s0;
+  const int cc = threadIdx.x & 127, x = x0 + cc;
+  for (int ql = threadIdx.x >> 7; ql < BV_Q; ql += 2) {
+    const int q = q0 + ql;
+    if (q >= h4 || x >= W) continue;
+    const float* col = s_t + (ql + nq + 1) * 128 + cc;    // cell row q
+    const float ctr = col[0];
+    float s0 = __fmul_rn(ctr, s_k[0]), s1 = s0, s2 = s0, s3 = s0;
     float a0 = ctr, b0 = ctr;
-    for (int m = 0; m < P.nq_v; m++) {
-      const float a1 = (q + m + 1 < h4) ? hr[(size_t)(q + m + 1) * W] : 0.f;
-      const float b1 = (q - m - 1 >= 0) ? hr[(size_t)(q - m - 1) * W] : 0.f;
-      const float4 k = __ldg(k4 + m);
+    for (int m = 0; m < nq; m++) {
+      const float a1 = col[(m + 1) * 128], b1 = col[-(m + 1) * 128];
+      const float4 k = *reinterpret_cast<const float4*>(s_k + 4 + 4 * m);
       // pixel row j, tap t = 4m + i (i = 1..4): above cell m + (j + i) / 4, below cell -(m + (i - j + 3) / 4)
       s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a0, b1), k.x)); s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a0, b1), k.y));
       s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a0, b1), k.z)); s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a1, b1), k.w));
@@ -672,10 +846,10 @@ __global__ void __launch_bounds__(128) fast_blur_v_kernel(FastP P) {
     }
     float* out = P.d_blur + ((size_t)b * P.h + 4 * q) * W + x;
     out[0] = s0; out[W] = s1; out[2 * (size_t)W] = s2; out[3 * (size_t)W] = s3;
-    lo = fminf(fminf(s0, s1), fminf(s2, s3)); hi = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+    lo = fminf(lo, fminf(fminf(s0, s1), fminf(s2, s3))); hi = fmaxf(hi, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
   }
   lo = block_reduce(lo, OpMinF(), s_f); hi = block_reduce(hi, OpMaxF(), s_f);
-  if (threadIdx.x == 0) { atomicMin(P.d_mm + b * 2, float_key(lo)); atomicMax(P.d_mm + b * 2 + 1, float_key(hi)); }
+  if (threadIdx.x == 0 && lo <= hi) { atomicMin(P.d_mm + b * 2, float_key(lo)); atomicMax(P.d_mm + b * 2 + 1, float_key(hi)); }
 }
 
 // ------------------------------------------------------------------------------------------------ K11: MatrixNorm2, x255, convertTo(CV_8U)
@@ -762,7 +936,7 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
   A(r_t64, RL * p.nctu); A(r_t32, RL * 3 * p.g32);
   A(d_bin, Bz * n4); A(d_sm, Bz * 4 * n4); A(d_smbit, Bz * p.nctu); A(d_thr, Bz * 20);
   A(d_tacc, Bz * 3 * p.g32); A(d_tval, Bz * 3 * p.g32); A(d_sval, Bz * 3 * p.g32); A(d_sraw, Bz * 4 * p.g32);
-  A(d_comb, Bz * n4); A(d_hrow, Bz * p.h4 * w); A(d_blur, Bz * (size_t)h * w); A(d_mm, Bz * 2);
+  A(d_comb, Bz * n4); A(d_hrow, Bz * p.h4 * w); A(d_blur, Bz * (size_t)h * w); A(d_mm, Bz * 2); A(d_cami, Bz * 24);
 #undef A
   // Gaussian taps (cv::GaussianBlur(FinalMap, Size(k, k), cvRound(H / 30), 0, BORDER_CONSTANT), TDecGop.cpp:323)
   std::vector<float> k;
@@ -799,6 +973,10 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
   s->smem_sp[1] = s->smem_sp[2] = ((size_t)(p.gh32 + 12) * (p.gw32 + 12) + 144) * 4;
   s->smem_h = ((size_t)p.w4 + p.hq + p.nq_h + 2) * 4;
   if (!e && (s->smem_tthr > 48000 || s->smem_sp[1] > 48000)) { set_error("fast version: picture too large for the block-grid kernels"); e = CDS_EINVAL; }
+  const size_t smem_sm = (size_t)(SM_G + p.PS - 1) * 128 * sizeof(float4);
+  if (!e && smem_sm > 200 * 1024) { set_error("fast version: fps %.1f needs a %zu-byte smoothing tile", fps, smem_sm); e = CDS_EINVAL; }
+  if (!e && smem_sm > 48 * 1024 &&
+      cudaFuncSetAttribute(fast_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sm) != cudaSuccess) { set_error("fast: cudaFuncSetAttribute"); e = CDS_ECUDA; }
   if (e) { fast_destroy(s); return e; }
   *out = s;
   return fast_clear(s, nullptr);
@@ -826,9 +1004,14 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
                    const uint16_t* bytes, void* out, int out_u8, int* cam_out, cudaStream_t st) {
   const FastP& p = s->p;
   if (n < 1 || n > p.B || first_poc < 0) { set_error("fast_run_batch: bad batch"); return CDS_EINVAL; }
-  fast_camera_kernel<<<n, CAM_T, 0, st>>>(p, first_poc, mvx, mvy, dep, bytes, cam_out);
+  CDS_CUDA(cudaMemsetAsync(p.d_cami, 0, (size_t)n * 24 * sizeof(int), st));
+  fast_cam_scan_kernel<<<dim3(ceil_div(p.n4, 1024), n), 256, 0, st>>>(p, first_poc, mvx, mvy, dep, bytes);
   CDS_LAUNCH_CHECK();
-  fast_smooth_kernel<<<dim3(ceil_div(p.n4 + p.nctu, 256), n), 256, 0, st>>>(p, first_poc);
+  fast_cam_vote_kernel<<<n, CAM_T, 0, st>>>(p, first_poc, cam_out);
+  CDS_LAUNCH_CHECK();
+  fast_smooth_kernel<<<dim3(ceil_div(p.n4, 128), ceil_div(n, SM_G)), dim3(128, SM_G), (size_t)(SM_G + p.PS - 1) * 128 * sizeof(float4), st>>>(p, first_poc, n);
+  CDS_LAUNCH_CHECK();
+  fast_smooth_bit_kernel<<<dim3(ceil_div(p.nctu, 128), n), 128, 0, st>>>(p, first_poc);
   CDS_LAUNCH_CHECK();
   if (!out) return CDS_OK;
   fast_thr_kernel<<<dim3(5, n), 256, 0, st>>>(p);
@@ -837,7 +1020,9 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
   CDS_LAUNCH_CHECK();
   fast_tthr_kernel<<<dim3(3, n), 128, s->smem_tthr, st>>>(p);
   CDS_LAUNCH_CHECK();
-  fast_spatial_kernel<<<dim3(3, n), 256, s->smem_sp[1], st>>>(p);
+  fast_spatial_kernel<<<dim3(4, n), SP_T, s->smem_sp[1], st>>>(p);
+  CDS_LAUNCH_CHECK();
+  fast_mvs_kernel<<<n, 256, 0, st>>>(p);
   CDS_LAUNCH_CHECK();
   fast_combine_kernel<<<dim3(ceil_div(p.n4, 256), n), 256, 0, st>>>(p);
   CDS_LAUNCH_CHECK();
@@ -845,7 +1030,7 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
   CDS_LAUNCH_CHECK();
   fast_blur_h_kernel<<<dim3(p.h4, n), 256, s->smem_h, st>>>(p);
   CDS_LAUNCH_CHECK();
-  fast_blur_v_kernel<<<dim3(ceil_div(p.w, 128), p.h4, n), 128, 0, st>>>(p);
+  fast_blur_v_kernel<<<dim3(ceil_div(p.w, 128), ceil_div(p.h4, BV_Q), n), 256, ((size_t)(BV_Q + 2 * (p.nq_v + 1)) * 128 + 4 + 4 * p.nq_v) * sizeof(float), st>>>(p);
   CDS_LAUNCH_CHECK();
   const int nb = ceil_div((int)(((size_t)p.h * p.w / 4)), 256);
   if (out_u8) fast_output_kernel<uint8_t><<<dim3(nb, n), 256, 0, st>>>(p, reinterpret_cast<uint8_t*>(out));
