@@ -150,6 +150,33 @@ def cpu_sample(a, n_out, ctx_frames, threads, seed=1234):
         ("reference" if use_ref else "port")
 
 
+def cpu_fast_sample(a, threads, nframes=6, seed=1234):
+    """The reference's fast version on the host cores: one synthetic clip per thread (the decoder is single-threaded; videos are
+    independent), `nframes` pictures each from FrameIndex 0 (its rings warm up from there), verbatim getFrame where oracle/_ref
+    exists + the fast-version oracle (pinned by the reference's golden PNGs).  Returns (pictures/s over all threads, detail)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as o                                         # checker / CPU baseline only
+    import compressd_domain_saliencyprediction_b200 as cds
+    from concurrent.futures import ThreadPoolExecutor
+    use_ref = o.ref(f"getframe_{a.width}x{a.height}") is not None
+    clips = [cds.ops.synth_clip(a.width, a.height, seed + t, nframes, first_poc=1) for t in range(threads)]
+    o.oracle()
+
+    def one(t):
+        hdr, tok, base, byts = clips[t]
+        fo = o.FastOracle(a.width, a.height, a.fps)
+        for f in range(nframes):
+            m = (o.ref_getframe if use_ref else o.orc_getframe)(a.width, a.height, hdr[f], tok[base[f]:base[f + 1]])
+            fo.frame(m[0], m[1], m[2], byts[f])
+        fo.close()
+    one(0)                                                      # warm the libraries up outside the timed region
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(threads)))
+    wall = time.perf_counter() - t0
+    return threads * nframes / wall, {"wall_s": round(wall, 3), "clips": threads, "pictures_per_clip": nframes, "stage_a": "reference getFrame" if use_ref else "port"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -329,6 +356,40 @@ def run_b200(a):
     t0 = time.perf_counter(); h_maps.copy_(big, non_blocking=True); torch.cuda.synchronize()
     e2e_f32["d2h_link_gbs"] = big.numel() * 4 / (time.perf_counter() - t0) / 1e9
     del big
+    # ---- the reference's FAST version (TDecGop.cpp:225-333 + salmat.cpp, no SVM) on the same synthetic syntax: what its decoder
+    #      computes per slice on the CPU; reported beside the headline (which is the nine-feature + RBF-SVM path BASELINE names) ----
+    fast_line = None
+    if not a.no_fast and w % 16 == 0:
+        fclip = cds.SaliencyClip(w, h, a.fps, fast=True, max_batch=B, out_u8=True)
+        d_u8 = d_maps.view(torch.uint8)
+
+        def fstep(poc, n, context=False):
+            for (p, i, ln) in runs(poc, n, DEV_CHUNK):
+                args = (fclip.handle, p, ln, P(d_byts, i * nctu * 2), P(d_hdr, i * nctu * 16), P(d_tok), P(d_base, i * 8))
+                if context:
+                    check(L.cds_clip_context_dev(*args, st), "cds_clip_context_dev")
+                else:
+                    check(L.cds_clip_process_dev(*args, P(d_u8), None, st), "cds_clip_process_dev")
+        fclip.seek(0)
+        fstep(0, halo, context=True)
+        fpoc = halo
+        fstep(fpoc, a.warmup * B); fpoc += a.warmup * B
+        barrier()
+        cds.take_launch_count()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        fstep(fpoc, a.steps * B)
+        f1.record(stream)
+        barrier()
+        fms = max_over_ranks(f0.elapsed_time(f1))
+        flaunches = cds.take_launch_count()
+        fe2e = e2e_leg(fclip, h_maps, 1)
+        fast_line = {"value": frames / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms / a.steps, "gpu_launches": int(flaunches),
+                     "e2e": {k: fe2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                     "PS": fclip.PS, "PT": fclip.PT, "dtype": "f32 (operation order of the reference: bit-identical 8-bit maps)",
+                     "what": "use_rbf = CDS_FUSION_FAST: CameraDect / Umean vote, ForwardFilter, MapThreshold, coarse-grid temporal and spatial "
+                             "maps, fixed FeatureWeight sum, cv::GaussianBlur, 8-bit map; same synthetic syntax, same batch"}
+        fclip.close()
     clip.seek((a.warmup + a.steps) * B)          # refill the temporal window for the per-stage profile pass below
     dev_step((a.warmup + a.steps) * B, halo, context=True)
 
@@ -338,6 +399,8 @@ def run_b200(a):
             "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B, "PS": a.PS, "PT": a.PT, "parallelism": f"video-shard x{world}", "numa_bound_cores": (len(numa_cpus) if numa_cpus else None),
                        "l2": "no explicit flush: one step streams several GB of intermediates (9 maps x B pictures at h/4 x W, 3 at full resolution), far above the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "e2e_f32_maps": e2e_f32, "gpu_launches": int(launches)}
+    if fast_line:
+        line["fast_version"] = fast_line
 
     # ---- per-stage device times, roofline of the dominant kernel (rank 0) ----
     if rank == 0:
@@ -420,6 +483,13 @@ def run_b200(a):
         line["cpu_baseline"] = {"value": 1.0 / pf, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{n_out} output pictures of the same workload after {ctx} context pictures on {cores} threads; "
                                           f"{KIND_TEXT[kind]}; per-picture s: {det}"}
+        if fast_line:
+            fthreads = min(cores, 16)
+            fv, fdet = cpu_fast_sample(a, fthreads)
+            fast_line["cpu_baseline"] = {"value": fv, "unit": UNIT, "cores": fthreads, "kind": "port",
+                                         "sample": f"{fdet['clips']} independent clips x {fdet['pictures_per_clip']} pictures (FrameIndex 0..), one per thread: "
+                                                   f"{fdet['stage_a']} + the fast-version oracle (TDecGop.cpp:225-333 + salmat.cpp restated, pinned by the "
+                                                   f"reference's 39 golden PNGs); wall {fdet['wall_s']} s"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -443,6 +513,7 @@ def main():
     ap.add_argument("--nsv", type=int, default=4096)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fast", action="store_true", help="skip the fast-version leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     a.PS = int(np.floor(a.fps * 0.3 + 0.5)); a.PT = int(np.floor(a.PS * 7 + 0.5))

@@ -42,7 +42,7 @@ struct FastP {
   int16_t *r_mvx, *r_mvy; uint8_t* r_dep; uint16_t* r_bytes; float* r_sc; int* r_cam;
   float *r_t64, *r_t32;
   uint8_t* d_bin; float *d_sm, *d_smbit, *d_thr, *d_tacc, *d_tval, *d_sval, *d_sraw, *d_comb, *d_hrow, *d_blur;
-  unsigned* d_mm; int* d_cami;
+  unsigned* d_mm; int* d_cami; float* d_camf;
   float *d_kh, *d_kv, *d_wt, *d_wm;
 };
 
@@ -314,7 +314,7 @@ __device__ __forceinline__ int direction_bin(float y, float x) {          // TDe
 
 // K1a, grid (chunks of 1024 cells, pictures): copy the picture into the raw ring, background mask, BackNum / StaticNum
 // (TDecGop.cpp:509-519), direction bin of every background cell (vote_alg :580-592) and the 16-bin histogram.
-// d_cami[b]: {BackNum, StaticNum, hist[16], max depth}
+// d_cami[b]: {BackNum, StaticNum, hist[16], max depth, max m_norm (float bits), max bytes}
 __global__ void __launch_bounds__(256)
 fast_cam_scan_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, const int16_t* __restrict__ mvy,
                      const uint8_t* __restrict__ dep, const uint16_t* __restrict__ bytes) {
@@ -322,12 +322,14 @@ fast_cam_scan_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, co
   const int n4 = P.n4, w4 = P.w4, lw = P.lw;
   const uint16_t* by = bytes + (size_t)b * P.nctu;
   __shared__ int s_i[32]; __shared__ int s_hist[8][16];
-  int mn = 65535;
-  for (int i = tid; i < P.nctu; i += 256) mn = min(mn, (int)by[i]);
+  int mn = 65535, mxb = 0;
+  for (int i = tid; i < P.nctu; i += 256) { mn = min(mn, (int)by[i]); mxb = max(mxb, (int)by[i]); }
   mn = block_reduce(mn, OpMinI(), s_i);
   if (blockIdx.x == 0) {
     uint16_t* rb = P.r_bytes + (size_t)slot * P.nctu;
     for (int i = tid; i < P.nctu; i += 256) rb[i] = by[i];
+    mxb = block_reduce(mxb, OpMaxI(), s_i);
+    if (tid == 0) P.d_cami[b * 24 + 20] = mxb;
   }
   const int k = (blockIdx.x * 256 + tid) * 4;
   int back = 0, stat = 0, mxd = 0; int bi[4] = {255, 255, 255, 255};
@@ -364,76 +366,72 @@ fast_cam_scan_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, co
   if (tid < 16) { int c = 0; for (int w = 0; w < 8; w++) c += s_hist[w][tid]; if (c) atomicAdd(ci + 2 + tid, c); }
 }
 
-// K1b, one CTA per picture: static / moving decision, winning bin (:600 first maximum), Umean of its members (exact sequential
-// float sums), compensation offsets, cvRound'ed camera motion, and the maximum of the compensated m_norm.
+// K1b, grid (component x / y, pictures): static / moving decision, winning bin (:600 first maximum), Umean of its members for one
+// component (exact sequential float sums).  d_camf[b] = {vx, vy}.
 constexpr int CAM_T = 512;
 
-__global__ void __launch_bounds__(CAM_T)
-fast_cam_vote_kernel(FastP P, int first_poc, int* __restrict__ cam_out) {
-  const int b = blockIdx.x, F = first_poc + b, slot = F % P.RL, tid = threadIdx.x;
+__global__ void __launch_bounds__(CAM_T) fast_cam_vote_kernel(FastP P, int first_poc) {
+  const int comp = blockIdx.x, b = blockIdx.y, F = first_poc + b, slot = F % P.RL, tid = threadIdx.x;
   const int n4 = P.n4;
-  const int16_t* mx = P.r_mvx + (size_t)slot * n4; const int16_t* my = P.r_mvy + (size_t)slot * n4;
+  const int16_t* m = (comp == 0 ? P.r_mvx : P.r_mvy) + (size_t)slot * n4;
   const uint8_t* bin = P.d_bin + (size_t)b * n4;
-  const uint16_t* rb = P.r_bytes + (size_t)slot * P.nctu;
   const int* ci = P.d_cami + b * 24;
-  __shared__ int s_i[32]; __shared__ float s_f[32]; __shared__ long long s_l[32];
+  __shared__ long long s_l[32];
   __shared__ SeqSumSmem<CAM_T> s_seq;
-  long long t_prof = clock64();
   const int back = ci[0], stat = ci[1];
-  const bool moving = stat <= back / 2;
-  int mxb = 0;
-  for (int i = tid; i < P.nctu; i += CAM_T) mxb = max(mxb, (int)rb[i]);
-  mxb = block_reduce(mxb, OpMaxI(), s_i);
-  float vx = 0.f, vy = 0.f;
-  if (moving) {
+  float v = 0.f;
+  if (stat <= back / 2) {                                   // TDecGop.cpp:529 (integer division)
     int best = 0, bc = -1;
     for (int j = 0; j < 16; j++) if (ci[2 + j] > bc) { bc = ci[2 + j]; best = j; }
     const int len = bc;
     // first loop of Umean: exact in float whenever every partial sum is (sum of |m| < 2^24 quarter-pels)
-    long long sx = 0, sy = 0, ax = 0, ay = 0;
-    for (int g = tid; g < n4 / 4; g += CAM_T) {
-      const uchar4 bb = reinterpret_cast<const uchar4*>(bin)[g];
-      if (bb.x == best || bb.y == best || bb.z == best || bb.w == best) {
-        const short4 x4 = reinterpret_cast<const short4*>(mx)[g], y4 = reinterpret_cast<const short4*>(my)[g];
-        if (bb.x == best) { sx += x4.x; sy += y4.x; ax += abs((int)x4.x); ay += abs((int)y4.x); }
-        if (bb.y == best) { sx += x4.y; sy += y4.y; ax += abs((int)x4.y); ay += abs((int)y4.y); }
-        if (bb.z == best) { sx += x4.z; sy += y4.z; ax += abs((int)x4.z); ay += abs((int)y4.z); }
-        if (bb.w == best) { sx += x4.w; sy += y4.w; ax += abs((int)x4.w); ay += abs((int)y4.w); }
-      }
-    }
-    sx = block_reduce(sx, OpAddL(), s_l); sy = block_reduce(sy, OpAddL(), s_l);
-    ax = block_reduce(ax, OpAddL(), s_l); ay = block_reduce(ay, OpAddL(), s_l);
-    FPROF(0);
-    for (int comp = 0; comp < 2; comp++) {
-      const int16_t* m = comp == 0 ? mx : my;
-      const long long s = comp == 0 ? sx : sy, a = comp == 0 ? ax : ay;
-      int cnt;
-      struct Raw { uchar4 b; short4 m; };
-      auto load = [&](int g) -> Raw { return Raw{reinterpret_cast<const uchar4*>(bin)[g], reinterpret_cast<const short4*>(m)[g]}; };
-      auto plain = [&](const Raw& r, float* t) -> unsigned {
-        t[0] = __fmul_rn((float)r.m.x, 0.25f); t[1] = __fmul_rn((float)r.m.y, 0.25f); t[2] = __fmul_rn((float)r.m.z, 0.25f); t[3] = __fmul_rn((float)r.m.w, 0.25f);
-        return (r.b.x == best ? 1u : 0u) | (r.b.y == best ? 2u : 0u) | (r.b.z == best ? 4u : 0u) | (r.b.w == best ? 8u : 0u);
-      };
-      const float sum1 = (a < (1ll << 24)) ? __fmul_rn((float)s, 0.25f) : block_seq_sum<CAM_T>(n4 / 4, load, plain, s_seq, &cnt);
-      const float mean = __fdiv_rn(sum1, (float)len);
-      const bool flag = mean > 0.f;
-      auto clamped = [&](const Raw& r, float* t) -> unsigned {          // TDecGop.cpp:633-639
-        const unsigned sel = plain(r, t);
+    long long s = 0, a = 0;
+    for (int g0 = 0; g0 < n4 / 4; g0 += 4 * CAM_T) {
+      uchar4 bb[4]; short4 mm[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) t[j] = ((flag && t[j] < mean) || (!flag && t[j] > mean)) ? t[j] : mean;
-        return sel;
-      };
-      const float sum2 = block_seq_sum<CAM_T>(n4 / 4, load, clamped, s_seq, &cnt);
-      const float v = __fdiv_rn(sum2, (float)len);
-      if (comp == 0) vx = v; else vy = v;
+      for (int u = 0; u < 4; u++) { const int g = min(g0 + u * CAM_T + tid, n4 / 4 - 1); bb[u] = reinterpret_cast<const uchar4*>(bin)[g]; mm[u] = reinterpret_cast<const short4*>(m)[g]; }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (g0 + u * CAM_T + tid < n4 / 4) {
+          if (bb[u].x == best) { s += mm[u].x; a += abs((int)mm[u].x); }
+          if (bb[u].y == best) { s += mm[u].y; a += abs((int)mm[u].y); }
+          if (bb[u].z == best) { s += mm[u].z; a += abs((int)mm[u].z); }
+          if (bb[u].w == best) { s += mm[u].w; a += abs((int)mm[u].w); }
+        }
     }
-    FPROF(2);
+    s = block_reduce(s, OpAddL(), s_l); a = block_reduce(a, OpAddL(), s_l);
+    int cnt;
+    struct Raw { uchar4 b; short4 m; };
+    auto load = [&](int g) -> Raw { return Raw{reinterpret_cast<const uchar4*>(bin)[g], reinterpret_cast<const short4*>(m)[g]}; };
+    auto plain = [&](const Raw& r, float* t) -> unsigned {
+      t[0] = __fmul_rn((float)r.m.x, 0.25f); t[1] = __fmul_rn((float)r.m.y, 0.25f); t[2] = __fmul_rn((float)r.m.z, 0.25f); t[3] = __fmul_rn((float)r.m.w, 0.25f);
+      return (r.b.x == best ? 1u : 0u) | (r.b.y == best ? 2u : 0u) | (r.b.z == best ? 4u : 0u) | (r.b.w == best ? 8u : 0u);
+    };
+    const float sum1 = (a < (1ll << 24)) ? __fmul_rn((float)s, 0.25f) : block_seq_sum<CAM_T>(n4 / 4, load, plain, s_seq, &cnt);
+    const float mean = __fdiv_rn(sum1, (float)len);
+    const bool flag = mean > 0.f;
+    auto clamped = [&](const Raw& r, float* t) -> unsigned {          // TDecGop.cpp:633-639
+      const unsigned sel = plain(r, t);
+#pragma unroll
+      for (int j = 0; j < 4; j++) t[j] = ((flag && t[j] < mean) || (!flag && t[j] > mean)) ? t[j] : mean;
+      return sel;
+    };
+    const float sum2 = block_seq_sum<CAM_T>(n4 / 4, load, clamped, s_seq, &cnt);
+    v = __fdiv_rn(sum2, (float)len);
   }
-  const float nx = moving ? -vx : -0.0f, ny = moving ? -vy : -0.0f;
-  // m_norm (CalDist :552) of the compensated field: its maximum feeds MatrixNorm (TDecGop.cpp:294)
+  if (tid == 0) P.d_camf[b * 2 + comp] = v;
+}
+
+// K1c, grid (chunks, pictures): maximum of the compensated m_norm (CalDist :552), which feeds MatrixNorm (TDecGop.cpp:294)
+__global__ void __launch_bounds__(256) fast_cam_norm_kernel(FastP P, int first_poc) {
+  const int b = blockIdx.y, slot = (first_poc + b) % P.RL, g = blockIdx.x * 256 + threadIdx.x;
+  __shared__ float s_f[32];
+  const int* ci = P.d_cami + b * 24;
+  const bool moving = ci[1] <= ci[0] / 2;
+  const float nx = moving ? -P.d_camf[b * 2] : -0.0f, ny = moving ? -P.d_camf[b * 2 + 1] : -0.0f;
   float mxn = 0.f;
-  for (int g = tid; g < n4 / 4; g += CAM_T) {
-    const short4 x4 = reinterpret_cast<const short4*>(mx)[g], y4 = reinterpret_cast<const short4*>(my)[g];
+  if (g < P.n4 / 4) {
+    const short4 x4 = reinterpret_cast<const short4*>(P.r_mvx + (size_t)slot * P.n4)[g], y4 = reinterpret_cast<const short4*>(P.r_mvy + (size_t)slot * P.n4)[g];
     const short xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -442,18 +440,27 @@ fast_cam_vote_kernel(FastP P, int first_poc, int* __restrict__ cam_out) {
     }
   }
   mxn = block_reduce(mxn, OpMaxF(), s_f);
-  FPROF(3);
-  if (tid == 0) {
-    float* sc = P.r_sc + (size_t)slot * 8;
-    const int mxd = ci[18];
-    sc[0] = nx; sc[1] = ny;
-    sc[2] = mxb > 0 ? rcp_scale((float)mxb) : 1.f;
-    sc[3] = mxd > 0 ? rcp_scale((float)mxd) : 1.f;
-    sc[4] = mxn > 0.f ? rcp_scale(mxn) : 1.f;
-    const int cx = moving ? __float2int_rn(vx) : 0, cy = moving ? __float2int_rn(vy) : 0;      // cvRound
-    P.r_cam[slot * 2] = cx; P.r_cam[slot * 2 + 1] = cy;
-    if (cam_out) { cam_out[b * 2] = cx; cam_out[b * 2 + 1] = cy; }
-  }
+  if (threadIdx.x == 0 && mxn > 0.f) atomicMax(reinterpret_cast<unsigned*>(P.d_cami + b * 24 + 19), __float_as_uint(mxn));
+}
+
+// K1d, one thread per picture: the per-picture scalars the later kernels read from the ring
+__global__ void fast_cam_final_kernel(FastP P, int first_poc, int n, int* __restrict__ cam_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const int slot = (first_poc + b) % P.RL;
+  const int* ci = P.d_cami + b * 24;
+  const bool moving = ci[1] <= ci[0] / 2;
+  const float vx = P.d_camf[b * 2], vy = P.d_camf[b * 2 + 1];
+  const int mxb = ci[20], mxd = ci[18];
+  const float mxn = __uint_as_float((unsigned)ci[19]);
+  float* sc = P.r_sc + (size_t)slot * 8;
+  sc[0] = moving ? -vx : -0.0f; sc[1] = moving ? -vy : -0.0f;
+  sc[2] = mxb > 0 ? rcp_scale((float)mxb) : 1.f;
+  sc[3] = mxd > 0 ? rcp_scale((float)mxd) : 1.f;
+  sc[4] = mxn > 0.f ? rcp_scale(mxn) : 1.f;
+  const int cx = moving ? __float2int_rn(vx) : 0, cy = moving ? __float2int_rn(vy) : 0;        // cvRound
+  P.r_cam[slot * 2] = cx; P.r_cam[slot * 2 + 1] = cy;
+  if (cam_out) { cam_out[b * 2] = cx; cam_out[b * 2 + 1] = cy; }
 }
 
 // ------------------------------------------------------------------------------------------------ K2: ForwardFilter (salmat.cpp:39-55)
@@ -936,7 +943,7 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
   A(r_t64, RL * p.nctu); A(r_t32, RL * 3 * p.g32);
   A(d_bin, Bz * n4); A(d_sm, Bz * 4 * n4); A(d_smbit, Bz * p.nctu); A(d_thr, Bz * 20);
   A(d_tacc, Bz * 3 * p.g32); A(d_tval, Bz * 3 * p.g32); A(d_sval, Bz * 3 * p.g32); A(d_sraw, Bz * 4 * p.g32);
-  A(d_comb, Bz * n4); A(d_hrow, Bz * p.h4 * w); A(d_blur, Bz * (size_t)h * w); A(d_mm, Bz * 2); A(d_cami, Bz * 24);
+  A(d_comb, Bz * n4); A(d_hrow, Bz * p.h4 * w); A(d_blur, Bz * (size_t)h * w); A(d_mm, Bz * 2); A(d_cami, Bz * 24); A(d_camf, Bz * 2);
 #undef A
   // Gaussian taps (cv::GaussianBlur(FinalMap, Size(k, k), cvRound(H / 30), 0, BORDER_CONSTANT), TDecGop.cpp:323)
   std::vector<float> k;
@@ -1007,7 +1014,11 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
   CDS_CUDA(cudaMemsetAsync(p.d_cami, 0, (size_t)n * 24 * sizeof(int), st));
   fast_cam_scan_kernel<<<dim3(ceil_div(p.n4, 1024), n), 256, 0, st>>>(p, first_poc, mvx, mvy, dep, bytes);
   CDS_LAUNCH_CHECK();
-  fast_cam_vote_kernel<<<n, CAM_T, 0, st>>>(p, first_poc, cam_out);
+  fast_cam_vote_kernel<<<dim3(2, n), CAM_T, 0, st>>>(p, first_poc);
+  CDS_LAUNCH_CHECK();
+  fast_cam_norm_kernel<<<dim3(ceil_div(p.n4 / 4, 256), n), 256, 0, st>>>(p, first_poc);
+  CDS_LAUNCH_CHECK();
+  fast_cam_final_kernel<<<ceil_div(n, 64), 64, 0, st>>>(p, first_poc, n, cam_out);
   CDS_LAUNCH_CHECK();
   fast_smooth_kernel<<<dim3(ceil_div(p.n4, 128), ceil_div(n, SM_G)), dim3(128, SM_G), (size_t)(SM_G + p.PS - 1) * 128 * sizeof(float4), st>>>(p, first_poc, n);
   CDS_LAUNCH_CHECK();
