@@ -346,7 +346,7 @@ fast_cam_scan_kernel(FastP P, int first_poc, const int16_t* __restrict__ mvx, co
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         back++;
-        if ((int)xs[j] * xs[j] + (int)ys[j] * ys[j] <= 32) stat++;       // mvx^2 + mvy^2 <= 2 pixels^2, in quarter-pel units
+        if ((unsigned)((int)xs[j] * xs[j]) + (unsigned)((int)ys[j] * ys[j]) <= 32u) stat++;   // mvx^2 + mvy^2 <= 2 pixels^2, in quarter-pel units
         bi[j] = direction_bin(__fmul_rn((float)ys[j], 0.25f), __fmul_rn((float)xs[j], 0.25f));
       }
     }
@@ -1047,6 +1047,62 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
   if (out_u8) fast_output_kernel<uint8_t><<<dim3(nb, n), 256, 0, st>>>(p, reinterpret_cast<uint8_t*>(out));
   else fast_output_kernel<float><<<dim3(nb, n), 256, 0, st>>>(p, reinterpret_cast<float*>(out));
   CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// ---- probes: the two sequential-sum emulations on caller-supplied data (tests feed them ties, binade crossings, mixed signs) ----
+namespace {
+__global__ void __launch_bounds__(256) probe_seq_sum_kernel(const float* __restrict__ v, const unsigned char* __restrict__ sel, int ngroups,
+                                                            float* __restrict__ out, int* __restrict__ count) {
+  __shared__ SeqSumSmem<256> s_seq;
+  struct Raw { float4 v; uchar4 s; };
+  auto load = [&](int g) -> Raw { return Raw{reinterpret_cast<const float4*>(v)[g], reinterpret_cast<const uchar4*>(sel)[g]}; };
+  auto eval = [&](const Raw& r, float* t) -> unsigned {
+    t[0] = r.v.x; t[1] = r.v.y; t[2] = r.v.z; t[3] = r.v.w;
+    return (r.s.x ? 1u : 0u) | (r.s.y ? 2u : 0u) | (r.s.z ? 4u : 0u) | (r.s.w ? 8u : 0u);
+  };
+  int cnt = 0;
+  const float S = block_seq_sum<256>(ngroups, load, eval, s_seq, &cnt);
+  if (threadIdx.x == 0) { *out = S; *count = cnt; }
+}
+__global__ void __launch_bounds__(32) probe_run_sum_kernel(const float* __restrict__ vals, int gh, int gw, int rows, int cols, int ms, double t,
+                                                           float* __restrict__ out, int* __restrict__ count) {
+  __shared__ float s_rv[128]; __shared__ int s_rn[128], s_rq[128];
+  int cnt = 0;
+  const float S = warp_select_sum_runs(vals, gh, gw, rows, cols, ms, t, s_rv, s_rn, s_rq, &cnt);
+  if (threadIdx.x == 0) { *out = S; *count = cnt; }
+}
+}  // namespace
+
+int fast_probe_seq_sum(const float* v, const unsigned char* sel, int n, float* sum, int* count) {
+  if (int e = ensure_device()) return e;
+  if (!v || !sel || !sum || !count || n < 4 || (n % 4)) { set_error("cds_probe_seq_sum: n must be a positive multiple of 4"); return CDS_EINVAL; }
+  float* dv = nullptr; unsigned char* ds = nullptr; float* dout = nullptr;
+  CDS_CUDA(cudaMalloc(&dv, (size_t)n * 4)); CDS_CUDA(cudaMalloc(&ds, (size_t)n)); CDS_CUDA(cudaMalloc(&dout, 16));
+  CDS_CUDA(cudaMemcpy(dv, v, (size_t)n * 4, cudaMemcpyHostToDevice)); CDS_CUDA(cudaMemcpy(ds, sel, (size_t)n, cudaMemcpyHostToDevice));
+  probe_seq_sum_kernel<<<1, 256>>>(dv, ds, n / 4, dout, reinterpret_cast<int*>(dout + 1));
+  CDS_LAUNCH_CHECK();
+  float h[2];
+  CDS_CUDA(cudaMemcpy(h, dout, 8, cudaMemcpyDeviceToHost));
+  *sum = h[0]; memcpy(count, &h[1], 4);
+  cudaFree(dv); cudaFree(ds); cudaFree(dout);
+  return CDS_OK;
+}
+
+int fast_probe_run_sum(const float* vals, int gh, int gw, int rows, int cols, int ms, double t, float* sum, int* count) {
+  if (int e = ensure_device()) return e;
+  if (!vals || !sum || !count || gh < 1 || gw < 1 || gw > 128 || ms < 1 || rows <= ms * (gh - 1) || rows > ms * gh || cols <= ms * (gw - 1) || cols > ms * gw) {
+    set_error("cds_probe_run_sum: bad geometry"); return CDS_EINVAL;
+  }
+  float* dv = nullptr; float* dout = nullptr;
+  CDS_CUDA(cudaMalloc(&dv, (size_t)gh * gw * 4)); CDS_CUDA(cudaMalloc(&dout, 16));
+  CDS_CUDA(cudaMemcpy(dv, vals, (size_t)gh * gw * 4, cudaMemcpyHostToDevice));
+  probe_run_sum_kernel<<<1, 32>>>(dv, gh, gw, rows, cols, ms, t, dout, reinterpret_cast<int*>(dout + 1));
+  CDS_LAUNCH_CHECK();
+  float h[2];
+  CDS_CUDA(cudaMemcpy(h, dout, 8, cudaMemcpyDeviceToHost));
+  *sum = h[0]; memcpy(count, &h[1], 4);
+  cudaFree(dv); cudaFree(dout);
   return CDS_OK;
 }
 

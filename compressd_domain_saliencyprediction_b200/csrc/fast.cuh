@@ -16,6 +16,9 @@ int fast_halo(const FastState* s);                      // pictures of temporal 
 int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const int16_t* mvy, const uint8_t* dep,
                    const uint16_t* bytes, void* out, int out_u8, int* cam_out, cudaStream_t st);
 int fast_get_cam(const FastState* s, int poc, int* xy);   // camera motion of a picture still in the ring (host copy)
+// probes (tests): `for (i < n) if (sel[i]) S = S + v[i];` and MapThreshold's sum over a map of replicated blocks, both in float
+int fast_probe_seq_sum(const float* v, const unsigned char* sel, int n, float* sum, int* count);
+int fast_probe_run_sum(const float* vals, int gh, int gw, int rows, int cols, int ms, double t, float* sum, int* count);
 // debug / tests: copy one intermediate of the last batch (see fast.cu) to the host
 int fast_debug_copy(FastState* s, const char* which, int frame_in_batch, void* dst, size_t bytes, cudaStream_t st);
 

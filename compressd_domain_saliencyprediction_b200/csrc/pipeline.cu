@@ -37,6 +37,7 @@ static const float kFeatureWeight[9] = {0.058f, 0.171f, -0.095f, 0.068f, -0.01f,
 
 struct cds_ctx {
   cds_params p;
+  bool maps_in = false;                // cds_clip_process_maps: d_mvx / d_mvy / d_dep already hold stage (a)'s output
   FastState* fast = nullptr;           // use_rbf == CDS_FUSION_FAST: the reference's fast version (fast.cu) replaces stages (c)-(e), (b), (d)
   int w, h, h4, w4, n4, ncol, nrow, nctu, B, RL, PS, PT, gk;
   double gs;
@@ -567,7 +568,7 @@ namespace {
 int run_context_stages(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
                        const int64_t* tok_base, cudaStream_t st) {
   prof_mark(c, ST_GETFRAME, st);
-  if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
+  if (!c->maps_in) if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
   if (c->fast) return fast_run_batch(c->fast, first_poc, n, c->d_mvx, c->d_mvy, c->d_dep, bytes, nullptr, 0, nullptr, st);
   prof_mark(c, ST_VOTE, st);
   if (int e = camera_motion_launch_f64(c->w, c->h, n, c->d_mvx, c->d_mvy, bytes, c->d_dep, c->r_Vx, c->r_Vy, c->r_mvn, c->r_bitn,
@@ -595,7 +596,7 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   if (c->fast) {          // TDecGop.cpp:270-332 for n pictures: stage (a), then the fast version's kernels (fast.cu)
     if (done_ev) *done_ev = nullptr;
     prof_mark(c, ST_GETFRAME, st);
-    if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
+    if (!c->maps_in) if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
     prof_mark(c, ST_FINAL, st);
     if (before_back) CDS_CUDA(cudaStreamWaitEvent(st, before_back, 0));
     if (int e = fast_run_batch(c->fast, first_poc, n, c->d_mvx, c->d_mvy, c->d_dep, bytes, maps_out, c->p.out_u8, cam_out, st)) return e;
@@ -869,6 +870,51 @@ extern "C" int cds_clip_process(cds_ctx* c, int first_poc, int nframes, const ui
   if (int e = process_host(c, first_poc, nframes, ctu_bytes, hdr, tok, tok_base, ntok, maps_out, cam_out)) return e;
   c->pending_first = c->next_poc;
   return CDS_OK;
+}
+
+// stage-(a) maps in (main.m:25-27,38-55 exchange format), maps out; one batch at a time, no copy / compute overlap
+extern "C" int cds_clip_process_maps(cds_ctx* c, int first_poc, int nframes, const int16_t* mvx, const int16_t* mvy,
+                                     const uint8_t* depth, const uint16_t* ctu_bytes, void* maps_out, int* cam_out) {
+  if (int e = ensure_device()) return e;
+  if (!c || !mvx || !mvy || !depth || !ctu_bytes || nframes < 1) { set_error("cds_clip_process_maps: bad arguments"); return CDS_EINVAL; }
+  if (first_poc != c->next_poc) { set_error("cds_clip_process_maps: expected poc %d, got %d (use cds_seek)", c->next_poc, first_poc); return CDS_EINVAL; }
+  if (c->pending) { set_error("cds_clip_process_maps: pictures submitted through cds_submit_frame are still pending"); return CDS_EINVAL; }
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4), n4 = c->n4;
+  std::vector<int> cam((size_t)2 * c->B);
+  int rc = CDS_OK;
+  c->maps_in = true;
+  for (int done = 0; done < nframes && !rc; done += c->B) {
+    const int n = std::min(c->B, nframes - done);
+    cudaError_t ce = cudaMemcpyAsync(c->d_mvx, mvx + (size_t)done * n4, (size_t)n * n4 * 2, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->d_mvy, mvy + (size_t)done * n4, (size_t)n * n4 * 2, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->d_dep, depth + (size_t)done * n4, (size_t)n * n4, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->d_bytes, ctu_bytes + (size_t)done * c->nctu, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) { set_error("cds_clip_process_maps: copy in: %s", cudaGetErrorString(ce)); rc = CDS_ECUDA; break; }
+    if (!maps_out) { rc = run_context_stages(c, first_poc + done, n, c->d_bytes, nullptr, nullptr, nullptr, st); }
+    else {
+      const int buf = c->out_flip; c->out_flip ^= 1;
+      rc = run_batch(c, first_poc + done, n, c->d_bytes, nullptr, nullptr, nullptr, c->d_out[buf], c->d_cam_stage, st);
+      if (!rc) rc = join_back(c, st);
+      if (!rc) {
+        ce = cudaMemcpyAsync((char*)maps_out + (size_t)done * px, c->d_out[buf], (size_t)n * px, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(cam.data(), c->d_cam_stage, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) { set_error("cds_clip_process_maps: copy out: %s", cudaGetErrorString(ce)); rc = CDS_ECUDA; }
+      }
+      c->last_first = first_poc + done; c->last_n = n; c->last_buf = buf;
+    }
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("cds_clip_process_maps: %s", cudaGetErrorString(cudaGetLastError())); rc = CDS_ECUDA; }
+    if (!rc && maps_out && cam_out) memcpy(cam_out + (size_t)2 * done, cam.data(), (size_t)n * 8);
+  }
+  c->maps_in = false;
+  if (rc) return rc;
+  c->next_poc = first_poc + nframes; c->pending_first = c->next_poc;
+  return CDS_OK;
+}
+
+extern "C" int cds_probe_seq_sum(const float* v, const unsigned char* sel, int n, float* sum, int* count) { return fast_probe_seq_sum(v, sel, n, sum, count); }
+extern "C" int cds_probe_run_sum(const float* vals, int gh, int gw, int rows, int cols, int ms, double t, float* sum, int* count) {
+  return fast_probe_run_sum(vals, gh, gw, rows, cols, ms, t, sum, count);
 }
 
 // ---- hook-style API (TDecGop.cpp:270-332): one picture at a time, batched internally ----

@@ -77,6 +77,19 @@ class SaliencyClip:
                                      _ptr(maps), _ptr(cam)), "cds_clip_process")
         return maps, cam
 
+    def process_maps(self, first_poc, mvx, mvy, depth, ctu_bytes, context_only=False):
+        """Stage-(a) maps in (the mv_x / mv_y / depth / bitmap arrays main.m:25-55 reads; see formats.py), saliency maps out."""
+        mvx = np.ascontiguousarray(mvx, np.int16); mvy = np.ascontiguousarray(mvy, np.int16)
+        depth = np.ascontiguousarray(depth, np.uint8); byts = np.ascontiguousarray(ctu_bytes, np.uint16)
+        F = mvx.shape[0]; h4, w4 = self.h // 4, self.w // 4
+        if mvx.shape != (F, h4, w4) or mvy.shape != mvx.shape or depth.shape != mvx.shape or byts.reshape(F, -1).shape[1] != nctu(self.w, self.h):
+            raise CdsError("process_maps: map shapes do not match the picture size")
+        maps = None if context_only else np.zeros((F, self.h, self.w), np.uint8 if self.out_u8 else np.float32)
+        cam = np.zeros((F, 2), np.int32)
+        check(lib().cds_clip_process_maps(self._h, int(first_poc), F, _ptr(mvx), _ptr(mvy), _ptr(depth), _ptr(byts),
+                                          None if context_only else _ptr(maps), _ptr(cam)), "cds_clip_process_maps")
+        return maps, cam
+
     def context(self, first_poc, hdr, tok, tok_base, ctu_bytes):
         """Feed pictures as temporal context only (frame-range sharding halo): no maps are produced."""
         hdr = np.ascontiguousarray(hdr, np.int32); tok = np.ascontiguousarray(tok, np.int16)

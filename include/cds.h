@@ -165,6 +165,17 @@ int cds_clip_process_dev(cds_ctx* ctx, int first_poc, int nframes, const uint16_
 int cds_clip_process(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* ctu_bytes,
                      const int32_t* hdr, const int16_t* tok, const int64_t* tok_base, size_t ntok,
                      void* maps_out, int* cam_out);
+/* The same clip step from stage-(a) MAPS instead of syntax — the reference's normal version exchanges exactly these between its
+ * decoder and MATLAB (main.m:25-27,38-55: mv_x / mv_y / depth h/4 x w/4 per picture and the bytes-per-CTU bitmap, as text files or
+ * .mat cell arrays; formats.py reads both).  HOST buffers: mvx, mvy [nframes][h/4*w/4] quarter-pel int16, depth u8 (0..3),
+ * ctu_bytes [nframes][nctu] u16.  Works in every fusion mode; maps_out NULL feeds the pictures as temporal context only. */
+int cds_clip_process_maps(cds_ctx* ctx, int first_poc, int nframes, const int16_t* mvx, const int16_t* mvy,
+                          const uint8_t* depth, const uint16_t* ctu_bytes, void* maps_out, int* cam_out);
+/* Probes of the fast version's sequential-float-sum emulation (csrc/fast.cu): the float32 result of
+ * `S = 0; for (i < n) if (sel[i]) S = S + v[i];` (salmat.cpp:155-162, TDecGop.cpp:622-640; n a multiple of 4), and of the same loop
+ * over a rows x cols raster of replicated blocks (gh x gw values, block size ms, elements > t selected).  Host buffers. */
+int cds_probe_seq_sum(const float* v, const unsigned char* sel, int n, float* sum, int* count);
+int cds_probe_run_sum(const float* vals, int gh, int gw, int rows, int cols, int ms, double t, float* sum, int* count);
 /* Drop all temporal state (start a new clip at POC 0). */
 int cds_reset(cds_ctx* ctx);
 /* Drop all temporal state and continue at picture `poc` (frame-range sharding: seek to

@@ -118,6 +118,9 @@ int orc_fast_frame(orc_fast* o, const int16_t* mvx, const int16_t* mvy, const ui
 /* cv::getGaussianKernel(n, sigma, CV_32F) and cv::GaussianBlur(CV_32F, BORDER_CONSTANT) as OpenCV 2.4.9 evaluates them */
 void orc_cv_gaussian_kernel(int n, double sigma, float* k);
 void orc_cv_gaussian_blur(const float* src, int rows, int cols, int ksize, double sigma, float* dst, float* tmp);
+/* the sequential float loops of MapThreshold / Umean, plainly (checkers for cds_probe_seq_sum / cds_probe_run_sum) */
+float orc_seq_sum_f32(const float* v, const unsigned char* sel, long n, int* count);
+float orc_run_sum_f32(const float* vals, int gh, int gw, int rows, int cols, int ms, double t, int* count);
 
 #ifdef __cplusplus
 }

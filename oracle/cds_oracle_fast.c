@@ -337,3 +337,17 @@ int orc_fast_frame(orc_fast* o, const int16_t* mvx, const int16_t* mvy, const ui
   o->frame++;
   return 0;
 }
+
+/* the two sequential float loops the GPU emulates, for the probe tests */
+float orc_seq_sum_f32(const float* v, const unsigned char* sel, long n, int* count) {
+  float s = 0; int c = 0;
+  for (long i = 0; i < n; i++) if (sel[i]) { s = s + v[i]; c++; }
+  *count = c;
+  return s;
+}
+float orc_run_sum_f32(const float* vals, int gh, int gw, int rows, int cols, int ms, double t, int* count) {
+  float s = 0; int c = 0; (void)gh;
+  for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) { float v = vals[(y / ms) * gw + x / ms]; if (v > t) { s = s + v; c++; } }
+  *count = c;
+  return s;
+}

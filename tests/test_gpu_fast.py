@@ -138,3 +138,130 @@ def test_reference_decoder_with_cds_hook_reproduces_its_own_golden_pngs(cds, tmp
     got, _ = clip.process(0, d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"])
     clip.close()
     assert np.array_equal(maps[:n], got)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# The sequential-float-sum emulation on adversarial data: ties on the running sum's ulp grid, binade crossings, mixed signs, terms
+# that vanish against the sum, terms larger than the sum.  Checker: the plain loops in oracle/cds_oracle_fast.c.
+def _seq_ref(v, sel):
+    import ctypes as C
+    L = o.oracle(); L.orc_seq_sum_f32.restype = C.c_float
+    L.orc_seq_sum_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+    cnt = C.c_int(0)
+    return np.float32(L.orc_seq_sum_f32(v.ctypes.data, sel.ctypes.data, v.size, C.byref(cnt))), cnt.value
+
+
+def _seq_gpu(cds, v, sel):
+    import ctypes as C
+    s = C.c_float(0); cnt = C.c_int(0)
+    cds._lib.check(cds.lib().cds_probe_seq_sum(v.ctypes.data_as(C.c_void_p), sel.ctypes.data_as(C.c_void_p), v.size, C.byref(s), C.byref(cnt)), "probe")
+    return np.float32(s.value), cnt.value
+
+
+SEQ_CASES = {
+    "uniform01": lambda r, n: r.random(n, dtype=np.float32),
+    "dyadic_ties": lambda r, n: (r.integers(1, 64, n) * 0.125).astype(np.float32),              # every term a tie candidate once ulp(S) = 0.25
+    "quarter_pel_mixed_sign": lambda r, n: (r.integers(-4000, 4001, n) * 0.25).astype(np.float32),
+    "large_then_tiny": lambda r, n: np.concatenate([np.full(64, 3.0e6, np.float32), r.random(n - 64, dtype=np.float32) * 0.2]),
+    "tiny_then_large": lambda r, n: np.concatenate([r.random(n - 64, dtype=np.float32) * 1e-3, np.full(64, 7.7e5, np.float32)]),
+    "constant_1000.25": lambda r, n: np.full(n, 1000.25, np.float32),
+    "wide_dynamic_range": lambda r, n: np.exp(r.uniform(-20, 12, n)).astype(np.float32),
+    "cancelling": lambda r, n: (np.where(np.arange(n) % 2 == 0, 1.0, -1.0) * r.random(n)).astype(np.float32),
+    "negative_only": lambda r, n: -r.random(n, dtype=np.float32) * 37,
+    "zeros_and_ones": lambda r, n: r.integers(0, 2, n).astype(np.float32),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SEQ_CASES))
+def test_sequential_float_sum_emulation_is_bit_exact(cds, case):
+    r = np.random.default_rng(abs(hash(case)) % 1000)
+    for n, dens in ((4096, 1.0), (129600, 0.3), (400000, 0.9), (518400, 0.02)):
+        v = np.ascontiguousarray(SEQ_CASES[case](r, n)[:n], np.float32)
+        sel = (r.random(n) < dens).astype(np.uint8)
+        want, wc = _seq_ref(v, sel)
+        got, gc = _seq_gpu(cds, v, sel)
+        assert gc == wc
+        assert got.tobytes() == want.tobytes(), (case, n, dens, float(got), float(want))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_replicated_block_sum_emulation_is_bit_exact(cds, seed):
+    import ctypes as C
+    L = o.oracle(); L.orc_run_sum_f32.restype = C.c_float
+    L.orc_run_sum_f32.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_double, C.c_void_p]
+    r = np.random.default_rng(seed)
+    for (rows, cols, ms) in ((1080, 1920, 32), (1080, 1920, 64), (270, 480, 16), (480, 832, 32), (2160, 3840, 32)):
+        gh, gw = -(-rows // ms), -(-cols // ms)
+        kinds = [r.random((gh, gw), dtype=np.float32),
+                 (r.integers(0, 17, (gh, gw)) * 0.0625).astype(np.float32),                       # ties once ulp(S) = 0.125
+                 np.where(r.random((gh, gw)) < 0.9, np.float32(1.0), r.random((gh, gw), dtype=np.float32)).astype(np.float32),
+                 np.full((gh, gw), 0.5625, np.float32)]
+        for vals in kinds:
+            vals = np.ascontiguousarray(vals, np.float32)
+            for t in (-1.0, 0.3, float(vals.max()) - float(vals.mean())):
+                wc = C.c_int(0)
+                want = np.float32(L.orc_run_sum_f32(vals.ctypes.data, gh, gw, rows, cols, ms, t, C.byref(wc)))
+                s = C.c_float(0); gc = C.c_int(0)
+                cds._lib.check(cds.lib().cds_probe_run_sum(vals.ctypes.data_as(C.c_void_p), gh, gw, rows, cols, ms, C.c_double(t), C.byref(s), C.byref(gc)), "probe")
+                assert gc.value == wc.value
+                assert np.float32(s.value).tobytes() == want.tobytes(), (rows, cols, ms, t, float(s.value), float(want))
+
+
+def _oracle_maps(w, h, fps, mvx, mvy, dep, byts):
+    fo = o.FastOracle(w, h, fps)
+    res = [fo.frame(mvx[f], mvy[f], dep[f], byts[f]) for f in range(mvx.shape[0])]
+    fo.close()
+    return np.stack([x[0] for x in res]), np.stack([x[1] for x in res]), np.stack([x[2] for x in res])
+
+
+@pytest.mark.parametrize("case", ["huge_mv", "uniform_pan_ties", "static_zero", "all_intra_flat", "sparse_extremes"])
+def test_fast_version_from_maps_on_adversarial_pictures(cds, case):
+    """cds_clip_process_maps (stage-(a) maps in) on inputs no bitstream fixture reaches: motion so large that Umean's first loop
+    is itself inexact (sum of |mv| >= 2^24 quarter-pels), a uniform pan whose terms tie on the sum's grid, static and flat pictures
+    (every MatrixNorm / MapThreshold takes its copy branch), maps with single extreme cells."""
+    w, h, fps, F = (1920, 1088, 50.0, 5) if case in ("huge_mv", "uniform_pan_ties") else (416, 240, 30.0, 14)
+    h4, w4, nctu = h // 4, w // 4, ((w + 63) // 64) * ((h + 63) // 64)
+    r = np.random.default_rng(42)
+    if case == "huge_mv":
+        mvx = r.integers(-30000, 30001, (F, h4, w4)).astype(np.int16); mvy = r.integers(-30000, 30001, (F, h4, w4)).astype(np.int16)
+        mvx[:, :, : w4 // 2] = 28000 + (mvx[:, :, : w4 // 2] % 7)                          # a dominant direction bin with a huge mean
+        dep = r.integers(0, 4, (F, h4, w4)).astype(np.uint8); byts = r.integers(0, 300, (F, nctu)).astype(np.uint16)
+    elif case == "uniform_pan_ties":
+        mvx = np.full((F, h4, w4), 4001, np.int16); mvy = np.full((F, h4, w4), -4001, np.int16)   # 1000.25 px: ties once ulp(S) = 0.5
+        mvx[:, ::7, ::5] += 8
+        dep = np.full((F, h4, w4), 2, np.uint8); byts = np.full((F, nctu), 57, np.uint16)
+    elif case == "static_zero":
+        mvx = np.zeros((F, h4, w4), np.int16); mvy = np.zeros((F, h4, w4), np.int16)
+        dep = r.integers(0, 4, (F, h4, w4)).astype(np.uint8); byts = r.integers(0, 4095, (F, nctu)).astype(np.uint16)
+    elif case == "all_intra_flat":
+        mvx = np.zeros((F, h4, w4), np.int16); mvy = np.zeros((F, h4, w4), np.int16)
+        dep = np.zeros((F, h4, w4), np.uint8); byts = np.zeros((F, nctu), np.uint16)
+    else:
+        mvx = np.zeros((F, h4, w4), np.int16); mvy = np.zeros((F, h4, w4), np.int16)
+        mvx[:, 5, 7] = 32767; mvy[:, 50, 90] = -32768
+        dep = np.zeros((F, h4, w4), np.uint8); dep[:, 0, 0] = 3
+        byts = np.full((F, nctu), 10, np.uint16); byts[:, 3] = 4095
+    want_u8, want_f32, want_cam = _oracle_maps(w, h, fps, mvx, mvy, dep, byts)
+    clip = cds.SaliencyClip(w, h, fps, fast=True, out_u8=False, max_batch=4)
+    got, cam = clip.process_maps(0, mvx, mvy, dep, byts)
+    clip.close()
+    assert np.array_equal(cam, want_cam), (cam, want_cam)
+    assert got.tobytes() == want_f32.tobytes(), float(np.nanmax(np.abs(got - want_f32)))
+    if case in ("huge_mv", "uniform_pan_ties"):
+        assert np.abs(want_cam).sum() > 0
+
+
+def test_process_maps_equals_process_from_syntax_in_the_svm_mode(cds):
+    """cds_clip_process_maps in the nine-feature + SVM mode: feeding the stage-(a) maps gives the bytes the syntax path gives."""
+    w, h, fps, F = 416, 240, 24.0, 9
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 3, F)
+    SV, coef, rho, gamma, labels = o.synth_model(64)
+    gm = cds.ops.SvmModel(SVs=SV * 0.5 + 1.0, sv_coef=coef, rho=rho, gamma=gamma, Label=labels)
+    a = cds.SaliencyClip(w, h, fps, model=gm, meanVec=np.full(9, 0.3), stdVec=np.full(9, 0.2), max_batch=4)
+    want, wcam = a.process(0, hdr, tok, base, byts)
+    a.close()
+    maps = [cds.ops.getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    b = cds.SaliencyClip(w, h, fps, model=gm, meanVec=np.full(9, 0.3), stdVec=np.full(9, 0.2), max_batch=4)
+    got, cam = b.process_maps(0, np.stack([m[0] for m in maps]), np.stack([m[1] for m in maps]), np.stack([m[2] for m in maps]), byts)
+    b.close()
+    assert np.array_equal(cam, wcam) and got.tobytes() == want.tobytes()
