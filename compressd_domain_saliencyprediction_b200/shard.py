@@ -12,8 +12,12 @@ def matlab_round(x):
     return int(np.floor(x + 0.5)) if x >= 0 else -int(np.floor(-x + 0.5))
 
 
-def halo_frames(fps):
-    """PS + PT - 2 with PS = round(0.3 fps), PT = round(7 PS) (main.m:119,129)."""
+def halo_frames(fps, fast=False):
+    """PS + PT - 2 with PS = round(0.3 fps), PT = round(7 PS) (main.m:119,129); fast version: PS = cvRound(0.3 fps),
+    PT = cvRound(0.7 fps) (salmat.cpp:18-19, round half to even)."""
+    if fast:
+        import numpy as np
+        return max(1, int(np.rint(fps * 0.3))) + max(1, int(np.rint(fps * 0.7))) - 2
     ps = matlab_round(fps * 0.3)
     return ps + matlab_round(ps * 7.0) - 2
 

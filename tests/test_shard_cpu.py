@@ -73,3 +73,12 @@ def test_frame_range_sharding_world2_gloo():
         assert p.exitcode == 0
     want = _causal(np.random.default_rng(11).standard_normal(nframes), halo)
     assert np.array_equal(got, want)         # same arithmetic on the same window -> bytewise identical
+
+
+def test_halo_of_the_fast_version():
+    """salmat.cpp:18-19: cvRound(0.3 fps) + cvRound(0.7 fps) - 2 pictures of context (cvRound rounds halves to even)."""
+    from compressd_domain_saliencyprediction_b200 import shard
+    assert shard.halo_frames(50.0, fast=True) == 15 + 35 - 2
+    assert shard.halo_frames(25.0, fast=True) == 8 + 18 - 2          # 7.5 -> 8, 17.5 -> 18
+    assert shard.halo_frames(30.0, fast=True) == 9 + 21 - 2
+    assert shard.halo_frames(50.0) == 15 + 105 - 2
