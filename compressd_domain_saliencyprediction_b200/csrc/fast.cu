@@ -119,11 +119,13 @@ __device__ __forceinline__ bool term_increment(float v, unsigned Cb, float lim, 
   return q0 == q1;
 }
 
+// A round covers 32 pieces of 128 consecutive cells (one warp x one chunk of T*4 cells); K = 32 / (T/32) chunks per round.
 template <int T>
 struct SeqSumSmem {
-  float terms[T * 4];
-  unsigned char sel[T];
-  int wqp[T / 32], wqn[T / 32], wflag[T / 32];
+  static constexpr int NW = T / 32, K = 32 / NW;
+  float terms[K][T * 4];
+  unsigned char sel[K][T];
+  int pp[32], pn[32], pf[32];          // per piece: positive ulps, negative ulps, flag (1: needs the sequential path, -1: empty)
   float S; int restart;
 };
 
@@ -132,21 +134,29 @@ struct SeqSumSmem {
 template <int T, typename LoadFn, typename EvalFn>
 __device__ float block_seq_sum(int ngroups, LoadFn load, EvalFn eval, SeqSumSmem<T>& sm, int* count_out) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = T / 32;
+  constexpr int NW = T / 32, K = 32 / NW;
   int cnt = 0;
   __syncthreads();
   if (tid == 0) sm.S = 0.f;
-  auto raw_n = load(min(tid, ngroups - 1));              // raw words of the next chunk stay in registers until they are needed
-  for (int g0 = 0; g0 < ngroups; g0 += T) {
-    float tn[4];
-    const unsigned sel = g0 + tid < ngroups ? eval(raw_n, tn) : 0u;
-    const float t0 = tn[0], t1 = tn[1], t2 = tn[2], t3 = tn[3];
-    raw_n = load(min(g0 + T + tid, ngroups - 1));        // prefetch
-    cnt += __popc(sel);
-    __syncthreads();                                   // the previous chunk's reads of sm.terms are over
-    *reinterpret_cast<float4*>(&sm.terms[tid * 4]) = make_float4(t0, t1, t2, t3);
-    sm.sel[tid] = (unsigned char)sel;
-    int first = 0;
+  decltype(load(0)) raw[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) raw[k] = load(min(k * T + tid, ngroups - 1));        // raw words of the next round stay in registers
+  for (int g0 = 0; g0 < ngroups; g0 += K * T) {
+    float t[K][4]; unsigned sel[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      sel[k] = g0 + k * T + tid < ngroups ? eval(raw[k], t[k]) : 0u;
+      raw[k] = load(min(g0 + (K + k) * T + tid, ngroups - 1));                      // prefetch
+      cnt += __popc(sel[k]);
+    }
+    __syncthreads();                                   // the previous round's reads of sm.terms are over
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      *reinterpret_cast<float4*>(&sm.terms[k][tid * 4]) = make_float4(t[k][0], t[k][1], t[k][2], t[k][3]);
+      sm.sel[k][tid] = (unsigned char)sel[k];
+    }
+    int first = 0;                                     // pieces before `first` are already in S
+    int regrids = 0;                                   // times this round had to be re-evaluated on a new grid
     while (true) {
       __syncthreads();
       const unsigned Sb = __float_as_uint(sm.S);
@@ -154,69 +164,81 @@ __device__ float block_seq_sum(int ngroups, LoadFn load, EvalFn eval, SeqSumSmem
       const bool bad = eb < 2u || eb >= 0xfeu;
       const unsigned Cb = (eb << 23) | 0x400000u;
       const float lim = __uint_as_float((eb - 1u) << 23);
-      int qp = 0, qn = 0, flag = bad ? 1 : 0;
-      if (wid >= first && !bad) {
-        const float tt[4] = {t0, t1, t2, t3};
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if ((sel >> j) & 1u) {
-            int q;
-            if (!term_increment(neg ? -tt[j] : tt[j], Cb, lim, &q)) flag = 1;
-            else if (q > 0) qp += q; else qn -= q;
-          }
-      }
+      for (int k = 0; k < K; k++) {
+        const int piece = k * NW + wid;
+        int qp = 0, qn = 0, flag = bad ? 1 : 0;
+        if (piece >= first && !bad) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { qp += __shfl_xor_sync(FULL, qp, o); qn += __shfl_xor_sync(FULL, qn, o); flag |= __shfl_xor_sync(FULL, flag, o); }
-      const unsigned anysel = __ballot_sync(FULL, sel != 0u);
-      if (lane == 0) { sm.wqp[wid] = qp; sm.wqn[wid] = qn; sm.wflag[wid] = anysel ? flag : -1; }      // -1: nothing selected in this piece
-      __syncthreads();
-      if (tid == 0) {
-        float S = sm.S; int restart = NW;
-        // the whole chunk at once when it is valid as one piece
-        unsigned tp = 0, tq = 0; int tf = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) if (w >= first && sm.wflag[w] >= 0) { tp += (unsigned)sm.wqp[w]; tq += (unsigned)sm.wqn[w]; tf |= sm.wflag[w]; }
-        {
-          const unsigned sb = __float_as_uint(S), ab = sb & 0x7fffffffu;
-          const unsigned m = (ab & 0x7fffffu) | 0x800000u;
-          if (!tf && m + tp <= 0xffffffu && (tq == 0u || m >= 0x800001u + tq)) {
-            S = __uint_as_float((sb & 0x80000000u) | (ab + tp - tq));
-            first = NW;
-          }
-        }
-        for (int w = first; w < NW; w++) {
-          if (sm.wflag[w] < 0) continue;
-          const unsigned sb = __float_as_uint(S), ab = sb & 0x7fffffffu;
-          const unsigned m = (ab & 0x7fffffu) | 0x800000u;
-          const unsigned wp = (unsigned)sm.wqp[w], wn = (unsigned)sm.wqn[w];
-          if (!sm.wflag[w] && m + wp <= 0xffffffu && (wn == 0u || m >= 0x800001u + wn)) {
-            S = __uint_as_float((sb & 0x80000000u) | (ab + wp - wn));
-          } else {
-            for (int i = w * 32; i < w * 32 + 32; i++) {
-              const unsigned sl = sm.sel[i];
-              if (sl & 1u) S = __fadd_rn(S, sm.terms[i * 4]);
-              if (sl & 2u) S = __fadd_rn(S, sm.terms[i * 4 + 1]);
-              if (sl & 4u) S = __fadd_rn(S, sm.terms[i * 4 + 2]);
-              if (sl & 8u) S = __fadd_rn(S, sm.terms[i * 4 + 3]);
+          for (int j = 0; j < 4; j++)
+            if ((sel[k] >> j) & 1u) {
+              int q;
+              if (!term_increment(neg ? -t[k][j] : t[k][j], Cb, lim, &q)) flag = 1;
+              else if (q > 0) qp += q; else qn -= q;
             }
-            const unsigned nb = __float_as_uint(S);
-            if (((nb >> 23) & 0xffu) != eb || (nb >> 31) != (Sb >> 31)) { restart = w + 1; break; }
-          }
         }
-        sm.S = S; sm.restart = restart;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { qp += __shfl_xor_sync(FULL, qp, o); qn += __shfl_xor_sync(FULL, qn, o); flag |= __shfl_xor_sync(FULL, flag, o); }
+        const unsigned anysel = __ballot_sync(FULL, sel[k] != 0u);
+        if (lane == 0) { sm.pp[piece] = qp; sm.pn[piece] = qn; sm.pf[piece] = anysel ? flag : -1; }
+      }
+      __syncthreads();
+      if (wid == 0) {
+        // lane l owns piece l: prefix sums of the increments decide how far the round can be applied in one step
+        float S = sm.S; int restart = 32;
+        const int pf = sm.pf[lane];
+        const unsigned pp = (lane >= first && pf >= 0) ? (unsigned)sm.pp[lane] : 0u, pn = (lane >= first && pf >= 0) ? (unsigned)sm.pn[lane] : 0u;
+        int from = first;
+        while (from < 32) {
+          const unsigned sb = __float_as_uint(S), ab = sb & 0x7fffffffu, m = (ab & 0x7fffffu) | 0x800000u;
+          unsigned cp = lane >= from ? pp : 0u, cn = lane >= from ? pn : 0u;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const unsigned up = __shfl_up_sync(FULL, cp, o), un = __shfl_up_sync(FULL, cn, o); if (lane >= o) { cp += up; cn += un; } }
+          // a sum that keeps changing binade (it hovers around zero, or it is still tiny) is walked float by float for the rest of the round
+          const bool walk = regrids > 2;
+          const bool inval = lane >= from && pf >= 0 && (walk || pf > 0 || m + cp > 0xffffffu || (cn != 0u && m < 0x800001u + cn));
+          const unsigned bal = __ballot_sync(FULL, inval);
+          const int stop = bal ? __ffs(bal) - 1 : 32;              // first piece that cannot be applied in closed form
+          const int lastok = stop - 1;
+          if (lastok >= from) {
+            const unsigned ap = __shfl_sync(FULL, cp, lastok), an = __shfl_sync(FULL, cn, lastok);
+            S = __uint_as_float((sb & 0x80000000u) | (ab + ap - an));
+          }
+          if (stop == 32) break;
+          // piece `stop` one float at a time (lane 0 computes, all lanes follow the same control flow)
+          const int k = stop / NW, w = stop - k * NW;
+          {                                                          // lane l fetches thread l's terms; the chain of additions reads them by shuffle
+            const float4 tq = *reinterpret_cast<const float4*>(&sm.terms[k][(w * 32 + lane) * 4]);
+            const unsigned sq = sm.sel[k][w * 32 + lane];
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) {
+              const unsigned sl = __shfl_sync(FULL, sq, i);
+              const float a0 = __shfl_sync(FULL, tq.x, i), a1 = __shfl_sync(FULL, tq.y, i), a2 = __shfl_sync(FULL, tq.z, i), a3 = __shfl_sync(FULL, tq.w, i);
+              if (sl & 1u) S = __fadd_rn(S, a0);
+              if (sl & 2u) S = __fadd_rn(S, a1);
+              if (sl & 4u) S = __fadd_rn(S, a2);
+              if (sl & 8u) S = __fadd_rn(S, a3);
+            }
+          }
+          from = stop + 1;
+          const unsigned nb = __float_as_uint(S);
+          if (!walk && (((nb >> 23) & 0xffu) != eb || (nb >> 31) != (Sb >> 31))) { restart = from; break; }     // new grid: re-evaluate the rest
+        }
+        if (lane == 0) { sm.S = S; sm.restart = restart; }
       }
       __syncthreads();
       first = sm.restart;
-      if (first >= NW) break;
+      if (first >= 32) break;
+      regrids++;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
   __syncthreads();
-  if (lane == 0) sm.wqp[wid] = cnt;
+  if (lane == 0) sm.pp[wid] = cnt;
   __syncthreads();
   int total = 0;
-  for (int w = 0; w < NW; w++) total += sm.wqp[w];
+  for (int w = 0; w < NW; w++) total += sm.pp[w];
   *count_out = total;
   return sm.S;
 }
@@ -380,6 +402,7 @@ __global__ void __launch_bounds__(CAM_T) fast_cam_vote_kernel(FastP P, int first
   __shared__ SeqSumSmem<CAM_T> s_seq;
   const int back = ci[0], stat = ci[1];
   float v = 0.f;
+  long long t_prof = clock64();
   if (stat <= back / 2) {                                   // TDecGop.cpp:529 (integer division)
     int best = 0, bc = -1;
     for (int j = 0; j < 16; j++) if (ci[2 + j] > bc) { bc = ci[2 + j]; best = j; }
@@ -400,6 +423,7 @@ __global__ void __launch_bounds__(CAM_T) fast_cam_vote_kernel(FastP P, int first
         }
     }
     s = block_reduce(s, OpAddL(), s_l); a = block_reduce(a, OpAddL(), s_l);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { const long long t_ = clock64(); g_fast_prof[0] = t_ - t_prof; t_prof = t_; }
     int cnt;
     struct Raw { uchar4 b; short4 m; };
     auto load = [&](int g) -> Raw { return Raw{reinterpret_cast<const uchar4*>(bin)[g], reinterpret_cast<const short4*>(m)[g]}; };
@@ -418,6 +442,7 @@ __global__ void __launch_bounds__(CAM_T) fast_cam_vote_kernel(FastP P, int first
     };
     const float sum2 = block_seq_sum<CAM_T>(n4 / 4, load, clamped, s_seq, &cnt);
     v = __fdiv_rn(sum2, (float)len);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { const long long t_ = clock64(); g_fast_prof[2] = t_ - t_prof; g_fast_prof[1] = len; g_fast_prof[3] = (a < (1ll << 24)); }
   }
   if (tid == 0) P.d_camf[b * 2 + comp] = v;
 }
@@ -475,11 +500,12 @@ __global__ void __launch_bounds__(128 * SM_G) fast_smooth_kernel(FastP P, int fi
   const int k = blockIdx.x * 128 + c, b0 = blockIdx.y * SM_G, F0 = first_poc + b0;
   const int n4 = P.n4, PS = P.PS, nf = SM_G + PS - 1;
   const int fbase = F0 - (PS - 1);                       // picture held by tile row 0
+  const int slot0 = ((fbase % P.RL) + P.RL) % P.RL;
   for (int i = tid; i < nf * 128; i += 128 * SM_G) {
     const int fr = i >> 7, cc = i & 127, f = fbase + fr, kk = blockIdx.x * 128 + cc;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f >= 0 && kk < n4 && f < first_poc + n) {
-      const int slot = f % P.RL;
+      const int slot = slot0 + fr < P.RL ? slot0 + fr : slot0 + fr - P.RL;
       const float* sc = P.r_sc + (size_t)slot * 8;
       const size_t o = (size_t)slot * n4 + kk;
       const float x = __fadd_rn(__fmul_rn((float)P.r_mvx[o], 0.25f), sc[0]), y = __fadd_rn(__fmul_rn((float)P.r_mvy[o], 0.25f), sc[1]);
@@ -495,9 +521,10 @@ __global__ void __launch_bounds__(128 * SM_G) fast_smooth_kernel(FastP P, int fi
   const int cnt = F < PS ? F + 1 : PS;
   const float rc = __double2float_rn(__ddiv_rn(1.0, (double)cnt));
   float ad = 0.f, an = 0.f, ax = 0.f, ay = 0.f;
+  const int i0 = F % PS;                                   // ring slot i holds picture F - i0 + i (i <= i0) or F - i0 + i - PS (i > i0)
+  const float4* col = s_raw + (F - i0 - fbase) * 128 + c;
   for (int i = 0; i < cnt; i++) {
-    const int f = F < PS ? i : F - ((F - i) % PS);        // the picture held by ring slot i
-    const float4 v = s_raw[(f - fbase) * 128 + c];
+    const float4 v = col[(i - (i > i0 ? PS : 0)) * 128];
     ad = __fadd_rn(__fmul_rn(v.x, rc), ad); an = __fadd_rn(__fmul_rn(v.y, rc), an);
     ax = __fadd_rn(__fmul_rn(v.z, rc), ax); ay = __fadd_rn(__fmul_rn(v.w, rc), ay);
   }
@@ -799,11 +826,13 @@ __global__ void __launch_bounds__(256) fast_blur_h_kernel(FastP P) {
     for (int m = 0; m < nq; m++) {
       const float c1 = s_row[p + m + 1];
       const float4 k = __ldg(k4 + m);
-      // pixel j, tap 4m + i reads cell m + (j + i) / 4
-      s0 = __fadd_rn(s0, __fmul_rn(c0, k.x)); s0 = __fadd_rn(s0, __fmul_rn(c0, k.y)); s0 = __fadd_rn(s0, __fmul_rn(c0, k.z)); s0 = __fadd_rn(s0, __fmul_rn(c0, k.w));
-      s1 = __fadd_rn(s1, __fmul_rn(c0, k.x)); s1 = __fadd_rn(s1, __fmul_rn(c0, k.y)); s1 = __fadd_rn(s1, __fmul_rn(c0, k.z)); s1 = __fadd_rn(s1, __fmul_rn(c1, k.w));
-      s2 = __fadd_rn(s2, __fmul_rn(c0, k.x)); s2 = __fadd_rn(s2, __fmul_rn(c0, k.y)); s2 = __fadd_rn(s2, __fmul_rn(c1, k.z)); s2 = __fadd_rn(s2, __fmul_rn(c1, k.w));
-      s3 = __fadd_rn(s3, __fmul_rn(c0, k.x)); s3 = __fadd_rn(s3, __fmul_rn(c1, k.y)); s3 = __fadd_rn(s3, __fmul_rn(c1, k.z)); s3 = __fadd_rn(s3, __fmul_rn(c1, k.w));
+      // pixel j, tap 4m + i reads cell m + (j + i) / 4: seven distinct products in the 16 (pixel, tap) pairs
+      const float x0 = __fmul_rn(c0, k.x), y0 = __fmul_rn(c0, k.y), z0 = __fmul_rn(c0, k.z), w0 = __fmul_rn(c0, k.w);
+      const float y1 = __fmul_rn(c1, k.y), z1 = __fmul_rn(c1, k.z), w1 = __fmul_rn(c1, k.w);
+      s0 = __fadd_rn(s0, x0); s0 = __fadd_rn(s0, y0); s0 = __fadd_rn(s0, z0); s0 = __fadd_rn(s0, w0);
+      s1 = __fadd_rn(s1, x0); s1 = __fadd_rn(s1, y0); s1 = __fadd_rn(s1, z0); s1 = __fadd_rn(s1, w1);
+      s2 = __fadd_rn(s2, x0); s2 = __fadd_rn(s2, y0); s2 = __fadd_rn(s2, z1); s2 = __fadd_rn(s2, w1);
+      s3 = __fadd_rn(s3, x0); s3 = __fadd_rn(s3, y1); s3 = __fadd_rn(s3, z1); s3 = __fadd_rn(s3, w1);
       c0 = c1;
     }
     reinterpret_cast<float4*>(P.d_hrow + ((size_t)b * P.h4 + r) * P.w)[p] = make_float4(s0, s1, s2, s3);
@@ -813,18 +842,18 @@ __global__ void __launch_bounds__(256) fast_blur_h_kernel(FastP P) {
 // Column pass (filter.cpp SymmColumnFilter): s = fl(x[0] * k[0]); s = fl(s + fl(fl(x[+t] + x[-t]) * k[t])), t = 1..half.  The row-pass
 // output is constant over the 4 pixel rows of a cell row; a thread computes the 4 pixel rows of one cell row q for one column.
 // A CTA stages BV_Q cell rows plus the nq_v + 1 rows above and below of a 128-column strip in shared memory.
-constexpr int BV_Q = 8;
+constexpr int BV_Q = 16;
 
 __global__ void __launch_bounds__(256) fast_blur_v_kernel(FastP P) {
-  extern __shared__ float s_t[];                          // [BV_Q + 2 * (nq_v + 1)][128] cell rows, then the taps
+  extern __shared__ __align__(16) float s_t[];            // [BV_Q + 2 * (nq_v + 1)][128] cell rows, then the taps
   const int x0 = blockIdx.x * 128, q0 = blockIdx.y * BV_Q, b = blockIdx.z;
   const int W = P.w, h4 = P.h4, nq = P.nq_v, nr = BV_Q + 2 * (nq + 1);
   float* s_k = s_t + nr * 128;
   __shared__ float s_f[32];
   const float* hr = P.d_hrow + (size_t)b * h4 * W;
-  for (int i = threadIdx.x; i < nr * 128; i += 256) {
-    const int rr = i >> 7, cc = i & 127, q = q0 - (nq + 1) + rr, x = x0 + cc;
-    s_t[i] = (q >= 0 && q < h4 && x < W) ? hr[(size_t)q * W + x] : 0.f;
+  for (int i = threadIdx.x; i < nr * 32; i += 256) {        // float4 columns: W % 4 == 0 and x0 % 128 == 0
+    const int rr = i >> 5, c4 = i & 31, q = q0 - (nq + 1) + rr, x = x0 + c4 * 4;
+    reinterpret_cast<float4*>(s_t)[i] = (q >= 0 && q < h4 && x < W) ? *reinterpret_cast<const float4*>(hr + (size_t)q * W + x) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int i = threadIdx.x; i < 4 + 4 * nq; i += 256) s_k[i] = P.d_kv[i];
   __syncthreads();
@@ -837,18 +866,17 @@ __global__ void __launch_bounds__(256) fast_blur_v_kernel(FastP P) {
     const float ctr = col[0];
     float s0 = __fmul_rn(ctr, s_k[0]), s1 = s0, s2 = s0, s3 = s0;
     float a0 = ctr, b0 = ctr;
+#pragma unroll 3
     for (int m = 0; m < nq; m++) {
       const float a1 = col[(m + 1) * 128], b1 = col[-(m + 1) * 128];
       const float4 k = *reinterpret_cast<const float4*>(s_k + 4 + 4 * m);
-      // pixel row j, tap t = 4m + i (i = 1..4): above cell m + (j + i) / 4, below cell -(m + (i - j + 3) / 4)
-      s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a0, b1), k.x)); s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a0, b1), k.y));
-      s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a0, b1), k.z)); s0 = __fadd_rn(s0, __fmul_rn(__fadd_rn(a1, b1), k.w));
-      s1 = __fadd_rn(s1, __fmul_rn(__fadd_rn(a0, b0), k.x)); s1 = __fadd_rn(s1, __fmul_rn(__fadd_rn(a0, b1), k.y));
-      s1 = __fadd_rn(s1, __fmul_rn(__fadd_rn(a1, b1), k.z)); s1 = __fadd_rn(s1, __fmul_rn(__fadd_rn(a1, b1), k.w));
-      s2 = __fadd_rn(s2, __fmul_rn(__fadd_rn(a0, b0), k.x)); s2 = __fadd_rn(s2, __fmul_rn(__fadd_rn(a1, b0), k.y));
-      s2 = __fadd_rn(s2, __fmul_rn(__fadd_rn(a1, b1), k.z)); s2 = __fadd_rn(s2, __fmul_rn(__fadd_rn(a1, b1), k.w));
-      s3 = __fadd_rn(s3, __fmul_rn(__fadd_rn(a1, b0), k.x)); s3 = __fadd_rn(s3, __fmul_rn(__fadd_rn(a1, b0), k.y));
-      s3 = __fadd_rn(s3, __fmul_rn(__fadd_rn(a1, b0), k.z)); s3 = __fadd_rn(s3, __fmul_rn(__fadd_rn(a1, b1), k.w));
+      // pixel row j, tap t = 4m + i (i = 1..4): above cell m + (j + i) / 4, below cell -(m + (i - j + 3) / 4); only four
+      // distinct (above + below) sums occur in the 16 (row, tap) pairs
+      const float p00 = __fadd_rn(a0, b0), p01 = __fadd_rn(a0, b1), p10 = __fadd_rn(a1, b0), p11 = __fadd_rn(a1, b1);
+      s0 = __fadd_rn(s0, __fmul_rn(p01, k.x)); s0 = __fadd_rn(s0, __fmul_rn(p01, k.y)); s0 = __fadd_rn(s0, __fmul_rn(p01, k.z)); s0 = __fadd_rn(s0, __fmul_rn(p11, k.w));
+      s1 = __fadd_rn(s1, __fmul_rn(p00, k.x)); s1 = __fadd_rn(s1, __fmul_rn(p01, k.y)); s1 = __fadd_rn(s1, __fmul_rn(p11, k.z)); s1 = __fadd_rn(s1, __fmul_rn(p11, k.w));
+      s2 = __fadd_rn(s2, __fmul_rn(p00, k.x)); s2 = __fadd_rn(s2, __fmul_rn(p10, k.y)); s2 = __fadd_rn(s2, __fmul_rn(p11, k.z)); s2 = __fadd_rn(s2, __fmul_rn(p11, k.w));
+      s3 = __fadd_rn(s3, __fmul_rn(p10, k.x)); s3 = __fadd_rn(s3, __fmul_rn(p10, k.y)); s3 = __fadd_rn(s3, __fmul_rn(p10, k.z)); s3 = __fadd_rn(s3, __fmul_rn(p11, k.w));
       a0 = a1; b0 = b1;
     }
     float* out = P.d_blur + ((size_t)b * P.h + 4 * q) * W + x;
@@ -905,6 +933,8 @@ void cv_gaussian_kernel_f32(int n, double sigma, std::vector<float>* k) {
 
 struct FastState {
   FastP p;
+  cudaStream_t side = nullptr;          // the temporal chain (temporal -> tthr) runs beside the threshold / spatial chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
   size_t smem_tthr = 0, smem_sp[3] = {0, 0, 0}, smem_h = 0;
 };
@@ -980,6 +1010,9 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
   s->smem_sp[1] = s->smem_sp[2] = ((size_t)(p.gh32 + 12) * (p.gw32 + 12) + 144) * 4;
   s->smem_h = ((size_t)p.w4 + p.hq + p.nq_h + 2) * 4;
   if (!e && (s->smem_tthr > 48000 || s->smem_sp[1] > 48000)) { set_error("fast version: picture too large for the block-grid kernels"); e = CDS_EINVAL; }
+  if (!e && (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
+             cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+             cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)) { set_error("fast: stream / event creation"); e = CDS_ECUDA; }
   const size_t smem_sm = (size_t)(SM_G + p.PS - 1) * 128 * sizeof(float4);
   if (!e && smem_sm > 200 * 1024) { set_error("fast version: fps %.1f needs a %zu-byte smoothing tile", fps, smem_sm); e = CDS_EINVAL; }
   if (!e && smem_sm > 48 * 1024 &&
@@ -991,6 +1024,9 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
 
 void fast_destroy(FastState* s) {
   if (!s) return;
+  if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   for (void* q : s->allocs) cudaFree(q);
   delete s;
 }
@@ -1025,16 +1061,21 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
   fast_smooth_bit_kernel<<<dim3(ceil_div(p.nctu, 128), n), 128, 0, st>>>(p, first_poc);
   CDS_LAUNCH_CHECK();
   if (!out) return CDS_OK;
+  // two independent latency-bound chains after the smoothing: MapThreshold -> spatial maps, and temporal maps -> their threshold
+  CDS_CUDA(cudaEventRecord(s->ev_fork, st));
+  CDS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+  fast_temporal_kernel<<<dim3(ceil_div(p.g32, 128), 3, n), 128, 0, s->side>>>(p, first_poc);
+  CDS_LAUNCH_CHECK();
+  fast_tthr_kernel<<<dim3(3, n), 128, s->smem_tthr, s->side>>>(p);
+  CDS_LAUNCH_CHECK();
+  CDS_CUDA(cudaEventRecord(s->ev_join, s->side));
   fast_thr_kernel<<<dim3(5, n), 256, 0, st>>>(p);
-  CDS_LAUNCH_CHECK();
-  fast_temporal_kernel<<<dim3(ceil_div(p.g32, 128), 3, n), 128, 0, st>>>(p, first_poc);
-  CDS_LAUNCH_CHECK();
-  fast_tthr_kernel<<<dim3(3, n), 128, s->smem_tthr, st>>>(p);
   CDS_LAUNCH_CHECK();
   fast_spatial_kernel<<<dim3(4, n), SP_T, s->smem_sp[1], st>>>(p);
   CDS_LAUNCH_CHECK();
   fast_mvs_kernel<<<n, 256, 0, st>>>(p);
   CDS_LAUNCH_CHECK();
+  CDS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
   fast_combine_kernel<<<dim3(ceil_div(p.n4, 256), n), 256, 0, st>>>(p);
   CDS_LAUNCH_CHECK();
   fast_mm_reset_kernel<<<ceil_div(n, 128), 128, 0, st>>>(p.d_mm, n);

@@ -35,4 +35,5 @@ print(f"fast version {w}x{h} @{fps} fps, batch {B}: {ms:.3f} ms per batch, {B / 
 if os.environ.get("CDS_FAST_PROF") is not None:
     a = np.zeros(32, np.int64)
     check(L.cds_debug_copy(clip.handle, b"fast_prof", 0, a.ctypes.data_as(C.c_void_p), a.nbytes), "prof")
+    print("cam_vote block (0,0) cycles: member sums", a[0], "Umean", a[2], "members", a[1], "first loop exact", a[3])
     print("thr job", os.environ["CDS_FAST_PROF"], "(cycles): stats", a[8], "sequential sum", a[9], "selected", a[10])
