@@ -261,7 +261,7 @@ def run_b200(a):
     DEV_CHUNK = 8                                  # batches per device-resident call (bounds the output buffer)
     d_maps = torch.empty((min(max(a.steps, a.warmup, nprof), DEV_CHUNK) * B, h, w), dtype=torch.float32, device=dev)
     h_maps = torch.empty((E2E_CHUNK * B, h, w), dtype=torch.float32).pin_memory()
-    h_cam = torch.zeros((E2E_CHUNK * B, 2), dtype=torch.int32)
+    h_cam = torch.zeros((4 * E2E_CHUNK * B, 2), dtype=torch.int32)
     torch.cuda.synchronize()
     stream = torch.cuda.Stream(device=dev)       # a real (non-NULL) stream: the kernels, the events and the timing all sit on it
     torch.cuda.set_stream(stream)
@@ -314,9 +314,9 @@ def run_b200(a):
 
     # ---- end to end through the host-buffer C-ABI: E2E_CHUNK batches per call so the library can overlap the
     #      device->host copy of batch i with the kernels of batch i+1; every step's copies are inside the timed region ----
-    def e2e_leg(cl, out_buf, bytes_per_px):
+    def e2e_leg(cl, out_buf, bytes_per_px, chunk=E2E_CHUNK):
         def hstep(poc, n, context=False):
-            for (p, i, ln) in runs(poc, n, E2E_CHUNK):
+            for (p, i, ln) in runs(poc, n, chunk):
                 args = (cl.handle, p, ln, P(h_byts, i * nctu * 2), P(h_hdr, i * nctu * 16), P(h_tok), P(h_base, i * 8), c_tok.size)
                 if context:
                     check(L.cds_clip_context(*args), "cds_clip_context")
@@ -327,13 +327,13 @@ def run_b200(a):
         poc = halo
         left = a.warmup
         while left > 0:
-            k = min(left, E2E_CHUNK)
+            k = min(left, chunk)
             hstep(poc, k * B); poc += k * B; left -= k
         barrier()
         t0 = time.perf_counter()
         left = a.steps
         while left > 0:
-            k = min(left, E2E_CHUNK)
+            k = min(left, chunk)
             hstep(poc, k * B); poc += k * B; left -= k
         barrier()
         sec = max_over_ranks(time.perf_counter() - t0)
@@ -345,9 +345,9 @@ def run_b200(a):
     # and imwrite()s it; main.m:312-320 writes the same 8-bit video).  The FP32 variant (the maps the parity tests compare at
     # 1e-4) is reported beside it: at N >= 4 its 8.3 MB per picture saturate the host's ingest bandwidth, not the GPUs.
     clip8 = cds.SaliencyClip(w, h, a.fps, model=model, meanVec=MEAN9, stdVec=STD9, use_rbf=True, max_batch=B, out_u8=True)
-    e2e = e2e_leg(clip8, h_maps, 1)
+    e2e = e2e_leg(clip8, h_maps, 1, 4 * E2E_CHUNK)      # the pinned buffer, sized for FP32 maps, holds 4x as many 8-bit maps
     clip8.close()
-    e2e["api"] = f"cds_clip_process (pinned host syntax in, 8-bit maps out to pinned host memory, as the reference hook writes them), {E2E_CHUNK} steps per call"
+    e2e["api"] = f"cds_clip_process (pinned host syntax in, 8-bit maps out to pinned host memory, as the reference hook writes them), up to {4 * E2E_CHUNK} steps per call"
     e2e_f32 = e2e_leg(clip, h_maps, 4)
     e2e_f32["api"] = f"cds_clip_process (pinned host syntax in, FP32 maps out to pinned host memory), {E2E_CHUNK} steps per call"
     # host link: device->host copy rate of the output buffer alone (explains the FP32 e2e number)
@@ -383,7 +383,7 @@ def run_b200(a):
         barrier()
         fms = max_over_ranks(f0.elapsed_time(f1))
         flaunches = cds.take_launch_count()
-        fe2e = e2e_leg(fclip, h_maps, 1)
+        fe2e = e2e_leg(fclip, h_maps, 1, 4 * E2E_CHUNK)
         fast_line = {"value": frames / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms / a.steps, "gpu_launches": int(flaunches),
                      "e2e": {k: fe2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
                      "PS": fclip.PS, "PT": fclip.PT, "dtype": "f32 (operation order of the reference: bit-identical 8-bit maps)",
