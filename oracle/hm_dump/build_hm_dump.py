@@ -91,6 +91,17 @@ def main():
     p = os.path.join(WORK, "source/Lib/TLibDecoder/TDecCu.h")
     s = open(p, encoding="latin-1").read()
     s = re.sub(r"#define LCUNUM\s+\d+", "#define LCUNUM 2100", s); open(p, "w", encoding="latin-1").write(s)
+    # parse-only producer: with CDS_PARSE_ONLY=1 in the environment the decoder still parses every CTU (CABAC, motion
+    # derivation, the hooks) but skips pixel reconstruction, deblocking and SAO - the saliency path needs syntax only
+    s = open(p, encoding="latin-1").read()
+    s = s.replace("#define FRAMERATE", "#include <stdlib.h>\nstatic inline bool cdsParseOnly() { static int v = -1; if (v < 0) { const char* e = getenv(\"CDS_PARSE_ONLY\"); v = (e && atoi(e)) ? 1 : 0; } return v == 1; }\n#define FRAMERATE", 1)
+    assert "cdsParseOnly" in s
+    open(p, "w", encoding="latin-1").write(s)
+    pc = os.path.join(WORK, "source/Lib/TLibDecoder/TDecCu.cpp")
+    s = open(pc, encoding="latin-1").read()
+    assert "  xDecompressCU( pcCU, 0,  0 );" in s
+    s = s.replace("  xDecompressCU( pcCU, 0,  0 );", "  if (!cdsParseOnly()) xDecompressCU( pcCU, 0,  0 );", 1)
+    open(pc, "w", encoding="latin-1").write(s)
     # (iii) TDecGop.cpp: keep 1-46, 119-224, 337-end (1-based)
     p = os.path.join(WORK, "source/Lib/TLibDecoder/TDecGop.cpp")
     L = open(p, encoding="latin-1").read().replace("\r", "").lstrip("﻿").lstrip("\xef\xbb\xbf").split("\n")
@@ -107,7 +118,11 @@ def main():
         block, extra = CDS_BLOCK, '#include "cds_hm_hook.h"\n'
         for hname in ("cds.h", "cds_hm_hook.h"):          # this repo's own headers into the scratch tree
             shutil.copy(os.path.join(HERE, "..", "..", "include", hname), os.path.join(WORK, "source/Lib/TLibDecoder", hname))
-    out = "\n".join(head) + "\n#include <math.h>\n" + extra + STATICS + "\n".join(mid) + block + "\n".join(tail) + "\n"
+    tail_s = "\n".join(tail)
+    assert "  m_pcLoopFilter->loopFilterPic( rpcPic );" in tail_s and "  if( pcSlice->getSPS()->getUseSAO() )" in tail_s
+    tail_s = tail_s.replace("  m_pcLoopFilter->loopFilterPic( rpcPic );", "  if (!cdsParseOnly()) m_pcLoopFilter->loopFilterPic( rpcPic );", 1)
+    tail_s = tail_s.replace("  if( pcSlice->getSPS()->getUseSAO() )", "  if( !cdsParseOnly() && pcSlice->getSPS()->getUseSAO() )", 1)
+    out = "\n".join(head) + "\n#include <math.h>\n" + extra + STATICS + "\n".join(mid) + block + tail_s + "\n"
     open(p, "w", encoding="latin-1").write(out)
     env = dict(os.environ)
     for lib in ("TLibVideoIO", "TLibCommon", "TLibDecoder", "TAppCommon"):

@@ -128,6 +128,12 @@ def test_reference_decoder_with_cds_hook_reproduces_its_own_golden_pngs(cds, tmp
     assert "[cds hook] 500 pictures" in r.stderr, r.stderr[-2000:]
     print(r.stderr.strip().splitlines()[-1])
     maps = np.fromfile(out, np.uint8).reshape(-1, h, w)
+    # the parse-only producer (no reconstruction / deblocking / SAO) must hand over the same syntax, hence the same maps
+    out2 = str(tmp_path / "maps_po.u8")
+    r2 = subprocess.run([dec, "-b", stream], env=dict(env, CDS_OUT=out2, CDS_PARSE_ONLY="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    print("parse-only:", r2.stderr.strip().splitlines()[-1])
+    assert np.array_equal(np.fromfile(out2, np.uint8).reshape(-1, h, w), maps)
     assert maps.shape[0] == 500
     n = d["png"].shape[0]
     per = (maps[:n] != d["png"]).reshape(n, -1).sum(1)

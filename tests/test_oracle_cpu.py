@@ -179,3 +179,20 @@ def test_standin_trained_model_fixture_loads_and_matches_reference_libsvm():
     r = o.ref_svm_predict(SV, coef, rho, gamma, labels, X, nsv0=int((coef > 0).sum()))
     if r is not None:
         assert np.array_equal(dec, r[0]) and np.array_equal(lab, r[1])
+
+
+def test_parse_only_hm_producer_captures_identical_syntax(tmp_path):
+    """the reference's hooked decoder with CDS_PARSE_ONLY=1 (reconstruction, deblocking and SAO skipped; patch applied by
+    oracle/hm_dump/build_hm_dump.py to a scratch copy) hands the hooks byte-identical per-CTU syntax.  All 32 bundled streams were
+    compared in the build container (profiles/r01_hm_parse_only.txt); this runs the one small stream that travels with oracle/_ref."""
+    import filecmp, subprocess
+    dumper = os.path.join(o.ROOT, "oracle", "_ref", "hm_syntax_dump")
+    stream = os.path.join(o.ROOT, "oracle", "_ref", "streams", "BasketballPass.bin")
+    if not (os.path.exists(dumper) and os.path.exists(stream)):
+        pytest.skip("hooked HM decoder / bitstream not built (needs the reference tree at build time)")
+    a, b = str(tmp_path / "full.bin"), str(tmp_path / "parse.bin")
+    for out, po in ((a, "0"), (b, "1")):
+        r = subprocess.run([dumper, "-b", stream], env=dict(os.environ, HM_SYNTAX_DUMP=out, CDS_PARSE_ONLY=po), stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL, timeout=300)
+        assert r.returncode == 0
+    assert os.path.getsize(a) > 1000000 and filecmp.cmp(a, b, shallow=False)
