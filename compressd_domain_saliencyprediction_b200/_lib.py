@@ -49,6 +49,8 @@ def _declare(L):
         "cds_clip_process_dev": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
         "cds_clip_process": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, sz, c_p, c_p]),
         "cds_clip_process_maps": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, c_p, c_p]),
+        "cds_getframe_semantic": (i32, [i32, i32, i32, c_p, c_p, c_p, c_p, c_p, c_p]),
+        "cds_getframe_semantic_dev": (i32, [i32, i32, i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
         "cds_probe_seq_sum": (i32, [c_p, c_p, i32, c_p, c_p]),
         "cds_probe_run_sum": (i32, [c_p, i32, i32, i32, i32, i32, C.c_double, c_p, c_p]),
         "cds_reset": (i32, [c_p]),

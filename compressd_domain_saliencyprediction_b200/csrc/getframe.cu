@@ -265,3 +265,60 @@ extern "C" int cds_getframe(int w, int h, const int32_t* hdr, const int16_t* tok
   if (herr) { set_error("cds_getframe: malformed CU token stream"); return CDS_EFORMAT; }
   return CDS_OK;
 }
+
+// ---- "semantic" stage (a): the hook hands over the CTU's 256 z-scan partitions (depth, prediction mode, L0 / L1
+// motion vector of 4x4-pixel units, what TComDataCU::getDepth / getPredictionMode / getCUMvField hold) instead of the token streams
+// of TDecCu::MVoutput; the kernel is a z-scan -> raster transpose.  Depth is identical to getFrame's; the motion maps differ from
+// the reference's in the few percent of cells where getFrame's aliasing quirks (code_mat_h.h:500,533) fire - an intentional deviation.
+namespace {
+__device__ __forceinline__ unsigned morton4(unsigned x, unsigned y) {      // HM g_auiRasterToZscan for 4x4 units inside a 64x64 CTU
+  x = (x | (x << 2)) & 0x33u; x = (x | (x << 1)) & 0x55u;
+  y = (y | (y << 2)) & 0x33u; y = (y | (y << 1)) & 0x55u;
+  return x | (y << 1);
+}
+__global__ void __launch_bounds__(256) semantic_scatter_kernel(int w4, int h4, int ncol, int nctu, const uint8_t* __restrict__ depth256,
+                                                               const uint8_t* __restrict__ pred256, const int16_t* __restrict__ mv256,
+                                                               int16_t* __restrict__ mvx, int16_t* __restrict__ mvy, uint8_t* __restrict__ depth) {
+  const int f = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x, n4 = w4 * h4;
+  if (k >= n4) return;
+  const int r = k / w4, c = k - r * w4;
+  const size_t part = ((size_t)f * nctu + (r >> 4) * ncol + (c >> 4)) * 256 + morton4(c & 15, r & 15);
+  const bool inter = pred256[part] == 0;                                 // MODE_INTER (TypeDef.h:440)
+  const size_t o = (size_t)f * n4 + k;
+  mvx[o] = inter ? mv256[part * 2] : (int16_t)0;
+  mvy[o] = inter ? mv256[part * 2 + 1] : (int16_t)0;
+  depth[o] = depth256[part];
+}
+}  // namespace
+
+extern "C" int cds_getframe_semantic_dev(int w, int h, int nframes, const uint8_t* depth256, const uint8_t* pred256, const int16_t* mv256,
+                                         int16_t* mvx, int16_t* mvy, uint8_t* depth, void* stream) {
+  if (int e = ensure_device()) return e;
+  if (!geometry_ok(w, h)) return CDS_EINVAL;
+  if (!depth256 || !pred256 || !mv256 || !mvx || !mvy || !depth || nframes < 1) { set_error("cds_getframe_semantic_dev: bad arguments"); return CDS_EINVAL; }
+  const int w4 = w / 4, h4 = h / 4, ncol = (w + 63) / 64, nctu = ncol * ((h + 63) / 64);
+  semantic_scatter_kernel<<<dim3(ceil_div(w4 * h4, 256), nframes), 256, 0, (cudaStream_t)stream>>>(w4, h4, ncol, nctu, depth256, pred256, mv256, mvx, mvy, depth);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+extern "C" int cds_getframe_semantic(int w, int h, int nframes, const uint8_t* depth256, const uint8_t* pred256, const int16_t* mv256,
+                                     int16_t* mvx, int16_t* mvy, uint8_t* depth) {
+  if (int e = ensure_device()) return e;
+  if (!geometry_ok(w, h)) return CDS_EINVAL;
+  if (!depth256 || !pred256 || !mv256 || !mvx || !mvy || !depth || nframes < 1) { set_error("cds_getframe_semantic: bad arguments"); return CDS_EINVAL; }
+  const size_t nctu = (size_t)((w + 63) / 64) * ((h + 63) / 64), np = (size_t)nframes * nctu * 256, nc = (size_t)nframes * (w / 4) * (h / 4);
+  uint8_t *d_d = nullptr, *d_p = nullptr, *o_d = nullptr; int16_t *d_m = nullptr, *o_x = nullptr, *o_y = nullptr;
+  int rc = CDS_OK;
+  if (cudaMalloc(&d_d, np) != cudaSuccess || cudaMalloc(&d_p, np) != cudaSuccess || cudaMalloc(&d_m, np * 4) != cudaSuccess ||
+      cudaMalloc(&o_d, nc) != cudaSuccess || cudaMalloc(&o_x, nc * 2) != cudaSuccess || cudaMalloc(&o_y, nc * 2) != cudaSuccess) {
+    set_error("cds_getframe_semantic: cudaMalloc"); rc = CDS_ENOMEM;
+  }
+  if (!rc && (cudaMemcpy(d_d, depth256, np, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(d_p, pred256, np, cudaMemcpyHostToDevice) != cudaSuccess ||
+              cudaMemcpy(d_m, mv256, np * 4, cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("cds_getframe_semantic: copy in"); rc = CDS_ECUDA; }
+  if (!rc) rc = cds_getframe_semantic_dev(w, h, nframes, d_d, d_p, d_m, o_x, o_y, o_d, nullptr);
+  if (!rc && (cudaMemcpy(mvx, o_x, nc * 2, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(mvy, o_y, nc * 2, cudaMemcpyDeviceToHost) != cudaSuccess ||
+              cudaMemcpy(depth, o_d, nc, cudaMemcpyDeviceToHost) != cudaSuccess)) { set_error("cds_getframe_semantic: copy out"); rc = CDS_ECUDA; }
+  cudaFree(d_d); cudaFree(d_p); cudaFree(d_m); cudaFree(o_d); cudaFree(o_x); cudaFree(o_y);
+  return rc;
+}

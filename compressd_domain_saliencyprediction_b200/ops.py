@@ -82,6 +82,18 @@ def getframe(w, h, hdr, tok):
     return mvx, mvy, depth
 
 
+def getframe_semantic(w, h, depth256, pred256, mv256):
+    """z-scan partition arrays of TComDataCU ([F][nctu][256] depth / prediction mode, [F][nctu][256][2] mv) ->
+    (mvx, mvy, depth) maps [F][h/4][w/4]."""
+    d = np.ascontiguousarray(depth256, np.uint8); p = np.ascontiguousarray(pred256, np.uint8); m = np.ascontiguousarray(mv256, np.int16)
+    F = d.shape[0]
+    if d.shape != (F, nctu(w, h), 256) or p.shape != d.shape or m.shape != (F, nctu(w, h), 256, 2):
+        raise CdsError("getframe_semantic: partition arrays do not match the picture size")
+    mvx = np.zeros((F, h // 4, w // 4), np.int16); mvy = np.zeros_like(mvx); depth = np.zeros((F, h // 4, w // 4), np.uint8)
+    check(lib().cds_getframe_semantic(w, h, F, _ptr(d), _ptr(p), _ptr(m), _ptr(mvx), _ptr(mvy), _ptr(depth)), "cds_getframe_semantic")
+    return mvx, mvy, depth
+
+
 def getFrame(mv_arr, pred_arr, cupu_arr, w, h):
     """getFrame(TDecCu::MV, TDecCu::Pred, TDecCu::CUPU, mv_x, mv_y, depth)   (TDecGop.cpp:270)"""
     hdr, tok = pack_ref_arrays(mv_arr, pred_arr, cupu_arr)

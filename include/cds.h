@@ -171,6 +171,14 @@ int cds_clip_process(cds_ctx* ctx, int first_poc, int nframes, const uint16_t* c
  * ctu_bytes [nframes][nctu] u16.  Works in every fusion mode; maps_out NULL feeds the pictures as temporal context only. */
 int cds_clip_process_maps(cds_ctx* ctx, int first_poc, int nframes, const int16_t* mvx, const int16_t* mvy,
                           const uint8_t* depth, const uint16_t* ctu_bytes, void* maps_out, int* cam_out);
+/* "Semantic" stage (a): the CTU's 256 z-scan partitions as TComDataCU holds them — depth256 / pred256
+ * [nframes][nctu][256] u8 (getDepth(), getPredictionMode(): 0 inter, 1 intra), mv256 [nframes][nctu][256][2] int16 quarter-pel
+ * (getCUMvField(L0 or L1)->getMv()) — transposed to the h/4 x w/4 maps of cds_getframe.  Depth equals getFrame's; the motion maps
+ * differ where getFrame's stream-aliasing quirks fire (an intentional deviation).  Feed the result to cds_clip_process_maps. */
+int cds_getframe_semantic(int w, int h, int nframes, const uint8_t* depth256, const uint8_t* pred256, const int16_t* mv256,
+                          int16_t* mvx, int16_t* mvy, uint8_t* depth);
+int cds_getframe_semantic_dev(int w, int h, int nframes, const uint8_t* depth256, const uint8_t* pred256, const int16_t* mv256,
+                              int16_t* mvx, int16_t* mvy, uint8_t* depth, void* stream);
 /* Probes of the fast version's sequential-float-sum emulation (csrc/fast.cu): the float32 result of
  * `S = 0; for (i < n) if (sel[i]) S = S + v[i];` (salmat.cpp:155-162, TDecGop.cpp:622-640; n a multiple of 4), and of the same loop
  * over a rows x cols raster of replicated blocks (gh x gw values, block size ms, elements > t selected).  Host buffers. */

@@ -36,8 +36,29 @@ DUMP = r'''
       for (int s = 0; s < 3; s++) for (int i = 0; i < n[s]; i++) { short v = (short)src[s][i]; fwrite(&v, 2, 1, s_dump); }
     }
     fflush(s_dump);
+    static FILE* s_sem = NULL; static int s_sem_init = 0;
+    if (!s_sem_init) { s_sem_init = 1; const char* pth = getenv("HM_SEMANTIC_DUMP"); if (pth) s_sem = fopen(pth, "wb"); }
+    if (s_sem) {      /* int32 poc, int32 nctu, then nctu x (256 depth, 256 pred mode, 256 x 2 int16 mv) in z-scan order */
+      fwrite(&poc, 4, 1, s_sem); fwrite(&nctu, 4, 1, s_sem);
+      for (int a = 0; a < nctu; a++) { fwrite(g_cdsSemDepth[a], 1, 256, s_sem); fwrite(g_cdsSemPred[a], 1, 256, s_sem); fwrite(g_cdsSemMv[a], 2, 512, s_sem); }
+      fflush(s_sem);
+    }
   }
 }
+'''
+
+# SURVEY 8(f).2 "semantic" capture: the CTU's 256 z-scan partitions as TComDataCU holds them (fixture generation for cds_getframe_semantic)
+SEMANTIC_GLOBALS = r'''
+unsigned char g_cdsSemDepth[LCUNUM][256]; unsigned char g_cdsSemPred[LCUNUM][256]; short g_cdsSemMv[LCUNUM][256][2];
+'''
+SEMANTIC_CAPTURE = r'''
+  { const UInt a_ = pcCU->getAddr(); const Int np_ = (Int)pcCU->getTotalNumPart();
+    for (Int i_ = 0; i_ < np_ && i_ < 256; i_++) {
+      const Int dir_ = pcCU->getInterDir(i_);
+      TComMv mv_;
+      if (pcCU->getPredictionMode(i_) == MODE_INTER) { if (dir_ & 1) mv_ = pcCU->getCUMvField(REF_PIC_LIST_0)->getMv(i_); else if (dir_ & 2) mv_ = pcCU->getCUMvField(REF_PIC_LIST_1)->getMv(i_); }
+      g_cdsSemDepth[a_][i_] = pcCU->getDepth(i_); g_cdsSemPred[a_][i_] = (unsigned char)pcCU->getPredictionMode(i_);
+      g_cdsSemMv[a_][i_][0] = (short)mv_.getHor(); g_cdsSemMv[a_][i_][1] = (short)mv_.getVer(); } }
 '''
 
 STATICS = r'''
@@ -48,6 +69,7 @@ float TDecCu::MV[LCUNUM][1000] = {0};
 float TDecCu::CUPU[LCUNUM][1000] = {0};
 float TDecCu::Pred[LCUNUM][1000] = {0};
 extern Bool g_md5_mismatch;
+extern unsigned char g_cdsSemDepth[LCUNUM][256]; extern unsigned char g_cdsSemPred[LCUNUM][256]; extern short g_cdsSemMv[LCUNUM][256][2];
 static Void calcAndPrintHashStatus(TComPicYuv& pic, const SEIDecodedPictureHash* pictureHashSEI);
 '''
 
@@ -100,7 +122,8 @@ def main():
     pc = os.path.join(WORK, "source/Lib/TLibDecoder/TDecCu.cpp")
     s = open(pc, encoding="latin-1").read()
     assert "  xDecompressCU( pcCU, 0,  0 );" in s
-    s = s.replace("  xDecompressCU( pcCU, 0,  0 );", "  if (!cdsParseOnly()) xDecompressCU( pcCU, 0,  0 );", 1)
+    s = s.replace("  xDecompressCU( pcCU, 0,  0 );", "  if (!cdsParseOnly()) xDecompressCU( pcCU, 0,  0 );\n" + SEMANTIC_CAPTURE, 1)
+    s = s.replace("Void TDecCu::decompressCU( TComDataCU* pcCU )", SEMANTIC_GLOBALS + "Void TDecCu::decompressCU( TComDataCU* pcCU )", 1)
     open(pc, "w", encoding="latin-1").write(s)
     # (iii) TDecGop.cpp: keep 1-46, 119-224, 337-end (1-based)
     p = os.path.join(WORK, "source/Lib/TLibDecoder/TDecGop.cpp")
