@@ -962,7 +962,7 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
   p.B = B;
   { const char* e = getenv("CDS_FAST_PROF"); p.prof_x = e ? atoi(e) : -1; }
   p.PS = std::max(1, cv_round_host(fps * 0.3)); p.PT = std::max(1, cv_round_host(fps * 0.7));     // salmat.cpp:18-19
-  p.RL = B + p.PS + p.PT;
+  p.RL = 2 * B + p.PS + p.PT;           // the front half (camera stages) of batch k+1 may fill its ring slots while the back half of batch k still reads
   p.ksize = cv_round_host((double)(h / 15)); if (p.ksize % 2 == 0) p.ksize++;                    // TDecGop.cpp:320-322
   p.half = p.ksize / 2;
   if (p.gw32 > 128 || p.lw > 128) { delete s; set_error("fast version: width %d too large", w); return CDS_EINVAL; }
@@ -1045,6 +1045,13 @@ int fast_clear(FastState* s, cudaStream_t st) {
 
 int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const int16_t* mvy, const uint8_t* dep,
                    const uint16_t* bytes, void* out, int out_u8, int* cam_out, cudaStream_t st) {
+  if (int e = fast_front(s, first_poc, n, mvx, mvy, dep, bytes, cam_out, st)) return e;
+  return fast_back(s, first_poc, n, out, out_u8, st);
+}
+
+// front half: CameraDect for the batch (raw ring slots, per-picture scalars, camera motion) - everything later pictures need from the camera stage
+int fast_front(FastState* s, int first_poc, int n, const int16_t* mvx, const int16_t* mvy, const uint8_t* dep, const uint16_t* bytes,
+               int* cam_out, cudaStream_t st) {
   const FastP& p = s->p;
   if (n < 1 || n > p.B || first_poc < 0) { set_error("fast_run_batch: bad batch"); return CDS_EINVAL; }
   CDS_CUDA(cudaMemsetAsync(p.d_cami, 0, (size_t)n * 24 * sizeof(int), st));
@@ -1056,6 +1063,13 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
   CDS_LAUNCH_CHECK();
   fast_cam_final_kernel<<<ceil_div(n, 64), 64, 0, st>>>(p, first_poc, n, cam_out);
   CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
+// back half: smoothing (also the temporal rings of the block grids) and, when `out` is given, everything up to the map
+int fast_back(FastState* s, int first_poc, int n, void* out, int out_u8, cudaStream_t st) {
+  const FastP& p = s->p;
+  if (n < 1 || n > p.B || first_poc < 0) { set_error("fast_run_batch: bad batch"); return CDS_EINVAL; }
   fast_smooth_kernel<<<dim3(ceil_div(p.n4, 128), ceil_div(n, SM_G)), dim3(128, SM_G), (size_t)(SM_G + p.PS - 1) * 128 * sizeof(float4), st>>>(p, first_poc, n);
   CDS_LAUNCH_CHECK();
   fast_smooth_bit_kernel<<<dim3(ceil_div(p.nctu, 128), n), 128, 0, st>>>(p, first_poc);

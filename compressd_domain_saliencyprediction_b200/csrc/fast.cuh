@@ -15,6 +15,11 @@ int fast_halo(const FastState* s);                      // pictures of temporal 
 // out ([n][h][w], u8 or f32) may be null: temporal context only.  cam_out (device, [n][2]) may be null.
 int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const int16_t* mvy, const uint8_t* dep,
                    const uint16_t* bytes, void* out, int out_u8, int* cam_out, cudaStream_t st);
+// the two halves of fast_run_batch: the front half of the next batch may run on another stream beside the back half of this one
+// (the ring holds 2 B + PS + PT pictures); the caller orders them with events
+int fast_front(FastState* s, int first_poc, int n, const int16_t* mvx, const int16_t* mvy, const uint8_t* dep, const uint16_t* bytes,
+               int* cam_out, cudaStream_t st);
+int fast_back(FastState* s, int first_poc, int n, void* out, int out_u8, cudaStream_t st);
 int fast_get_cam(const FastState* s, int poc, int* xy);   // camera motion of a picture still in the ring (host copy)
 // probes (tests): `for (i < n) if (sel[i]) S = S + v[i];` and MapThreshold's sum over a map of replicated blocks, both in float
 int fast_probe_seq_sum(const float* v, const unsigned char* sel, int n, float* sum, int* count);

@@ -37,6 +37,9 @@ static const float kFeatureWeight[9] = {0.058f, 0.171f, -0.095f, 0.068f, -0.01f,
 
 struct cds_ctx {
   cds_params p;
+  // fast version, device-resident entry point: front half (stage a + camera stages) of batch k+1 on fast_front_stream beside the back half of batch k
+  cudaStream_t fast_front_stream = nullptr; cudaEvent_t ev_ff[2] = {nullptr, nullptr}, ev_fb[2] = {nullptr, nullptr}, ev_fstart = nullptr;
+  int ff_flip = 0; bool fast_ovl = false, fast_ovl_active = false;
   bool maps_in = false;                // cds_clip_process_maps: d_mvx / d_mvy / d_dep already hold stage (a)'s output
   FastState* fast = nullptr;           // use_rbf == CDS_FUSION_FAST: the reference's fast version (fast.cu) replaces stages (c)-(e), (b), (d)
   int w, h, h4, w4, n4, ncol, nrow, nctu, B, RL, PS, PT, gk;
@@ -457,6 +460,11 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   if (fm) {
     if (!e) e = fast_create(p->w, p->h, p->fps, B, &c->fast);
     if (!e) { c->PS = fast_halo(c->fast) + 2; c->PT = 0; }
+    if (!e && (cudaStreamCreateWithFlags(&c->fast_front_stream, cudaStreamNonBlocking) != cudaSuccess ||
+               cudaEventCreateWithFlags(&c->ev_fstart, cudaEventDisableTiming) != cudaSuccess)) { set_error("cudaStreamCreate fast front"); e = CDS_ECUDA; }
+    for (int b = 0; b < 2 && !e; b++)
+      if (cudaEventCreateWithFlags(&c->ev_ff[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fb[b], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
+    { const char* ov = getenv("CDS_OVERLAP"); c->fast_ovl = !(ov && ov[0] == '0'); }
   }
 #undef A
 #define A(ptr, count) if (!e && !fm) e = dalloc(c, &c->ptr, (size_t)(count))
@@ -529,6 +537,9 @@ extern "C" void cds_destroy(cds_ctx* c) {
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->back_stream) { cudaStreamSynchronize(c->back_stream); cudaStreamDestroy(c->back_stream); }
+  if (c->fast_front_stream) { cudaStreamSynchronize(c->fast_front_stream); cudaStreamDestroy(c->fast_front_stream); }
+  if (c->ev_fstart) cudaEventDestroy(c->ev_fstart);
+  for (int b = 0; b < 2; b++) { if (c->ev_ff[b]) cudaEventDestroy(c->ev_ff[b]); if (c->ev_fb[b]) cudaEventDestroy(c->ev_fb[b]); }
   for (int b = 0; b < 2; b++) { if (c->ev_front[b]) cudaEventDestroy(c->ev_front[b]); if (c->ev_back[b]) cudaEventDestroy(c->ev_back[b]); }
   for (int b = 0; b < 2; b++) { if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); }
   if (c->h_cam_pin) cudaFreeHost(c->h_cam_pin);
@@ -595,6 +606,20 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
               cudaEvent_t* done_ev = nullptr) {
   if (c->fast) {          // TDecGop.cpp:270-332 for n pictures: stage (a), then the fast version's kernels (fast.cu)
     if (done_ev) *done_ev = nullptr;
+    if (c->fast_ovl_active && !c->prof_on && !c->maps_in) {
+      // front half on its own stream: it waited for the start of this API call (inputs resident) and waits for the back half of
+      // batch k-2, whose ring reads end where this batch's ring writes begin; the back half follows on `st`
+      const int pz = c->ff_flip; c->ff_flip ^= 1;
+      cudaStream_t sf = c->fast_front_stream;
+      CDS_CUDA(cudaStreamWaitEvent(sf, c->ev_fb[pz], 0));
+      if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, sf)) return e;
+      if (int e = fast_front(c->fast, first_poc, n, c->d_mvx, c->d_mvy, c->d_dep, bytes, cam_out, sf)) return e;
+      CDS_CUDA(cudaEventRecord(c->ev_ff[pz], sf));
+      CDS_CUDA(cudaStreamWaitEvent(st, c->ev_ff[pz], 0));
+      if (int e = fast_back(c->fast, first_poc, n, maps_out, c->p.out_u8, st)) return e;
+      CDS_CUDA(cudaEventRecord(c->ev_fb[pz], st));
+      return CDS_OK;
+    }
     prof_mark(c, ST_GETFRAME, st);
     if (!c->maps_in) if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
     prof_mark(c, ST_FINAL, st);
@@ -765,12 +790,20 @@ extern "C" int cds_clip_process_dev(cds_ctx* c, int first_poc, int nframes, cons
   if (first_poc != c->next_poc) { set_error("cds_clip_process_dev: expected poc %d, got %d (use cds_seek)", c->next_poc, first_poc); return CDS_EINVAL; }
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
-  for (int done = 0; done < nframes; done += c->B) {
-    const int n = std::min(c->B, nframes - done);
-    if (int e = run_batch(c, first_poc + done, n, ctu_bytes + (size_t)done * c->nctu, hdr + (size_t)done * c->nctu * 4, tok,
-                          tok_base + done, maps_out ? (char*)maps_out + (size_t)done * px : nullptr,
-                          cam_out ? cam_out + 2 * done : nullptr, st)) return e;
+  if (c->fast && c->fast_ovl && nframes > c->B) {          // several batches in one call: let the halves of consecutive batches overlap
+    CDS_CUDA(cudaEventRecord(c->ev_fstart, st));
+    CDS_CUDA(cudaStreamWaitEvent(c->fast_front_stream, c->ev_fstart, 0));
+    c->fast_ovl_active = true;
   }
+  int rc = CDS_OK;
+  for (int done = 0; done < nframes && !rc; done += c->B) {
+    const int n = std::min(c->B, nframes - done);
+    rc = run_batch(c, first_poc + done, n, ctu_bytes + (size_t)done * c->nctu, hdr + (size_t)done * c->nctu * 4, tok,
+                   tok_base + done, maps_out ? (char*)maps_out + (size_t)done * px : nullptr,
+                   cam_out ? cam_out + 2 * done : nullptr, st);
+  }
+  c->fast_ovl_active = false;
+  if (rc) return rc;
   if (int e = join_back(c, st)) return e;
   c->next_poc = first_poc + nframes;
   return CDS_OK;

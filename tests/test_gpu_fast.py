@@ -271,3 +271,30 @@ def test_process_maps_equals_process_from_syntax_in_the_svm_mode(cds):
     got, cam = b.process_maps(0, np.stack([m[0] for m in maps]), np.stack([m[1] for m in maps]), np.stack([m[2] for m in maps]), byts)
     b.close()
     assert np.array_equal(cam, wcam) and got.tobytes() == want.tobytes()
+
+
+def test_fast_version_bit_exact_on_every_bundled_geometry(cds):
+    """Two pictures of each of the 24 bundled streams the reference handles (416x240, 832x480, 1024x768, 1280x800, 1920x1080;
+    tests/golden/all_streams.npz): 8-bit maps and camera votes identical to the oracle."""
+    d = np.load(os.path.join(GOLD, "all_streams.npz"))
+    seen = set()
+    for k, name in enumerate(d["names"]):
+        w, h = int(d[f"w{k}"]), int(d[f"h{k}"])
+        hdr, tok, base, byts = d[f"hdr{k}"], d[f"tok{k}"], d[f"base{k}"], d[f"bytes{k}"]
+        want, _, wcam = _oracle_clip(w, h, 30.0, hdr, tok, base, byts)
+        clip = cds.SaliencyClip(w, h, 30.0, fast=True, out_u8=True, max_batch=2)
+        got, cam = clip.process(0, hdr, tok, base, byts)
+        clip.close()
+        assert np.array_equal(cam, wcam) and np.array_equal(got, want), str(name)
+        seen.add((w, h))
+    assert len(seen) >= 4
+
+
+@pytest.mark.parametrize("w,h,F", [(2560, 1600, 3), (3840, 2160, 2)])
+def test_fast_version_bit_exact_at_large_sizes(cds, w, h, F):
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 17, F)
+    want_u8, want_f32, want_cam = _oracle_clip(w, h, 50.0, hdr, tok, base, byts)
+    clip = cds.SaliencyClip(w, h, 50.0, fast=True, out_u8=False, max_batch=2)
+    got, cam = clip.process(0, hdr, tok, base, byts)
+    clip.close()
+    assert np.array_equal(cam, want_cam) and got.tobytes() == want_f32.tobytes()

@@ -19,15 +19,15 @@ F = (2 + steps) * B
 hdr, tok, base, byts = cds.ops.synth_clip(w, h, 1234, F, first_poc=1)
 dev = torch.device("cuda", 0)
 d_hdr, d_tok, d_base, d_byts = (torch.from_numpy(x).to(dev) for x in (hdr, tok, base, byts))
-out = torch.empty((B, h, w), dtype=torch.uint8, device=dev)
+out = torch.empty((steps * B, h, w), dtype=torch.uint8, device=dev)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); st = C.c_void_p(stream.cuda_stream)
 P = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
-def step(i):
-    check(L.cds_clip_process_dev(clip.handle, i * B, B, P(d_byts, i * B * nctu * 2), P(d_hdr, i * B * nctu * 16), P(d_tok), P(d_base, i * B * 8), P(out), None, st), "process")
+def step(i, nb=1):        # nb batches in ONE call: the library may overlap the halves of consecutive batches
+    check(L.cds_clip_process_dev(clip.handle, i * B, nb * B, P(d_byts, i * B * nctu * 2), P(d_hdr, i * B * nctu * 16), P(d_tok), P(d_base, i * B * 8), P(out), None, st), "process")
 step(0); step(1); torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 e0.record(stream)
-for i in range(2, 2 + steps): step(i)
+step(2, steps)
 e1.record(stream); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"fast version {w}x{h} @{fps} fps, batch {B}: {ms:.3f} ms per batch, {B / ms * 1e3:.0f} pictures/s (device-resident, u8 maps)")
