@@ -18,6 +18,11 @@
  *                           matlab/svm_model_matlab.c:211 matlab_matrix_to_model, svm.cpp:2641 svm_load_model
  *   cds_camera_motion    <- main.m:77-105 + cm_judge.m + mv_vote.m + direction_cluster.m
  *   cds_magnitude_vote   <- magnitude_vote.m:1
+ *   cds_create(use_rbf = CDS_FUSION_FAST) <- the decoder's own per-slice arithmetic: TDecGop.cpp:225-333 (tail of decompressSlice),
+ *                           :486-656 (CameraDect, vote_alg, max, Umean), salmat.cpp (ForwardFilter, MapThreshold, Generate*Map)
+ *   cds_clip_process_maps <- main.m:25-27,38-55: the per-picture mv_x / mv_y / depth / bitmap arrays MATLAB reads from the decoder's
+ *                           text files or .mat cell arrays (writer code_mat_h.cpp:28-57)
+ *   cds_getframe_semantic <- TComDataCU::getDepth / getPredictionMode / getCUMvField (the partitions TDecCu::MVoutput walks, TDecCu.cpp:165-289)
  *   cds_clip_*           <- main.m:113-305 (per-clip loop) / TDecGop.cpp:225-333 (per-slice hook)
  */
 #ifndef CDS_H
