@@ -37,6 +37,8 @@ def _model(cds, nsv):
     dict(w=416, h=240, fps=10.0, F=26, first=0, rbf=1, batch=8),     # PS 3, PT 21: full temporal window reached
     dict(w=416, h=240, fps=10.0, F=10, first=0, rbf=0, batch=4),     # linear fusion branch (main.m:258-272)
     dict(w=200, h=136, fps=7.0, F=9, first=0, rbf=1, batch=32),      # ragged CTU edge (136 = 2*64 + 8), tiny batch remainder
+    dict(w=1280, h=720, fps=10.0, F=5, first=0, rbf=1, batch=4),     # 720p (720 = 11*64 + 16): the geometry of the bundled Vidyo / FourPeople clips,
+                                                                     # which the reference's own getFrame mishandles (its CTU-row count)
 ])
 def test_clip_maps_vs_oracle(cds, cfg):
     w, h, F = cfg["w"], cfg["h"], cfg["F"]
