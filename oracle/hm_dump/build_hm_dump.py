@@ -24,7 +24,7 @@ DUMP = r'''
   /* ---- syntax dump (replaces the reference's OpenCV saliency block) ---- */
   {
     static FILE* s_dump = NULL;
-    if (!s_dump) { const char* pth = getenv("HM_SYNTAX_DUMP"); s_dump = fopen(pth ? pth : "syntax_dump.bin", "wb"); }
+    if (!s_dump) { const char* pth = getenv("HM_SYNTAX_DUMP"); s_dump = fopen(pth ? pth : (getenv("HM_PACKED_FD") ? "/dev/null" : "syntax_dump.bin"), "wb"); }
     int poc = pcSlice->getPOC();
     int nctu = (int)rpcPic->getNumCUsInFrame();
     fwrite(&poc, 4, 1, s_dump); fwrite(&nctu, 4, 1, s_dump);
@@ -36,6 +36,31 @@ DUMP = r'''
       for (int s = 0; s < 3; s++) for (int i = 0; i < n[s]; i++) { short v = (short)src[s][i]; fwrite(&v, 2, 1, s_dump); }
     }
     fflush(s_dump);
+    /* packed wire format on an inherited file descriptor (HM_PACKED_FD): the decoder as a producer PROCESS for a GPU-owning
+       consumer (compressd_domain_saliencyprediction_b200/feeder.py).  Record: int32 poc, nctu, ntok; int32 hdr[nctu][4] =
+       {token offset, n_cupu, n_pred, n_mv}; uint16 bytes[nctu]; int16 tok[ntok] (per CTU: cupu | pred | mv), as include/cds.h */
+    static FILE* s_pk = NULL; static int s_pk_init = 0;
+    if (!s_pk_init) { s_pk_init = 1; const char* fd = getenv("HM_PACKED_FD"); if (fd) s_pk = fdopen(atoi(fd), "wb"); }
+    if (s_pk) {
+      static int* ph = NULL; static unsigned short* pb = NULL; static short* pt = NULL; static int cap = 0;
+      if (!ph) { ph = (int*)malloc(sizeof(int) * 4 * LCUNUM); pb = (unsigned short*)malloc(2 * LCUNUM); }
+      int ntok = 0;
+      for (int a = 0; a < nctu; a++) {
+        float* src[3] = { TDecCu::CUPU[a], TDecCu::Pred[a], TDecCu::MV[a] };
+        ph[4 * a] = ntok;
+        for (int s = 0; s < 3; s++) { int n = 0; while (src[s][n] != 999) n++; ph[4 * a + 1 + s] = n; ntok += n; }
+        int by = (int)TDecCu::bits[a]; pb[a] = (unsigned short)(by < 0 ? 0 : by > 65535 ? 65535 : by);
+      }
+      if (ntok > cap) { cap = ntok + 4096; free(pt); pt = (short*)malloc(2 * (size_t)cap); }
+      int o = 0;
+      for (int a = 0; a < nctu; a++) {
+        float* src[3] = { TDecCu::CUPU[a], TDecCu::Pred[a], TDecCu::MV[a] };
+        for (int s = 0; s < 3; s++) for (int i = 0; i < ph[4 * a + 1 + s]; i++) pt[o++] = (short)src[s][i];
+      }
+      int head[3] = { poc, nctu, ntok };
+      fwrite(head, 4, 3, s_pk); fwrite(ph, 16, nctu, s_pk); fwrite(pb, 2, nctu, s_pk); fwrite(pt, 2, ntok, s_pk);
+      fflush(s_pk);
+    }
     static FILE* s_sem = NULL; static int s_sem_init = 0;
     if (!s_sem_init) { s_sem_init = 1; const char* pth = getenv("HM_SEMANTIC_DUMP"); if (pth) s_sem = fopen(pth, "wb"); }
     if (s_sem) {      /* int32 poc, int32 nctu, then nctu x (256 depth, 256 pred mode, 256 x 2 int16 mv) in z-scan order */

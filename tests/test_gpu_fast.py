@@ -298,3 +298,29 @@ def test_fast_version_bit_exact_at_large_sizes(cds, w, h, F):
     got, cam = clip.process(0, hdr, tok, base, byts)
     clip.close()
     assert np.array_equal(cam, want_cam) and got.tobytes() == want_f32.tobytes()
+
+
+def test_feeder_many_streams_one_gpu_process(cds):
+    """parse-only decoder PROCESSES (the reference's hooked HM, packed syntax on a pipe) feed one GPU-owning process.
+    Two streams of different sizes decode concurrently; the maps equal the direct path's and the reference's golden PNGs."""
+    dumper = os.path.join(o.ROOT, "oracle", "_ref", "hm_syntax_dump")
+    sdir = os.path.join(o.ROOT, "oracle", "_ref", "streams")
+    if not (os.path.exists(dumper) and os.path.exists(os.path.join(sdir, "BasketballDrill.bin"))):
+        pytest.skip("hooked HM decoder / bitstreams not built (needs the reference tree at build time)")
+    res = cds.feeder.run_streams(dumper, [(os.path.join(sdir, "BasketballDrill.bin"), 832, 480), (os.path.join(sdir, "BasketballPass.bin"), 416, 240)],
+                                 fps=50.0, batch=32, collect=True, fast=True, out_u8=True)
+    assert res["per_stream"] == [500, 500]
+    print(f"feeder: {res['pictures']} pictures of 2 streams in {res['seconds']:.2f} s")
+    d = np.load(os.path.join(GOLD, "fast_BasketballDrill.npz"))
+    n = d["png"].shape[0]
+    per = (res["maps"][0][:n] != d["png"]).reshape(n, -1).sum(1)
+    assert per.sum() <= 3 and (per == 0).sum() >= 36
+    clip = cds.SaliencyClip(832, 480, 50.0, fast=True, out_u8=True, max_batch=32)
+    got, cam = clip.process(0, d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"])
+    clip.close()
+    assert np.array_equal(res["maps"][0][:n], got) and np.array_equal(res["cams"][0][:n], cam)
+    p = np.load(os.path.join(GOLD, "real_BasketballPass.npz"))
+    clip = cds.SaliencyClip(416, 240, 50.0, fast=True, out_u8=True, max_batch=32)
+    got, _ = clip.process(0, p["hdr"], p["tok"], p["tok_base"], p["ctu_bytes"])
+    clip.close()
+    assert np.array_equal(res["maps"][1][:got.shape[0]], got)
