@@ -324,3 +324,19 @@ def test_feeder_many_streams_one_gpu_process(cds):
     got, _ = clip.process(0, p["hdr"], p["tok"], p["tok_base"], p["ctu_bytes"])
     clip.close()
     assert np.array_equal(res["maps"][1][:got.shape[0]], got)
+
+
+def test_fast_version_random_geometries_rates_and_batches(cds):
+    """A seeded sweep over picture sizes (widths k*16, heights k*8 from 64 up), frame rates (PS / PT from cvRound, incl. 29.97 and 25 whose
+    halves round to even) and batch sizes: every case bit-identical to the oracle (tools/fast_fuzz.py runs larger sweeps)."""
+    r = np.random.default_rng(20)
+    for i in range(24):
+        w = int(r.integers(4, 60)) * 16; h = int(r.integers(8, 90)) * 8
+        fps = float(r.choice([7.0, 10.0, 15.0, 24.0, 25.0, 29.97, 30.0, 50.0, 60.0]))
+        F = int(r.integers(1, 12)); batch = int(r.integers(1, 9)); seed = int(r.integers(0, 10000))
+        hdr, tok, base, byts = cds.ops.synth_clip(w, h, seed, F)
+        want_u8, want_f32, want_cam = _oracle_clip(w, h, fps, hdr, tok, base, byts)
+        clip = cds.SaliencyClip(w, h, fps, fast=True, out_u8=False, max_batch=batch)
+        got, cam = clip.process(0, hdr, tok, base, byts)
+        clip.close()
+        assert np.array_equal(cam, want_cam) and got.tobytes() == want_f32.tobytes(), (i, w, h, fps, F, batch, seed)
