@@ -189,3 +189,25 @@ def test_sudoku_host_entry_vs_oracle_signed_map(cds):
     got = cds.ops.Sudoku_contrastcpp5(a, 11.0, 1, 48)
     want = o.orc_sudoku(a, 11.0, 1, 48)
     assert np.max(np.abs(got - want)) <= REL_TOL
+
+
+def test_random_geometries_rates_and_batches(cds):
+    """A seeded sweep over picture sizes (multiples of 8 from 72 up), frame rates and batch sizes, RBF and linear fusion: camera votes
+    exact, maps within 1e-4 (tools/main_fuzz.py runs larger sweeps)."""
+    r = np.random.default_rng(3)
+    mdl, gm = _model(cds, 200)
+    o.oracle().orc_set_threads(16)
+    worst = 0.0
+    for i in range(12):
+        w = int(r.integers(9, 90)) * 8; h = int(r.integers(9, 70)) * 8
+        fps = float(r.choice([7.0, 10.0, 13.0, 24.0])); F = int(r.integers(2, 9)); batch = int(r.integers(1, 6)); seed = int(r.integers(0, 10000))
+        rbf = int(r.integers(0, 4) > 0)
+        packed, ints = _clip(cds, w, h, seed, F)
+        want, wcam, _ = o.orc_process_clip(w, h, fps, *ints, mdl, MEAN9, STD9, first_out=0, use_rbf=rbf)
+        clip = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, use_rbf=bool(rbf), max_batch=batch)
+        got, cam = clip.process(0, *packed)
+        clip.close()
+        err = float(np.max(np.abs(got - np.nan_to_num(want))))
+        worst = max(worst, err)
+        assert np.array_equal(cam, wcam) and err <= REL_TOL, (i, w, h, fps, F, batch, rbf, seed, err)
+    print("worst abs error over the sweep", worst)
