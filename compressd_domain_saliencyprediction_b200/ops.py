@@ -139,6 +139,13 @@ class SvmModel:
                   "cds_svm_model_create")
         self.Label = tuple(Label)
 
+    @classmethod
+    def from_mat(cls, path):
+        """(model, meanVec, stdVec) from a svmRBFmodel_all.mat (main.m:113; layout of svm_model_matlab.c:17-29)."""
+        from . import formats
+        m = formats.load_svm_model_mat(path)
+        return cls(SVs=m["SVs"], sv_coef=m["sv_coef"], rho=m["rho"], gamma=m["gamma"], Label=m["Label"]), m["meanVec"], m["stdVec"]
+
     @property
     def handle(self):
         return self._h

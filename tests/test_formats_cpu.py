@@ -42,3 +42,30 @@ def test_saliency_mat_and_png(tmp_path):
     formats.write_png_per_poc(tmp_path / "HMdata", maps, first_poc=5)
     img = cv2.imread(str(tmp_path / "HMdata" / "6.png"), cv2.IMREAD_GRAYSCALE)
     assert img.shape == (48, 64) and np.array_equal(img, np.rint(maps[1] * 255).astype(np.uint8))
+
+
+def test_svmrbfmodel_all_mat_round_trip(tmp_path):
+    """svmRBFmodel_all.mat (main.m:113) as libsvm's MATLAB interface lays the model struct out (svm_model_matlab.c:17-29): the 11 fields
+    in their fixed order, sparse SVs, plus meanVec / stdVec; and the committed stand-in file equals the libsvm text model it came from."""
+    import os
+    import scipy.io as sio
+    import scipy.sparse as sp
+    import _oracle as o
+    from compressd_domain_saliencyprediction_b200 import formats
+    r = np.random.default_rng(4)
+    SV = r.standard_normal((17, 9)); SV[::3, 4] = 0.0
+    coef = np.concatenate([r.random(9), -r.random(8)])
+    p = str(tmp_path / "svmRBFmodel_all.mat")
+    formats.save_svm_model_mat(p, SV, coef, 0.25, 1 / 9, (1, -1), np.arange(9) * 0.1, np.arange(1, 10) * 0.5)
+    raw = sio.loadmat(p)
+    assert raw["model"].dtype.names == ("Parameters", "nr_class", "totalSV", "rho", "Label", "sv_indices", "ProbA", "ProbB", "nSV", "sv_coef", "SVs")
+    s = raw["model"][0, 0]
+    assert sp.issparse(s["SVs"]) and s["SVs"].shape == (17, 9) and s["sv_coef"].shape == (17, 1)
+    assert s["Parameters"].reshape(-1).tolist()[:2] == [0.0, 2.0] and s["nSV"].reshape(-1).tolist() == [9.0, 8.0]
+    m = formats.load_svm_model_mat(p)
+    assert np.array_equal(m["SVs"], SV) and np.array_equal(m["sv_coef"], coef) and m["rho"] == 0.25 and m["Label"] == (1, -1)
+    assert np.array_equal(m["meanVec"], np.arange(9) * 0.1) and np.array_equal(m["stdVec"], np.arange(1, 10) * 0.5)
+    g = os.path.join(o.ROOT, "tests", "golden")
+    SVt, coeft, rhot, gammat, labelst = o.load_libsvm_model(os.path.join(g, "standin_svmRBFmodel.model"))
+    mm = formats.load_svm_model_mat(os.path.join(g, "standin_svmRBFmodel_all.mat"))
+    assert np.array_equal(mm["SVs"], SVt) and np.array_equal(mm["sv_coef"], coeft) and mm["rho"] == rhot and mm["gamma"] == gammat

@@ -146,6 +146,11 @@ def test_trained_standin_model_on_real_clips(cds, name):
     gm = cds.ops.SvmModel(path=path)
     mdl = o.load_libsvm_model(path)
     assert gm.totalSV == mdl[0].shape[0] and gm.nfeat == 9
+    # the same model as the file the reference loads (main.m:113): svmRBFmodel_all.mat with model / meanVec / stdVec
+    gmat, mean_m, std_m = cds.ops.SvmModel.from_mat(os.path.join(GOLD, "standin_svmRBFmodel_all.mat"))
+    assert gmat.totalSV == gm.totalSV and np.array_equal(mean_m, st["meanVec"]) and np.array_equal(std_m, st["stdVec"])
+    Xp = np.random.default_rng(1).standard_normal((64, 9))
+    assert np.array_equal(gmat.decision_values(Xp)[0], gm.decision_values(Xp)[0])
     first = max(0, F - (6 if w > 1000 else 12))
     want, _, _ = o.orc_process_clip(w, h, 10.0, mvx, mvy, dep, byts, mdl, st["meanVec"], st["stdVec"], first_out=first, use_rbf=1)
     want = np.nan_to_num(want)
