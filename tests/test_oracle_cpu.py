@@ -196,3 +196,26 @@ def test_parse_only_hm_producer_captures_identical_syntax(tmp_path):
                            stderr=subprocess.DEVNULL, timeout=300)
         assert r.returncode == 0
     assert os.path.getsize(a) > 1000000 and filecmp.cmp(a, b, shallow=False)
+
+
+def test_reference_libsvmpredict_mexfunction_through_the_mex_standin():
+    """The reference's own matlab/svmpredict.c + svm_model_matlab.c, compiled verbatim against oracle/shim_mx/mex.h (struct arrays, sparse
+    SVs, transpose call-back), reproduce libsvm's heart_scale known answer (matlab/README:179-181) and the oracle's decision values:
+    this pins the stand-in the GPU binding test (tests/test_gpu_bindings.py) relies on."""
+    import ctypes as C
+    so = os.path.join(o.ORACLE_DIR, "_ref", "libref_svmpredict.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built")
+    L = C.CDLL(so)
+    d = np.load(os.path.join(o.ROOT, "tests", "golden", "svm_heart_scale.npz"))
+    SV = np.ascontiguousarray(d["SV"], np.float64); coef = np.ascontiguousarray(d["coef"], np.float64)
+    X = np.asfortranarray(d["X"], np.float64); y = np.ascontiguousarray(d["y"], np.float64)
+    N, F = X.shape
+    lab = np.zeros(N); acc = np.zeros(3); dec = np.zeros(N); msg = C.create_string_buffer(1024)
+    L.mx_libsvmpredict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int,
+                                   C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    rc = L.mx_libsvmpredict(o._ptr(y), o._ptr(X), N, F, SV.shape[0], o._ptr(SV), o._ptr(coef), float(d["rho"]), float(d["gamma"]), int(d["labels"][0]),
+                            int(d["labels"][1]), int((coef > 0).sum()), b"", o._ptr(lab), o._ptr(acc), o._ptr(dec), msg, 1024)
+    assert rc == 0, msg.value
+    assert int((lab == y).sum()) == 234 and abs(acc[0] - 100.0 * 234 / 270) < 1e-9
+    assert np.array_equal(dec, d["dec_ref"])
