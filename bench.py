@@ -483,6 +483,10 @@ def run_b200(a):
         line["cpu_baseline"] = {"value": 1.0 / pf, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"{n_out} output pictures of the same workload after {ctx} context pictures on {cores} threads; "
                                           f"{KIND_TEXT[kind]}; per-picture s: {det}"}
+        # the reference itself is single-threaded (quote the speed-up against one core and against the whole host)
+        pf1, det1, _ = cpu_sample(a, 1, 6, 1)
+        line["cpu_baseline"]["single_core"] = {"value": 1.0 / pf1, "unit": UNIT, "cores": 1,
+                                               "sample": f"1 output picture after 6 context pictures on one thread; per-picture s: {det1}"}
         if fast_line:
             fthreads = min(cores, 16)
             fv, fdet = cpu_fast_sample(a, fthreads)
