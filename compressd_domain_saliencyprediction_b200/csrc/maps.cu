@@ -287,33 +287,43 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __r
     }
   }
   __syncthreads();
-  const int o = blockIdx.y * 256 + threadIdx.x;
+  // two horizontally adjacent cells per thread (w4 is even): the (slot, shift, weight) of a term is fetched once for both
+  const int o = (blockIdx.y * 256 + threadIdx.x) * 2;
   if (o >= n4) return;
   const int r = o / w4, c = o - r * w4;
   const size_t cur = (size_t)(poc % RL) * n4 + o;
-  const float4 ref = sm4[cur];
-  const float rx = ref.x, ry = ref.y, rb = ref.z, rd = ref.w;
-  float am = 0.f, ab = 0.f, ad = 0.f;
+  const float4 ref0 = sm4[cur], ref1 = sm4[cur + 1];
+  float am0 = 0.f, ab0 = 0.f, ad0 = 0.f, am1 = 0.f, ab1 = 0.f, ad1 = 0.f;
   const float4* __restrict__ w4tab = reinterpret_cast<const float4*>(wtab);
 #pragma unroll 2
   for (int j = 1; j <= jmax; j++) {
     const int4 t = s_tab[j];
     const int sr = r - t.z, sc = c - t.y;                          // immove: +x moves content right, +y down, zero fill
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) p = __ldg(sm4 + (t.x + sr * w4 + sc));   // one LDG.128 for the four maps
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+    if ((unsigned)sr < (unsigned)h4) {
+      const float4* __restrict__ row = sm4 + (t.x + sr * w4);
+      if ((unsigned)sc < (unsigned)w4) p0 = __ldg(row + sc);       // one LDG.128 for the four maps
+      if ((unsigned)(sc + 1) < (unsigned)w4) p1 = __ldg(row + sc + 1);
+    }
     const float4 wj = __ldg(w4tab + j);
-    const float dx = rx - p.x, dy = ry - p.y;
-    am = fmaf(wj.x, sqrt_approx(fmaf(dx, dx, dy * dy)), am);      // :195
-    ab = fmaf(wj.y, fabsf(rb - p.z), ab);                          // :196
-    ad = fmaf(wj.z, fabsf(rd - p.w), ad);                          // :197
+    const float dx0 = ref0.x - p0.x, dy0 = ref0.y - p0.y, dx1 = ref1.x - p1.x, dy1 = ref1.y - p1.y;
+    am0 = fmaf(wj.x, sqrt_approx(fmaf(dx0, dx0, dy0 * dy0)), am0);   // :195
+    am1 = fmaf(wj.x, sqrt_approx(fmaf(dx1, dx1, dy1 * dy1)), am1);
+    ab0 = fmaf(wj.y, fabsf(ref0.z - p0.z), ab0);                     // :196
+    ab1 = fmaf(wj.y, fabsf(ref1.z - p1.z), ab1);
+    ad0 = fmaf(wj.z, fabsf(ref0.w - p0.w), ad0);                     // :197
+    ad1 = fmaf(wj.z, fabsf(ref1.w - p1.w), ad1);
   }
   float* X = Xmaps + (size_t)f * 9 * n4 + o;
-  X[(size_t)1 * n4] = am; X[(size_t)4 * n4] = ab; X[(size_t)7 * n4] = ad;
+  *reinterpret_cast<float2*>(X + (size_t)1 * n4) = make_float2(am0, am1);
+  *reinterpret_cast<float2*>(X + (size_t)4 * n4) = make_float2(ab0, ab1);
+  *reinterpret_cast<float2*>(X + (size_t)7 * n4) = make_float2(ad0, ad1);
 }
 
 int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float4* sm4, const int* cam_ring,
                     const float* wtab, float* Xmaps, cudaStream_t st) {
-  dim3 grid(B, ceil_div(h4 * w4, 256));
+  dim3 grid(B, ceil_div(h4 * w4, 512));
+  if ((w4 & 1) || ((h4 * w4) & 1)) { set_error("temporal: odd cell-grid width %d", w4); return CDS_EINVAL; }
   if (PT > TMP_MAXJ) { set_error("temporal: PT %d exceeds %d", PT, TMP_MAXJ); return CDS_EINVAL; }
   temporal_kernel<<<grid, 256, (size_t)PT * sizeof(int4), st>>>(h4, w4, PT, ring_len, first_poc, sm4, cam_ring, wtab, Xmaps);
   CDS_LAUNCH_CHECK();
