@@ -65,7 +65,8 @@ def test_fast_version_bit_exact_vs_oracle_on_real_clips(cds, name, batch):
         assert np.all(np.abs(want_cam).sum(1) > 0), want_cam
 
 
-@pytest.mark.parametrize("w,h,fps,F,seed", [(416, 240, 50.0, 60, 5), (832, 480, 24.0, 30, 9), (1024, 768, 30.0, 12, 2), (1280, 720, 60.0, 8, 4)])
+@pytest.mark.parametrize("w,h,fps,F,seed", [(416, 240, 50.0, 60, 5), (832, 480, 24.0, 30, 9), (1024, 768, 30.0, 12, 2), (1280, 720, 60.0, 8, 4),
+                                            (416, 240, 24.0, 100, 6)])      # ring of 2*7 + 7 + 17 = 38 pictures: wraps twice
 def test_fast_version_bit_exact_vs_oracle_on_synthetic_pans(cds, w, h, fps, F, seed):
     """Synthetic syntax with a global pan per picture: the camera branch fires, the clip runs past PS + PT pictures (ring wrap),
     and batches of 7 split the clip at positions unrelated to PS / PT."""
