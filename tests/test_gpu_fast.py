@@ -341,3 +341,16 @@ def test_fast_version_random_geometries_rates_and_batches(cds):
         got, cam = clip.process(0, hdr, tok, base, byts)
         clip.close()
         assert np.array_equal(cam, want_cam) and got.tobytes() == want_f32.tobytes(), (i, w, h, fps, F, batch, seed)
+
+
+@pytest.mark.parametrize("fps", [120.0, 240.0])
+def test_fast_version_high_frame_rates(cds, fps):
+    """PS = cvRound(0.3 fps) = 36 / 72: the smoothing tile needs more than the default 48 KB of dynamic shared memory."""
+    w, h, F = 208, 120, 9
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 12, F)
+    want_u8, want_f32, want_cam = _oracle_clip(w, h, fps, hdr, tok, base, byts)
+    clip = cds.SaliencyClip(w, h, fps, fast=True, out_u8=False, max_batch=4)
+    assert clip.PS == int(np.rint(0.3 * fps))
+    got, cam = clip.process(0, hdr, tok, base, byts)
+    clip.close()
+    assert np.array_equal(cam, want_cam) and got.tobytes() == want_f32.tobytes()
