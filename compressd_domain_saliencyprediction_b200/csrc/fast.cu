@@ -10,15 +10,18 @@
 //   * elementwise stages run one thread per cell; maxima / minima are order-free;
 //   * cv::sum / cv::mean: groups of 4 consecutive floats added in float, groups accumulated in double (parallel tree; the
 //     double sum's own order only matters below 1e-15);
-//   * the sequential float sums of MapThreshold (salmat.cpp:155-162) and Umean (TDecGop.cpp:622-640) are emulated by ONE lane
-//     per sum while the other 31 lanes of its warp select and compact the terms in raster order; maps that are replicated
-//     blocks (bit map, the three full-resolution temporal maps) use a closed form for "add the same float n times" that is
-//     exact inside a binade (seq_add_run), so a 1920x1080 map costs H x (selected blocks per block row) steps, not H x W;
+//   * the sequential float sums of MapThreshold (salmat.cpp:155-162) and Umean (TDecGop.cpp:622-640) are evaluated in parallel
+//     and still bit-exactly: inside one binade of the running sum every addition moves it by an integer number of ulps that
+//     does not depend on the sum, so pieces of the sequence reduce as integers (block_seq_sum); only the additions that cross
+//     a binade, ties, and terms comparable to the sum are done one float at a time.  Maps that are replicated blocks (bit map,
+//     the three full-resolution temporal maps) use the same idea on runs "add v n times" (warp_select_sum_runs, seq_add_run),
+//     so a 1920x1080 map costs about one step per block row, not H x W additions;
 //   * the H x W feature maps are never materialised: all nine are constant on 4x4-pixel cells (or 32 / 64-pixel blocks), so
 //     the weighted sum is formed per cell and only the final Gaussian runs at pixel resolution, in the tap order of
 //     cv::GaussianBlur (row pass: taps in order from zero; column pass: centre tap, then symmetric pairs).
-// Data layout: raw ring [RL] of stage-(a) maps in their narrow types (int16 mv, u8 depth, u16 bytes per CTU) + 8 floats and
-// 2 ints per picture; coarse temporal rings (CTU grid, 32-pixel grid); everything else is batch-local.
+// Data layout: raw ring [RL = 2B + PS + PT] of stage-(a) maps in their narrow types (int16 mv, u8 depth, u16 bytes per CTU) + 8 floats
+// and 2 ints per picture; coarse temporal rings (CTU grid, 32-pixel grid); everything else is batch-local.  fast_front (camera
+// stages) and fast_back (smoothing .. map) are the two halves the clip context may run on different streams.
 #include "fast.cuh"
 #include <math.h>
 #include <string.h>
