@@ -384,9 +384,35 @@ def run_b200(a):
         fms = max_over_ranks(f0.elapsed_time(f1))
         flaunches = cds.take_launch_count()
         fe2e = e2e_leg(fclip, h_maps, 1, 4 * E2E_CHUNK)
+        # per-stage device times of the fast version (single-batch calls, no overlap, the two chains one after the other) and the
+        # roofline of its dominant kernel: the column pass of cv::GaussianBlur in the reference's rounding order = per 4 taps and 4
+        # pixel rows 4 additions (above + below), 16 products, 16 additions, none of which may be fused: 9 * ceil(half / 4) + 1
+        # FP32 lane-instructions per pixel (82 at 1080p); ceiling = the FFMA issue rate measured in this run
+        fstage, froof = None, None
+        if rank == 0:
+            names = L.cds_profile_stage_names().decode().split(",")
+            fclip.seek(0)
+            fstep(0, halo, context=True)
+            check(L.cds_profile_enable(fclip.handle, 1), "profile")
+            for k in range(3):
+                fstep(halo + k * B, B)
+            msv = (C.c_double * 24)(); calls = (C.c_long * 24)()
+            check(L.cds_profile_read(fclip.handle, msv, calls, 24), "profile_read")
+            check(L.cds_profile_enable(fclip.handle, 0), "profile")
+            fstage = {n: msv[i] / 3 for i, n in enumerate(names) if n.startswith("fast_") or n == "getframe"}
+            pkf = (C.c_double * 3)()
+            check(L.cds_measure_peaks(C.byref(pkf, 0), C.byref(pkf, 8), C.byref(pkf, 16)), "peaks")
+            ksize = int(h / 15); ksize += (ksize % 2 == 0)
+            per_px = 9 * (-(-(ksize // 2) // 4)) + 1
+            t = fstage["fast_blur_v"] * 1e-3
+            froof = {"kernel": "fast_blur_v", "bound": "fp32", "achieved": per_px * float(h) * w * B / t / 1e12, "peak": pkf[1] / 1e12, "unit": "T lane-instr/s",
+                     "frac": per_px * float(h) * w * B / t / pkf[1], "ms_per_launch": t * 1e3, "share_of_step": fstage["fast_blur_v"] / sum(fstage.values()),
+                     "traffic": None,
+                     "work": f"{per_px} FP32 lane-instructions per pixel ({ksize}-tap cv::GaussianBlur column pass, rounding order of the reference: no FMA); "
+                             "peak = measured FFMA issue rate (cds_measure_peaks, this run)"}
         fast_line = {"value": frames / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms / a.steps, "gpu_launches": int(flaunches),
                      "e2e": {k: fe2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
-                     "PS": fclip.PS, "PT": fclip.PT, "dtype": "f32 (operation order of the reference: bit-identical 8-bit maps)",
+                     "stage_ms_per_step": fstage, "roofline": froof, "PS": fclip.PS, "PT": fclip.PT, "dtype": "f32 (operation order of the reference: bit-identical 8-bit maps)",
                      "what": "use_rbf = CDS_FUSION_FAST: CameraDect / Umean vote, ForwardFilter, MapThreshold, coarse-grid temporal and spatial "
                              "maps, fixed FeatureWeight sum, cv::GaussianBlur, 8-bit map; same synthetic syntax, same batch"}
         fclip.close()

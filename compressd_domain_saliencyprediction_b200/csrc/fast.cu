@@ -938,6 +938,8 @@ struct FastState {
   FastP p;
   cudaStream_t side = nullptr;          // the temporal chain (temporal -> tthr) runs beside the threshold / spatial chain
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  void (*mark)(void* user, int stage, cudaStream_t st) = nullptr;   // per-stage timing hook of the clip context (cds_profile_*)
+  void* mark_user = nullptr; bool profiling = false;
   std::vector<void*> allocs;
   size_t smem_tthr = 0, smem_sp[3] = {0, 0, 0}, smem_h = 0;
 };
@@ -1057,9 +1059,12 @@ int fast_front(FastState* s, int first_poc, int n, const int16_t* mvx, const int
                int* cam_out, cudaStream_t st) {
   const FastP& p = s->p;
   if (n < 1 || n > p.B || first_poc < 0) { set_error("fast_run_batch: bad batch"); return CDS_EINVAL; }
+  auto M = [&](int stage) { if (s->profiling && s->mark) s->mark(s->mark_user, stage, st); };
+  M(FAST_ST_CAM_SCAN);
   CDS_CUDA(cudaMemsetAsync(p.d_cami, 0, (size_t)n * 24 * sizeof(int), st));
   fast_cam_scan_kernel<<<dim3(ceil_div(p.n4, 1024), n), 256, 0, st>>>(p, first_poc, mvx, mvy, dep, bytes);
   CDS_LAUNCH_CHECK();
+  M(FAST_ST_CAM_VOTE);
   fast_cam_vote_kernel<<<dim3(2, n), CAM_T, 0, st>>>(p, first_poc);
   CDS_LAUNCH_CHECK();
   fast_cam_norm_kernel<<<dim3(ceil_div(p.n4 / 4, 256), n), 256, 0, st>>>(p, first_poc);
@@ -1073,34 +1078,45 @@ int fast_front(FastState* s, int first_poc, int n, const int16_t* mvx, const int
 int fast_back(FastState* s, int first_poc, int n, void* out, int out_u8, cudaStream_t st) {
   const FastP& p = s->p;
   if (n < 1 || n > p.B || first_poc < 0) { set_error("fast_run_batch: bad batch"); return CDS_EINVAL; }
+  auto M = [&](int stage) { if (s->profiling && s->mark) s->mark(s->mark_user, stage, st); };
+  M(FAST_ST_SMOOTH);
   fast_smooth_kernel<<<dim3(ceil_div(p.n4, 128), ceil_div(n, SM_G)), dim3(128, SM_G), (size_t)(SM_G + p.PS - 1) * 128 * sizeof(float4), st>>>(p, first_poc, n);
   CDS_LAUNCH_CHECK();
   fast_smooth_bit_kernel<<<dim3(ceil_div(p.nctu, 128), n), 128, 0, st>>>(p, first_poc);
   CDS_LAUNCH_CHECK();
   if (!out) return CDS_OK;
   // two independent latency-bound chains after the smoothing: MapThreshold -> spatial maps, and temporal maps -> their threshold
-  CDS_CUDA(cudaEventRecord(s->ev_fork, st));
-  CDS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
-  fast_temporal_kernel<<<dim3(ceil_div(p.g32, 128), 3, n), 128, 0, s->side>>>(p, first_poc);
+  // (side by side on two streams; one after the other when the stages are being timed)
+  cudaStream_t sd = s->profiling ? st : s->side;
+  M(FAST_ST_TEMPORAL);
+  if (!s->profiling) {
+    CDS_CUDA(cudaEventRecord(s->ev_fork, st));
+    CDS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+  }
+  fast_temporal_kernel<<<dim3(ceil_div(p.g32, 128), 3, n), 128, 0, sd>>>(p, first_poc);
   CDS_LAUNCH_CHECK();
-  fast_tthr_kernel<<<dim3(3, n), 128, s->smem_tthr, s->side>>>(p);
+  fast_tthr_kernel<<<dim3(3, n), 128, s->smem_tthr, sd>>>(p);
   CDS_LAUNCH_CHECK();
-  CDS_CUDA(cudaEventRecord(s->ev_join, s->side));
+  if (!s->profiling) CDS_CUDA(cudaEventRecord(s->ev_join, s->side));
+  M(FAST_ST_THR_SPATIAL);
   fast_thr_kernel<<<dim3(5, n), 256, 0, st>>>(p);
   CDS_LAUNCH_CHECK();
   fast_spatial_kernel<<<dim3(4, n), SP_T, s->smem_sp[1], st>>>(p);
   CDS_LAUNCH_CHECK();
   fast_mvs_kernel<<<n, 256, 0, st>>>(p);
   CDS_LAUNCH_CHECK();
-  CDS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+  if (!s->profiling) CDS_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+  M(FAST_ST_COMBINE_BLUR_H);
   fast_combine_kernel<<<dim3(ceil_div(p.n4, 256), n), 256, 0, st>>>(p);
   CDS_LAUNCH_CHECK();
   fast_mm_reset_kernel<<<ceil_div(n, 128), 128, 0, st>>>(p.d_mm, n);
   CDS_LAUNCH_CHECK();
   fast_blur_h_kernel<<<dim3(p.h4, n), 256, s->smem_h, st>>>(p);
   CDS_LAUNCH_CHECK();
+  M(FAST_ST_BLUR_V);
   fast_blur_v_kernel<<<dim3(ceil_div(p.w, 128), ceil_div(p.h4, BV_Q), n), 256, ((size_t)(BV_Q + 2 * (p.nq_v + 1)) * 128 + 4 + 4 * p.nq_v) * sizeof(float), st>>>(p);
   CDS_LAUNCH_CHECK();
+  M(FAST_ST_OUTPUT);
   const int nb = ceil_div((int)(((size_t)p.h * p.w / 4)), 256);
   if (out_u8) fast_output_kernel<uint8_t><<<dim3(nb, n), 256, 0, st>>>(p, reinterpret_cast<uint8_t*>(out));
   else fast_output_kernel<float><<<dim3(nb, n), 256, 0, st>>>(p, reinterpret_cast<float*>(out));
@@ -1163,6 +1179,9 @@ int fast_probe_run_sum(const float* vals, int gh, int gw, int rows, int cols, in
   cudaFree(dv); cudaFree(dout);
   return CDS_OK;
 }
+
+void fast_set_marker(FastState* s, void (*mark)(void*, int, cudaStream_t), void* user) { s->mark = mark; s->mark_user = user; }
+void fast_profile(FastState* s, bool on) { s->profiling = on; }
 
 int fast_get_cam(const FastState* s, int poc, int* xy) {
   CDS_CUDA(cudaMemcpy(xy, s->p.r_cam + 2 * (poc % s->p.RL), 8, cudaMemcpyDeviceToHost));

@@ -20,6 +20,12 @@ int fast_run_batch(FastState* s, int first_poc, int n, const int16_t* mvx, const
 int fast_front(FastState* s, int first_poc, int n, const int16_t* mvx, const int16_t* mvy, const uint8_t* dep, const uint16_t* bytes,
                int* cam_out, cudaStream_t st);
 int fast_back(FastState* s, int first_poc, int n, void* out, int out_u8, cudaStream_t st);
+// per-stage timing: the clip context's marker is called at the start of each stage while profiling is on (the two chains then run
+// one after the other instead of side by side)
+enum FastStage { FAST_ST_CAM_SCAN = 0, FAST_ST_CAM_VOTE, FAST_ST_SMOOTH, FAST_ST_TEMPORAL, FAST_ST_THR_SPATIAL, FAST_ST_COMBINE_BLUR_H,
+                 FAST_ST_BLUR_V, FAST_ST_OUTPUT, FAST_ST_COUNT };
+void fast_set_marker(FastState* s, void (*mark)(void* user, int stage, cudaStream_t st), void* user);
+void fast_profile(FastState* s, bool on);
 int fast_get_cam(const FastState* s, int poc, int* xy);   // camera motion of a picture still in the ring (host copy)
 // probes (tests): `for (i < n) if (sel[i]) S = S + v[i];` and MapThreshold's sum over a map of replicated blocks, both in float
 int fast_probe_seq_sum(const float* v, const unsigned char* sel, int n, float* sum, int* count);

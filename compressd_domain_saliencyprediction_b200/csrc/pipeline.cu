@@ -108,9 +108,12 @@ struct cds_ctx {
 };
 
 enum Stage { ST_GETFRAME = 0, ST_VOTE, ST_SMOOTH, ST_THRESH, ST_TEMPORAL, ST_CONTRAST_PREP, ST_CONTRAST_W5, ST_CONTRAST_W24,
-             ST_CONTRAST_W48, ST_CONTRAST_POST, ST_FULLRES_H, ST_FULLRES_V, ST_TEMPORAL_STATS, ST_RESIZE200, ST_SVM, ST_FINAL, ST_COUNT };
+             ST_CONTRAST_W48, ST_CONTRAST_POST, ST_FULLRES_H, ST_FULLRES_V, ST_TEMPORAL_STATS, ST_RESIZE200, ST_SVM, ST_FINAL,
+             ST_FAST0 /* + FastStage: the fast version's stages (fast.cuh) */, ST_COUNT = ST_FAST0 + FAST_ST_COUNT };
+static_assert(ST_COUNT <= 24, "prof_ms / prof_calls hold 24 stages");
 static const char* kStageNames = "getframe,vote,smooth,thresh_small,temporal,contrast_prep,contrast_win5,contrast_win24,contrast_win48,"
-                                 "contrast_post,fullres_hpass,fullres_vpass,temporal_stats,resize200,svm_rbf,final_map";
+                                 "contrast_post,fullres_hpass,fullres_vpass,temporal_stats,resize200,svm_rbf,final_map,"
+                                 "fast_cam_scan,fast_cam_vote,fast_smooth,fast_temporal,fast_thr_spatial,fast_combine_blur_h,fast_blur_v,fast_output";
 
 static void prof_mark(cds_ctx* c, int stage, cudaStream_t st) {
   if (!c->prof_on) return;
@@ -465,6 +468,7 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
     for (int b = 0; b < 2 && !e; b++)
       if (cudaEventCreateWithFlags(&c->ev_ff[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fb[b], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
     { const char* ov = getenv("CDS_OVERLAP"); c->fast_ovl = !(ov && ov[0] == '0'); }
+    if (!e) fast_set_marker(c->fast, [](void* user, int stage, cudaStream_t st) { prof_mark(static_cast<cds_ctx*>(user), ST_FAST0 + stage, st); }, c);
   }
 #undef A
 #define A(ptr, count) if (!e && !fm) e = dalloc(c, &c->ptr, (size_t)(count))
@@ -622,7 +626,6 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     }
     prof_mark(c, ST_GETFRAME, st);
     if (!c->maps_in) if (int e = getframe_launch(c->w, c->h, n, hdr, tok, tok_base, c->d_mvx, c->d_mvy, c->d_dep, c->d_err, st)) return e;
-    prof_mark(c, ST_FINAL, st);
     if (before_back) CDS_CUDA(cudaStreamWaitEvent(st, before_back, 0));
     if (int e = fast_run_batch(c->fast, first_poc, n, c->d_mvx, c->d_mvy, c->d_dep, bytes, maps_out, c->p.out_u8, cam_out, st)) return e;
     prof_mark(c, -1, st);
@@ -1007,6 +1010,7 @@ extern "C" int cds_profile_enable(cds_ctx* c, int on) {
   if (!c) { set_error("cds_profile_enable: null context"); return CDS_EINVAL; }
   CDS_CUDA(cudaStreamSynchronize(c->stream));
   c->prof_on = on != 0; c->ev_used = 0; c->ev_marks.clear();
+  if (c->fast) fast_profile(c->fast, c->prof_on);
   for (int i = 0; i < 24; i++) { c->prof_ms[i] = 0; c->prof_calls[i] = 0; }
   return CDS_OK;
 }
