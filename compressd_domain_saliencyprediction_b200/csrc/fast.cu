@@ -122,12 +122,14 @@ __device__ __forceinline__ bool term_increment(float v, unsigned Cb, float lim, 
   return q0 == q1;
 }
 
-// A round covers 32 pieces of 128 consecutive cells (one warp x one chunk of T*4 cells); K = 32 / (T/32) chunks per round.
+// A round covers 32 pieces of 128 * SEQ_G consecutive cells (one warp x one chunk of T * 4 * SEQ_G cells; a thread owns SEQ_G groups
+// of 4 consecutive cells per chunk); K = 32 / (T/32) chunks per round.
+constexpr int SEQ_G = 1;     // 2 (8 cells per thread and chunk, half as many rounds) measured 10 % slower: the rounds are work bound, not latency bound
 template <int T>
 struct SeqSumSmem {
   static constexpr int NW = T / 32, K = 32 / NW;
-  float terms[K][T * 4];
-  unsigned char sel[K][T];
+  float terms[K][T * 4 * SEQ_G];
+  unsigned char sel[K][T];             // SEQ_G * 4 selection bits per thread
   int pp[32], pn[32], pf[32];          // per piece: positive ulps, negative ulps, flag (1: needs the sequential path, -1: empty)
   float S; int restart;
 };
@@ -137,25 +139,35 @@ struct SeqSumSmem {
 template <int T, typename LoadFn, typename EvalFn>
 __device__ float block_seq_sum(int ngroups, LoadFn load, EvalFn eval, SeqSumSmem<T>& sm, int* count_out) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = T / 32, K = 32 / NW;
+  constexpr int NW = T / 32, K = 32 / NW, G = SEQ_G;
   int cnt = 0;
   __syncthreads();
   if (tid == 0) sm.S = 0.f;
-  decltype(load(0)) raw[K];
+  decltype(load(0)) raw[K][G];
 #pragma unroll
-  for (int k = 0; k < K; k++) raw[k] = load(min(k * T + tid, ngroups - 1));        // raw words of the next round stay in registers
-  for (int g0 = 0; g0 < ngroups; g0 += K * T) {
-    float t[K][4]; unsigned sel[K];
+  for (int k = 0; k < K; k++)
+#pragma unroll
+    for (int u = 0; u < G; u++) raw[k][u] = load(min((k * T + tid) * G + u, ngroups - 1));   // raw words of the next round stay in registers
+  for (int g0 = 0; g0 < ngroups; g0 += K * T * G) {
+    float t[K][G][4]; unsigned sel[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      sel[k] = g0 + k * T + tid < ngroups ? eval(raw[k], t[k]) : 0u;
-      raw[k] = load(min(g0 + (K + k) * T + tid, ngroups - 1));                      // prefetch
+      sel[k] = 0u;
+#pragma unroll
+      for (int u = 0; u < G; u++) {
+        const int g = g0 + (k * T + tid) * G + u;
+        const unsigned su = g < ngroups ? eval(raw[k][u], t[k][u]) : 0u;
+        sel[k] |= su << (4 * u);
+        raw[k][u] = load(min(g + K * T * G, ngroups - 1));                               // prefetch
+      }
       cnt += __popc(sel[k]);
     }
     __syncthreads();                                   // the previous round's reads of sm.terms are over
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      *reinterpret_cast<float4*>(&sm.terms[k][tid * 4]) = make_float4(t[k][0], t[k][1], t[k][2], t[k][3]);
+#pragma unroll
+      for (int u = 0; u < G; u++)
+        *reinterpret_cast<float4*>(&sm.terms[k][(tid * G + u) * 4]) = make_float4(t[k][u][0], t[k][u][1], t[k][u][2], t[k][u][3]);
       sm.sel[k][tid] = (unsigned char)sel[k];
     }
     int first = 0;                                     // pieces before `first` are already in S
@@ -173,12 +185,14 @@ __device__ float block_seq_sum(int ngroups, LoadFn load, EvalFn eval, SeqSumSmem
         int qp = 0, qn = 0, flag = bad ? 1 : 0;
         if (piece >= first && !bad) {
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            if ((sel[k] >> j) & 1u) {
-              int q;
-              if (!term_increment(neg ? -t[k][j] : t[k][j], Cb, lim, &q)) flag = 1;
-              else if (q > 0) qp += q; else qn -= q;
-            }
+          for (int u = 0; u < G; u++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if ((sel[k] >> (4 * u + j)) & 1u) {
+                int q;
+                if (!term_increment(neg ? -t[k][u][j] : t[k][u][j], Cb, lim, &q)) flag = 1;
+                else if (q > 0) qp += q; else qn -= q;
+              }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { qp += __shfl_xor_sync(FULL, qp, o); qn += __shfl_xor_sync(FULL, qn, o); flag |= __shfl_xor_sync(FULL, flag, o); }
@@ -208,19 +222,24 @@ __device__ float block_seq_sum(int ngroups, LoadFn load, EvalFn eval, SeqSumSmem
             S = __uint_as_float((sb & 0x80000000u) | (ab + ap - an));
           }
           if (stop == 32) break;
-          // piece `stop` one float at a time (lane 0 computes, all lanes follow the same control flow)
+          // piece `stop` one float at a time: lane l fetches thread l's terms, the chain of additions reads them by shuffle
           const int k = stop / NW, w = stop - k * NW;
-          {                                                          // lane l fetches thread l's terms; the chain of additions reads them by shuffle
-            const float4 tq = *reinterpret_cast<const float4*>(&sm.terms[k][(w * 32 + lane) * 4]);
+          {
+            float4 tq[G];
+#pragma unroll
+            for (int u = 0; u < G; u++) tq[u] = *reinterpret_cast<const float4*>(&sm.terms[k][((w * 32 + lane) * G + u) * 4]);
             const unsigned sq = sm.sel[k][w * 32 + lane];
-#pragma unroll 8
+#pragma unroll 4
             for (int i = 0; i < 32; i++) {
               const unsigned sl = __shfl_sync(FULL, sq, i);
-              const float a0 = __shfl_sync(FULL, tq.x, i), a1 = __shfl_sync(FULL, tq.y, i), a2 = __shfl_sync(FULL, tq.z, i), a3 = __shfl_sync(FULL, tq.w, i);
-              if (sl & 1u) S = __fadd_rn(S, a0);
-              if (sl & 2u) S = __fadd_rn(S, a1);
-              if (sl & 4u) S = __fadd_rn(S, a2);
-              if (sl & 8u) S = __fadd_rn(S, a3);
+#pragma unroll
+              for (int u = 0; u < G; u++) {
+                const float a0 = __shfl_sync(FULL, tq[u].x, i), a1 = __shfl_sync(FULL, tq[u].y, i), a2 = __shfl_sync(FULL, tq[u].z, i), a3 = __shfl_sync(FULL, tq[u].w, i);
+                if (sl & (1u << (4 * u))) S = __fadd_rn(S, a0);
+                if (sl & (2u << (4 * u))) S = __fadd_rn(S, a1);
+                if (sl & (4u << (4 * u))) S = __fadd_rn(S, a2);
+                if (sl & (8u << (4 * u))) S = __fadd_rn(S, a3);
+              }
             }
           }
           from = stop + 1;
