@@ -198,6 +198,13 @@ def run_reference(a):
             "data": "synthetic", "config": {"workload": workload_name(a), "frames_per_step": n_out},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if not a.no_fast and a.width % 16 == 0:
+        # the reference's fast version (what its decoder computes per slice) on the same host cores, beside the headline path
+        fthreads = min(cores, 16)
+        fv, fdet = cpu_fast_sample(a, fthreads)
+        line["fast_version"] = {"value": fv, "unit": UNIT, "cores": fthreads, "kind": "port",
+                                "sample": f"{fdet['clips']} independent clips x {fdet['pictures_per_clip']} pictures, one per thread: {fdet['stage_a']} + the "
+                                          f"fast-version oracle (TDecGop.cpp:225-333 + salmat.cpp restated, pinned by the reference's 39 golden PNGs)"}
     print(json.dumps(line), flush=True)
     return 0
 
