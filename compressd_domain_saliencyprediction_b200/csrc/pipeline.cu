@@ -171,9 +171,18 @@ temporal_thresh_partial_kernel(const float* __restrict__ Y, long HW, const float
   const float lim = (valid ? 1.f : 0.f) - (float)(sumn / (double)HW);       // max(Yn) - ave
   const float* __restrict__ y = Y + (size_t)(nine_stored ? f * 9 + 1 + 3 * j : tm) * HW;
   double sb = 0; int nb = 0;
-  for (long i = blockIdx.x * 256L + threadIdx.x; i < HW; i += (long)gridDim.x * 256) {
-    const float v = valid ? (y[i] - mn) * inv : 0.f;
-    if (v > lim) { sb += v; nb++; }
+  const float4* __restrict__ y4 = reinterpret_cast<const float4*>(y);      // HW is a multiple of 4 (w % 8 == 0); two 16-byte loads in flight per thread
+  const long n4v = HW >> 2, stride = (long)gridDim.x * 256;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n4v; i += 2 * stride) {
+    const float4 a = y4[i];
+    const bool two = i + stride < n4v;
+    const float4 b = two ? y4[i + stride] : make_float4(mn, mn, mn, mn);
+    const float va[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float v = valid ? (va[k] - mn) * inv : 0.f;
+      if (v > lim && (k < 4 || two)) { sb += v; nb++; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { sb += __shfl_xor_sync(0xffffffffu, sb, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
