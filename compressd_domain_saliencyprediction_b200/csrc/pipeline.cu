@@ -376,6 +376,30 @@ normalize_out_kernel(const float* __restrict__ raw, long HW, const float* __rest
   }
 }
 
+// the same, four pixels per thread (HW is a multiple of 4; used when `out` is aligned for 4-wide stores)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+normalize_out4_kernel(const float* __restrict__ raw, long HW, const float* __restrict__ fstats, OutT* __restrict__ out) {
+  const int f = blockIdx.y;
+  const float mn = fstats[(size_t)f * 4], mx = fstats[(size_t)f * 4 + 1];
+  const float den = mx - mn;
+  const float4* __restrict__ r4 = reinterpret_cast<const float4*>(raw + (size_t)f * HW);
+  for (long p = blockIdx.x * 256L + threadIdx.x; p < (HW >> 2); p += (long)gridDim.x * 256) {
+    const float4 q = r4[p];
+    float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = den > 0.f ? (v[k] - mn) / den : 0.f;
+    if (sizeof(OutT) == 1) {
+      uchar4 o;
+      o.x = (unsigned char)__float2int_rn(fminf(fmaxf(v[0], 0.f), 1.f) * 255.f); o.y = (unsigned char)__float2int_rn(fminf(fmaxf(v[1], 0.f), 1.f) * 255.f);
+      o.z = (unsigned char)__float2int_rn(fminf(fmaxf(v[2], 0.f), 1.f) * 255.f); o.w = (unsigned char)__float2int_rn(fminf(fmaxf(v[3], 0.f), 1.f) * 255.f);
+      reinterpret_cast<uchar4*>(out + (size_t)f * HW)[p] = o;
+    } else {
+      reinterpret_cast<float4*>(out + (size_t)f * HW)[p] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -605,7 +629,10 @@ int run_context_stages(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, 
 template <typename OutT>
 int launch_normalize(cds_ctx* c, int n, void* out, cudaStream_t st) {
   dim3 grid(256, n);
-  normalize_out_kernel<OutT><<<grid, 256, 0, st>>>(c->d_raw, c->HW, c->d_fstats, reinterpret_cast<OutT*>(out));
+  if ((c->HW & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & (4 * sizeof(OutT) - 1)) == 0)
+    normalize_out4_kernel<OutT><<<grid, 256, 0, st>>>(c->d_raw, c->HW, c->d_fstats, reinterpret_cast<OutT*>(out));
+  else
+    normalize_out_kernel<OutT><<<grid, 256, 0, st>>>(c->d_raw, c->HW, c->d_fstats, reinterpret_cast<OutT*>(out));
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
