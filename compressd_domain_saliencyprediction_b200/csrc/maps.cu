@@ -485,6 +485,14 @@ int contrast_post_mv_launch(const float* rawx, const float* rawy, const unsigned
 // horizontal: T[m][r][4c+ph] = sum_d G[ph][d] X[m][r][c+d].  One CTA per (row, map); the zero-padded row sits in smem.
 // A thread owns HP_CPT = 4 adjacent cells (16 outputs) and slides a 4-value window along the row: per 4 taps one
 // conflict-free LDS.128 of inputs and four broadcast LDS.128 of weights feed 64 FFMAs.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
 constexpr int HP_CPT = 4;
 __global__ void __launch_bounds__(128)
 fullres_hpass_kernel(const float* __restrict__ X, int h4, int w4, int dmin, int nt, int nt4, const float4* __restrict__ G,
@@ -500,26 +508,28 @@ fullres_hpass_kernel(const float* __restrict__ X, int h4, int w4, int dmin, int 
   __syncthreads();
   float4* __restrict__ out = reinterpret_cast<float4*>(T + ((size_t)m * h4 + r) * (size_t)w4 * 4);
   for (int c0 = threadIdx.x * HP_CPT; c0 < w4; c0 += blockDim.x * HP_CPT) {
-    float4 acc[HP_CPT];
+    // packed FP32 (fma.rn.f32x2): the four phases of a cell are two register pairs, the input value is broadcast into a pair
+    unsigned long long alo[HP_CPT], ahi[HP_CPT];
 #pragma unroll
-    for (int k = 0; k < HP_CPT; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < HP_CPT; k++) { alo[k] = pack2(0.f, 0.f); ahi[k] = pack2(0.f, 0.f); }
     float4 w0 = *reinterpret_cast<const float4*>(srow + c0);          // x[c0 + t .. c0 + t + 3]
     for (int t = 0; t < nt4; t += 4) {
       const float4 w1 = *reinterpret_cast<const float4*>(srow + c0 + t + 4);
-      const float win[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float win[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+      unsigned long long xx[7];
+#pragma unroll
+      for (int i = 0; i < 7; i++) xx[i] = pack2(win[i], win[i]);
 #pragma unroll
       for (int tt = 0; tt < 4; tt++) {
         const float4 g = sG[t + tt];
+        const unsigned long long glo = pack2(g.x, g.y), ghi = pack2(g.z, g.w);
 #pragma unroll
-        for (int k = 0; k < HP_CPT; k++) {
-          const float x = win[tt + k];
-          acc[k].x = fmaf(g.x, x, acc[k].x); acc[k].y = fmaf(g.y, x, acc[k].y); acc[k].z = fmaf(g.z, x, acc[k].z); acc[k].w = fmaf(g.w, x, acc[k].w);
-        }
+        for (int k = 0; k < HP_CPT; k++) { alo[k] = ffma2(glo, xx[tt + k], alo[k]); ahi[k] = ffma2(ghi, xx[tt + k], ahi[k]); }
       }
       w0 = w1;
     }
 #pragma unroll
-    for (int k = 0; k < HP_CPT; k++) if (c0 + k < w4) out[c0 + k] = acc[k];
+    for (int k = 0; k < HP_CPT; k++) if (c0 + k < w4) out[c0 + k] = make_float4(lo2(alo[k]), hi2(alo[k]), lo2(ahi[k]), hi2(ahi[k]));
   }
 }
 
@@ -543,14 +553,6 @@ int fullres_hpass_launch(const float* X, int nmaps, int h4, int w4, const Polyph
 constexpr int VP_RPT = 4;
 constexpr int VP_ROWS = 32;                     // cell rows per tile
 constexpr int VP_COLS4 = 32;                    // float4 columns per CTA
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ float lo2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
-__device__ __forceinline__ float hi2(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int n = valid ? 16 : 0;
