@@ -499,6 +499,12 @@ def run_b200(a):
                       "reread_gbs": B * (a.PT - 1) * 4.0 * h4 * w4 * 4 / t / 1e9, "traffic": traffic.get("temporal"), "ms_per_launch": t * 1e3,
                       "share_of_step": stage_ms["temporal"] / tot,
                       "work": "unique bytes: (B + PT - 1) pictures x 4 smoothed h/4 x w/4 FP32 maps in, 3 maps out; reread_gbs counts every tap's read (cache hits)"})
+        # an HBM-bound map pass: the mysterythrehold statistics of the three full-resolution temporal maps read each map once
+        t = stage_ms["temporal_stats"] * 1e-3
+        sbytes = 3.0 * B * h * w * 4
+        roofs.append({"kernel": "temporal_thresh_partial", "bound": "hbm", "achieved": sbytes / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": sbytes / t / 1e9 / hbm,
+                      "traffic": None, "ms_per_launch": t * 1e3, "share_of_step": stage_ms["temporal_stats"] / tot,
+                      "work": "3 full-resolution FP32 maps per picture read once (16-byte loads, two in flight per thread); the stage time includes the tiny finalize kernel"})
         roofs.sort(key=lambda r: -r["share_of_step"])
         line["roofline"] = roofs[0]
         line["roofline_all"] = roofs[1:]
