@@ -11,6 +11,11 @@ namespace cds {
 void set_error(const char* fmt, ...);
 int ensure_device();            // CDS_OK or CDS_ENODEVICE; never falls back to the CPU
 void count_launch(int n = 1);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(function, device) attribute: remember the largest value set for each pair
+// (thread-safe; a second device or a second host thread in the same process gets its own cudaFuncSetAttribute).
+int ensure_dyn_smem_impl(const void* func, size_t bytes);
+template <typename K> inline int ensure_dyn_smem(K kernel, size_t bytes) { return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kernel), bytes); }
+int device_sm_count();          // multiprocessors of the current device (cached per device)
 
 #define CDS_CUDA(expr)                                                              \
   do {                                                                              \

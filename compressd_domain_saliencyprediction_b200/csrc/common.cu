@@ -2,6 +2,7 @@
 #include "cds_common.cuh"
 #include <stdarg.h>
 #include <atomic>
+#include <map>
 #include <mutex>
 
 namespace cds {
@@ -38,6 +39,31 @@ int ensure_device() {
     return CDS_ENODEVICE;
   }
   return CDS_OK;
+}
+
+int ensure_dyn_smem_impl(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  int dev = 0;
+  CDS_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = done[{func, dev}];
+  if (bytes > have) {
+    if (bytes > 48 * 1024) CDS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return CDS_OK;
+}
+
+int device_sm_count() {
+  static std::mutex mu;
+  static std::map<int, int> sms;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  int& n = sms[dev];
+  if (!n && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  return n;
 }
 
 int DevBuf::reserve(size_t bytes) {

@@ -189,12 +189,7 @@ static int launch_sep_cfg(const float* pad, float* out, unsigned* mx, int nmaps,
   using Cfg = SepCfg<WIN, CPT, NWARPS>;
   SepWeights<WIN> w;
   for (int i = 0; i < WIN; i++) { w.gr[i] = gr[i]; w.gc[i] = gc[i]; }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CDS_CUDA(cudaFuncSetAttribute(contrast_sep_kernel<WIN, CPT, NWARPS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  if (int e = ensure_dyn_smem(contrast_sep_kernel<WIN, CPT, NWARPS>, Cfg::SMEM_BYTES)) return e;
   const int len = WIN / 2;
   dim3 grid(ceil_div(C, Cfg::TC), ceil_div(R, Cfg::TR), nmaps);
   contrast_sep_kernel<WIN, CPT, NWARPS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
@@ -228,11 +223,7 @@ int contrast_generic_launch(const float* pad, const float* dW, float* out, unsig
   if (win < 1 || win > 64) { set_error("contrast: win %d out of range 1..64", win); return CDS_EINVAL; }
   const int HS = 16 + win - 1;
   const size_t smem = (size_t)(win * win + HS * HS) * 4;
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    CDS_CUDA(cudaFuncSetAttribute(contrast_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
+  if (int e = ensure_dyn_smem(contrast_generic_kernel, smem)) return e;
   dim3 grid(ceil_div(C, 16), ceil_div(R, 16), nmaps);
   contrast_generic_kernel<<<grid, 256, smem, st>>>(pad, dW, out, mx, R, C, R + 2 * len, C + 2 * len, win, len);
   CDS_LAUNCH_CHECK();

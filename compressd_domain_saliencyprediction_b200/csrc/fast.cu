@@ -1039,8 +1039,7 @@ int fast_create(int w, int h, double fps, int B, FastState** out) {
              cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)) { set_error("fast: stream / event creation"); e = CDS_ECUDA; }
   const size_t smem_sm = (size_t)(SM_G + p.PS - 1) * 128 * sizeof(float4);
   if (!e && smem_sm > 200 * 1024) { set_error("fast version: fps %.1f needs a %zu-byte smoothing tile", fps, smem_sm); e = CDS_EINVAL; }
-  if (!e && smem_sm > 48 * 1024 &&
-      cudaFuncSetAttribute(fast_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sm) != cudaSuccess) { set_error("fast: cudaFuncSetAttribute"); e = CDS_ECUDA; }
+  if (!e) e = ensure_dyn_smem(fast_smooth_kernel, smem_sm);      // monotonic per device: a later, smaller context must not lower it
   if (e) { fast_destroy(s); return e; }
   *out = s;
   return fast_clear(s, nullptr);

@@ -101,7 +101,9 @@ getframe_kernel(int w, int h, int nframes, const int32_t* __restrict__ hdr, cons
   const int off = hd[0], ncupu = hd[1], npred = hd[2], nmv = hd[3];
   const int h4 = h >> 2, w4 = w >> 2;
   const int R40 = (line / ncol) * 16, C40 = (line % ncol) * 16;
-  bool bad = ncupu < 1 || ncupu > GF_MAX_CUPU || npred < 0 || npred > GF_MAX_PRED || nmv < 0 || nmv > GF_MAX_MV;
+  bool bad = ncupu < 1 || ncupu > GF_MAX_CUPU || npred < 0 || npred > GF_MAX_PRED || nmv < 0 || nmv > GF_MAX_MV || off < 0;
+  // the three streams must lie inside this picture's slice of the token buffer (a corrupt offset must not read a neighbour's tokens)
+  if (!bad && tok_base) bad = (long)off + ncupu + npred + nmv > (long)(tok_base[f + 1] - tok_base[f]);
   if (!bad) {
     const int16_t* src = tok + (tok_base ? tok_base[f] : 0) + off;
     for (int i = lane; i < ncupu; i += 32) S.cupu[i] = src[i];
@@ -184,17 +186,18 @@ getframe_kernel(int w, int h, int nframes, const int32_t* __restrict__ hdr, cons
     S.puy[j] = (int16_t)gf_ext_at(S, 4 * j + 3, nmv, npred, T, a0);
   }
   __syncwarp();
-  // ---- 3. substitute and store (16 lanes write one 32-byte row segment) ----
+  // ---- 3. substitute and store: a lane owns two adjacent cells (w4 is even), so mv_x / mv_y leave as 4-byte and depth as
+  //         2-byte vector stores; 8 lanes cover one 16-cell row of the CTU (32 contiguous bytes per mv map) ----
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int cell = lane + 32 * k;
+  for (int k = 0; k < 4; k++) {
+    const int cell = 2 * (lane + 32 * k);
     const int R4 = R40 + (cell >> 4), C4 = C40 + (cell & 15);
     if (R4 < h4 && C4 < w4) {
-      const int L = S.label[cell];
+      const int L0 = S.label[cell], L1 = S.label[cell + 1];
       const size_t o = ((size_t)f * h4 + R4) * w4 + C4;
-      mvx[o] = (int16_t)gf_subst(L, S.pux, x);
-      mvy[o] = (int16_t)gf_subst(L, S.puy, x);
-      depth[o] = S.depth[cell];
+      *reinterpret_cast<short2*>(mvx + o) = make_short2((short)gf_subst(L0, S.pux, x), (short)gf_subst(L1, S.pux, x));
+      *reinterpret_cast<short2*>(mvy + o) = make_short2((short)gf_subst(L0, S.puy, x), (short)gf_subst(L1, S.puy, x));
+      *reinterpret_cast<uchar2*>(depth + o) = make_uchar2(S.depth[cell], S.depth[cell + 1]);
     }
   }
 }

@@ -253,6 +253,11 @@ int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, 
 // temporal difference with accumulated camera motion (main.m:174-199, immove.m)
 // grid: x = picture in batch (fast, so the pictures that share ring data run together), y = cell tile
 // =================================================================================================
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
 constexpr int TMP_MAXJ = 1024;      // PT - 1 <= 7 * round(0.3 * 240) - 1 = 503
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -298,7 +303,7 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __r
 #pragma unroll 2
   for (int j = 1; j <= jmax; j++) {
     const int4 t = s_tab[j];
-    const int sr = r - t.z, sc = c - t.y;                          // immove: +x moves content right, +y down, zero fill
+    const int sr = r - max(t.z, 0), sc = c - t.y;                  // immove: +-x moves content right / left, +y down, zero fill; -y: no shift (immove.m:19 quirk)
     float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
     if ((unsigned)sr < (unsigned)h4) {
       const float4* __restrict__ row = sm4 + (t.x + sr * w4);
@@ -320,12 +325,160 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __r
   *reinterpret_cast<float2*>(X + (size_t)7 * n4) = make_float2(ad0, ad1);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Grouped variant (the default).  The kernel above streams, for every output picture, all PT-1 ring pictures from L2:
+// B * (PT-1) * n4 * 16 B per batch (13.8 GB at 1080p / 50 fps / B = 64, ~11 TB/s: the L2 is the wall).  Consecutive output
+// pictures read almost the same ring pictures, so here one CTA owns a 16 x 32 cell tile for a GROUP of TG consecutive
+// pictures: it walks the ring pictures q = poc_last-1 ... poc_first-(PT-1) once, stages the part of picture q that the
+// group's (shifted) reads touch in shared memory with cp.async (three buffers, prefetch distance 2, zero fill outside the
+// picture = immove's zero padding) and accumulates it into the TG pictures' registers.  L2 traffic drops by ~TG / halo
+// overhead; what remains is one LDS.128 per (cell, picture, q) term, i.e. the shared-memory bandwidth.
+// Every picture still adds its terms in ascending j with the same fmaf sequence, so the result is bit-identical to the
+// kernel above and independent of where the picture sits in a batch (sharded == unsharded bytewise).
+// The accumulated camera shift differs per (picture, q); the staged window covers the spread of the group's shifts up to
+// TW_R x TW_C cells, pairs whose shifted tile falls outside it (very fast pans) read from global memory instead.
+// -------------------------------------------------------------------------------------------------
+constexpr int TG = 8;                          // pictures per group
+constexpr int TT_R = 16, TT_C = 32;            // tile: one warp per row of 32 cells
+constexpr int TW_R = TT_R + 8, TW_C = TT_C + 16;   // staged window capacity
+constexpr int T_STAGES = 3;
+
+__global__ void __launch_bounds__(TT_R * TT_C, 1)
+temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, const float4* __restrict__ sm4,
+                      const int* __restrict__ cam, const float* __restrict__ wtab, float* __restrict__ Xmaps) {
+  extern __shared__ __align__(16) unsigned char t_smem[];
+  float4* stage = reinterpret_cast<float4*>(t_smem);                                   // [T_STAGES][TW_R * TW_C]
+  float4* s_w = stage + T_STAGES * TW_R * TW_C;                                        // [PT] weights
+  int2* s_shift = reinterpret_cast<int2*>(s_w + PT);                                   // [TG][PT] {sx, max(sy, 0)} per (picture, j)
+  int4* s_win = reinterpret_cast<int4*>(s_shift + TG * PT);                            // [nq] {sxmax, symax, cols, rows} per ring picture
+  const int n4 = h4 * w4;
+  const int ntc = (w4 + TT_C - 1) / TT_C;
+  const int r0 = (blockIdx.x / ntc) * TT_R, c0 = (blockIdx.x % ntc) * TT_C;
+  const int f0 = blockIdx.y * TG, ng = min(TG, n - f0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int poc0 = first_poc + f0;
+  const int q_hi = poc0 + ng - 2;                                  // newest ring picture any picture of the group reads
+  const int q_lo = max(0, poc0 - (PT - 1));
+  const int nq = q_hi - q_lo + 1;                                  // may be <= 0 (first picture of a clip on its own)
+
+  for (int j = threadIdx.x; j < PT; j += blockDim.x) s_w[j] = reinterpret_cast<const float4*>(wtab)[j];
+  if (warp < ng) {                                 // warp g: inclusive scan of x_cammov / y_cammov over j for picture g (main.m:189-190)
+    const int poc = poc0 + warp, jmax = min(PT - 1, poc);
+    int cx = 0, cy = 0;
+    for (int j0 = 1; j0 <= jmax; j0 += 32) {
+      const int j = j0 + lane;
+      int vx = 0, vy = 0;
+      if (j <= jmax) { const int cs = ((poc - j + 1) % RL) * 2; vx = cam[cs]; vy = cam[cs + 1]; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
+        if (lane >= o) { vx += tx; vy += ty; }
+      }
+      const int camX = cx + vx, camY = cy + vy;
+      if (j <= jmax) {
+        const int sx = camX >= 0 ? (camX + 2) >> 2 : -((-camX + 2) >> 2);   // round(camX/4), half away from zero
+        const int sy = camY >= 0 ? (camY + 2) >> 2 : -((-camY + 2) >> 2);
+        s_shift[warp * PT + j] = make_int2(sx, max(sy, 0));                // immove.m:19 quirk: a negative mov_y does not shift
+      }
+      cx += __shfl_sync(0xffffffffu, vx, 31); cy += __shfl_sync(0xffffffffu, vy, 31);
+    }
+  }
+  __syncthreads();
+  for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {        // window of ring picture q: the spread of the group's shifts
+    const int q = q_hi - qi;
+    int sxmin = 1 << 30, sxmax = -(1 << 30), symin = 1 << 30, symax = -(1 << 30);
+    for (int g = 0; g < ng; g++) {
+      const int poc = poc0 + g, j = poc - q;
+      if (j >= 1 && j <= min(PT - 1, poc)) {
+        const int2 sh = s_shift[g * PT + j];
+        sxmin = min(sxmin, sh.x); sxmax = max(sxmax, sh.x); symin = min(symin, sh.y); symax = max(symax, sh.y);
+      }
+    }
+    s_win[qi] = sxmax >= sxmin ? make_int4(sxmax, symax, min(TT_C + sxmax - sxmin, TW_C), min(TT_R + symax - symin, TW_R)) : make_int4(0, 0, 0, 0);
+  }
+  __syncthreads();
+
+  auto stage_q = [&](int qi) {
+    if (qi < nq) {
+      const int4 wn = s_win[qi];
+      const int cols = wn.z, cnt = wn.z * wn.w;
+      const float4* __restrict__ src = sm4 + (size_t)((q_hi - qi) % RL) * n4;
+      float4* dst = stage + (qi % T_STAGES) * (TW_R * TW_C);
+      const int wr0 = r0 - wn.y, wc0 = c0 - wn.x;
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int lr = i / cols, lc = i - lr * cols;
+        const int gr = wr0 + lr, gc = wc0 + lc;
+        const bool ok = (unsigned)gr < (unsigned)h4 && (unsigned)gc < (unsigned)w4;
+        cp_async16_zfill(dst + lr * TW_C + lc, ok ? (const void*)(src + (size_t)gr * w4 + gc) : (const void*)sm4, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int r = r0 + warp, c = c0 + lane;
+  const bool inside = r < h4 && c < w4;
+  float4 ref[TG];
+  float am[TG], ab[TG], ad[TG];
+#pragma unroll
+  for (int g = 0; g < TG; g++) {
+    ref[g] = (inside && g < ng) ? sm4[(size_t)((poc0 + g) % RL) * n4 + (size_t)r * w4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    am[g] = 0.f; ab[g] = 0.f; ad[g] = 0.f;
+  }
+  stage_q(0); stage_q(1);
+  for (int qi = 0; qi < nq; qi++) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                            // window qi has landed for everyone; everyone is done with window qi - 1
+    stage_q(qi + 2);                            // into the buffer window qi - 1 used
+    const int q = q_hi - qi;
+    const int4 wn = s_win[qi];
+    const float4* __restrict__ buf = stage + (qi % T_STAGES) * (TW_R * TW_C);
+    const float4* __restrict__ gsrc = sm4 + (size_t)(q % RL) * n4;
+#pragma unroll
+    for (int g = 0; g < TG; g++) {
+      const int poc = poc0 + g, j = poc - q;
+      if (g < ng && j >= 1 && j <= min(PT - 1, poc)) {                 // CTA-uniform
+        const int2 sh = s_shift[g * PT + j];
+        const int dx = wn.x - sh.x, dy = wn.y - sh.y;                  // >= 0: offset of this pair's source tile inside the window
+        float4 p;
+        if (dx + TT_C <= wn.z && dy + TT_R <= wn.w) p = buf[(warp + dy) * TW_C + lane + dx];
+        else {                                                          // shift spread beyond the window capacity: straight from L2
+          const int sr = r - sh.y, sc = c - sh.x;
+          p = ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) ? __ldg(gsrc + (size_t)sr * w4 + sc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4 wj = s_w[j];
+        const float ddx = ref[g].x - p.x, ddy = ref[g].y - p.y;
+        am[g] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[g]);   // main.m:195
+        ab[g] = fmaf(wj.y, fabsf(ref[g].z - p.z), ab[g]);                    // :196
+        ad[g] = fmaf(wj.z, fabsf(ref[g].w - p.w), ad[g]);                    // :197
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (inside) {
+#pragma unroll
+    for (int g = 0; g < TG; g++)
+      if (g < ng) {
+        float* X = Xmaps + (size_t)(f0 + g) * 9 * n4 + (size_t)r * w4 + c;
+        X[(size_t)1 * n4] = am[g]; X[(size_t)4 * n4] = ab[g]; X[(size_t)7 * n4] = ad[g];
+      }
+  }
+}
+
 int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, const float4* sm4, const int* cam_ring,
                     const float* wtab, float* Xmaps, cudaStream_t st) {
-  dim3 grid(B, ceil_div(h4 * w4, 512));
-  if ((w4 & 1) || ((h4 * w4) & 1)) { set_error("temporal: odd cell-grid width %d", w4); return CDS_EINVAL; }
   if (PT > TMP_MAXJ) { set_error("temporal: PT %d exceeds %d", PT, TMP_MAXJ); return CDS_EINVAL; }
-  temporal_kernel<<<grid, 256, (size_t)PT * sizeof(int4), st>>>(h4, w4, PT, ring_len, first_poc, sm4, cam_ring, wtab, Xmaps);
+  static const int impl = [] { const char* e = getenv("CDS_TEMPORAL_IMPL"); return (e && !strcmp(e, "stream")) ? 0 : 1; }();
+  if (impl == 0 && !(w4 & 1)) {
+    dim3 grid(B, ceil_div(h4 * w4, 512));
+    temporal_kernel<<<grid, 256, (size_t)PT * sizeof(int4), st>>>(h4, w4, PT, ring_len, first_poc, sm4, cam_ring, wtab, Xmaps);
+    CDS_LAUNCH_CHECK();
+    return CDS_OK;
+  }
+  const int nq_max = PT - 1 + TG;
+  const size_t smem = (size_t)T_STAGES * TW_R * TW_C * 16 + (size_t)PT * 16 + (size_t)TG * PT * 8 + (size_t)nq_max * 16;
+  if (int e = ensure_dyn_smem(temporal_group_kernel, smem)) return e;
+  dim3 grid(ceil_div(h4, TT_R) * ceil_div(w4, TT_C), ceil_div(B, TG));
+  temporal_group_kernel<<<grid, TT_R * TT_C, smem, st>>>(h4, w4, PT, ring_len, first_poc, B, sm4, cam_ring, wtab, Xmaps);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
@@ -553,11 +706,6 @@ int fullres_hpass_launch(const float* X, int nmaps, int h4, int w4, const Polyph
 constexpr int VP_RPT = 4;
 constexpr int VP_ROWS = 32;                     // cell rows per tile
 constexpr int VP_COLS4 = 32;                    // float4 columns per CTA
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
 __global__ void __launch_bounds__(256, 2)
 fullres_vpass_kernel(const float* __restrict__ T, int h4, int W, int dmin, int nt, const float4* __restrict__ G,
                      float* __restrict__ Ystore, const int* __restrict__ store_index, float* __restrict__ partial) {
@@ -936,16 +1084,11 @@ int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polypha
     const int nstages = (int)std::min<size_t>(vtc::MAX_STAGES, fixed < 220 * 1024 ? (220 * 1024 - fixed) / vtc::STAGE_BYTES : 0);
     const size_t smem = fixed + (size_t)nstages * vtc::STAGE_BYTES;
     if (nstages >= 4) {
-      static size_t attr_set = 0;
-      if (smem > attr_set) {
-        CDS_CUDA(cudaFuncSetAttribute(fullres_vpass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-      }
+      if (int e = ensure_dyn_smem(fullres_vpass_tc_kernel, smem)) return e;
       const int nstrips = ceil_div(W, vtc::TN);
       CUtensorMap tmap;
       if (int e = vpass_tc_tensor_map(T, nmaps, h4, W, &tmap)) return e;
-      static int sms = 0;
-      if (!sms) { int dev = 0; CDS_CUDA(cudaGetDevice(&dev)); CDS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+      const int sms = device_sm_count();
       dim3 grid(std::min(sms, nstrips * nmaps));
 fullres_vpass_tc_kernel<<<grid, vtc::THREADS, smem, st>>>(tmap, nmaps, h4, W, P.dmin, kp, nstages, img, Ystore, store_index, partial);
       CDS_LAUNCH_CHECK();
@@ -955,11 +1098,7 @@ fullres_vpass_tc_kernel<<<grid, vtc::THREADS, smem, st>>>(tmap, nmaps, h4, W, P.
   }
   dim3 grid(ceil_div(W / 4, VP_COLS4), nmaps);
   const size_t smem = (size_t)(P.nt + 2 * (VP_RPT - 1)) * 16 + (size_t)2 * (VP_ROWS + P.nt + VP_RPT - 2) * VP_COLS4 * 16;
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    CDS_CUDA(cudaFuncSetAttribute(fullres_vpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
+  if (int e = ensure_dyn_smem(fullres_vpass_kernel, smem)) return e;
   fullres_vpass_kernel<<<grid, 256, smem, st>>>(T, h4, W, P.dmin, P.nt, reinterpret_cast<const float4*>(P.d_g), Ystore, store_index, partial);
   CDS_LAUNCH_CHECK();
   *nblocks_out = grid.x;
@@ -1137,11 +1276,7 @@ banded_cols_kernel(const float* __restrict__ in, int rows, int in_cols, const fl
 int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st) {
   dim3 grid(ceil_div(rows, BC_ROWS), nmaps);
   const size_t smem = (size_t)BC_ROWS * (in_cols + 1) * 4;
-  static size_t attr_set = 48 * 1024;
-  if (smem > attr_set) {
-    CDS_CUDA(cudaFuncSetAttribute(banded_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
+  if (int e = ensure_dyn_smem(banded_cols_kernel, smem)) return e;
   banded_cols_kernel<<<grid, 256, smem, st>>>(in, rows, in_cols, B.d_wT, B.d_start, B.nt, B.n_out, out);
   CDS_LAUNCH_CHECK();
   return CDS_OK;

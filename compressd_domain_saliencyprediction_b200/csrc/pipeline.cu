@@ -86,7 +86,9 @@ struct cds_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   int last_buf = 0, out_flip = 0;
-  int* d_cam_stage = nullptr;            // [2][B][2] camera motion of the batch in each output buffer
+  int* d_cam_stage = nullptr;            // [B][2] camera motion of one batch (cds_clip_process_maps: one batch in flight at a time)
+  int* d_cam_call = nullptr; size_t d_cam_cap = 0;   // [nframes][2] camera motion of a whole cds_clip_process call: every batch gathers into its
+                                                     // own slice, so no batch can overwrite values a queued device->host copy has not read yet
   int* h_cam_pin = nullptr; size_t h_cam_cap = 0;   // pinned staging: a device->host copy into pageable memory would block the host and serialise the pipeline
   // staging for host-buffer entry points
   uint16_t* d_bytes = nullptr; int32_t* d_hdr = nullptr; int16_t* d_tok = nullptr; int64_t* d_tokbase = nullptr;
@@ -530,7 +532,7 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   A(d_fpartial, (size_t)B * c->nblkf * 4); A(d_fstats, (size_t)B * 4);
 #undef A
 #define A(ptr, count) if (!e) e = dalloc(c, &c->ptr, (size_t)(count))
-  A(d_cam_stage, (size_t)4 * B);
+  A(d_cam_stage, (size_t)2 * B);
   A(d_bytes, (size_t)B * c->nctu); A(d_hdr, (size_t)B * c->nctu * 4); A(d_tokbase, (size_t)B + 1);
   c->tok_cap = (size_t)B * c->nctu * 160;
   A(d_tok, c->tok_cap);
@@ -879,6 +881,14 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
     CDS_CUDA(cudaHostAlloc((void**)&c->h_cam_pin, (size_t)2 * nframes * sizeof(int), cudaHostAllocDefault));
     c->h_cam_cap = (size_t)2 * nframes;
   }
+  if (cam_out && !context_only && (size_t)2 * nframes > c->d_cam_cap) {      // every entry point returns synchronised: nothing is in flight here
+    void* q = nullptr;
+    if (cudaMalloc(&q, (size_t)2 * nframes * sizeof(int) + 256) != cudaSuccess) { set_error("cds_clip_process: cannot allocate the camera-motion buffer"); return CDS_ENOMEM; }
+    bool swapped = false;
+    for (void*& a : c->allocs) if (c->d_cam_call && a == (void*)c->d_cam_call) { cudaFree(a); a = q; swapped = true; }
+    if (!swapped) c->allocs.push_back(q);
+    c->d_cam_call = reinterpret_cast<int*>(q); c->d_cam_cap = (size_t)2 * nframes;
+  }
   int bi = 0;
   for (int done = 0; done < nframes; done += c->B, bi++) {
     const int n = std::min(c->B, nframes - done);
@@ -897,20 +907,20 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
     // before_back = the copy that last read d_out[buf] has finished (a never-recorded event is a no-op)
     cudaEvent_t done_ev = nullptr;
     if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out[buf],
-                          cam_out ? c->d_cam_stage + (size_t)buf * 2 * c->B : nullptr, st, c->ev_copied[buf], &done_ev)) return e;
+                          cam_out ? c->d_cam_call + (size_t)2 * done : nullptr, st, c->ev_copied[buf], &done_ev)) return e;
     if (!done_ev) { CDS_CUDA(cudaEventRecord(c->ev_done[buf], st)); done_ev = c->ev_done[buf]; }
     else CDS_CUDA(cudaEventRecord(c->ev_done[buf], st));          // front half (incl. the camera-motion gather) done
     CDS_CUDA(cudaStreamWaitEvent(cs, done_ev, 0));
     CDS_CUDA(cudaStreamWaitEvent(cs, c->ev_done[buf], 0));
     if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)done * px, c->d_out[buf], (size_t)n * px, cudaMemcpyDeviceToHost, cs));
-    if (cam_out)
-      CDS_CUDA(cudaMemcpyAsync(c->h_cam_pin + 2 * done, c->d_cam_stage + (size_t)buf * 2 * c->B, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
     CDS_CUDA(cudaEventRecord(c->ev_copied[buf], cs));
     c->last_first = first_poc + done; c->last_n = n; c->last_buf = buf;
   }
   int herr = 0;
   if (int e = join_back(c, st)) return e;
   CDS_CUDA(cudaMemcpyAsync(&herr, c->d_err, 4, cudaMemcpyDeviceToHost, st));
+  if (cam_out && !context_only)     // one copy for the call, after every front half (the gathers run on st)
+    CDS_CUDA(cudaMemcpyAsync(c->h_cam_pin, c->d_cam_call, (size_t)2 * nframes * sizeof(int), cudaMemcpyDeviceToHost, st));
   CDS_CUDA(cudaStreamSynchronize(st));
   CDS_CUDA(cudaStreamSynchronize(cs));
   if (cam_out && !context_only) memcpy(cam_out, c->h_cam_pin, (size_t)2 * nframes * sizeof(int));

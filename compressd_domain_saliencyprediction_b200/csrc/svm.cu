@@ -315,11 +315,7 @@ int svm_predict_launch(const cds_svm_model* m, const float* X, long N, float* de
     auto kern = poly == 0 ? svm_rbf9_tc_kernel<0> : poly == 1 ? svm_rbf9_tc_kernel<1> : poly == 2 ? svm_rbf9_tc_kernel<2>
               : poly == 3 ? svm_rbf9_tc_kernel<3> : svm_rbf9_tc_kernel<4>;
     const int smem_bytes = tc::SMEM_BYTES;   // (padding it so that one CTA fits per SM, to leave room for overlapped kernels, measured 6 % slower)
-    static bool attr_done = false;
-    if (!attr_done) {
-      CDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      attr_done = true;
-    }
+    if (int e = ensure_dyn_smem(kern, smem_bytes)) return e;
     const unsigned grid = (unsigned)((N + tc::TM - 1) / tc::TM);
     kern<<<grid, tc::THREADS, smem_bytes, st>>>(X, N, m->d_tiles, m->ntiles, m->ntiles_pos, (float)sqrt(2 * g2), (float)m->rho, dec);
   } else if (m->nfeat == 9) {
@@ -462,6 +458,9 @@ extern "C" int cds_svm_model_load(const char* path, cds_svm_model** out) {
       if (end == p || *end != ':') break;
       p = end + 1;
       double v = strtod(p, &end); p = end;
+      if (idx < 1 || idx > 64) {      // libsvm feature indices are 1-based; 0 marks a precomputed-kernel model, which this path does not serve
+        fclose(f); set_error("cds_svm_model_load: SV %d has feature index %ld (expected 1..64)", i, idx); return CDS_EFORMAT;
+      }
       rows[i].push_back({(int)idx, v});
       if (idx > maxidx) maxidx = (int)idx;
     }

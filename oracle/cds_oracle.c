@@ -408,11 +408,13 @@ void orc_mysterythrehold(double* a, long n, int im_height, int im_width) {
   for (long i = 0; i < n; i++) a[i] = a[i] / (mx2 + 0.000001);                     /* :7 */
 }
 
-/* immove.m:1-35 — positive mov_x shifts content right, positive mov_y shifts it down; zero fill */
+/* immove.m:1-35 — positive mov_x shifts content right, negative left, positive mov_y shifts it down; zero fill.
+ * QUIRK reproduced: immove.m:19 takes [m2,n2] = size(temp) (the map BEFORE the row padding), so m2 == m and the
+ * mov_y <= 0 branches (:25, :31) slice rows 1..m of [temp; padY]: a negative mov_y does NOT shift the rows. */
 void orc_immove(const double* im, int rows, int cols, int mov_x, int mov_y, double* out) {
   for (int r = 0; r < rows; r++)
     for (int c = 0; c < cols; c++) {
-      int sr = r - mov_y, sc = c - mov_x;
+      int sr = r - (mov_y > 0 ? mov_y : 0), sc = c - mov_x;
       out[(size_t)r * cols + c] = (sr >= 0 && sr < rows && sc >= 0 && sc < cols) ? im[(size_t)sr * cols + sc] : 0.0;
     }
 }

@@ -166,6 +166,44 @@ def test_malformed_stream_is_reported(cds):
     a.close()
 
 
+@pytest.mark.parametrize("bad_off", [-5, 10 ** 8, "past_picture"])
+def test_corrupt_ctu_offset_is_reported(cds, bad_off):
+    """A CTU header whose token offset is negative, past the end of the buffer or reaching into the next picture's
+    tokens is a format error on every entry point (the kernel never reads outside the picture's own token slice)."""
+    w, h = 416, 240
+    packed, _ = _clip(cds, w, h, 3, 3)
+    hdr, tok, base, byts = packed
+    hb = hdr.copy()
+    hb[1, 5, 0] = (base[2] - base[1]) - 2 if bad_off == "past_picture" else bad_off
+    mdl, gm = _model(cds, 32)
+    a = cds.SaliencyClip(w, h, 10.0, model=gm, meanVec=MEAN9, stdVec=STD9)
+    with pytest.raises(cds.CdsError):
+        a.process(0, hb, tok, base, byts)
+    a.seek(0)
+    got, _ = a.process(0, hdr, tok, base, byts)              # the context stays usable afterwards
+    assert np.isfinite(got).all()
+    a.close()
+
+
+def test_svm_model_file_with_index_zero_is_rejected(cds, tmp_path):
+    """libsvm indices are 1-based (svm.cpp:2641 svm_load_model); '0:' (precomputed-kernel syntax) or a negative index must
+    be a format error, not a write before the SV row."""
+    import os
+    src = os.path.join(os.path.dirname(__file__), "golden", "svm_heart_scale.model")
+    text = open(src).read()
+    head, svs = text.split("SV\n", 1)
+    lines = svs.splitlines()
+    for repl in ("0:0.5", "-3:0.5"):
+        bad = lines[:]
+        first = bad[2].split()
+        bad[2] = " ".join([first[0], repl] + first[2:])
+        pth = tmp_path / "bad.model"
+        pth.write_text(head + "SV\n" + "\n".join(bad) + "\n")
+        with pytest.raises(cds.CdsError):
+            cds.ops.SvmModel(path=str(pth))
+    cds.ops.SvmModel(path=src)                                   # the untouched file still loads
+
+
 def test_create_rejects_bad_parameters(cds):
     with pytest.raises(cds.CdsError):
         cds.SaliencyClip(417, 240, 25.0, use_rbf=False)
