@@ -30,7 +30,6 @@ def _declare(L):
         "cds_getframe": (i32, [i32, i32, c_p, c_p, sz, c_p, c_p, c_p]),
         "cds_syntax_pack_ref": (i64, [i32, c_p, c_p, c_p, c_p, c_p]),
         "cds_getframe_dev": (i32, [i32, i32, i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
-        "cds_synth_frame": (i64, [i32, i32, C.c_uint64, i32, c_p, c_p, sz, c_p]),
         "cds_svm_model_create": (i32, [i32, i32, c_p, c_p, f64, f64, i32, i32, C.POINTER(c_p)]),
         "cds_svm_model_load": (i32, [C.c_char_p, C.POINTER(c_p)]),
         "cds_svm_model_free": (None, [c_p]),

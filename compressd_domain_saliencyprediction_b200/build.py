@@ -6,6 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcds_b200.so")
+SYNTH_LIB = os.path.join(HERE, "libcds_synth.so")       # host-only synthetic syntax producer (no CUDA): csrc_host/synth.cpp
+SYNTH_SRC = os.path.join(HERE, "csrc_host", "synth.cpp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -26,8 +28,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_synth(force=False):
+    """g++ only: the synthetic producer must stay loadable where no CUDA runtime is mapped."""
+    hdr = os.path.join(HERE, "..", "include", "cds_synth.h")
+    if not force and os.path.exists(SYNTH_LIB) and os.path.getmtime(SYNTH_LIB) > max(os.path.getmtime(SYNTH_SRC), os.path.getmtime(hdr)):
+        return SYNTH_LIB
+    r = subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SYNTH_LIB, SYNTH_SRC],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("libcds_synth.so build failed:\n" + r.stdout)
+    return SYNTH_LIB
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link libcds_b200.so next to this file."""
+    build_synth(force)
     if not force and not needs_build():
         return LIB
     objdir = os.path.join(HERE, "build")

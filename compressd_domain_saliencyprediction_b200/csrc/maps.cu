@@ -259,7 +259,7 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 constexpr int TMP_MAXJ = 1024;      // PT - 1 <= 7 * round(0.3 * 240) - 1 = 503
-__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __global__ void __launch_bounds__(256)
 temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __restrict__ sm4 /*{mvx, mvy, bit, depth} smoothed*/,
@@ -338,10 +338,11 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __r
 // The accumulated camera shift differs per (picture, q); the staged window covers the spread of the group's shifts up to
 // TW_R x TW_C cells, pairs whose shifted tile falls outside it (very fast pans) read from global memory instead.
 // -------------------------------------------------------------------------------------------------
-constexpr int TG = 8;                          // pictures per group
+constexpr int TG = 8;                          // pictures per group (the offset table below is read as two int4)
 constexpr int TT_R = 16, TT_C = 32;            // tile: one warp per row of 32 cells
 constexpr int TW_R = TT_R + 8, TW_C = TT_C + 16;   // staged window capacity
-constexpr int T_STAGES = 3;
+constexpr int T_STAGES = 8, T_DIST = T_STAGES - 1;   // cp.async ring: windows of the next T_DIST ring pictures in flight (most come from HBM: the ring exceeds the L2)
+static_assert(TG == 8 && T_STAGES == TG && TW_R <= 2 * TT_R && TW_C <= 64, "temporal_group_kernel: offset table read as two int4; two rows per warp, two columns per lane");
 
 __global__ void __launch_bounds__(TT_R * TT_C, 1)
 temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, const float4* __restrict__ sm4,
@@ -350,7 +351,8 @@ temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, cons
   float4* stage = reinterpret_cast<float4*>(t_smem);                                   // [T_STAGES][TW_R * TW_C]
   float4* s_w = stage + T_STAGES * TW_R * TW_C;                                        // [PT] weights
   int2* s_shift = reinterpret_cast<int2*>(s_w + PT);                                   // [TG][PT] {sx, max(sy, 0)} per (picture, j)
-  int4* s_win = reinterpret_cast<int4*>(s_shift + TG * PT);                            // [nq] {sxmax, symax, cols, rows} per ring picture
+  int4* s_win = reinterpret_cast<int4*>(s_shift + TG * PT);                            // [nq_max] {sxmax, symax, cols, rows} per ring picture
+  int* s_off = reinterpret_cast<int*>(s_win + (PT - 1 + TG));                          // [nq_max][TG] offset of the pair's source tile in the window; -1 read from global; -2 no term
   const int n4 = h4 * w4;
   const int ntc = (w4 + TT_C - 1) / TT_C;
   const int r0 = (blockIdx.x / ntc) * TT_R, c0 = (blockIdx.x % ntc) * TT_C;
@@ -394,23 +396,41 @@ temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, cons
         sxmin = min(sxmin, sh.x); sxmax = max(sxmax, sh.x); symin = min(symin, sh.y); symax = max(symax, sh.y);
       }
     }
-    s_win[qi] = sxmax >= sxmin ? make_int4(sxmax, symax, min(TT_C + sxmax - sxmin, TW_C), min(TT_R + symax - symin, TW_R)) : make_int4(0, 0, 0, 0);
+    const int4 wn = sxmax >= sxmin ? make_int4(sxmax, symax, min(TT_C + sxmax - sxmin, TW_C), min(TT_R + symax - symin, TW_R)) : make_int4(0, 0, 0, 0);
+    s_win[qi] = wn;
+    for (int g = 0; g < TG; g++) {
+      const int poc = poc0 + g, j = poc - q;
+      int off = -2;
+      if (g < ng && j >= 1 && j <= min(PT - 1, poc)) {
+        const int2 sh = s_shift[g * PT + j];
+        const int dx = wn.x - sh.x, dy = wn.y - sh.y;                  // >= 0
+        off = (dx + TT_C <= wn.z && dy + TT_R <= wn.w) ? dy * TW_C + dx : -1;
+      }
+      s_off[qi * TG + g] = off;
+    }
   }
   __syncthreads();
 
+  // Warp w copies window rows w and w + 16, lane l columns l and l + 32 (the window is at most TW_R x TW_C = 24 x 48): no
+  // per-element index arithmetic.  The ring slot of the staged picture is tracked incrementally (q runs downwards).
+  int st_slot = ((q_hi % RL) + RL) % RL;
+  const int t_idx = (r0 + warp) * w4 + c0 + lane;          // this thread's own cell; window element (lr, lc) = cell - (symax, sxmax) + (16 a, 32 b)
   auto stage_q = [&](int qi) {
     if (qi < nq) {
       const int4 wn = s_win[qi];
-      const int cols = wn.z, cnt = wn.z * wn.w;
-      const float4* __restrict__ src = sm4 + (size_t)((q_hi - qi) % RL) * n4;
-      float4* dst = stage + (qi % T_STAGES) * (TW_R * TW_C);
-      const int wr0 = r0 - wn.y, wc0 = c0 - wn.x;
-      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const int lr = i / cols, lc = i - lr * cols;
-        const int gr = wr0 + lr, gc = wc0 + lc;
-        const bool ok = (unsigned)gr < (unsigned)h4 && (unsigned)gc < (unsigned)w4;
-        cp_async16_zfill(dst + lr * TW_C + lc, ok ? (const void*)(src + (size_t)gr * w4 + gc) : (const void*)sm4, ok);
-      }
+      const float4* __restrict__ src = sm4 + (size_t)st_slot * n4;
+      float4* dst = stage + (qi % T_STAGES) * (TW_R * TW_C) + warp * TW_C + lane;
+      const int gr0 = r0 + warp - wn.y, gc0 = c0 + lane - wn.x, idx0 = t_idx - wn.y * w4 - wn.x;
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          if (warp + a * TT_R < wn.w && lane + b * 32 < wn.z) {
+            const bool ok = (unsigned)(gr0 + a * TT_R) < (unsigned)h4 && (unsigned)(gc0 + b * 32) < (unsigned)w4;
+            cp_async16_zfill(dst + a * TT_R * TW_C + b * 32, src + (ok ? idx0 + a * TT_R * w4 + b * 32 : 0), ok);
+          }
+        }
+      st_slot = st_slot == 0 ? RL - 1 : st_slot - 1;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -424,32 +444,63 @@ temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, cons
     ref[g] = (inside && g < ng) ? sm4[(size_t)((poc0 + g) % RL) * n4 + (size_t)r * w4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
     am[g] = 0.f; ab[g] = 0.f; ad[g] = 0.f;
   }
-  stage_q(0); stage_q(1);
-  for (int qi = 0; qi < nq; qi++) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();                            // window qi has landed for everyone; everyone is done with window qi - 1
-    stage_q(qi + 2);                            // into the buffer window qi - 1 used
-    const int q = q_hi - qi;
-    const int4 wn = s_win[qi];
-    const float4* __restrict__ buf = stage + (qi % T_STAGES) * (TW_R * TW_C);
-    const float4* __restrict__ gsrc = sm4 + (size_t)(q % RL) * n4;
 #pragma unroll
-    for (int g = 0; g < TG; g++) {
-      const int poc = poc0 + g, j = poc - q;
-      if (g < ng && j >= 1 && j <= min(PT - 1, poc)) {                 // CTA-uniform
-        const int2 sh = s_shift[g * PT + j];
-        const int dx = wn.x - sh.x, dy = wn.y - sh.y;                  // >= 0: offset of this pair's source tile inside the window
-        float4 p;
-        if (dx + TT_C <= wn.z && dy + TT_R <= wn.w) p = buf[(warp + dy) * TW_C + lane + dx];
-        else {                                                          // shift spread beyond the window capacity: straight from L2
-          const int sr = r - sh.y, sc = c - sh.x;
-          p = ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) ? __ldg(gsrc + (size_t)sr * w4 + sc) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int d = 0; d < T_DIST; d++) stage_q(d);
+  const float4* __restrict__ mine = stage + warp * TW_C + lane;
+  int q_slot = ((q_hi % RL) + RL) % RL;
+  // Weights of the eight pictures at ring picture q are wtab[j0 + g], j0 = poc0 - q: a sliding window kept in registers.  The loop
+  // is unrolled by TG so that the window rotates by renaming (picture g reads W[(g + u) % TG] in sub-iteration u) and the cp.async
+  // buffer index is static.  wtab's y and z columns are the same (delta 46 for bit and depth).
+  auto wload = [&](int j) { const float4 t = s_w[min(max(j, 0), PT - 1)]; return make_float2(t.x, t.y); };
+  float2 Wr[TG];
+#pragma unroll
+  for (int g = 0; g < TG; g++) Wr[g] = wload(poc0 - q_hi + g);
+  for (int qi0 = 0; qi0 < nq; qi0 += TG) {
+#pragma unroll
+    for (int u = 0; u < TG; u++) {
+      const int qi = qi0 + u;
+      if (qi < nq) {                             // CTA-uniform
+        asm volatile("cp.async.wait_group %0;" ::"n"(T_DIST - 1) : "memory");
+        __syncthreads();                         // window qi has landed for everyone; everyone is done with window qi - 1
+        stage_q(qi + T_DIST);                    // into the buffer window qi - 1 used
+        const int q = q_hi - qi;
+        const float4* __restrict__ buf = mine + u * (TW_R * TW_C);       // qi % T_STAGES == u (T_STAGES == TG)
+        const int4 o03 = *reinterpret_cast<const int4*>(s_off + qi * TG), o47 = *reinterpret_cast<const int4*>(s_off + qi * TG + 4);
+        const int offs[TG] = {o03.x, o03.y, o03.z, o03.w, o47.x, o47.y, o47.z, o47.w};
+        if ((o03.x | o03.y | o03.z | o03.w | o47.x | o47.y | o47.z | o47.w) >= 0) {
+          // every picture of the group has a term for q and every source tile lies in the staged window: straight-line code
+#pragma unroll
+          for (int g = 0; g < TG; g++) {
+            const float4 p = buf[offs[g]];
+            const float2 wj = Wr[(g + u) % TG];
+            const float ddx = ref[g].x - p.x, ddy = ref[g].y - p.y;
+            am[g] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[g]);   // main.m:195
+            ab[g] = fmaf(wj.y, fabsf(ref[g].z - p.z), ab[g]);                    // :196
+            ad[g] = fmaf(wj.y, fabsf(ref[g].w - p.w), ad[g]);                    // :197
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < TG; g++) {
+            const int off = offs[g];
+            if (off != -2) {                                                  // CTA-uniform
+              const int j = poc0 + g - q;
+              float4 p;
+              if (off >= 0) p = buf[off];
+              else {                                                          // shift spread beyond the window capacity: straight from L2
+                const int2 sh = s_shift[g * PT + j];
+                const int sr = r - sh.y, sc = c - sh.x;
+                p = ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) ? __ldg(sm4 + (size_t)q_slot * n4 + (size_t)sr * w4 + sc) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              const float2 wj = Wr[(g + u) % TG];
+              const float ddx = ref[g].x - p.x, ddy = ref[g].y - p.y;
+              am[g] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[g]);
+              ab[g] = fmaf(wj.y, fabsf(ref[g].z - p.z), ab[g]);
+              ad[g] = fmaf(wj.y, fabsf(ref[g].w - p.w), ad[g]);
+            }
+          }
         }
-        const float4 wj = s_w[j];
-        const float ddx = ref[g].x - p.x, ddy = ref[g].y - p.y;
-        am[g] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[g]);   // main.m:195
-        ab[g] = fmaf(wj.y, fabsf(ref[g].z - p.z), ab[g]);                    // :196
-        ad[g] = fmaf(wj.z, fabsf(ref[g].w - p.w), ad[g]);                    // :197
+        Wr[u] = wload(poc0 - q + TG);            // picture 0's weight is spent: the slot takes picture 7's weight for q - 1
+        q_slot = q_slot == 0 ? RL - 1 : q_slot - 1;
       }
     }
   }
@@ -475,7 +526,7 @@ int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, 
     return CDS_OK;
   }
   const int nq_max = PT - 1 + TG;
-  const size_t smem = (size_t)T_STAGES * TW_R * TW_C * 16 + (size_t)PT * 16 + (size_t)TG * PT * 8 + (size_t)nq_max * 16;
+  const size_t smem = (size_t)T_STAGES * TW_R * TW_C * 16 + (size_t)PT * 16 + (size_t)TG * PT * 8 + (size_t)nq_max * 16 + (size_t)nq_max * TG * 4;
   if (int e = ensure_dyn_smem(temporal_group_kernel, smem)) return e;
   dim3 grid(ceil_div(h4, TT_R) * ceil_div(w4, TT_C), ceil_div(B, TG));
   temporal_group_kernel<<<grid, TT_R * TT_C, smem, st>>>(h4, w4, PT, ring_len, first_poc, B, sm4, cam_ring, wtab, Xmaps);

@@ -77,8 +77,13 @@ struct cds_ctx {
   float *d_xsvm = nullptr, *d_dec = nullptr;         // [B][40000][9], [B][40000]
   float* d_xsvm2[2] = {nullptr, nullptr};            // d_xsvm and a second copy: the back half of batch i (SVM -> map) overlaps the front half of batch i+1
   cudaStream_t back_stream = nullptr;
-  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr};
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr}, ev_mid = nullptr;
   int xs_flip = 0, last_xs = 0; bool overlap = true;
+  // Deferred back half (RBF branch, overlap on): the SVM + final-map chain of batch i is launched from the MIDDLE of batch
+  // i+1's front half, right before its contrast kernels, so that the MUFU-bound persistent SVM kernel and the FP32-bound
+  // contrast kernel start together and share every SM for their whole duration (or from join_back when no batch follows).
+  struct PendingBack { bool valid = false; int slot = 0, n = 0, tag = -1; void* maps_out = nullptr; cudaEvent_t before_back = nullptr; } pb;
+  int retired_tag = -1; cudaEvent_t retired_ev = nullptr;     // set when a back half has been enqueued: its tag and completion event
   float *d_fparam = nullptr, *d_C = nullptr;         // [9][4] mean, 1/std, weight; [B][200][200]
   float *d_T2 = nullptr, *d_raw = nullptr;           // [B][200][W], [B][H][W]
   float *d_fpartial = nullptr, *d_fstats = nullptr;  // final min/max
@@ -543,7 +548,12 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
                cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming) != cudaSuccess)) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
   }
   if (!e && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate copy"); e = CDS_ECUDA; }
-  if (!e && cudaStreamCreateWithFlags(&c->back_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate back"); e = CDS_ECUDA; }
+  if (!e) {           // the back stream outranks the front stream: the persistent SVM CTAs are placed before the contrast CTAs that start with them
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&c->back_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_mid, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaStreamCreate back"); e = CDS_ECUDA; }
+  }
   for (int b = 0; b < 2 && !e; b++)
     if (cudaEventCreateWithFlags(&c->ev_front[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_back[b], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
   { const char* ov = getenv("CDS_OVERLAP"); c->overlap = !(ov && ov[0] == '0') && p->use_rbf == CDS_FUSION_RBF; }
@@ -578,6 +588,7 @@ extern "C" void cds_destroy(cds_ctx* c) {
   if (c->back_stream) { cudaStreamSynchronize(c->back_stream); cudaStreamDestroy(c->back_stream); }
   if (c->fast_front_stream) { cudaStreamSynchronize(c->fast_front_stream); cudaStreamDestroy(c->fast_front_stream); }
   if (c->ev_fstart) cudaEventDestroy(c->ev_fstart);
+  if (c->ev_mid) cudaEventDestroy(c->ev_mid);
   for (int b = 0; b < 2; b++) { if (c->ev_ff[b]) cudaEventDestroy(c->ev_ff[b]); if (c->ev_fb[b]) cudaEventDestroy(c->ev_fb[b]); }
   for (int b = 0; b < 2; b++) { if (c->ev_front[b]) cudaEventDestroy(c->ev_front[b]); if (c->ev_back[b]) cudaEventDestroy(c->ev_back[b]); }
   for (int b = 0; b < 2; b++) { if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); }
@@ -639,15 +650,52 @@ int launch_normalize(cds_ctx* c, int n, void* out, cudaStream_t st) {
   return CDS_OK;
 }
 
+// (d) RBF-SVM, then pm_norm -> imresize -> imfilter -> centre prior -> pm_norm (main.m:297-304) for the batch whose z-scored
+// features sit in d_xsvm2[slot].  On `sb`; prof marks only when sb is the profiled stream.
+int launch_back_rbf(cds_ctx* c, int slot, int n, void* maps_out, cudaStream_t sb, bool mark) {
+  const int H = c->h, W = c->w;
+  if (mark) prof_mark(c, ST_SVM, sb);
+  if (int e = svm_predict_launch(c->p.model, c->d_xsvm2[slot], (long)n * 40000, c->d_dec, sb)) return e;
+  if (mark) prof_mark(c, ST_FINAL, sb);
+  dec_minmax_norm_kernel<<<n, 1024, 0, sb>>>(c->d_dec, c->d_C);
+  CDS_LAUNCH_CHECK();
+  if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, sb)) return e;
+  const int thr = fir_threads(W / 4);
+  dim3 grid(ceil_div(W / 4, thr), ceil_div(H, FR_ROWS), n);
+  final_rows_kernel<<<grid, thr, (size_t)(c->Bv.nt + c->Bv.span4) * 16, sb>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
+  CDS_LAUNCH_CHECK();
+  if (int e = stats_finalize_launch(c->d_fpartial, n, grid.x * grid.y, c->d_fstats, sb)) return e;
+  if (maps_out) {
+    if (int e = c->p.out_u8 ? launch_normalize<uint8_t>(c, n, maps_out, sb) : launch_normalize<float>(c, n, maps_out, sb)) return e;
+  }
+  return CDS_OK;
+}
+
+// enqueue the deferred back half on the back stream; `with` (optional) is an event of the front stream it should start with
+int flush_pending_back(cds_ctx* c, cudaEvent_t with) {
+  if (!c->pb.valid) return CDS_OK;
+  const cds_ctx::PendingBack pb = c->pb;
+  c->pb.valid = false;
+  cudaStream_t sb = c->back_stream;
+  CDS_CUDA(cudaStreamWaitEvent(sb, c->ev_front[pb.slot], 0));
+  if (with) CDS_CUDA(cudaStreamWaitEvent(sb, with, 0));
+  if (pb.before_back) CDS_CUDA(cudaStreamWaitEvent(sb, pb.before_back, 0));
+  if (int e = launch_back_rbf(c, pb.slot, pb.n, pb.maps_out, sb, false)) return e;
+  CDS_CUDA(cudaEventRecord(c->ev_back[pb.slot], sb));
+  c->retired_tag = pb.tag; c->retired_ev = c->ev_back[pb.slot];
+  return CDS_OK;
+}
+
 // The batch has a front half (stages a, c, e, b and the 200x200 features; FP32-pipe bound) and a back half (SVM -> final map;
-// MUFU / tensor bound).  With `overlap` the back half runs on the context's back stream, so it shares the SMs with the front
-// half of the next batch; xsvm is double buffered and events order the halves.  `before_back` (optional) must have happened
-// before the back half writes maps_out.  Returns the event that marks the end of the batch in *done_ev (nullptr: on `st`).
+// MUFU / tensor bound).  With `overlap` the back half is deferred (cds_ctx::pb) and runs on the context's high-priority back
+// stream beside the contrast kernels of the NEXT batch; xsvm is double buffered and events order the halves.  `before_back`
+// (optional) must have happened before the back half writes maps_out.  When a back half (this batch's or the previous one's)
+// has been enqueued, c->retired_tag / c->retired_ev name it (retired_ev == nullptr: it ended on `st`).
 int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
               const int64_t* tok_base, void* maps_out, int* cam_out, cudaStream_t st, cudaEvent_t before_back = nullptr,
-              cudaEvent_t* done_ev = nullptr) {
+              int tag = 0) {
   if (c->fast) {          // TDecGop.cpp:270-332 for n pictures: stage (a), then the fast version's kernels (fast.cu)
-    if (done_ev) *done_ev = nullptr;
+    c->retired_tag = tag; c->retired_ev = nullptr;
     if (c->fast_ovl_active && !c->prof_on && !c->maps_in) {
       // front half on its own stream: it waited for the start of this API call (inputs resident) and waits for the back half of
       // batch k-2, whose ring reads end where this batch's ring writes begin; the back half follows on `st`
@@ -674,8 +722,7 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   if (ov) c->xs_flip ^= 1;
   c->last_xs = slot;
   float* xsvm = c->d_xsvm2[slot];
-  cudaStream_t sb = ov ? c->back_stream : st;
-  if (done_ev) *done_ev = nullptr;
+  if (!ov) if (int e = flush_pending_back(c, nullptr)) return e;          // a mode switch (profiling on) must not strand a deferred half
   if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));      // the back half of batch i-2 has finished reading xsvm[slot]
   const int h4 = c->h4, w4 = c->w4, n4 = c->n4, H = c->h, W = c->w, RL = c->RL;
   const float* fparam = c->d_fparam;
@@ -709,6 +756,11 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
       CDS_LAUNCH_CHECK();
       if (int e = contrast_prep_f64_launch(c->d_cxy, 2 * n, h4, w4, 24, c->d_keys64, c->d_padM, st)) return e;
     }
+    // ---- mid-point: the previous batch's SVM starts together with this batch's contrast kernels ----
+    if (ov && c->pb.valid) {
+      CDS_CUDA(cudaEventRecord(c->ev_mid, st));
+      if (int e = flush_pending_back(c, c->ev_mid)) return e;
+    }
     // bit: 5x5 window on the CTU grid
     prof_mark(c, ST_CONTRAST_W5, st);
     if (int e = contrast_generic_launch(c->d_padB, c->d_w5, c->d_rawB, mB, n, sbR, sbC, 5, 2, st)) return e;
@@ -740,7 +792,10 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     temporal_thresh_finalize_kernel<<<3 * n, 32, 0, st>>>(c->d_partial2, c->nblk2, c->d_stats9, c->d_xf);
     CDS_LAUNCH_CHECK();
   }
-  int nbf = 0;
+  if (cam_out) {      // cam_out is a DEVICE pointer here: gather the ring slots of this batch (front half: it reads the ring)
+    gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, RL, first_poc, n, cam_out);
+    CDS_LAUNCH_CHECK();
+  }
   if (c->p.use_rbf) {
     // ---- features at 200x200 (main.m:275-294) ----
     prof_mark(c, ST_RESIZE200, st);
@@ -753,55 +808,32 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
       assemble_features_kernel<<<grid, 256, 0, st>>>(c->d_F200, c->d_Ft, c->d_stats9, c->d_xf, fparam, xsvm);
       CDS_LAUNCH_CHECK();
     }
-    // ---- (d) RBF-SVM, then pm_norm -> imresize -> imfilter -> centre prior (main.m:297-304) ----
-    if (cam_out) {      // cam_out is a DEVICE pointer here: gather the ring slots of this batch (front half: it reads the ring)
-      gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, RL, first_poc, n, cam_out);
-      CDS_LAUNCH_CHECK();
-    }
-    if (ov) {
+    if (ov) {          // the back half is deferred to the next batch's mid-point (or to join_back)
       CDS_CUDA(cudaEventRecord(c->ev_front[slot], st));
-      CDS_CUDA(cudaStreamWaitEvent(sb, c->ev_front[slot], 0));
+      c->pb.valid = true; c->pb.slot = slot; c->pb.n = n; c->pb.tag = tag; c->pb.maps_out = maps_out; c->pb.before_back = before_back;
+      return CDS_OK;
     }
-    if (before_back) CDS_CUDA(cudaStreamWaitEvent(sb, before_back, 0));
-    prof_mark(c, ST_SVM, st);
-    if (int e = svm_predict_launch(c->p.model, xsvm, (long)n * 40000, c->d_dec, sb)) return e;
-    prof_mark(c, ST_FINAL, st);
-    dec_minmax_norm_kernel<<<n, 1024, 0, sb>>>(c->d_dec, c->d_C);
-    CDS_LAUNCH_CHECK();
-    if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, sb)) return e;
-    {
-      const int thr = fir_threads(W / 4);
-      dim3 grid(ceil_div(W / 4, thr), ceil_div(H, FR_ROWS), n);
-      final_rows_kernel<<<grid, thr, (size_t)(c->Bv.nt + c->Bv.span4) * 16, sb>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
-      CDS_LAUNCH_CHECK();
-      nbf = grid.x * grid.y;
-    }
+    if (before_back) CDS_CUDA(cudaStreamWaitEvent(st, before_back, 0));
+    if (int e = launch_back_rbf(c, slot, n, maps_out, st, true)) return e;
   } else {
-    if (cam_out) {
-      gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, RL, first_poc, n, cam_out);
-      CDS_LAUNCH_CHECK();
-    }
-    if (before_back) CDS_CUDA(cudaStreamWaitEvent(sb, before_back, 0));
+    if (before_back) CDS_CUDA(cudaStreamWaitEvent(st, before_back, 0));
     prof_mark(c, ST_FINAL, st);
     dim3 grid(128, n);
     linear_comb_kernel<<<grid, 256, 0, st>>>(c->d_Y, c->HW, c->d_stats9, c->d_xf, fparam, c->d_dist, c->d_raw, c->d_fpartial);
     CDS_LAUNCH_CHECK();
-    nbf = 128;
+    if (int e = stats_finalize_launch(c->d_fpartial, n, 128, c->d_fstats, st)) return e;
+    if (maps_out) {
+      if (int e = c->p.out_u8 ? launch_normalize<uint8_t>(c, n, maps_out, st) : launch_normalize<float>(c, n, maps_out, st)) return e;
+    }
   }
-  if (int e = stats_finalize_launch(c->d_fpartial, n, nbf, c->d_fstats, sb)) return e;
-  if (maps_out) {
-    if (int e = c->p.out_u8 ? launch_normalize<uint8_t>(c, n, maps_out, sb) : launch_normalize<float>(c, n, maps_out, sb)) return e;
-  }
-  if (ov) {
-    CDS_CUDA(cudaEventRecord(c->ev_back[slot], sb));
-    if (done_ev) *done_ev = c->ev_back[slot];
-  }
+  c->retired_tag = tag; c->retired_ev = nullptr;
   prof_mark(c, -1, st);
   return CDS_OK;
 }
 
 // make `st` wait for every back half still in flight (end of an API call: the caller's stream then covers all the work)
 int join_back(cds_ctx* c, cudaStream_t st) {
+  if (int e = flush_pending_back(c, nullptr)) return e;     // no batch follows: the last back half runs on its own
   if (c->overlap && c->p.use_rbf)
     for (int b = 0; b < 2; b++) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[b], 0));
   return CDS_OK;
@@ -889,6 +921,20 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
     if (!swapped) c->allocs.push_back(q);
     c->d_cam_call = reinterpret_cast<int*>(q); c->d_cam_cap = (size_t)2 * nframes;
   }
+  // a batch's maps leave for the host when its back half has been enqueued ("retired"): at once without overlap, from the middle of
+  // the next batch (or from join_back) with it
+  struct HostBatch { int buf, done, n; };
+  std::vector<HostBatch> hb((size_t)nb);
+  auto drain_retired = [&]() -> int {
+    if (c->retired_tag < 0) return CDS_OK;
+    const HostBatch b = hb[(size_t)c->retired_tag];
+    c->retired_tag = -1;
+    if (c->retired_ev) CDS_CUDA(cudaStreamWaitEvent(cs, c->retired_ev, 0));
+    else { CDS_CUDA(cudaEventRecord(c->ev_done[b.buf], st)); CDS_CUDA(cudaStreamWaitEvent(cs, c->ev_done[b.buf], 0)); }
+    if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)b.done * px, c->d_out[b.buf], (size_t)b.n * px, cudaMemcpyDeviceToHost, cs));
+    CDS_CUDA(cudaEventRecord(c->ev_copied[b.buf], cs));
+    return CDS_OK;
+  };
   int bi = 0;
   for (int done = 0; done < nframes; done += c->B, bi++) {
     const int n = std::min(c->B, nframes - done);
@@ -904,20 +950,18 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
       continue;
     }
     const int buf = c->out_flip; c->out_flip ^= 1;
+    hb[bi] = {buf, done, n};
     // before_back = the copy that last read d_out[buf] has finished (a never-recorded event is a no-op)
-    cudaEvent_t done_ev = nullptr;
+    c->retired_tag = -1;
     if (int e = run_batch(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out[buf],
-                          cam_out ? c->d_cam_call + (size_t)2 * done : nullptr, st, c->ev_copied[buf], &done_ev)) return e;
-    if (!done_ev) { CDS_CUDA(cudaEventRecord(c->ev_done[buf], st)); done_ev = c->ev_done[buf]; }
-    else CDS_CUDA(cudaEventRecord(c->ev_done[buf], st));          // front half (incl. the camera-motion gather) done
-    CDS_CUDA(cudaStreamWaitEvent(cs, done_ev, 0));
-    CDS_CUDA(cudaStreamWaitEvent(cs, c->ev_done[buf], 0));
-    if (host_out) CDS_CUDA(cudaMemcpyAsync((char*)host_out + (size_t)done * px, c->d_out[buf], (size_t)n * px, cudaMemcpyDeviceToHost, cs));
-    CDS_CUDA(cudaEventRecord(c->ev_copied[buf], cs));
+                          cam_out ? c->d_cam_call + (size_t)2 * done : nullptr, st, c->ev_copied[buf], bi)) return e;
+    if (int e = drain_retired()) return e;
     c->last_first = first_poc + done; c->last_n = n; c->last_buf = buf;
   }
+  c->retired_tag = -1;
   int herr = 0;
   if (int e = join_back(c, st)) return e;
+  if (!context_only) if (int e = drain_retired()) return e;
   CDS_CUDA(cudaMemcpyAsync(&herr, c->d_err, 4, cudaMemcpyDeviceToHost, st));
   if (cam_out && !context_only)     // one copy for the call, after every front half (the gathers run on st)
     CDS_CUDA(cudaMemcpyAsync(c->h_cam_pin, c->d_cam_call, (size_t)2 * nframes * sizeof(int), cudaMemcpyDeviceToHost, st));

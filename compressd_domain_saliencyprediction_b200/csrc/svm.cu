@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -267,6 +268,186 @@ svm_rbf9_tc_kernel(const float* __restrict__ X, long N, const float* __restrict_
   }
 }
 
+// =================================================================================================
+// Persistent variant of the kernel above: ONE CTA per SM walks the 128-instance tiles of the whole launch, so the kernel
+// can share every SM with a kernel that is bound by a different pipe (the FP32-issue-bound contrast kernel of the next
+// batch, pipeline.cu): it holds 10 warps, <= 128 registers per thread and 98 KB of shared memory per SM for its whole life
+// and leaves the rest to the co-resident CTAs.  Roles: warps 0-7 epilogue (TMEM lane quadrant = warp % 4, column half =
+// warp / 4, so two warps per scheduler alternate between tcgen05.ld latency and MUFU issue), warp 8 MMA issuer + TMEM
+// allocation, warp 9 producer (lane 0 streams the SV tile images; the whole warp builds the A tile of the NEXT instance
+// tile into the second A buffer, so the MMA pipe never waits for it).  mbarrier phases run on global counters across tiles.
+// =================================================================================================
+namespace tcp {
+using namespace tc;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int RED_BYTES = 2 * 2 * TM * 4;                  // [tile parity][pos | neg][instance]
+constexpr int SMEM_BYTES = 2 * A_BYTES + STAGES * TILE_BYTES + BAR_BYTES + RED_BYTES;
+}  // namespace tcp
+
+template <int POLY_OF_8>
+__global__ void __maxnreg__(128)
+svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict__ tiles, int ntiles, int ntiles_pos,
+                    float xscale, float rho, float* __restrict__ dec) {
+  using namespace tcp;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                        // 2 x [hi|lo][k chunk][128 instances][4]
+  uint8_t* sB = smem + 2 * A_BYTES;                          // STAGES tile images
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * TILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+  auto afull = [&](int b) { return bar0 + 8u * (2 * STAGES + 4 + b); };
+  auto aempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 6 + b); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long ntile_inst = (N + TM - 1) / TM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(tfull(b), 1); mbar_init(tempty(b), EPI_WARPS); mbar_init(afull(b), 1); mbar_init(aempty(b), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == EPI_WARPS + 1) {                               // ---- producer warp ----
+    auto build_a = [&](long tile, int k) {                   // the whole warp: 4 instances per lane -> A buffer k & 1
+      const int ab = k & 1;
+      mbar_wait(aempty(ab), ((k >> 1) & 1) ^ 1);
+      uint8_t* A = sA + ab * A_BYTES;
+#pragma unroll 1
+      for (int i = 0; i < TM / 32; i++) {
+        const int inst = lane + 32 * i;
+        const long n = tile * TM + inst;
+        float xa[KPAD];
+        float s2 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 9; d++) { const float v = (n < N) ? __ldg(X + n * 9 + d) * xscale : 0.f; xa[d] = v; s2 = fmaf(v, v, s2); }
+        xa[9] = 1.f; xa[10] = -0.5f * s2;
+#pragma unroll
+        for (int d = 11; d < KPAD; d++) xa[d] = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < 4; kc++) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) { hi[j] = tf32_rna(xa[4 * kc + j]); lo[j] = tf32_rna(xa[4 * kc + j] - __uint_as_float(hi[j])); }
+          *reinterpret_cast<uint4*>(A + (kc * TM + inst) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(A + HALF_BYTES + (kc * TM + inst) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(afull(ab));
+    };
+    long g = 0; int k = 0;
+    if ((long)blockIdx.x < ntile_inst) build_a(blockIdx.x, 0);
+    for (long tile = blockIdx.x; tile < ntile_inst; tile += gridDim.x, k++) {
+      if (lane == 0) {
+        for (int t = 0; t < ntiles; t++, g++) {
+          const int s = (int)(g % STAGES);
+          mbar_wait(empty(s), (uint32_t)((g / STAGES) & 1) ^ 1u);
+          mbar_expect_tx(full(s), TILE_BYTES);
+          bulk_g2s(smem_u32(sB + s * TILE_BYTES), tiles + (size_t)t * TILE_FLOATS, TILE_BYTES, full(s));
+        }
+      }
+      __syncwarp();
+      if (tile + gridDim.x < ntile_inst) build_a(tile + gridDim.x, k + 1);
+    }
+  } else if (warp == EPI_WARPS) {
+    if (lane == 0) {                                         // ---- MMA issuer ----
+      long g = 0; int k = 0;
+      for (long tile = blockIdx.x; tile < ntile_inst; tile += gridDim.x, k++) {
+        const int ab = k & 1;
+        mbar_wait(afull(ab), (k >> 1) & 1);
+        const uint32_t a_hi = smem_u32(sA + ab * A_BYTES), a_lo = a_hi + HALF_BYTES;
+        for (int t = 0; t < ntiles; t++, g++) {
+          const int s = (int)(g % STAGES), buf = (int)(g & 1);
+          mbar_wait(tempty(buf), (uint32_t)((g >> 1) & 1) ^ 1u);
+          mbar_wait(full(s), (uint32_t)((g / STAGES) & 1));
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(sB + s * TILE_BYTES), b_lo = b_hi + HALF_BYTES;
+          const uint32_t d = tmem_base + (uint32_t)buf * TN;
+          const uint32_t LBO = TN * 16, SBO = 128;
+#define CDS_DESC(base, ks) smem_desc((base) + (ks) * KSTEP_BYTES, LBO, SBO)
+          mma_tf32(d, CDS_DESC(a_lo, 0), CDS_DESC(b_hi, 0), IDESC, 0u);   // small terms first
+          mma_tf32(d, CDS_DESC(a_lo, 1), CDS_DESC(b_hi, 1), IDESC, 1u);
+          mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_lo, 0), IDESC, 1u);
+          mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_lo, 1), IDESC, 1u);
+          mma_tf32(d, CDS_DESC(a_hi, 0), CDS_DESC(b_hi, 0), IDESC, 1u);
+          mma_tf32(d, CDS_DESC(a_hi, 1), CDS_DESC(b_hi, 1), IDESC, 1u);
+#undef CDS_DESC
+          mma_commit(empty(s));
+          mma_commit(tfull(buf));
+        }
+        mma_commit(aempty(ab));                              // every MMA that reads this A buffer has completed when this fires
+      }
+    }
+  } else {                                                   // ---- epilogue warps 0-7 ----
+    const int quad = warp & 3, half = warp >> 2;
+    long g = 0; int k = 0;
+    for (long tile = blockIdx.x; tile < ntile_inst; tile += gridDim.x, k++) {
+      float accp[4] = {0.f, 0.f, 0.f, 0.f}, accn[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int t = 0; t < ntiles; t++, g++) {
+        const int buf = (int)(g & 1);
+        mbar_wait(tfull(buf), (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TN + half * (TN / 2));
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        auto consume = [&](const uint32_t (&v)[32]) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float e[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const float x = __uint_as_float(v[j + q]);
+              e[q] = (q < POLY_OF_8) ? ex2_poly(x) : ex2_approx(x);
+            }
+            a0 += e[0] + e[4]; a1 += e[1] + e[5]; a2 += e[2] + e[6]; a3 += e[3] + e[7];
+          }
+        };
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        tmem_ld_wait();
+        tmem_ld32(taddr + 32, vb);
+        consume(va);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));             // this warp's share of the accumulator is in registers
+        consume(vb);
+        if (t < ntiles_pos) { accp[0] += a0; accp[1] += a1; accp[2] += a2; accp[3] += a3; }
+        else                { accn[0] += a0; accn[1] += a1; accn[2] += a2; accn[3] += a3; }
+      }
+      // the two column halves of an instance meet in shared memory (buffer k & 1: one named barrier per tile is enough)
+      const float P = (accp[0] + accp[1]) + (accp[2] + accp[3]), Q = (accn[0] + accn[1]) + (accn[2] + accn[3]);
+      float* rb = red + (k & 1) * 2 * TM;
+      const int inst = quad * 32 + lane;
+      if (half == 1) { rb[inst] = P; rb[TM + inst] = Q; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) {
+        const long n = tile * TM + inst;
+        if (n < N) dec[n] = (P + rb[inst]) - (Q + rb[TM + inst]) - rho;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // Generic feature count (<= 64): difference form in libsvm's own order, one instance per thread.
 __global__ void __launch_bounds__(128)
 svm_rbf_generic_kernel(const float* __restrict__ X, long N, int F, const float* __restrict__ SV,
@@ -316,6 +497,20 @@ int svm_predict_launch(const cds_svm_model* m, const float* X, long N, float* de
               : poly == 3 ? svm_rbf9_tc_kernel<3> : svm_rbf9_tc_kernel<4>;
     const int smem_bytes = tc::SMEM_BYTES;   // (padding it so that one CTA fits per SM, to leave room for overlapped kernels, measured 6 % slower)
     if (int e = ensure_dyn_smem(kern, smem_bytes)) return e;
+    // CDS_SVM_PERSIST=0 selects the non-persistent kernel (two CTAs per SM, owns the whole SM); the default persistent kernel is
+    // built to share the SMs with the FP32-bound contrast kernel of the next batch (pipeline.cu)
+    static const int persist = [] { const char* e = getenv("CDS_SVM_PERSIST"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (persist) {
+      static const int polyp = [] { const char* e = getenv("CDS_SVM_POLY"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : v > 4 ? 4 : v; }();
+      auto kp = polyp == 0 ? svm_rbf9_tcp_kernel<0> : polyp == 1 ? svm_rbf9_tcp_kernel<1> : polyp == 2 ? svm_rbf9_tcp_kernel<2>
+              : polyp == 3 ? svm_rbf9_tcp_kernel<3> : svm_rbf9_tcp_kernel<4>;
+      if (int e = ensure_dyn_smem(kp, tcp::SMEM_BYTES)) return e;
+      const long ntile_inst = (N + tc::TM - 1) / tc::TM;
+      const unsigned gridp = (unsigned)std::min<long>(device_sm_count(), ntile_inst);
+      kp<<<gridp, tcp::THREADS, tcp::SMEM_BYTES, st>>>(X, N, m->d_tiles, m->ntiles, m->ntiles_pos, (float)sqrt(2 * g2), (float)m->rho, dec);
+      CDS_LAUNCH_CHECK();
+      return CDS_OK;
+    }
     const unsigned grid = (unsigned)((N + tc::TM - 1) / tc::TM);
     kern<<<grid, tc::THREADS, smem_bytes, st>>>(X, N, m->d_tiles, m->ntiles, m->ntiles_pos, (float)sqrt(2 * g2), (float)m->rho, dec);
   } else if (m->nfeat == 9) {

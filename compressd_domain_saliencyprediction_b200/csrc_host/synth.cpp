@@ -1,4 +1,5 @@
-// synth.cpp — synthetic per-CTU HEVC syntax (host).  Stands in for the HM16.0 CABAC parser (the
+// synth.cpp — synthetic per-CTU HEVC syntax (host only; built into libcds_synth.so, which holds no CUDA code, so the
+// CPU arms of bench.py and the CPU tests can generate inputs without mapping the product library).  Stands in for the HM16.0 CABAC parser (the
 // reference host producer, timed separately) in throughput runs and fuzz tests; statistics follow
 // SURVEY.md section 8(d).  The streams are LEGAL in the sense of TDecCu::MVoutput
 // (TDecCu.cpp:165-289): depth-first CU tokens (99 = split, else PartSize, 15 = block outside the
@@ -7,7 +8,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
-#include "../../include/cds.h"
+#include "../../include/cds_synth.h"
 
 namespace {
 
@@ -93,7 +94,7 @@ struct Gen {
 
 extern "C" long cds_synth_frame(int w, int h, uint64_t seed, int poc, int32_t* hdr, int16_t* tok, size_t tok_cap,
                                 uint16_t* ctu_bytes) {
-  if (!hdr || !tok || !ctu_bytes || w < 8 || h < 8 || (w % 8) || (h % 8)) return CDS_EINVAL;
+  if (!hdr || !tok || !ctu_bytes || w < 8 || h < 8 || (w % 8) || (h % 8)) return -1;
   const int ncol = (w + 63) / 64, nrow = (h + 63) / 64;
   Rng fr(mix(seed, (uint64_t)poc));
   const bool adv = (seed >> 60) & 1;
@@ -108,7 +109,7 @@ extern "C" long cds_synth_frame(int w, int h, uint64_t seed, int poc, int32_t* h
     g.cupu = cupu; g.pred = pred; g.mv = mv;
     g.node(0, 0, 64, 0);
     const size_t n = (size_t)g.ncupu + g.npred + g.nmv;
-    if (off + n > tok_cap) return CDS_ENOMEM;
+    if (off + n > tok_cap) return -2;
     hdr[a * 4 + 0] = (int32_t)off; hdr[a * 4 + 1] = g.ncupu; hdr[a * 4 + 2] = g.npred; hdr[a * 4 + 3] = g.nmv;
     memcpy(tok + off, cupu, g.ncupu * 2); off += g.ncupu;
     memcpy(tok + off, pred, g.npred * 2); off += g.npred;
@@ -120,19 +121,3 @@ extern "C" long cds_synth_frame(int w, int h, uint64_t seed, int poc, int32_t* h
   return (long)off;
 }
 
-extern "C" long cds_syntax_pack_ref(int nctu, const float* MV, const float* Pred, const float* CUPU,
-                                    int32_t* hdr, int16_t* tok) {
-  if (nctu < 1 || !MV || !Pred || !CUPU || !hdr || !tok) return CDS_EINVAL;
-  long off = 0;
-  for (int a = 0; a < nctu; a++) {
-    const float* src[3] = {CUPU + (size_t)a * 1000, Pred + (size_t)a * 1000, MV + (size_t)a * 1000};
-    hdr[a * 4 + 0] = (int32_t)off;
-    for (int s = 0; s < 3; s++) {
-      int n = 0;
-      while (n < 1000 && src[s][n] != 999.f) { tok[off + n] = (int16_t)src[s][n]; n++; }   // 999 sentinel, TDecCu.cpp:159-161
-      if (n == 1000) return CDS_EFORMAT;
-      hdr[a * 4 + 1 + s] = n; off += n;
-    }
-  }
-  return off;
-}

@@ -101,24 +101,7 @@ def getFrame(mv_arr, pred_arr, cupu_arr, w, h):
     return mvx.astype(np.float32), mvy.astype(np.float32), depth.astype(np.float32)
 
 
-def synth_frame(w, h, seed, poc):
-    """Synthetic per-CTU syntax for throughput runs.  Returns hdr, tok, ctu_bytes."""
-    n = nctu(w, h)
-    hdr = np.zeros((n, 4), np.int32)
-    tok = np.zeros(1300 * n, np.int16)
-    byts = np.zeros(n, np.uint16)
-    nt = lib().cds_synth_frame(w, h, C.c_uint64(seed), poc, _ptr(hdr), _ptr(tok), tok.size, _ptr(byts))
-    check(nt, "cds_synth_frame")
-    return hdr, tok[:nt].copy(), byts
-
-
-def synth_clip(w, h, seed, nframes, first_poc=0):
-    """nframes pictures packed for the batch entry points: hdr[F][nctu][4], tok, tok_base[F+1], bytes[F][nctu]."""
-    hdrs, toks, byts, base = [], [], [], [0]
-    for f in range(nframes):
-        hd, tk, by = synth_frame(w, h, seed, first_poc + f)
-        hdrs.append(hd); toks.append(tk); byts.append(by); base.append(base[-1] + tk.size)
-    return np.stack(hdrs), np.concatenate(toks), np.array(base, np.int64), np.stack(byts)
+from .synth import synth_frame, synth_clip  # noqa: E402,F401  (host-only libcds_synth.so; kept here for the tests' ops.synth_* spelling)
 
 
 # ------------------------------------------------------------------------------------------ (d)

@@ -85,14 +85,6 @@ long cds_syntax_pack_ref(int nctu, const float* MV, const float* Pred, const flo
 int cds_getframe_dev(int w, int h, int nframes, const int32_t* hdr, const int16_t* tok,
                      const int64_t* tok_base, int16_t* mvx, int16_t* mvy, uint8_t* depth, void* stream);
 
-/* Synthetic syntax producer (stands in for HM CABAC parsing in throughput runs).
- * Fills hdr[nctu*4], tok (capacity tok_cap int16), ctu_bytes[nctu] for picture `poc` of the clip
- * identified by `seed`.  Seed bit 60 selects adversarial statistics (deep trees, many intra / NxN /
- * AMP CUs, small MVs that collide with PU labels) used by the differential fuzz tests.
- * Returns the number of tokens written or <0. */
-long cds_synth_frame(int w, int h, uint64_t seed, int poc, int32_t* hdr, int16_t* tok, size_t tok_cap,
-                     uint16_t* ctu_bytes);
-
 /* ------------------------------------------------------------------------------------------
  * (d) libsvm C-SVC / RBF decision values
  * ------------------------------------------------------------------------------------------ */

@@ -10,8 +10,8 @@ import pytest
 import _oracle as o
 
 
-def _declared():
-    txt = open(os.path.join(o.ROOT, "include", "cds.h")).read()
+def _declared(header="cds.h"):
+    txt = open(os.path.join(o.ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(cds_[a-z0-9_]+)\s*\(", txt)))
 
@@ -24,6 +24,19 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/cds.h but not exported by libcds_b200.so"
     assert L._cds_missing == []
+
+
+def test_synth_library_is_host_only_and_exports_its_header():
+    """include/cds_synth.h is served by libcds_synth.so, which must not pull in the CUDA runtime or the product library
+    (bench.py's reference arm and the CPU tests generate their inputs with it)."""
+    import subprocess
+    from compressd_domain_saliencyprediction_b200 import synth
+    L = synth.synth_lib()
+    for n in _declared("cds_synth.h"):
+        assert hasattr(L, n), n
+    so = os.path.join(os.path.dirname(synth.__file__), "libcds_synth.so")
+    needed = subprocess.run(["objdump", "-p", so], capture_output=True, text=True).stdout
+    assert "libcudart" not in needed and "libcuda" not in needed and "libcds_b200" not in needed
 
 
 def test_ctypes_table_covers_header():
