@@ -42,6 +42,7 @@ def _declare(L):
         "cds_magnitude_vote": (i32, [c_p, i32, c_p]),
         "cds_create": (i32, [c_p, C.POINTER(c_p)]),
         "cds_destroy": (None, [c_p]),
+        "cds_acquire_frame_buffers": (i32, [c_p, c_p, c_p, c_p, c_p]),
         "cds_submit_frame": (i32, [c_p, i32, c_p, c_p, c_p, sz]),
         "cds_get_map": (i32, [c_p, i32, c_p, c_p]),
         "cds_flush": (i32, [c_p]),

@@ -15,10 +15,13 @@
 // the staged halo holds no zero.
 #include "cds_common.cuh"
 #include <math.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
 namespace cds {
+
+constexpr int CONTRAST_SCHED_WORDS = 1 + 1024;     // [0] tile counter, [1 + smid] live CTAs per SM
 
 template <int WIN>
 struct SepWeights {
@@ -84,63 +87,87 @@ __device__ __forceinline__ void sep_accumulate(const float* __restrict__ sbase, 
   }
 }
 
-// grid: (ceil(C/TC), ceil(R/16), nmaps)
+// Persistent: a CTA walks tiles t = blockIdx.x, + gridDim.x, ... of the (column tile, row tile, map) space, column tile fastest
+// so that CTAs running together stage neighbouring halos.  The grid is (SMs x CTAs per SM) at most; the pipeline caps the CTAs
+// per SM when the kernel has to leave room for the persistent SVM kernel that runs beside it (pipeline.cu, svm.cu).
+// With `sched` (device words: [0] next tile, [1 + smid] live CTAs on that SM; zeroed before the launch) the tiles are handed out by
+// an atomic counter and at most `cap` CTAs stay alive per SM — the launch over-subscribes every SM and the surplus CTAs retire
+// at once, so the kernel occupies exactly `cap` CTA slots on every SM wherever the block scheduler put its CTAs.
+// One tile per CTA when the grid covers the tile space (gridDim.x == ntiles: the default, and the fastest standalone form — the
+// block scheduler's own hand-out staggers the staging phases of the CTAs that share an SM); persistent otherwise.
 template <int WIN, int CPT, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 contrast_sep_kernel(const float* __restrict__ pad, float* __restrict__ out,
-                    unsigned* __restrict__ out_max_bits, int R, int C, int pr, int pc,
-                    const __grid_constant__ SepWeights<WIN> w) {
+                    unsigned* __restrict__ out_max_bits, int R, int C, int pr, int pc, int ntx, int nty, int ntiles,
+                    unsigned* __restrict__ sched, int cap, const __grid_constant__ SepWeights<WIN> w) {
   using Cfg = SepCfg<WIN, CPT, NWARPS>;
   constexpr int LEN = WIN / 2;
   extern __shared__ __align__(16) float smem[];
-  __shared__ int s_has_zero;
-  const int tile_c0 = blockIdx.x * Cfg::TC;
-  const int tile_r0 = blockIdx.y * Cfg::TR;
-  const int map = blockIdx.z;
-  const float* __restrict__ P = pad + (size_t)map * pr * pc;
-  if (threadIdx.x == 0) s_has_zero = 0;
-  __syncthreads();
-  // stage the halo tile (padded coordinates: output (r,c) sees padded rows r..r+WIN-1)
-  int zero_seen = 0;
-  for (int idx = threadIdx.x; idx < Cfg::HR * Cfg::PITCH; idx += Cfg::THREADS) {
-    const int hr = idx / Cfg::PITCH, hc = idx - hr * Cfg::PITCH;
-    const int gr_ = tile_r0 + hr, gc_ = tile_c0 + hc;
-    float v = 1.f;   // out-of-range filler (never contributes to a stored output)
-    if (gr_ < pr && gc_ < pc) { v = __ldg(P + (size_t)gr_ * pc + gc_); zero_seen |= (v == 0.f); }
-    smem[idx] = v;
-  }
-  if (zero_seen) s_has_zero = 1;
-  __syncthreads();
-
+  __shared__ int s_has_zero, s_tile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lr = lane & 15, lc = lane >> 4;
   const int cb = (warp * 2 + lc) * CPT;            // column base inside the tile
   const float* sbase = smem + lr * Cfg::PITCH + cb;
-  float c[CPT], acc[CPT];
-#pragma unroll
-  for (int k = 0; k < CPT; k++) { c[k] = sbase[LEN * Cfg::PITCH + LEN + k]; acc[k] = 0.f; }
-  if (s_has_zero) sep_accumulate<WIN, CPT, true>(sbase, Cfg::PITCH, c, acc, w);
-  else            sep_accumulate<WIN, CPT, false>(sbase, Cfg::PITCH, c, acc, w);
-
-  const int r = tile_r0 + lr, c0 = tile_c0 + cb;
-  float mx = 0.f;
-  if (r < R) {
-    float* o = out + ((size_t)map * R + r) * C + c0;
-    if (c0 + CPT <= C && (C % 4) == 0 && (CPT % 4) == 0) {
-#pragma unroll
-      for (int k = 0; k < CPT; k += 4)
-        *reinterpret_cast<float4*>(o + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
-#pragma unroll
-      for (int k = 0; k < CPT; k++) mx = fmaxf(mx, acc[k]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < CPT; k++)
-        if (c0 + k < C) { o[k] = acc[k]; mx = fmaxf(mx, acc[k]); }
+  if (sched) {
+    if (threadIdx.x == 0) {
+      unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      const bool live = cap <= 0 || atomicAdd(sched + 1 + smid, 1u) < (unsigned)cap;
+      s_tile = live ? (int)atomicAdd(sched, 1u) : ntiles;
     }
+    __syncthreads();
   }
-  if (out_max_bits) {
-    mx = warp_max(mx);
-    if (lane == 0) atomic_max_nonneg(out_max_bits + map, mx);
+  for (int tile = sched ? s_tile : (int)blockIdx.x; tile < ntiles;) {
+    const int tx = tile % ntx, trest = tile / ntx;
+    const int tile_c0 = tx * Cfg::TC;
+    const int tile_r0 = (trest % nty) * Cfg::TR;
+    const int map = trest / nty;
+    const float* __restrict__ P = pad + (size_t)map * pr * pc;
+    if (threadIdx.x == 0) s_has_zero = 0;
+    __syncthreads();                               // also: everyone has finished reading the previous tile
+    // stage the halo tile (padded coordinates: output (r,c) sees padded rows r..r+WIN-1)
+    int zero_seen = 0;
+    for (int idx = threadIdx.x; idx < Cfg::HR * Cfg::PITCH; idx += Cfg::THREADS) {
+      const int hr = idx / Cfg::PITCH, hc = idx - hr * Cfg::PITCH;
+      const int gr_ = tile_r0 + hr, gc_ = tile_c0 + hc;
+      float v = 1.f;   // out-of-range filler (never contributes to a stored output)
+      if (gr_ < pr && gc_ < pc) { v = __ldg(P + (size_t)gr_ * pc + gc_); zero_seen |= (v == 0.f); }
+      smem[idx] = v;
+    }
+    if (zero_seen) s_has_zero = 1;
+    __syncthreads();
+
+    float c[CPT], acc[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) { c[k] = sbase[LEN * Cfg::PITCH + LEN + k]; acc[k] = 0.f; }
+    if (s_has_zero) sep_accumulate<WIN, CPT, true>(sbase, Cfg::PITCH, c, acc, w);
+    else            sep_accumulate<WIN, CPT, false>(sbase, Cfg::PITCH, c, acc, w);
+
+    const int r = tile_r0 + lr, c0 = tile_c0 + cb;
+    float mx = 0.f;
+    if (r < R) {
+      float* o = out + ((size_t)map * R + r) * C + c0;
+      if (c0 + CPT <= C && (C % 4) == 0 && (CPT % 4) == 0) {
+#pragma unroll
+        for (int k = 0; k < CPT; k += 4)
+          *reinterpret_cast<float4*>(o + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+#pragma unroll
+        for (int k = 0; k < CPT; k++) mx = fmaxf(mx, acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < CPT; k++)
+          if (c0 + k < C) { o[k] = acc[k]; mx = fmaxf(mx, acc[k]); }
+      }
+    }
+    if (out_max_bits) {
+      mx = warp_max(mx);
+      if (lane == 0) atomic_max_nonneg(out_max_bits + map, mx);
+    }
+    if (sched) {
+      __syncthreads();                             // everyone has read s_tile (and the shared tile) of this round
+      if (threadIdx.x == 0) s_tile = (int)atomicAdd(sched, 1u);
+      __syncthreads();
+      tile = s_tile;
+    } else tile += gridDim.x;
   }
 }
 
@@ -185,22 +212,30 @@ contrast_generic_kernel(const float* __restrict__ pad, const float* __restrict__
 
 template <int WIN, int CPT, int NWARPS>
 static int launch_sep_cfg(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C,
-                          const float* gr, const float* gc, cudaStream_t st) {
+                          const float* gr, const float* gc, int ctas_per_sm, unsigned* sched, cudaStream_t st) {
   using Cfg = SepCfg<WIN, CPT, NWARPS>;
   SepWeights<WIN> w;
   for (int i = 0; i < WIN; i++) { w.gr[i] = gr[i]; w.gc[i] = gc[i]; }
   if (int e = ensure_dyn_smem(contrast_sep_kernel<WIN, CPT, NWARPS>, Cfg::SMEM_BYTES)) return e;
   const int len = WIN / 2;
-  dim3 grid(ceil_div(C, Cfg::TC), ceil_div(R, Cfg::TR), nmaps);
+  const int ntx = ceil_div(C, Cfg::TC), nty = ceil_div(R, Cfg::TR);
+  const long ntiles = (long)ntx * nty * nmaps;
+  if (ntiles > 0x7fffffffL) { set_error("contrast: %ld tiles", ntiles); return CDS_EINVAL; }
+  const int fit = std::max(1, (int)((227 * 1024) / (Cfg::SMEM_BYTES + 1024)));          // CTAs per SM by shared memory
+  // default: one CTA per tile.  With a scheduler block: over-subscribe (`fit` CTAs per SM), the kernel keeps `ctas_per_sm` of them
+  // alive on each SM.  With a cap but no scheduler block: a static persistent grid of that many CTAs per SM.
+  const int per_sm = (!sched && ctas_per_sm > 0) ? std::min(ctas_per_sm, fit) : fit;
+  const unsigned grid = (sched || ctas_per_sm > 0) ? (unsigned)std::min<long>(ntiles, (long)device_sm_count() * per_sm) : (unsigned)ntiles;
+  if (sched) CDS_CUDA(cudaMemsetAsync(sched, 0, CONTRAST_SCHED_WORDS * sizeof(unsigned), st));
   contrast_sep_kernel<WIN, CPT, NWARPS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
-      pad, out, mx, R, C, R + 2 * len, C + 2 * len, w);
+      pad, out, mx, R, C, R + 2 * len, C + 2 * len, ntx, nty, (int)ntiles, sched, ctas_per_sm, w);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
 
 template <int WIN, int CPT>
 static int launch_sep_win(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C,
-                          const float* gr, const float* gc, cudaStream_t st) {
+                          const float* gr, const float* gc, int ctas_per_sm, unsigned* sched, cudaStream_t st) {
   // choose the block width (warps of 2*CPT columns) that wastes the fewest columns
   const int units = ceil_div(C, 2 * CPT);
   int best = 4, best_waste = 1 << 30;
@@ -209,11 +244,11 @@ static int launch_sep_win(const float* pad, float* out, unsigned* mx, int nmaps,
     if (waste < best_waste) { best_waste = waste; best = nw; }
   }
   switch (best) {
-    case 4: return launch_sep_cfg<WIN, CPT, 4>(pad, out, mx, nmaps, R, C, gr, gc, st);
-    case 5: return launch_sep_cfg<WIN, CPT, 5>(pad, out, mx, nmaps, R, C, gr, gc, st);
-    case 6: return launch_sep_cfg<WIN, CPT, 6>(pad, out, mx, nmaps, R, C, gr, gc, st);
-    case 7: return launch_sep_cfg<WIN, CPT, 7>(pad, out, mx, nmaps, R, C, gr, gc, st);
-    default: return launch_sep_cfg<WIN, CPT, 8>(pad, out, mx, nmaps, R, C, gr, gc, st);
+    case 4: return launch_sep_cfg<WIN, CPT, 4>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
+    case 5: return launch_sep_cfg<WIN, CPT, 5>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
+    case 6: return launch_sep_cfg<WIN, CPT, 6>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
+    case 7: return launch_sep_cfg<WIN, CPT, 7>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
+    default: return launch_sep_cfg<WIN, CPT, 8>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
   }
 }
 
@@ -232,10 +267,12 @@ int contrast_generic_launch(const float* pad, const float* dW, float* out, unsig
 
 // Separable weights given as host arrays gr[win], gc[win].  dW_scratch (device, win*win floats) is
 // only needed for window sizes without a specialised kernel.
+// ctas_per_sm: 0 = as many persistent CTAs per SM as fit; > 0 caps them (room for a co-resident kernel).
+// sched (optional, CONTRAST_SCHED_WORDS device words owned by the caller): dynamic tile hand-out and an exact per-SM cap.
 int contrast_sep_launch(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C, int win,
-                        const float* gr, const float* gc, float* dW_scratch, cudaStream_t st) {
-  if (win == 48) return launch_sep_win<48, 8>(pad, out, mx, nmaps, R, C, gr, gc, st);
-  if (win == 24) return launch_sep_win<24, 8>(pad, out, mx, nmaps, R, C, gr, gc, st);
+                        const float* gr, const float* gc, float* dW_scratch, cudaStream_t st, int ctas_per_sm, unsigned* sched) {
+  if (win == 48) return launch_sep_win<48, 8>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
+  if (win == 24) return launch_sep_win<24, 8>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
   if (!dW_scratch) { set_error("contrast: window %d needs a weight scratch buffer", win); return CDS_EINVAL; }
   std::vector<float> W((size_t)win * win);
   for (int i = 0; i < win; i++) for (int j = 0; j < win; j++) W[(size_t)i * win + j] = gr[i] * gc[j];
@@ -282,7 +319,7 @@ extern "C" int cds_contrast_sep_dev(const float* pad, float* out, unsigned* out_
   gaussian_factor(win, delta, g);
   std::lock_guard<std::mutex> lk(g_mu);
   if (int e = g_w.reserve(64 * 64 * 4)) return e;
-  return contrast_sep_launch(pad, out, out_max_bits, nmaps, rows, cols, win, g, g, g_w.as<float>(), (cudaStream_t)stream);
+  return contrast_sep_launch(pad, out, out_max_bits, nmaps, rows, cols, win, g, g, g_w.as<float>(), (cudaStream_t)stream, 0, nullptr);
 }
 
 extern "C" int cds_contrast5(const double* pad, int m1, int n1, const double* W, int len, int win,
@@ -325,7 +362,7 @@ extern "C" int cds_contrast5(const double* pad, int m1, int n1, const double* W,
     const double w00 = W[(size_t)a0 * win + b0];
     for (int a = 0; a < win; a++) gr[a] = (float)W[(size_t)a * win + b0];
     for (int b = 0; b < win; b++) gc[b] = (float)(W[(size_t)a0 * win + b] / w00);
-    rc = contrast_sep_launch(g_f.as<float>(), g_o.as<float>(), nullptr, 1, R, C, win, gr, gc, g_w.as<float>(), st);
+    rc = contrast_sep_launch(g_f.as<float>(), g_o.as<float>(), nullptr, 1, R, C, win, gr, gc, g_w.as<float>(), st, 0, nullptr);
   } else {
     std::vector<float> Wf((size_t)win * win);
     for (size_t i = 0; i < Wf.size(); i++) Wf[i] = (float)W[i];

@@ -8,7 +8,7 @@
 
 namespace cds {
 int contrast_sep_launch(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C, int win,
-                        const float* gr, const float* gc, float* dW_scratch, cudaStream_t st);
+                        const float* gr, const float* gc, float* dW_scratch, cudaStream_t st, int ctas_per_sm, unsigned* sched);
 int contrast_generic_launch(const float* pad, const float* dW, float* out, unsigned* mx, int nmaps,
                             int R, int C, int win, int len, cudaStream_t st);
 void gaussian_factor(int win, double delta, float* g);
@@ -41,7 +41,7 @@ static int contrast_host(const double* map, int rows, int cols, int block_cus, i
   float g[64];
   gaussian_factor(win, delta, g);
   CDS_CUDA(cudaStreamSynchronize(st));
-  if (int e = contrast_sep_launch(g_pad.as<float>(), g_raw.as<float>(), g_keys.as<unsigned>() + 2, 1, srows, scols, win, g, g, g_W.as<float>(), st)) return e;
+  if (int e = contrast_sep_launch(g_pad.as<float>(), g_raw.as<float>(), g_keys.as<unsigned>() + 2, 1, srows, scols, win, g, g, g_W.as<float>(), st, 0, nullptr)) return e;
   if (int e = contrast_post_launch(g_raw.as<float>(), g_keys.as<unsigned>() + 2, 1, srows, scols, block_cus, rows, cols, g_out.as<float>(), 0, st)) return e;
   unsigned hk[4];
   CDS_CUDA(cudaMemcpyAsync(hf.data(), g_out.p, n * 4, cudaMemcpyDeviceToHost, st));

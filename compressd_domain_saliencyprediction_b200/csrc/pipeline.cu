@@ -24,7 +24,7 @@ int camera_motion_launch_f64(int w, int h, int nframes, const int16_t* mvx, cons
                              const uint8_t* depth, double* Vx, double* Vy, float* mvn, float* bitn, float* depn, int* cam,
                              double* ave, int* flag, int first_slot, int ring_len, cudaStream_t st);
 int contrast_sep_launch(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C, int win,
-                        const float* gr, const float* gc, float* dW_scratch, cudaStream_t st);
+                        const float* gr, const float* gc, float* dW_scratch, cudaStream_t st, int ctas_per_sm, unsigned* sched);
 void gaussian_factor(int win, double delta, float* g);
 int contrast_generic_launch(const float* pad, const float* dW, float* out, unsigned* mx, int nmaps,
                             int R, int C, int win, int len, cudaStream_t st);
@@ -67,6 +67,7 @@ struct cds_ctx {
   float *d_subD = nullptr, *d_padD = nullptr, *d_rawD = nullptr;   // depth contrast
   float *d_padM = nullptr, *d_rawM = nullptr;        // mvx | mvy: [2B]
   unsigned *d_keys = nullptr, *d_maxbits = nullptr;   // [4][B][2], [4][B]
+  unsigned* d_sched = nullptr;                        // 2 x 2048 words: tile counter + per-SM CTA counts of the two capped contrast launches
   float *d_T = nullptr;                // [9B][h4][W]
   float *d_Y = nullptr;                // [3B or 9B][H][W]
   int* d_store_index = nullptr;        // [9B]
@@ -84,6 +85,8 @@ struct cds_ctx {
   // contrast kernel start together and share every SM for their whole duration (or from join_back when no batch follows).
   struct PendingBack { bool valid = false; int slot = 0, n = 0, tag = -1; void* maps_out = nullptr; cudaEvent_t before_back = nullptr; } pb;
   int retired_tag = -1; cudaEvent_t retired_ev = nullptr;     // set when a back half has been enqueued: its tag and completion event
+  // CDS_TRACE=1: timed events around the co-scheduled kernels of the first batches, printed by cds_destroy (development aid)
+  bool trace = false; std::vector<cudaEvent_t> tr_ev; int tr_batches = 0;
   float *d_fparam = nullptr, *d_C = nullptr;         // [9][4] mean, 1/std, weight; [B][200][200]
   float *d_T2 = nullptr, *d_raw = nullptr;           // [B][200][W], [B][H][W]
   float *d_fpartial = nullptr, *d_fstats = nullptr;  // final min/max
@@ -98,10 +101,21 @@ struct cds_ctx {
   // staging for host-buffer entry points
   uint16_t* d_bytes = nullptr; int32_t* d_hdr = nullptr; int16_t* d_tok = nullptr; int64_t* d_tokbase = nullptr;
   size_t tok_cap = 0;
-  // hook API state
-  std::vector<uint16_t> h_bytes; std::vector<int32_t> h_hdr; std::vector<int16_t> h_tok; std::vector<int64_t> h_base;
-  int pending = 0, pending_first = 0, last_first = -1, last_n = 0;
-  std::vector<int> h_cam;
+  // ---- hook API state (cds_acquire_frame_buffers / cds_submit_frame / cds_get_map / cds_flush) ----
+  // Two PINNED staging batches: the decoder thread writes picture k+1's tokens straight into one while the other is on its way to
+  // the device (asynchronous H2D + kernel chain on the stream; nothing waits for the GPU until a map is asked for).
+  struct HookStage {
+    uint16_t* bytes = nullptr; int32_t* hdr = nullptr; int16_t* tok = nullptr; int64_t* base = nullptr;   // cudaHostAlloc
+    size_t tok_cap = 0, tok_used = 0; int n = 0, first = 0; cudaEvent_t h2d_done = nullptr; bool in_flight = false;
+  } hs[2];
+  // Two PINNED result batches (maps + camera motion): a batch's maps stay retrievable until two further batches were launched.
+  struct HookOut {
+    void* maps = nullptr; int* cam = nullptr; int first = -1, n = 0; cudaEvent_t ready = nullptr, cam_ready = nullptr; bool copy_queued = false;
+  } ho[2];
+  int* d_cam_hook = nullptr;           // [2][B][2]
+  int hs_cur = 0, ho_cur = 0; bool hook_ready = false, acquired = false;
+  size_t hook_pic_tok = 0;             // worst-case tokens of one picture (1300 per CTU)
+  int pending = 0, pending_first = 0, last_first = -1, last_n = 0;   // pending: pictures submitted but not launched yet
   cudaStream_t stream = nullptr;
   int nblk = 0, nblk2 = 0, nblkf = 0;
   std::vector<void*> allocs;
@@ -131,6 +145,30 @@ static void prof_mark(cds_ctx* c, int stage, cudaStream_t st) {
 }
 
 namespace {
+
+enum { TR_MID = 0, TR_C48_START, TR_C48_END, TR_FRONT_END, TR_SVM_START, TR_SVM_END, TR_BACK_END, TR_N };
+constexpr int TR_MAX_BATCHES = 24;
+void trace_mark(cds_ctx* c, int batch, int which, cudaStream_t st) {
+  if (!c->trace || batch < 0 || batch >= TR_MAX_BATCHES) return;
+  if (c->tr_ev.empty()) { c->tr_ev.resize((size_t)TR_MAX_BATCHES * TR_N, nullptr); for (auto& e : c->tr_ev) cudaEventCreate(&e); }
+  cudaEventRecord(c->tr_ev[(size_t)batch * TR_N + which], st);
+}
+void trace_dump(cds_ctx* c) {
+  if (!c->trace || c->tr_ev.empty()) return;
+  cudaDeviceSynchronize();
+  static const char* nm[TR_N] = {"mid", "c48_start", "c48_end", "front_end", "svm_start", "svm_end", "back_end"};
+  for (int b = 1; b < std::min(c->tr_batches, TR_MAX_BATCHES); b++) {
+    fprintf(stderr, "[cds trace] batch %2d (ms after its mid-point; svm/back = previous batch's):", b);
+    for (int k = 0; k < TR_N; k++) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, c->tr_ev[(size_t)b * TR_N + TR_MID], c->tr_ev[(size_t)b * TR_N + k]) == cudaSuccess) fprintf(stderr, " %s %.3f", nm[k], t);
+    }
+    fprintf(stderr, "\n");
+  }
+  cudaGetLastError();
+  for (auto& e : c->tr_ev) cudaEventDestroy(e);
+  c->tr_ev.clear();
+}
 
 template <typename T>
 int dalloc(cds_ctx* c, T** p, size_t count) {
@@ -468,6 +506,8 @@ int build_operators(cds_ctx* c) {
 
 }  // namespace
 
+namespace { int join_back(cds_ctx* c, cudaStream_t st); void hook_reset(cds_ctx* c); void hook_free(cds_ctx* c); }
+
 extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   if (int e = ensure_device()) return e;
   if (!p || !out) { set_error("cds_create: null argument"); return CDS_EINVAL; }
@@ -519,7 +559,7 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   A(d_subB, (size_t)B * sbR * sbC); A(d_padB, (size_t)B * (sbR + 4) * (sbC + 4)); A(d_rawB, (size_t)B * sbR * sbC);
   A(d_subD, (size_t)B * sdR * sdC); A(d_padD, (size_t)B * (sdR + 24) * (sdC + 24)); A(d_rawD, (size_t)B * sdR * sdC);
   A(d_padM, (size_t)2 * B * (h4 + 48) * (w4 + 48)); A(d_rawM, (size_t)2 * B * n4);
-  A(d_keys, (size_t)4 * B * 2); A(d_maxbits, (size_t)4 * B); A(d_w5, 64 * 64);
+  A(d_keys, (size_t)4 * B * 2); A(d_maxbits, (size_t)4 * B); A(d_w5, 64 * 64); A(d_sched, 4096);
   A(d_T, (size_t)9 * B * h4 * W);
   A(d_Y, (size_t)(p->use_rbf ? 3 : 9) * B * HW);
   A(d_store_index, (size_t)9 * B);
@@ -557,6 +597,7 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   for (int b = 0; b < 2 && !e; b++)
     if (cudaEventCreateWithFlags(&c->ev_front[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_back[b], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
   { const char* ov = getenv("CDS_OVERLAP"); c->overlap = !(ov && ov[0] == '0') && p->use_rbf == CDS_FUSION_RBF; }
+  { const char* tr = getenv("CDS_TRACE"); c->trace = tr && tr[0] == '1'; }
 #undef A
   float* d_fparam = nullptr;
   if (!e && !fm) e = dalloc(c, &d_fparam, 36);
@@ -574,8 +615,6 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
     if (cudaMemcpy(c->d_store_index, si.data(), si.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("cudaMemcpy store_index"); e = CDS_ECUDA; }
   }
   if (e) { cds_destroy(c); return e; }
-  c->h_bytes.resize((size_t)B * c->nctu); c->h_hdr.resize((size_t)B * c->nctu * 4); c->h_base.assign(B + 1, 0);
-  c->h_cam.assign((size_t)2 * B, 0);
   cds_seek(c, 0);
   *out = c;
   return CDS_OK;
@@ -583,6 +622,7 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
 
 extern "C" void cds_destroy(cds_ctx* c) {
   if (!c) return;
+  trace_dump(c);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->back_stream) { cudaStreamSynchronize(c->back_stream); cudaStreamDestroy(c->back_stream); }
@@ -593,6 +633,7 @@ extern "C" void cds_destroy(cds_ctx* c) {
   for (int b = 0; b < 2; b++) { if (c->ev_front[b]) cudaEventDestroy(c->ev_front[b]); if (c->ev_back[b]) cudaEventDestroy(c->ev_back[b]); }
   for (int b = 0; b < 2; b++) { if (c->ev_done[b]) cudaEventDestroy(c->ev_done[b]); if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); }
   if (c->h_cam_pin) cudaFreeHost(c->h_cam_pin);
+  hook_free(c);
   fast_destroy(c->fast);
   for (void* q : c->allocs) cudaFree(q);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -603,12 +644,14 @@ extern "C" void cds_destroy(cds_ctx* c) {
 
 extern "C" int cds_seek(cds_ctx* c, int poc) {
   if (!c || poc < 0) { set_error("cds_seek: bad arguments"); return CDS_EINVAL; }
+  join_back(c, c->stream);
   cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->fast) {
     if (int e = fast_clear(c->fast, c->stream)) return e;
     cudaStreamSynchronize(c->stream);
     c->next_poc = poc; c->pending = 0; c->pending_first = poc; c->last_first = -1; c->last_n = 0;
-    c->h_tok.clear();
+    hook_reset(c);
     return CDS_OK;
   }
   const size_t rb = (size_t)c->RL * c->n4 * 4;
@@ -618,7 +661,7 @@ extern "C" int cds_seek(cds_ctx* c, int poc) {
   for (double* r : {c->r_Vx, c->r_Vy}) CDS_CUDA(cudaMemset(r, 0, 2 * rb));
   CDS_CUDA(cudaMemset(c->r_cam, 0, (size_t)c->RL * 8));
   c->next_poc = poc; c->pending = 0; c->pending_first = poc; c->last_first = -1; c->last_n = 0;
-  c->h_tok.clear();
+  hook_reset(c);
   return CDS_OK;
 }
 extern "C" int cds_reset(cds_ctx* c) { return cds_seek(c, 0); }
@@ -655,7 +698,9 @@ int launch_normalize(cds_ctx* c, int n, void* out, cudaStream_t st) {
 int launch_back_rbf(cds_ctx* c, int slot, int n, void* maps_out, cudaStream_t sb, bool mark) {
   const int H = c->h, W = c->w;
   if (mark) prof_mark(c, ST_SVM, sb);
+  trace_mark(c, c->tr_batches, TR_SVM_START, sb);
   if (int e = svm_predict_launch(c->p.model, c->d_xsvm2[slot], (long)n * 40000, c->d_dec, sb)) return e;
+  trace_mark(c, c->tr_batches, TR_SVM_END, sb);
   if (mark) prof_mark(c, ST_FINAL, sb);
   dec_minmax_norm_kernel<<<n, 1024, 0, sb>>>(c->d_dec, c->d_C);
   CDS_LAUNCH_CHECK();
@@ -681,6 +726,7 @@ int flush_pending_back(cds_ctx* c, cudaEvent_t with) {
   if (with) CDS_CUDA(cudaStreamWaitEvent(sb, with, 0));
   if (pb.before_back) CDS_CUDA(cudaStreamWaitEvent(sb, pb.before_back, 0));
   if (int e = launch_back_rbf(c, pb.slot, pb.n, pb.maps_out, sb, false)) return e;
+  trace_mark(c, c->tr_batches, TR_BACK_END, sb);
   CDS_CUDA(cudaEventRecord(c->ev_back[pb.slot], sb));
   c->retired_tag = pb.tag; c->retired_ev = c->ev_back[pb.slot];
   return CDS_OK;
@@ -726,6 +772,15 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));      // the back half of batch i-2 has finished reading xsvm[slot]
   const int h4 = c->h4, w4 = c->w4, n4 = c->n4, H = c->h, W = c->w, RL = c->RL;
   const float* fparam = c->d_fparam;
+  // Where the previous batch's deferred back half (persistent MUFU-bound SVM, then the final-map chain) joins this batch's front
+  // half: 0 = at its start, beside the latency / bandwidth-bound stages (a), (c), smoothing, threshold, temporal; 1 = at the
+  // mid-point, beside the FP32-bound contrast kernels (then capped to CDS_CO_CTAS CTAs per SM); 2 = after the contrast kernels.
+  static const int back_at = [] { const char* e = getenv("CDS_BACK_AT"); const int v = e ? atoi(e) : 0; return v < 0 || v > 2 ? 0 : v; }();
+  if (ov && c->pb.valid && back_at == 0) {
+    trace_mark(c, c->tr_batches, TR_MID, st);
+    CDS_CUDA(cudaEventRecord(c->ev_mid, st));
+    if (int e = flush_pending_back(c, c->ev_mid)) return e;
+  }
   if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, st)) return e;
   // ---- thresholded smoothed maps and temporal features -> X slots 0,3,6 / 1,4,7 ----
   prof_mark(c, ST_THRESH, st);
@@ -756,10 +811,16 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
       CDS_LAUNCH_CHECK();
       if (int e = contrast_prep_f64_launch(c->d_cxy, 2 * n, h4, w4, 24, c->d_keys64, c->d_padM, st)) return e;
     }
-    // ---- mid-point: the previous batch's SVM starts together with this batch's contrast kernels ----
-    if (ov && c->pb.valid) {
+    // ---- mid-point: the previous batch's SVM starts together with this batch's contrast kernels.  Both are persistent; the
+    //      contrast kernels then keep to `co_ctas` CTAs per SM, which leaves the shared memory, registers and warp slots of one
+    //      SVM CTA free on every SM whichever of the two is placed first ----
+    int co_ctas = 0;
+    if (back_at == 1) trace_mark(c, c->tr_batches, TR_MID, st);
+    if (ov && c->pb.valid && back_at == 1) {
       CDS_CUDA(cudaEventRecord(c->ev_mid, st));
       if (int e = flush_pending_back(c, c->ev_mid)) return e;
+      static const int co = [] { const char* e = getenv("CDS_CO_CTAS"); const int v = e ? atoi(e) : 3; return v < 0 ? 0 : v; }();
+      co_ctas = co;
     }
     // bit: 5x5 window on the CTU grid
     prof_mark(c, ST_CONTRAST_W5, st);
@@ -767,11 +828,18 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     // depth: 24x24 window on the 8-px grid
     prof_mark(c, ST_CONTRAST_W24, st);
     gaussian_factor(24, 13.0, g);
-    if (int e = contrast_sep_launch(c->d_padD, c->d_rawD, mD, n, sdR, sdC, 24, g, g, nullptr, st)) return e;
+    if (int e = contrast_sep_launch(c->d_padD, c->d_rawD, mD, n, sdR, sdC, 24, g, g, nullptr, st, co_ctas, co_ctas ? c->d_sched : nullptr)) return e;
     // mvx | mvy as 2n maps in one launch: 48x48 window on the 4-px grid (the dominant FP32 kernel)
     prof_mark(c, ST_CONTRAST_W48, st);
+    trace_mark(c, c->tr_batches, TR_C48_START, st);
     gaussian_factor(48, 11.0, g);
-    if (int e = contrast_sep_launch(c->d_padM, c->d_rawM, mX, 2 * n, h4, w4, 48, g, g, nullptr, st)) return e;   // mX,mY contiguous
+    if (int e = contrast_sep_launch(c->d_padM, c->d_rawM, mX, 2 * n, h4, w4, 48, g, g, nullptr, st, co_ctas, co_ctas ? c->d_sched + 2048 : nullptr)) return e;   // mX,mY contiguous
+    trace_mark(c, c->tr_batches, TR_C48_END, st);
+    if (ov && c->pb.valid && back_at == 2) {
+      trace_mark(c, c->tr_batches, TR_MID, st);
+      CDS_CUDA(cudaEventRecord(c->ev_mid, st));
+      if (int e = flush_pending_back(c, c->ev_mid)) return e;
+    }
     prof_mark(c, ST_CONTRAST_POST, st);
     if (int e = contrast_post_launch(c->d_rawB, mB, n, sbR, sbC, 16, h4, w4, c->d_X, 5, st)) return e;
     if (int e = contrast_post_launch(c->d_rawD, mD, n, sdR, sdC, 2, h4, w4, c->d_X, 8, st)) return e;
@@ -809,6 +877,8 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
       CDS_LAUNCH_CHECK();
     }
     if (ov) {          // the back half is deferred to the next batch's mid-point (or to join_back)
+      trace_mark(c, c->tr_batches, TR_FRONT_END, st);
+      c->tr_batches++;
       CDS_CUDA(cudaEventRecord(c->ev_front[slot], st));
       c->pb.valid = true; c->pb.slot = slot; c->pb.n = n; c->pb.tag = tag; c->pb.maps_out = maps_out; c->pb.before_back = before_back;
       return CDS_OK;
@@ -1043,18 +1113,138 @@ extern "C" int cds_probe_run_sum(const float* vals, int gh, int gw, int rows, in
   return fast_probe_run_sum(vals, gh, gw, rows, cols, ms, t, sum, count);
 }
 
-// ---- hook-style API (TDecGop.cpp:270-332): one picture at a time, batched internally ----
-static int hook_flush(cds_ctx* c) {
-  if (c->pending == 0) return CDS_OK;
-  const int n = c->pending, first = c->pending_first;
-  c->h_base[n] = (int64_t)c->h_tok.size();
-  c->pending = 0;
-  std::vector<int> cam((size_t)2 * n);
-  int e = process_host(c, first, n, c->h_bytes.data(), c->h_hdr.data(), c->h_tok.data(), c->h_base.data(), c->h_tok.size(),
-                       nullptr, cam.data());
-  c->h_tok.clear();
-  if (e) return e;
-  c->h_cam = cam;
+// ---- hook-style API (TDecCu.cpp:153-289 capture, TDecGop.cpp:270-332 per-slice tail): one picture at a time, batched internally,
+//      asynchronous: pinned staging in, stream-ordered H2D + kernels + D2H into pinned result buffers, no host wait before cds_get_map ----
+namespace {
+
+void hook_reset(cds_ctx* c) {
+  for (auto& S : c->hs) { S.n = 0; S.tok_used = 0; S.in_flight = false; }
+  for (auto& O : c->ho) { O.first = -1; O.n = 0; O.copy_queued = false; }
+  c->acquired = false;
+}
+
+void hook_free(cds_ctx* c) {
+  for (auto& S : c->hs) {
+    if (S.bytes) cudaFreeHost(S.bytes); if (S.hdr) cudaFreeHost(S.hdr); if (S.tok) cudaFreeHost(S.tok); if (S.base) cudaFreeHost(S.base);
+    if (S.h2d_done) cudaEventDestroy(S.h2d_done);
+    S = cds_ctx::HookStage();
+  }
+  for (auto& O : c->ho) {
+    if (O.maps) cudaFreeHost(O.maps); if (O.cam) cudaFreeHost(O.cam);
+    if (O.ready) cudaEventDestroy(O.ready); if (O.cam_ready) cudaEventDestroy(O.cam_ready);
+    O = cds_ctx::HookOut();
+  }
+  c->hook_ready = false;
+}
+
+// first use of the hook API: pinned staging / result buffers (contexts that only see the batch entry points never pay for them)
+int hook_init(cds_ctx* c) {
+  if (c->hook_ready) return CDS_OK;
+  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
+  c->hook_pic_tok = (size_t)c->nctu * 1300;                  // worst case 1237 tokens per CTU (85 + 256 + 896)
+  const size_t cap = (size_t)c->B * c->nctu * 320 + c->hook_pic_tok;   // typical streams: < 320 per CTU; a batch closes early when a worst-case picture might not fit
+  cudaError_t e = cudaSuccess;
+  for (auto& S : c->hs) {
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&S.bytes, (size_t)c->B * c->nctu * 2, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&S.hdr, (size_t)c->B * c->nctu * 16, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&S.tok, cap * 2, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&S.base, (size_t)(c->B + 1) * 8, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.h2d_done, cudaEventDisableTiming);
+    S.tok_cap = cap;
+  }
+  for (auto& O : c->ho) {
+    if (e == cudaSuccess) e = cudaHostAlloc(&O.maps, (size_t)c->B * px, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&O.cam, (size_t)c->B * 8, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&O.ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&O.cam_ready, cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { set_error("hook buffers: %s", cudaGetErrorString(e)); hook_free(c); return CDS_ENOMEM; }
+  if (cap > c->tok_cap) {                                     // device token staging holds a whole staging batch
+    CDS_CUDA(cudaStreamSynchronize(c->stream));
+    void* q = nullptr;
+    if (cudaMalloc(&q, cap * 2 + 256) != cudaSuccess) { set_error("hook buffers: cannot stage %zu tokens on the device", cap); hook_free(c); return CDS_ENOMEM; }
+    for (void*& a : c->allocs) if (a == (void*)c->d_tok) { cudaFree(a); a = q; }
+    c->d_tok = reinterpret_cast<int16_t*>(q); c->tok_cap = cap;
+  }
+  if (!c->d_cam_hook) if (int er = dalloc(c, &c->d_cam_hook, (size_t)4 * c->B)) { hook_free(c); return er; }
+  hook_reset(c);
+  c->hook_ready = true;
+  return CDS_OK;
+}
+
+// a back half has been enqueued (run_batch / join_back set retired_tag = result slot): queue its maps for the host
+int hook_drain_retired(cds_ctx* c) {
+  if (c->retired_tag < 0) return CDS_OK;
+  const int slot = c->retired_tag & 1, buf = c->retired_tag >> 1;
+  c->retired_tag = -1;
+  cds_ctx::HookOut& O = c->ho[slot];
+  cudaStream_t cs = c->copy_stream;
+  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
+  if (c->retired_ev) CDS_CUDA(cudaStreamWaitEvent(cs, c->retired_ev, 0));
+  else { CDS_CUDA(cudaEventRecord(c->ev_done[buf], c->stream)); CDS_CUDA(cudaStreamWaitEvent(cs, c->ev_done[buf], 0)); }
+  CDS_CUDA(cudaMemcpyAsync(O.maps, c->d_out[buf], (size_t)O.n * px, cudaMemcpyDeviceToHost, cs));
+  CDS_CUDA(cudaEventRecord(c->ev_copied[buf], cs));
+  CDS_CUDA(cudaEventRecord(O.ready, cs));
+  O.copy_queued = true;
+  return CDS_OK;
+}
+
+// enqueue the staged pictures: H2D, kernel chain, D2H — and return
+int hook_launch(cds_ctx* c) {
+  cds_ctx::HookStage& S = c->hs[c->hs_cur];
+  if (S.n == 0) return CDS_OK;
+  cudaStream_t st = c->stream;
+  const int n = S.n, first = S.first;
+  S.base[n] = (int64_t)S.tok_used;
+  // whatever happens below, these pictures are consumed: the next picture expected is first + n (a failed batch does not wedge the context)
+  c->pending = 0; c->pending_first = first + n; c->acquired = false;
+  c->hs_cur ^= 1;
+  int rc = CDS_OK;
+  auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && !rc) { set_error("cds_submit_frame: %s: %s", what, cudaGetErrorString(e)); rc = CDS_ECUDA; } };
+  cu(cudaMemcpyAsync(c->d_bytes, S.bytes, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, st), "copy in");
+  cu(cudaMemcpyAsync(c->d_hdr, S.hdr, (size_t)n * c->nctu * 16, cudaMemcpyHostToDevice, st), "copy in");
+  cu(cudaMemcpyAsync(c->d_tok, S.tok, S.tok_used * 2, cudaMemcpyHostToDevice, st), "copy in");
+  cu(cudaMemcpyAsync(c->d_tokbase, S.base, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "copy in");
+  cu(cudaEventRecord(S.h2d_done, st), "event");
+  S.in_flight = true; S.n = 0; S.tok_used = 0;
+  if (rc) return rc;
+  const int slot = c->ho_cur; c->ho_cur ^= 1;
+  const int buf = c->out_flip; c->out_flip ^= 1;
+  cds_ctx::HookOut& O = c->ho[slot];
+  O.first = first; O.n = n; O.copy_queued = false;
+  int* dcam = c->d_cam_hook + (size_t)slot * 2 * c->B;
+  c->retired_tag = -1;
+  rc = run_batch(c, first, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out[buf], dcam, st, c->ev_copied[buf], slot | (buf << 1));
+  if (rc) { O.first = -1; O.n = 0; return rc; }
+  // camera motion: gathered by the front half on st; its copy stays on st, so the gather of batch k+2 (same slot) cannot overtake it
+  cu(cudaMemcpyAsync(O.cam, dcam, (size_t)n * 8, cudaMemcpyDeviceToHost, st), "copy out");
+  cu(cudaEventRecord(O.cam_ready, st), "event");
+  if (rc) return rc;
+  if (int e = hook_drain_retired(c)) return e;
+  c->next_poc = first + n;
+  c->last_first = first; c->last_n = n; c->last_buf = buf;
+  return CDS_OK;
+}
+
+}  // namespace
+
+/* Hook 2: pinned buffers for the NEXT picture (TDecCu::decompressCU / MVoutput write their tokens here instead of the
+ * float[LCUNUM][1000] statics).  Valid until the matching cds_submit_frame. */
+extern "C" int cds_acquire_frame_buffers(cds_ctx* c, uint16_t** ctu_bytes, int32_t** hdr, int16_t** tok, size_t* tok_capacity) {
+  if (int e = ensure_device()) return e;
+  if (!c || !ctu_bytes || !hdr || !tok) { set_error("cds_acquire_frame_buffers: null argument"); return CDS_EINVAL; }
+  if (int e = hook_init(c)) return e;
+  cds_ctx::HookStage* S = &c->hs[c->hs_cur];
+  if (S->n > 0 && S->tok_cap - S->tok_used < c->hook_pic_tok) {          // a worst-case picture might not fit: close the batch early
+    if (int e = hook_launch(c)) return e;
+    S = &c->hs[c->hs_cur];
+  }
+  if (S->n == 0 && S->in_flight) { CDS_CUDA(cudaEventSynchronize(S->h2d_done)); S->in_flight = false; }   // its previous batch has left for the device
+  *ctu_bytes = S->bytes + (size_t)S->n * c->nctu;
+  *hdr = S->hdr + (size_t)S->n * c->nctu * 4;
+  *tok = S->tok + S->tok_used;
+  if (tok_capacity) *tok_capacity = S->tok_cap - S->tok_used;
+  c->acquired = true;
   return CDS_OK;
 }
 
@@ -1062,31 +1252,65 @@ extern "C" int cds_submit_frame(cds_ctx* c, int poc, const uint16_t* ctu_bytes, 
   if (int e = ensure_device()) return e;
   if (!c || !ctu_bytes || !hdr || !tok) { set_error("cds_submit_frame: null argument"); return CDS_EINVAL; }
   if (poc != c->pending_first + c->pending) { set_error("cds_submit_frame: pictures must arrive in POC order (expected %d, got %d)", c->pending_first + c->pending, poc); return CDS_EINVAL; }
-  const int k = c->pending;
-  memcpy(c->h_bytes.data() + (size_t)k * c->nctu, ctu_bytes, (size_t)c->nctu * 2);
-  memcpy(c->h_hdr.data() + (size_t)k * c->nctu * 4, hdr, (size_t)c->nctu * 16);
-  c->h_base[k] = (int64_t)c->h_tok.size();
-  c->h_tok.insert(c->h_tok.end(), tok, tok + ntok);
-  c->pending = k + 1;
-  if (c->pending == c->B) { if (int e = hook_flush(c)) return e; c->pending_first = poc + 1; }
+  if (ntok > (size_t)c->nctu * 1300) { set_error("cds_submit_frame: %zu tokens for %d CTUs", ntok, c->nctu); return CDS_EFORMAT; }
+  if (int e = hook_init(c)) return e;
+  uint16_t* sb; int32_t* sh; int16_t* stk; size_t cap;
+  const bool was_acquired = c->acquired;
+  if (int e = cds_acquire_frame_buffers(c, &sb, &sh, &stk, &cap)) return e;      // (re)computes the slot of this picture; may close a full batch
+  if (!(was_acquired && ctu_bytes == sb && hdr == sh && tok == stk)) {          // caller's own buffers: one copy into the pinned slot
+    memcpy(sb, ctu_bytes, (size_t)c->nctu * 2);
+    memcpy(sh, hdr, (size_t)c->nctu * 16);
+    memcpy(stk, tok, ntok * 2);
+  }
+  cds_ctx::HookStage& S = c->hs[c->hs_cur];
+  if (S.n == 0) S.first = poc;
+  S.base[S.n] = (int64_t)S.tok_used;
+  S.tok_used += ntok; S.n++;
+  c->pending = S.n; c->pending_first = S.first; c->acquired = false;
+  if (S.n == c->B) return hook_launch(c);
   return CDS_OK;
 }
 
+/* Enqueue whatever is staged (a partial batch) and every deferred back half; does not wait for the GPU. */
 extern "C" int cds_flush(cds_ctx* c) {
   if (!c) { set_error("cds_flush: null context"); return CDS_EINVAL; }
-  const int n = c->pending, first = c->pending_first;
-  if (int e = hook_flush(c)) return e;
-  c->pending_first = first + n;
+  if (c->hook_ready) if (int e = hook_launch(c)) return e;
+  c->retired_tag = -1;
+  if (int e = join_back(c, c->stream)) return e;
+  if (c->hook_ready) if (int e = hook_drain_retired(c)) return e;
   return CDS_OK;
 }
 
 extern "C" int cds_get_map(cds_ctx* c, int poc, void* dst, int* cam_xy) {
   if (!c || !dst) { set_error("cds_get_map: null argument"); return CDS_EINVAL; }
-  if (poc >= c->pending_first && poc < c->pending_first + c->pending) { if (int e = cds_flush(c)) return e; }
+  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
+  if (c->hook_ready) {
+    if (poc >= c->pending_first && poc < c->pending_first + c->pending) { if (int e = hook_launch(c)) return e; }
+    for (auto& O : c->ho) {
+      if (poc < O.first || poc >= O.first + O.n) continue;
+      if (!O.copy_queued) {                                   // its back half is still deferred: no batch followed yet
+        c->retired_tag = -1;
+        if (int e = join_back(c, c->stream)) return e;
+        if (int e = hook_drain_retired(c)) return e;
+      }
+      if (!O.copy_queued) { set_error("cds_get_map: picture %d was never rendered", poc); return CDS_EINVAL; }
+      CDS_CUDA(cudaEventSynchronize(O.ready));
+      CDS_CUDA(cudaEventSynchronize(O.cam_ready));
+      int herr = 0;                                           // malformed token streams are reported where the maps are collected
+      CDS_CUDA(cudaMemcpy(&herr, c->d_err, 4, cudaMemcpyDeviceToHost));
+      if (herr) { CDS_CUDA(cudaMemset(c->d_err, 0, 4)); set_error("cds_get_map: malformed CU token stream at or before picture %d", poc); return CDS_EFORMAT; }
+      memcpy(dst, (const char*)O.maps + (size_t)(poc - O.first) * px, px);
+      if (cam_xy) { cam_xy[0] = O.cam[2 * (poc - O.first)]; cam_xy[1] = O.cam[2 * (poc - O.first) + 1]; }
+      return CDS_OK;
+    }
+  }
+  if (c->hook_ready && (c->ho[0].first >= 0 || c->ho[1].first >= 0)) {
+    set_error("cds_get_map: picture %d is not in the two result batches that stay retrievable", poc); return CDS_EINVAL;
+  }
+  // batch entry points with maps_out == NULL leave their last batch on the device
   if (poc < c->last_first || poc >= c->last_first + c->last_n) {
     set_error("cds_get_map: picture %d is not in the most recent batch [%d, %d)", poc, c->last_first, c->last_first + c->last_n); return CDS_EINVAL;
   }
-  const size_t px = (size_t)c->HW * (c->p.out_u8 ? 1 : 4);
   CDS_CUDA(cudaMemcpy(dst, (char*)c->d_out[c->last_buf] + (size_t)(poc - c->last_first) * px, px, cudaMemcpyDeviceToHost));
   if (cam_xy && c->fast) return fast_get_cam(c->fast, poc, cam_xy);
   if (cam_xy) CDS_CUDA(cudaMemcpy(cam_xy, c->r_cam + 2 * (poc % c->RL), 8, cudaMemcpyDeviceToHost));

@@ -100,7 +100,23 @@ class SaliencyClip:
         check(lib().cds_clip_context(self._h, int(first_poc), F, _ptr(byts), _ptr(hdr), _ptr(tok), _ptr(tok_base), tok.size),
               "cds_clip_context")
 
-    # hook-style surface (TDecGop.cpp:270-332): one picture per call
+    # hook-style surface (TDecCu.cpp:153-289 capture, TDecGop.cpp:270-332 per-slice tail): one picture per call
+    def acquire_frame_buffers(self):
+        """Pinned views (ctu_bytes[nctu] u16, hdr[nctu][4] i32, tok[capacity] i16) for the next picture: fill them in place and
+        pass them to submit_frame_acquired(poc, ntok) — the zero-copy hand-off the decoder hook uses."""
+        pb, ph, pt, cap = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_size_t()
+        check(lib().cds_acquire_frame_buffers(self._h, C.byref(pb), C.byref(ph), C.byref(pt), C.byref(cap)), "cds_acquire_frame_buffers")
+        n = nctu(self.w, self.h)
+        byts = np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_uint16)), (n,))
+        hdr = np.ctypeslib.as_array(C.cast(ph, C.POINTER(C.c_int32)), (n, 4))
+        tok = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int16)), (cap.value,))
+        self._acq = (pb, ph, pt)
+        return byts, hdr, tok
+
+    def submit_frame_acquired(self, poc, ntok):
+        pb, ph, pt = self._acq
+        check(lib().cds_submit_frame(self._h, int(poc), pb, ph, pt, int(ntok)), "cds_submit_frame")
+
     def submit_frame(self, poc, ctu_bytes, hdr, tok):
         hdr = np.ascontiguousarray(hdr, np.int32); tok = np.ascontiguousarray(tok, np.int16)
         byts = np.ascontiguousarray(ctu_bytes, np.uint16)

@@ -141,14 +141,26 @@ typedef struct {
 
 int cds_create(const cds_params* p, cds_ctx** out);
 void cds_destroy(cds_ctx* ctx);
-/* Hook 3 (TDecGop.cpp:270-332): hand one picture's packed syntax (host memory) to the GPU. Pictures
- * must arrive in POC order starting at 0.  Asynchronous: returns after enqueueing. */
+/* Hook 2 (TDecCu::decompressCU / MVoutput, TDecCu.cpp:153-161, 165-289): PINNED host buffers for the next picture's packed
+ * syntax, owned by the context — ctu_bytes[nctu], hdr[nctu][4], tok[*tok_capacity] (room for a worst-case picture, 1300 tokens
+ * per CTU).  The decoder thread appends its int16 tokens and per-CTU counts there directly (no 999-terminated float[1000] rows,
+ * no conversion pass) and then calls cds_submit_frame with these same pointers, which makes the hand-off zero-copy.  The pointers
+ * are valid until that cds_submit_frame.  May close a batch early (and launch it) when the token pool is nearly full. */
+int cds_acquire_frame_buffers(cds_ctx* ctx, uint16_t** ctu_bytes, int32_t** hdr, int16_t** tok, size_t* tok_capacity);
+/* Hook 3 (the per-slice tail of TDecGop::decompressSlice, TDecGop.cpp:270-332): hand one picture's packed syntax to the GPU.
+ * Pictures must arrive in POC order (starting at 0 or at the cds_seek position).  With the pointers of
+ * cds_acquire_frame_buffers nothing is copied; any other host memory is copied once into the pinned staging batch.
+ * ASYNCHRONOUS: the call only records the picture; when a batch of max_batch pictures is complete it enqueues the host->device
+ * copies, the kernel chain and the device->host copy of the maps on the context's streams and returns without waiting for the
+ * GPU (the decoder thread goes on parsing the next pictures while the batch runs). */
 int cds_submit_frame(cds_ctx* ctx, int poc, const uint16_t* ctu_bytes, const int32_t* hdr,
                      const int16_t* tok, size_t ntok);
-/* Blocks until picture `poc` is finished and copies its saliency map (h x w, row-major; FP32 or u8
- * according to out_u8) and camera motion (may be NULL) to host memory. */
+/* Waits until picture `poc` is finished (only for its own batch) and copies its saliency map (h x w, row-major; FP32 or u8
+ * according to out_u8) and camera motion (may be NULL) out of the context's pinned result buffer.  A still-staged partial batch
+ * that contains `poc` is launched first.  The maps of a batch stay retrievable until two further batches have been launched.
+ * A malformed token stream in the batch is reported here (CDS_EFORMAT). */
 int cds_get_map(cds_ctx* ctx, int poc, void* dst, int* cam_xy);
-/* Flush any partially filled batch. */
+/* Launch any partially filled batch and every deferred stage; does not wait for the GPU (cds_get_map does). */
 int cds_flush(cds_ctx* ctx);
 /* Batch entry points used by bench.py.  Process `nframes` pictures [first .. first+nframes) whose
  * packed syntax is resident on the DEVICE (dev pointers; layout as cds_getframe_dev, ctu_bytes

@@ -2,14 +2,19 @@
  *
  * Header-only C++ (no CUDA, no link-time dependency: the library is dlopen'ed), meant to be included by the
  * reference's TLibDecoder/TDecGop.cpp in place of its OpenCV saliency block (TDecGop.cpp:47-118 globals,
- * :225-333 per-slice block).  The capture hooks of the reference stay as they are
- * (TDecSlice.cpp:333-341 bytes per CTU, TDecCu.cpp:153-289 CU / PU / MV token streams into the statics
- * TDecCu::bits / MV / CUPU / Pred, TDecCu.h:100-106); once per slice this header
- *   1. converts those statics to the packed wire format  (cds_syntax_pack_ref),
- *   2. hands the picture to the GPU                      (cds_submit_frame, returns immediately),
- *   3. drains finished batches                           (cds_get_map) into <CDS_OUT> (raw maps, POC order),
- * and flushes the tail when the process exits.  It also keeps two clocks, so HM's CABAC parse / reconstruction
- * (the host producer) is timed separately from the saliency hand-off, as the north star asks.
+ * :225-333 per-slice block) and by TLibDecoder/TDecCu.cpp for the capture hook.
+ *
+ * Capture (hook 2, TDecCu::decompressCU / MVoutput, TDecCu.cpp:153-289): instead of the float[LCUNUM][1000] statics
+ * TDecCu::MV / CUPU / Pred with their 999 terminators (TDecCu.h:100-106), the walk appends int16 tokens to three small
+ * per-CTU scratch arrays and CdsHmHook::onCtu() copies them, with their lengths and the CTU's byte count
+ * (TDecSlice.cpp:333-341), straight into the PINNED staging buffers the library handed out (cds_acquire_frame_buffers).
+ * Hand-off (hook 3, the tail of TDecGop::decompressSlice, TDecGop.cpp:270-332): CdsHmHook::onSliceDone() calls
+ * cds_submit_frame with those same pointers (zero copy; asynchronous: the GPU works on batch k while HM parses batch k+1)
+ * and drains the maps of the batch BEFORE the one just launched (cds_get_map waits for that batch only) into <CDS_OUT>
+ * (raw maps, POC order); the tail is drained when the process exits.  Two clocks keep HM's CABAC parse / reconstruction
+ * (the host producer) apart from the saliency hand-off + GPU wait, as the north star asks.
+ * CdsHmHook::onSlice() is the older entry that converts the reference's statics (cds_syntax_pack_ref) — kept for decoders that
+ * leave TDecCu.cpp untouched.
  *
  * Environment:
  *   CDS_LIB        path of libcds_b200.so                       (required)
@@ -35,7 +40,36 @@
 
 class CdsHmHook {
  public:
-  /* MV / Pred / CUPU: the reference's float[nctu][1000] statics (999-terminated); bits: float[nctu]. */
+  /* Hook 2, once per CTU from TDecCu::decompressCU: the three token streams of CTU `addr` (int16, no terminators) and its bytes. */
+  void onCtu(int width, int height, int nctu, int addr, int bytes, const short* cupu, int ncupu, const short* pred, int npred, const short* mv, int nmv) {
+    const double t0 = now();
+    if (!open(width, height, nctu)) return;
+    if (!acq_) {
+      if (!acquire_ || acquire_(ctx_, &a_bytes_, &a_hdr_, &a_tok_, &a_cap_) != CDS_OK) { fail("cds_acquire_frame_buffers"); return; }
+      acq_ = true; ntok_ = 0;
+    }
+    if (addr < 0 || addr >= nctu || ntok_ + (size_t)(ncupu + npred + nmv) > a_cap_) { fail("token buffer overflow"); return; }
+    int32_t* h = a_hdr_ + 4 * (size_t)addr;
+    h[0] = (int32_t)ntok_; h[1] = ncupu; h[2] = npred; h[3] = nmv;
+    memcpy(a_tok_ + ntok_, cupu, 2 * (size_t)ncupu); ntok_ += ncupu;
+    memcpy(a_tok_ + ntok_, pred, 2 * (size_t)npred); ntok_ += npred;
+    memcpy(a_tok_ + ntok_, mv, 2 * (size_t)nmv); ntok_ += nmv;
+    a_bytes_[addr] = (uint16_t)(bytes < 0 ? 0 : bytes > 65535 ? 65535 : bytes);
+    t_hook_ += now() - t0;
+    if (t_first_ == 0) t_first_ = t0;
+  }
+  /* Hook 3, once per slice NAL (one slice per picture): submit the picture captured by onCtu and drain finished maps. */
+  void onSliceDone(int poc) {
+    const double t0 = now();
+    if (!ctx_ || failed_ || !acq_) return;
+    acq_ = false;
+    if (submit_(ctx_, poc, a_bytes_, a_hdr_, a_tok_, ntok_) != CDS_OK) { fail("cds_submit_frame"); return; }
+    submitted_ = poc + 1;
+    /* the batch launched last is still running: collect the one before it (already finished or nearly so) */
+    if (submitted_ - drained_ >= 2 * batch_) drain(drained_ + batch_);
+    t_hook_ += now() - t0;
+  }
+  /* Older entry: MV / Pred / CUPU are the reference's float[nctu][1000] statics (999-terminated); bits: float[nctu]. */
   void onSlice(int poc, int width, int height, int nctu, const float* bits, const float* MV, const float* Pred, const float* CUPU) {
     const double t0 = now();
     if (!open(width, height, nctu)) return;
@@ -45,7 +79,7 @@ class CdsHmHook {
     for (int a = 0; a < nctu; a++) bytes_[a] = (uint16_t)bits[a];
     if (submit_(ctx_, poc, bytes_.data(), hdr_.data(), tok_.data(), (size_t)ntok) != CDS_OK) { fail("cds_submit_frame"); return; }
     submitted_ = poc + 1;
-    if (submitted_ - drained_ >= batch_) drain(submitted_);       /* a full batch has just been launched and finished */
+    if (submitted_ - drained_ >= 2 * batch_) drain(drained_ + batch_);
     t_hook_ += now() - t0;
     if (t_first_ == 0) t_first_ = t0;
   }
@@ -57,9 +91,9 @@ class CdsHmHook {
     drain(submitted_);                                             /* cds_get_map flushes the partial batch */
     t_hook_ += now() - t0;
     const double wall = now() - t_first_;
-    fprintf(stderr, "[cds hook] %d pictures: total %.3f s, saliency hand-off + GPU wait %.3f s (%.3f ms/picture), "
+    fprintf(stderr, "[cds hook] %d pictures: total %.3f s, saliency hand-off + GPU wait %.3f s (%.3f ms/picture, %.1f %% of the wall time), "
             "HM parse + reconstruction %.3f s (%.3f ms/picture)\n", submitted_, wall, t_hook_, 1e3 * t_hook_ / (submitted_ ? submitted_ : 1),
-            wall - t_hook_, 1e3 * (wall - t_hook_) / (submitted_ ? submitted_ : 1));
+            100.0 * t_hook_ / (wall > 0 ? wall : 1), wall - t_hook_, 1e3 * (wall - t_hook_) / (submitted_ ? submitted_ : 1));
     destroy_(ctx_); ctx_ = NULL;
     if (model_) model_free_(model_);
     if (out_) fclose(out_);
@@ -72,6 +106,7 @@ class CdsHmHook {
   typedef int (*create_fn)(const cds_params*, cds_ctx**);
   typedef void (*destroy_fn)(cds_ctx*);
   typedef int (*submit_fn)(cds_ctx*, int, const uint16_t*, const int32_t*, const int16_t*, size_t);
+  typedef int (*acquire_fn)(cds_ctx*, uint16_t**, int32_t**, int16_t**, size_t*);
   typedef int (*getmap_fn)(cds_ctx*, int, void*, int*);
   typedef int (*load_fn)(const char*, cds_svm_model**);
   typedef void (*mfree_fn)(cds_svm_model*);
@@ -94,6 +129,7 @@ class CdsHmHook {
     pack_ = (pack_fn)dlsym(so, "cds_syntax_pack_ref"); create_ = (create_fn)dlsym(so, "cds_create"); destroy_ = (destroy_fn)dlsym(so, "cds_destroy");
     submit_ = (submit_fn)dlsym(so, "cds_submit_frame"); getmap_ = (getmap_fn)dlsym(so, "cds_get_map"); load_ = (load_fn)dlsym(so, "cds_svm_model_load");
     model_free_ = (mfree_fn)dlsym(so, "cds_svm_model_free"); err_ = (err_fn)dlsym(so, "cds_last_error");
+    acquire_ = (acquire_fn)dlsym(so, "cds_acquire_frame_buffers");
     if (!pack_ || !create_ || !destroy_ || !submit_ || !getmap_ || !load_ || !model_free_ || !err_) { fprintf(stderr, "[cds hook] missing symbols in %s\n", lib); failed_ = true; return false; }
     cds_params p; memset(&p, 0, sizeof(p));
     p.w = w; p.h = h; p.fps = getenv("CDS_FPS") ? atof(getenv("CDS_FPS")) : 50.0;
@@ -124,7 +160,8 @@ class CdsHmHook {
 
   cds_ctx* ctx_ = NULL; cds_svm_model* model_ = NULL; FILE* out_ = NULL;
   pack_fn pack_ = NULL; create_fn create_ = NULL; destroy_fn destroy_ = NULL; submit_fn submit_ = NULL; getmap_fn getmap_ = NULL;
-  load_fn load_ = NULL; mfree_fn model_free_ = NULL; err_fn err_ = NULL;
+  load_fn load_ = NULL; mfree_fn model_free_ = NULL; err_fn err_ = NULL; acquire_fn acquire_ = NULL;
+  uint16_t* a_bytes_ = NULL; int32_t* a_hdr_ = NULL; int16_t* a_tok_ = NULL; size_t a_cap_ = 0, ntok_ = 0; bool acq_ = false;
   std::vector<int32_t> hdr_; std::vector<int16_t> tok_; std::vector<uint16_t> bytes_; std::vector<char> map_;
   size_t px_ = 0; int batch_ = 32, submitted_ = 0, drained_ = 0; bool failed_ = false;
   double t_hook_ = 0, t_first_ = 0;

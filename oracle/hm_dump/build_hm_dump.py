@@ -104,14 +104,36 @@ CDS_BLOCK = r'''
   /* ---- B200 saliency path (replaces the reference's OpenCV saliency block) ---- */
   {
     CdsHmHook& s_cds_hook = CdsHmHook::get();
-    TComSPS* sps = pcSlice->getSPS();
-    Window& cw = sps->getConformanceWindow();
-    const int cw_w = (int)sps->getPicWidthInLumaSamples() - cw.getWindowLeftOffset() - cw.getWindowRightOffset();
-    const int cw_h = (int)sps->getPicHeightInLumaSamples() - cw.getWindowTopOffset() - cw.getWindowBottomOffset();
-    s_cds_hook.onSlice(pcSlice->getPOC(), cw_w, cw_h, (int)rpcPic->getNumCUsInFrame(), TDecCu::bits, &TDecCu::MV[0][0],
-                       &TDecCu::Pred[0][0], &TDecCu::CUPU[0][0]);
+    if (getenv("CDS_HOOK_LEGACY")) {      /* the older hand-off through the float statics (kept to compare the two) */
+      TComSPS* sps = pcSlice->getSPS();
+      Window& cw = sps->getConformanceWindow();
+      const int cw_w = (int)sps->getPicWidthInLumaSamples() - cw.getWindowLeftOffset() - cw.getWindowRightOffset();
+      const int cw_h = (int)sps->getPicHeightInLumaSamples() - cw.getWindowTopOffset() - cw.getWindowBottomOffset();
+      s_cds_hook.onSlice(pcSlice->getPOC(), cw_w, cw_h, (int)rpcPic->getNumCUsInFrame(), TDecCu::bits, &TDecCu::MV[0][0],
+                         &TDecCu::Pred[0][0], &TDecCu::CUPU[0][0]);
+    } else {
+      s_cds_hook.onSliceDone(pcSlice->getPOC());
+    }
   }
 }
+'''
+
+# --mode cds, hook 2: TDecCu::decompressCU hands the CTU's int16 token streams to the binding (no float statics, no 999 scan).
+# The reference's MVoutput writes `TDecCu::X[pcCU->getAddr()][i] = v; i++;` (TDecCu.cpp:165-289); in the scratch copy the same
+# statements also append to three per-CTU int16 scratch arrays, which decompressCU passes on.
+CDS_CTU_GLOBALS = r'''
+#include "cds_hm_hook.h"
+static short g_cdsCupu[128], g_cdsPred[320], g_cdsMv[1400];
+'''
+CDS_CTU_CALL = r'''
+  if (!getenv("CDS_HOOK_LEGACY")) {
+    TComSPS* sps_ = pcCU->getSlice()->getSPS();
+    Window& cw_ = sps_->getConformanceWindow();
+    const int w_ = (int)sps_->getPicWidthInLumaSamples() - cw_.getWindowLeftOffset() - cw_.getWindowRightOffset();
+    const int h_ = (int)sps_->getPicHeightInLumaSamples() - cw_.getWindowTopOffset() - cw_.getWindowBottomOffset();
+    CdsHmHook::get().onCtu(w_, h_, (int)pcCU->getPic()->getNumCUsInFrame(), (int)pcCU->getAddr(), (int)pcCU->getTotalBits(),
+                           g_cdsCupu, q, g_cdsPred, f, g_cdsMv, p);
+  }
 '''
 
 
@@ -149,6 +171,16 @@ def main():
     assert "  xDecompressCU( pcCU, 0,  0 );" in s
     s = s.replace("  xDecompressCU( pcCU, 0,  0 );", "  if (!cdsParseOnly()) xDecompressCU( pcCU, 0,  0 );\n" + SEMANTIC_CAPTURE, 1)
     s = s.replace("Void TDecCu::decompressCU( TComDataCU* pcCU )", SEMANTIC_GLOBALS + "Void TDecCu::decompressCU( TComDataCU* pcCU )", 1)
+    if mode == "cds":
+        # every capture statement of MVoutput also appends the int16 token; decompressCU then hands the CTU over
+        n0 = s.count("TDecCu::MV[pcCU->getAddr()][p] = ")
+        s = re.sub(r"TDecCu::MV\[pcCU->getAddr\(\)\]\[p\] = ([^;]+); p\+\+;", r"{ g_cdsMv[p] = (short)(\1); TDecCu::MV[pcCU->getAddr()][p] = \1; p++; }", s)
+        s = re.sub(r"TDecCu::CUPU\[pcCU->getAddr\(\)\]\[q\] = ([^;]+);\s*q\+\+;", r"{ g_cdsCupu[q] = (short)(\1); TDecCu::CUPU[pcCU->getAddr()][q] = \1; q++; }", s)
+        s = re.sub(r"TDecCu::Pred\[pcCU->getAddr\(\)\]\[f\] = ([^;]+); f\+\+;", r"{ g_cdsPred[f] = (short)(\1); TDecCu::Pred[pcCU->getAddr()][f] = \1; f++; }", s)
+        assert s.count("g_cdsMv[p] = ") >= 13 and s.count("g_cdsCupu[q] = ") == 2 and s.count("g_cdsPred[f] = ") == 1, (n0, s.count("g_cdsMv[p] = "), s.count("g_cdsCupu[q] = "), s.count("g_cdsPred[f] = "))
+        s = s.replace("  TDecCu::Pred[pcCU->getAddr()][f] = 999;", "  TDecCu::Pred[pcCU->getAddr()][f] = 999;\n" + CDS_CTU_CALL, 1)
+        assert "onCtu(" in s
+        s = s.replace("Void TDecCu::decompressCU( TComDataCU* pcCU )", CDS_CTU_GLOBALS + "Void TDecCu::decompressCU( TComDataCU* pcCU )", 1)
     open(pc, "w", encoding="latin-1").write(s)
     # (iii) TDecGop.cpp: keep 1-46, 119-224, 337-end (1-based)
     p = os.path.join(WORK, "source/Lib/TLibDecoder/TDecGop.cpp")

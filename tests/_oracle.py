@@ -10,6 +10,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 _ORC = None
 _REF = {}
+SAN = os.environ.get("CDS_ORACLE_SAN") == "1"      # load the ASan + UBSan builds (oracle/Makefile `sanitize`; needs LD_PRELOAD=libasan)
 
 
 def _ptr(a):
@@ -19,10 +20,10 @@ def _ptr(a):
 def oracle():
     global _ORC
     if _ORC is None:
-        so = os.path.join(ORACLE_DIR, "_build", "libcds_oracle.so")
+        so = os.path.join(ORACLE_DIR, "_build", "san" if SAN else "", "libcds_oracle.so")
         src = os.path.join(ORACLE_DIR, "cds_oracle.c")
         if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "sanitize" if SAN else "oracle"])
         L = C.CDLL(so)
         if hasattr(L, "orc_magnitude_vote"):
             L.orc_magnitude_vote.restype = C.c_double
@@ -33,7 +34,7 @@ def oracle():
 def ref(name):
     """oracle/_ref/libref_<name>.so or None (built only where /root/reference exists)."""
     if name not in _REF:
-        so = os.path.join(ORACLE_DIR, "_ref", f"libref_{name}.so")
+        so = os.path.join(ORACLE_DIR, "_ref", "san" if SAN else "", f"libref_{name}.so")
         _REF[name] = C.CDLL(so) if os.path.exists(so) else None
     return _REF[name]
 

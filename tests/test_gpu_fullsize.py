@@ -128,3 +128,48 @@ def test_full_temporal_window_at_50fps_vs_oracle(cds):
     for k in range(2):
         err = np.max(np.abs(got[F - 2 + k] - np.nan_to_num(want[k])))
         assert err <= 1e-4, (k, err)
+
+
+def test_exact_benchmark_configuration_vs_oracle(cds):
+    """BASELINE.json configs[2] exactly as bench.py times it: 1920x1080, 50 fps (PS 15, PT 105), batches of 64 pictures, the
+    nSV 4096 stand-in model.  120 pictures: the first 64 go in as temporal context, the next 56 are rendered (a second, ragged
+    batch whose back half overlaps nothing); pictures 118 and 119 have the full 119-picture history and are compared with the
+    oracle, whose heavy kernels are the reference's own computecontrast5 / libsvm where oracle/_ref exists."""
+    w, h, fps, F, B = 1920, 1080, 50.0, 120, 64
+    o.oracle().orc_set_threads(16)
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 1234, F, first_poc=1)
+    ints = [o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    mvx = np.stack([m[0] for m in ints]); mvy = np.stack([m[1] for m in ints]); dep = np.stack([m[2] for m in ints])
+    SV, coef, rho, gamma, labels = o.synth_model(4096)                     # bench.py's model, unshifted
+    mdl = (SV, coef, rho, gamma, labels)
+    gm = cds.ops.SvmModel(SVs=SV, sv_coef=coef, rho=rho, gamma=gamma, Label=labels)
+    o.use_reference_kernels(mdl)
+    try:
+        want, wcam, _ = o.orc_process_clip(w, h, fps, mvx, mvy, dep, byts, mdl, MEAN9, STD9, first_out=F - 2, use_rbf=1)
+    finally:
+        o.use_reference_kernels(None)
+    clip = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=B)
+    clip.context(0, hdr[:B], tok, base[:B + 1], byts[:B])
+    got, cam = clip.process(B, hdr[B:], tok, base[B:], byts[B:])
+    clip.close()
+    assert np.array_equal(cam, wcam[B:])
+    assert np.any(wcam[:, 1] < 0) and np.any(wcam[:, 1] > 0)             # immove's one-sided vertical shift is exercised
+    for k in range(2):
+        err = np.max(np.abs(got[F - B - 2 + k] - np.nan_to_num(want[k])))
+        assert err <= 1e-4, (k, err)
+
+
+@pytest.mark.parametrize("grid", [(400, 640), (540, 960)])
+def test_contrast_large_grids_vs_verbatim_reference(cds, grid):
+    """The 2560x1600 and 3840x2160 mv-contrast shapes (48x48 window): other tile-width choices of the separable kernel than
+    1080p's, against the reference's own computecontrast5.cpp (oracle/_ref) where it exists, else the restatement."""
+    rows, cols = grid
+    rng = np.random.default_rng(rows)
+    a = rng.standard_normal((rows, cols)) * 2
+    a[rng.random(a.shape) < 0.05] = a.min()
+    pad, W, ln, win = o.sudoku_inputs(a, 11.0, 1, 48)
+    got = cds.ops.computecontrast5(pad, W, ln, win, rows, cols)
+    want = o.ref_computecontrast5(pad, W, ln, win, rows, cols)
+    if want is None:
+        want = o.orc_computecontrast5(pad, W, ln, win, rows, cols)
+    assert np.max(np.abs(got - want)) <= 1e-4 * np.max(np.abs(want))

@@ -70,11 +70,15 @@ def _write_libsvm_model(path, SV, coef, rho, gamma):
             f.write(f"{c:.17g} " + " ".join(f"{i + 1}:{v:.17g}" for i, v in enumerate(s)) + " \n")
 
 
-def test_hm_decoder_with_cds_hook_end_to_end(cds, tmp_path):
+@pytest.mark.parametrize("legacy", [False, True])
+def test_hm_decoder_with_cds_hook_end_to_end(cds, tmp_path, legacy):
     """The reference's HM-16.0 decoder, rebuilt with include/cds_hm_hook.h in place of its OpenCV block
     (oracle/_ref/hm_cds_decoder, built by oracle/hm_dump/build_hm_dump.py --mode cds), decodes a bundled bitstream:
     CABAC parse on the host, hooks -> packed syntax -> libcds_b200.so -> maps.  The maps of the first pictures must be
-    bytewise identical to the library fed with the same pictures' syntax from the fixture."""
+    bytewise identical to the library fed with the same pictures' syntax from the fixture.
+    legacy = False: TDecCu::decompressCU appends int16 tokens straight into the library's pinned staging buffers
+    (cds_acquire_frame_buffers) and the per-slice hook only submits (asynchronous); legacy = True: the older hand-off that
+    converts the reference's float[LCUNUM][1000] statics per slice.  Both must give the same bytes."""
     import subprocess
     dec = os.path.join(o.ROOT, "oracle", "_ref", "hm_cds_decoder")
     stream = os.path.join(o.ROOT, "oracle", "_ref", "streams", "BasketballPass.bin")
@@ -87,6 +91,8 @@ def test_hm_decoder_with_cds_hook_end_to_end(cds, tmp_path):
     out = str(tmp_path / "maps.f32")
     env = dict(os.environ, CDS_LIB=cds.lib_path(), CDS_OUT=out, CDS_FPS="50", CDS_SVM_MODEL=mpath, CDS_BATCH="16",
                CDS_MEAN=",".join(["0.3"] * 9), CDS_STD=",".join(["0.2"] * 9))
+    if legacy:
+        env["CDS_HOOK_LEGACY"] = "1"
     r = subprocess.run([dec, "-b", stream], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "[cds hook] 500 pictures" in r.stderr, r.stderr[-2000:]
