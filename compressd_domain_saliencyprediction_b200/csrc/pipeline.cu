@@ -773,9 +773,11 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   const int h4 = c->h4, w4 = c->w4, n4 = c->n4, H = c->h, W = c->w, RL = c->RL;
   const float* fparam = c->d_fparam;
   // Where the previous batch's deferred back half (persistent MUFU-bound SVM, then the final-map chain) joins this batch's front
-  // half: 0 = at its start, beside the latency / bandwidth-bound stages (a), (c), smoothing, threshold, temporal; 1 = at the
-  // mid-point, beside the FP32-bound contrast kernels (then capped to CDS_CO_CTAS CTAs per SM); 2 = after the contrast kernels.
-  static const int back_at = [] { const char* e = getenv("CDS_BACK_AT"); const int v = e ? atoi(e) : 0; return v < 0 || v > 2 ? 0 : v; }();
+  // half (CDS_BACK_AT): 1 (default) = at the mid-point, beside the FP32-bound contrast kernels, which are then capped to
+  // CDS_CO_CTAS CTAs per SM; 0 = at its start, beside stages (a), (c), smoothing, threshold, temporal; 2 = after the contrast
+  // kernels.  Measured at 1080p / nSV 4096 / 64 pictures: 11.53 ms per batch for 1, 13.1 for 0 (the resident SVM CTAs keep the
+  // register-hungry temporal and vote kernels off the SMs), 12.2 for 2, 12.7 without any overlap.
+  static const int back_at = [] { const char* e = getenv("CDS_BACK_AT"); const int v = e ? atoi(e) : 1; return v < 0 || v > 2 ? 1 : v; }();
   if (ov && c->pb.valid && back_at == 0) {
     trace_mark(c, c->tr_batches, TR_MID, st);
     CDS_CUDA(cudaEventRecord(c->ev_mid, st));

@@ -66,3 +66,45 @@ def evaluate_clip(maps, xy, offsets):
         if np.isfinite(a) and np.isfinite(n):
             aucs.append(a); nsss.append(n)
     return (float(np.mean(aucs)) if aucs else float("nan")), (float(np.mean(nsss)) if nsss else float("nan")), len(aucs)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's fixation database (video_database.mat, MATLAB v7.3; main.m:3-18, 325-346)
+# ------------------------------------------------------------------------------------------------
+def load_fixation_database(path):
+    """video_database.mat (through the minimal HDF5 reader mat73.py) or the .npz extract of it (tests/golden/fixations_all.npz)
+    -> {"names": [33 str], "size": [33][2] (w, h), "frames": [33], "fps": [33], "fixdata": [N][6]} with fixdata columns
+    SubjectIndex, VideoIndex (1-based), Timestamp ms, GazeDuration ms, FixationPointX, FixationPointY."""
+    if str(path).endswith(".npz"):
+        d = np.load(path, allow_pickle=False)
+        return {"names": [str(s) for s in d["names"]], "size": d["size"].astype(np.float64), "frames": d["frames"].astype(np.int64),
+                "fps": d["fps"].astype(np.float64), "fixdata": d["fixdata"].astype(np.float64)}
+    from . import mat73
+    db = mat73.load(path)["video_database"]
+    vi = db["videos_info"]
+    return {"names": list(db["video_names_list"]), "size": np.asarray(vi["size"], np.float64).reshape(-1, 2),
+            "frames": np.asarray(vi["frames"]).reshape(-1).astype(np.int64), "fps": np.asarray(vi["framerate_fps"], np.float64).reshape(-1),
+            "fixdata": np.asarray(db["fixdata"], np.float64)}
+
+
+def fixations_per_picture(db, name, pocs=None):
+    """main.m:325-346 for one clip: a fixation covers pictures ceil(start / T) .. ceil((start + duration) / T) (1-based,
+    T = 1000 / fps), clipped to the clip; positions outside the picture are dropped.
+    -> (xy [M][2] float32 in picture order, offsets [len(pocs) + 1]) for the given 0-based pictures (default: all)."""
+    k = db["names"].index(name)
+    w, h = db["size"][k]
+    nframes = int(db["frames"][k]); T = 1000.0 / float(db["fps"][k])
+    pocs = np.arange(nframes) if pocs is None else np.asarray(pocs)
+    per = {int(p): [] for p in pocs}
+    rows = db["fixdata"][db["fixdata"][:, 1] == k + 1]
+    for row in rows:
+        x, y = row[4], row[5]
+        if not (0 < x <= w and 0 < y <= h):
+            continue
+        s = max(1, int(np.ceil(row[2] / T))); e = min(nframes, int(np.ceil((row[2] + row[3]) / T)))
+        for kk in range(s, e + 1):                             # 1-based picture index kk <-> poc kk - 1
+            if kk - 1 in per:
+                per[kk - 1].append((x, y))
+    xy = np.array([p for poc in pocs for p in per[int(poc)]], np.float32).reshape(-1, 2)
+    off = np.cumsum([0] + [len(per[int(poc)]) for poc in pocs]).astype(np.int32)
+    return xy, off
