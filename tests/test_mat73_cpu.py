@@ -49,7 +49,7 @@ def test_hdf5_reader_on_the_reference_database():
     fx = metrics.load_fixation_database(os.path.join(GOLD, "fixations_all.npz"))
     assert db["names"] == fx["names"]
     for k in ("size", "frames", "fps", "fixdata"):
-        assert np.array_equal(np.asarray(db[k], np.float32), np.asarray(fx[k], np.float32)), k
+        assert np.array_equal(np.asarray(db[k], np.float32), np.asarray(fx[k], np.float32), equal_nan=True), k
 
 
 def test_hdf5_reader_rejects_other_files(tmp_path):
