@@ -64,6 +64,20 @@ def workload_name(a):
             f"(stand-in model), batch {a.batch} pictures/step")
 
 
+REF_CTX, REF_OUT = 14, 2      # reference arm: output pictures per step and context pictures before them
+
+
+def common_config(a, world):
+    """The same dictionary in both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "width": a.width, "height": a.height, "fps": a.fps, "nsv": a.nsv, "PS": a.PS, "PT": a.PT,
+            "frames_per_step_per_gpu": a.batch, "parallelism": f"video-shard x{world}",
+            "l2": "B200 arm: no explicit flush; one step streams several GB of intermediates (9 maps x B pictures at h/4 x W, 3 at full "
+                  "resolution), far above the 126 MB L2",
+            "reference_arm": f"bounded sample of the same workload: each step renders {REF_OUT} pictures after {REF_CTX} context pictures "
+                             f"(temporal window truncated to {REF_CTX + 1} of {a.PS + a.PT - 1} pictures, which makes the CPU arm FASTER: "
+                             "its cost per picture is contrast + SVM, which do not depend on the window)"}
+
+
 # ----------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi, started before and killed after the timed region; exact PID only)
 # ----------------------------------------------------------------------------------------------
@@ -182,7 +196,7 @@ def run_reference(a):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_out, ctx = 2, 14
+    n_out, ctx = REF_OUT, REF_CTX
     times = []
     kind = "port"
     for s in range(a.warmup + a.steps):
@@ -195,8 +209,10 @@ def run_reference(a):
               f"(temporal window truncated to {ctx + 1} of {a.PS + a.PT - 1} pictures) on {cores} threads; " + KIND_TEXT[kind])
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": per_frame * 1e3 * n_out, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": workload_name(a), "frames_per_step": n_out},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "data": "synthetic", "config": common_config(a, a.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "threads_note": "the reference itself is single-threaded; this arm cuts its kernels into bands over all host threads, "
+                                             "which scales sub-linearly (r01: 16 threads = 9.5x one thread, 32 = 16)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     if not a.no_fast and a.width % 16 == 0:
         # the reference's fast version (what its decoder computes per slice) on the same host cores, beside the headline path
@@ -213,6 +229,89 @@ def run_reference(a):
 # B200 arm
 # ----------------------------------------------------------------------------------------------
 E2E_CHUNK = 3        # batches handed to cds_clip_process per call on the e2e leg (bounds the pinned output buffer)
+
+
+def parity_check(a, cds, model):
+    """max |map - oracle map| for the last picture of a clip with the full temporal history (PS + PT - 1 pictures of this
+    workload, its model, its frame rate), through the host-buffer C-ABI call.  The oracle's heavy kernels are the reference's own
+    computecontrast5 / libsvm where oracle/_ref exists.  Untimed; the tolerance is the north star's 1e-4."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as o                                         # the checker
+    w, h, B = a.width, a.height, a.batch
+    F = a.PS + a.PT - 1
+    hdr, tok, base, byts = cds.ops.synth_clip(w, h, 4242, F, first_poc=1)
+    mdl = synth_model(a.nsv)
+    L = o.oracle()
+    L.orc_set_threads(int(os.cpu_count() or 1))
+    t0 = time.perf_counter()
+    ints = [o.orc_getframe(w, h, hdr[f], tok[base[f]:base[f + 1]]) for f in range(F)]
+    mvx = np.stack([m[0] for m in ints]); mvy = np.stack([m[1] for m in ints]); dep = np.stack([m[2] for m in ints])
+    kind = "reference" if o.use_reference_kernels(mdl) else "port"
+    try:
+        want, wcam, _ = o.orc_process_clip(w, h, a.fps, mvx, mvy, dep, byts, mdl, MEAN9, STD9, first_out=F - 1, use_rbf=1)
+    finally:
+        o.use_reference_kernels(None)
+    t_cpu = time.perf_counter() - t0
+    clip = cds.SaliencyClip(w, h, a.fps, model=model, meanVec=MEAN9, stdVec=STD9, use_rbf=True, max_batch=B)
+    nctx = ((F - 1) // B) * B
+    if nctx:
+        clip.context(0, hdr[:nctx], tok, base[:nctx + 1], byts[:nctx])
+    got, cam = clip.process(nctx, hdr[nctx:], tok, base[nctx:], byts[nctx:])
+    clip.close()
+    err = float(np.max(np.abs(got[-1] - np.nan_to_num(want[0]))))
+    return {"max_abs_err": err, "tolerance": 1e-4, "ok": bool(err <= 1e-4 and np.array_equal(cam, wcam[nctx:])),
+            "camera_votes_exact": bool(np.array_equal(cam, wcam[nctx:])), "picture": F - 1, "history": F - 1, "oracle": kind,
+            "oracle_seconds": round(t_cpu, 2), "maps": "pm_norm'ed to [0, 1]: absolute error = relative to the map range"}
+
+
+def sweep(a, cds, L, dev, stream, st):
+    """Device-resident frames/s of BASELINE.json's other configurations (416x240, 2560x1600, 3840x2160 at the headline's nSV, and
+    nSV 1024 / 16384 at the headline's size), 3 timed steps each after the temporal window has been filled."""
+    import torch
+    from compressd_domain_saliencyprediction_b200._lib import check
+    out = []
+    cases = [(416, 240, a.nsv), (2560, 1600, a.nsv), (3840, 2160, a.nsv), (a.width, a.height, 1024), (a.width, a.height, 16384)]
+    for (w, h, nsv) in cases:
+        B = a.batch
+        nctu = cds.ops.nctu(w, h)
+        SV, coef, rho, gamma, labels = synth_model(nsv)
+        mdl = cds.ops.SvmModel(SVs=SV, sv_coef=coef, rho=rho, gamma=gamma, Label=labels)
+        clip = cds.SaliencyClip(w, h, a.fps, model=mdl, meanVec=MEAN9, stdVec=STD9, use_rbf=True, max_batch=B)
+        halo = -(-(a.PS + a.PT - 2) // B) * B
+        nwarm, nstep = 1, 3
+        clip_len = 2 * B                                       # replayed: bounded host memory at 4K
+        hdr, tok, base, byts = cds.ops.synth_clip(w, h, 99, clip_len, first_poc=1)
+        d_hdr, d_tok, d_base, d_byts = (torch.from_numpy(x).to(dev) for x in (hdr, tok, base, byts))
+        d_maps = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+        P = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+
+        def step(poc, context=False):
+            i = poc % clip_len
+            args = (clip.handle, poc, B, P(d_byts, i * nctu * 2), P(d_hdr, i * nctu * 16), P(d_tok), P(d_base, i * 8))
+            if context:
+                check(L.cds_clip_context_dev(*args, st), "cds_clip_context_dev")
+            else:
+                check(L.cds_clip_process_dev(*args, P(d_maps), None, st), "cds_clip_process_dev")
+        clip.seek(0)
+        poc = 0
+        for _ in range(halo // B):
+            step(poc, context=True); poc += B
+        for _ in range(nwarm):
+            step(poc); poc += B
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nstep):
+            step(poc); poc += B
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out.append({"width": w, "height": h, "nsv": nsv, "fps_setting": a.fps, "batch": B, "steps": nstep, "value": nstep * B / (ms * 1e-3),
+                    "unit": UNIT, "ms_per_step": ms / nstep})
+        clip.close()
+        del d_maps, d_hdr, d_tok, d_base, d_byts
+        torch.cuda.empty_cache()
+    return {"what": "device-resident, one batch per call (no cross-batch overlap), synthetic syntax, same pipeline as the headline", "cases": out}
 
 
 def run_b200(a):
@@ -363,6 +462,9 @@ def run_b200(a):
     t0 = time.perf_counter(); h_maps.copy_(big, non_blocking=True); torch.cuda.synchronize()
     e2e_f32["d2h_link_gbs"] = big.numel() * 4 / (time.perf_counter() - t0) / 1e9
     del big
+    e2e["f32_value"] = e2e_f32["value"]; e2e["f32_ms_per_step"] = e2e_f32["ms_per_step"]
+    e2e["f32_d2h_bytes_per_step"] = e2e_f32["d2h_bytes_per_step"]; e2e["d2h_link_gbs"] = e2e_f32["d2h_link_gbs"]
+    e2e["maps"] = "value: 8-bit maps (what the reference hook writes, TDecGop.cpp:327-332); f32_value: FP32 maps (what the 1e-4 parity tests compare)"
     # ---- the reference's FAST version (TDecGop.cpp:225-333 + salmat.cpp, no SVM) on the same synthetic syntax: what its decoder
     #      computes per slice on the CPU; reported beside the headline (which is the nine-feature + RBF-SVM path BASELINE names) ----
     fast_line = None
@@ -429,8 +531,7 @@ def run_b200(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B, "PS": a.PS, "PT": a.PT, "parallelism": f"video-shard x{world}", "numa_bound_cores": (len(numa_cpus) if numa_cpus else None),
-                       "l2": "no explicit flush: one step streams several GB of intermediates (9 maps x B pictures at h/4 x W, 3 at full resolution), far above the 126 MB L2"},
+            "config": common_config(a, world), "numa_bound_cores": (len(numa_cpus) if numa_cpus else None),
             "clocks": clocks, "e2e": e2e, "e2e_f32_maps": e2e_f32, "gpu_launches": int(launches)}
     if fast_line:
         line["fast_version"] = fast_line
@@ -447,9 +548,9 @@ def run_b200(a):
         check(L.cds_profile_enable(clip.handle, 0), "profile")
         stage_ms = {n: msv[i] / nprof for i, n in enumerate(names) if not n.startswith("fast_")}
         tot = sum(stage_ms.values())
-        pk = (C.c_double * 3)()
-        check(L.cds_measure_peaks(C.byref(pk, 0), C.byref(pk, 8), C.byref(pk, 16)), "peaks")
-        pair_ips, ffma_ips, mufu_ips = pk[0], pk[1], pk[2]
+        pk = (C.c_double * 4)()
+        check(L.cds_measure_peaks_ex(pk, 4), "peaks")
+        pair_ips, ffma_ips, mufu_ips, indep_ips = pk[0], pk[1], pk[2], pk[3]
         peaks_hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         pairs = contrast_pairs(w, h)
         traffic = {}
@@ -461,7 +562,8 @@ def run_b200(a):
         for key in ("win48", "win24"):
             t = stage_ms[f"contrast_{key}"] * 1e-3
             roofs.append({"kernel": f"contrast_{key}", "bound": "fp32", "achieved": pairs[key] * B * 3 / t / 1e12, "peak": pair_ips * 1.5 / 1e12,
-                          "unit": "TFLOP/s", "frac": pairs[key] * B * 2 / t / pair_ips, "traffic": traffic.get(f"contrast_{key}"),
+                          "unit": "TFLOP/s", "frac": pairs[key] * B * 2 / t / pair_ips, "frac_of_ffma_rate": pairs[key] * B * 2 / t / ffma_ips,
+                          "traffic": traffic.get(f"contrast_{key}"),
                           "ms_per_launch": t * 1e3, "share_of_step": stage_ms[f"contrast_{key}"] / tot,
                           "work": "3 FLOP (FADD+FFMA) per (cell, neighbour) pair; peak = measured FADD+FFMA issue rate x 1.5 FLOP/instr (cds_measure_peaks, this run)"})
         # SVM (svm_rbf9_tc_kernel): exponents from a tcgen05 TF32x3 GEMM (K padded to 16, three MMAs), then 1 MUFU.EX2 + 1 FADD per
@@ -486,10 +588,12 @@ def run_b200(a):
         vbytes = 9.0 * B * h4 * w * 4 + 3.0 * B * h * w * 4
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         tf32_peak = 0.5 * mp.get("bf16_tflops_sustained", 1400.0)
-        roofs.append({"kernel": "fullres_vpass_tc", "bound": "tensor", "achieved": tflop / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                      "frac": tflop / t / 1e12 / tf32_peak, "hbm_gbs": vbytes / t / 1e9, "hbm_frac": vbytes / t / 1e9 / hbm,
+        useful = 9.0 * B * h * w * nt * 2          # the FIR itself: nt cell taps per output sample
+        roofs.append({"kernel": "fullres_vpass_tc", "bound": "tensor", "achieved": useful / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                      "frac": useful / t / 1e12 / tf32_peak, "issued_tflops": tflop / t / 1e12, "issued_frac": tflop / t / 1e12 / tf32_peak,
+                      "hbm_gbs": vbytes / t / 1e9, "hbm_frac": vbytes / t / 1e9 / hbm,
                       "traffic": traffic.get("fullres_vpass"), "ms_per_launch": t * 1e3, "share_of_step": stage_ms["fullres_vpass"] / tot,
-                      "work": f"banded GEMM 128 x {kp} x 256 per tile, TF32 hi/lo split (3 MMAs); peak = half the measured sustained bf16 rate; "
+                      "work": f"achieved = USEFUL flops (2 x {nt} taps per output); issued = banded GEMM 128 x {kp} x 256 per tile x 3 MMAs (TF32 hi/lo split, band padding); peak = half the measured sustained bf16 rate; "
                               f"equivalent FIR: {nt} taps x 4 phases; algorithmic bytes = 9 T maps in + 3 full-resolution maps out"})
         # temporal pass: unique bytes per launch = the (B + PT - 1) ring pictures it touches (4 smoothed maps) + 3 maps out per picture.
         # Every picture re-reads its PT - 1 predecessors, but those are L1 / L2 hits: the kernel is LSU / issue bound (ncu: l1tex 88 %), not HBM bound.
@@ -510,9 +614,19 @@ def run_b200(a):
         line["roofline_all"] = roofs[1:]
         line["stage_ms_per_step"] = stage_ms
         line["peaks_measured"] = {"fp32_fadd_ffma_lane_instr_per_s": pair_ips, "ffma_lane_instr_per_s": ffma_ips, "mufu_ex2_per_s": mufu_ips,
+                                  "fadd_ffma_independent_lane_instr_per_s": indep_ips,
+                                  "fp32_note": "pair = 16 chains of FADD -> FFMA (every FFMA consumes its own FADD, as in the contrast kernel); independent = "
+                                               "the same opcodes without that dependence; both opcodes issue on the FMA pipe",
                                   "hbm_gbs": peaks_hbm,
                                   "hbm_source": "MEASURED_PEAKS.json (of measured)" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback"}
     clip.close()
+
+    # ---- parity check (untimed, rank 0, N=1): one picture of THIS workload, full temporal history, against the oracle ----
+    if rank == 0 and world == 1 and not a.no_cpu:
+        line["parity_check"] = parity_check(a, cds, model)
+    # ---- the other BASELINE configurations, device-resident, a few steps each (rank 0, N=1; not the headline) ----
+    if rank == 0 and world == 1 and not a.no_sweep:
+        line["sweep"] = sweep(a, cds, L, dev, stream, st)
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ----
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -557,6 +671,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fast", action="store_true", help="skip the fast-version leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the sweep over BASELINE's other configurations")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     a.PS = int(np.floor(a.fps * 0.3 + 0.5)); a.PT = int(np.floor(a.PS * 7 + 0.5))

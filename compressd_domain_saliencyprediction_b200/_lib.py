@@ -55,6 +55,7 @@ def _declare(L):
         "cds_probe_run_sum": (i32, [c_p, i32, i32, i32, i32, i32, C.c_double, c_p, c_p]),
         "cds_reset": (i32, [c_p]),
         "cds_measure_peaks": (i32, [c_p, c_p, c_p]),
+        "cds_measure_peaks_ex": (i32, [c_p, i32]),
         "cds_seek": (i32, [c_p, i32]),
         "cds_clip_context_dev": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, c_p]),
         "cds_clip_context": (i32, [c_p, i32, i32, c_p, c_p, c_p, c_p, sz]),

@@ -47,7 +47,15 @@ int ensure_dyn_smem_impl(const void* func, size_t bytes) {
   int dev = 0;
   CDS_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(mu);
-  size_t& have = done[{func, dev}];
+  auto it = done.find({func, dev});
+  if (it == done.end()) {
+    // Ask for the largest shared-memory carve-out whenever one of these kernels runs.  The L1 / shared split of an SM can only change
+    // while the SM is empty: a persistent kernel that configured "just enough" shared memory for itself would keep every CTA of a
+    // co-scheduled kernel (pipeline.cu: SVM beside contrast) off its SMs until it exits.
+    CDS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    it = done.emplace(std::make_pair(func, dev), (size_t)0).first;
+  }
+  size_t& have = it->second;
   if (bytes > have) {
     if (bytes > 48 * 1024) CDS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     have = bytes;

@@ -21,6 +21,8 @@
 #include <string.h>
 #include <math.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 namespace cds {
 
@@ -249,6 +251,24 @@ int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, 
   return CDS_OK;
 }
 
+// host: tiled FP32 tensor map with zero fill outside (cuTensorMapEncodeTiled through the runtime's driver entry point)
+static int encode_tensor_map_f32_3d(const void* base, const cuuint64_t dims[3], const cuuint64_t strides[2], const cuuint32_t box[3], CUtensorMap* out) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    CDS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return CDS_ECUDA; }
+    encode = (encode_fn)fn;
+  }
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu", (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2]); return CDS_ECUDA; }
+  return CDS_OK;
+}
+
 // =================================================================================================
 // temporal difference with accumulated camera motion (main.m:174-199, immove.m)
 // grid: x = picture in batch (fast, so the pictures that share ring data run together), y = cell tile
@@ -330,24 +350,36 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __r
 // B * (PT-1) * n4 * 16 B per batch (13.8 GB at 1080p / 50 fps / B = 64, ~11 TB/s: the L2 is the wall).  Consecutive output
 // pictures read almost the same ring pictures, so here one CTA owns a 16 x 32 cell tile for a GROUP of TG consecutive
 // pictures: it walks the ring pictures q = poc_last-1 ... poc_first-(PT-1) once, stages the part of picture q that the
-// group's (shifted) reads touch in shared memory with cp.async (three buffers, prefetch distance 2, zero fill outside the
-// picture = immove's zero padding) and accumulates it into the TG pictures' registers.  L2 traffic drops by ~TG / halo
+// group's (shifted) reads touch in shared memory — one TMA box per ring picture into an 8-deep mbarrier ring, issued by a single
+// thread, zero fill outside the picture = immove's zero padding; no block-wide barrier in the loop — and accumulates it into the
+// TG pictures' registers.  L2 traffic drops by ~TG / halo
 // overhead; what remains is one LDS.128 per (cell, picture, q) term, i.e. the shared-memory bandwidth.
 // Every picture still adds its terms in ascending j with the same fmaf sequence, so the result is bit-identical to the
 // kernel above and independent of where the picture sits in a batch (sharded == unsharded bytewise).
 // The accumulated camera shift differs per (picture, q); the staged window covers the spread of the group's shifts up to
 // TW_R x TW_C cells, pairs whose shifted tile falls outside it (very fast pans) read from global memory instead.
 // -------------------------------------------------------------------------------------------------
+// exp(-j / 26) (mv) and exp(-j / 46) (bit, depth), main.m:120-122,195-197: the same for every clip, so the grouped kernel reads them
+// from constant memory through the uniform datapath (j is warp-uniform) instead of keeping a rotating window in vector registers
+__constant__ float2 c_temporal_w[TMP_MAXJ];
 constexpr int TG = 8;                          // pictures per group (the offset table below is read as two int4)
-constexpr int TT_R = 16, TT_C = 32;            // tile: one warp per row of 32 cells
-constexpr int TW_R = TT_R + 8, TW_C = TT_C + 16;   // staged window capacity
-constexpr int T_STAGES = 8, T_DIST = T_STAGES - 1;   // cp.async ring: windows of the next T_DIST ring pictures in flight (most come from HBM: the ring exceeds the L2)
-static_assert(TG == 8 && T_STAGES == TG && TW_R <= 2 * TT_R && TW_C <= 64, "temporal_group_kernel: offset table read as two int4; two rows per warp, two columns per lane");
+constexpr int TGT = 8;                         // pictures per thread; TGT = 4 splits the group over two thread sets (1024 threads, 64 registers): measured slower (1.35 vs 1.21 ms)
+constexpr int TT_R = 15, TT_C = 32;            // tile: one warp per row of 32 cells; 15 consumer warps + the producer warp = 512 threads (128 registers each)
+constexpr int TW_R = TT_R + 4, TW_C = TT_C + 8;    // staged window = the TMA box: tile + the spread of the group's shifts it can absorb
+constexpr int T_STAGES = 8;                        // TMA ring: the windows of the next 8 ring pictures in flight (most come from HBM: the ring exceeds the L2)
+constexpr int T_STAGE_BYTES = TW_R * TW_C * 16;
+constexpr int T_SETS = TG / TGT, T_CONSUMERS = T_SETS * TT_R * TT_C, T_WARPS = T_CONSUMERS / 32;
+constexpr int T_THREADS = T_CONSUMERS + 32;    // + one producer warp: a single thread that only keeps the TMA ring full, decoupled from the consumers' arithmetic
+static_assert(TG == 8 && T_STAGES == TG && T_STAGES % TGT == 0 && T_STAGE_BYTES % 128 == 0 && T_THREADS <= 1024,
+              "temporal_group_kernel: offset table read as two int4; static stage index; weight window rotation; TMA destination alignment");
 
-__global__ void __launch_bounds__(TT_R * TT_C, 1)
-temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, const float4* __restrict__ sm4,
+__global__ void __launch_bounds__(T_THREADS, 1)
+temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4][w4 * 4] FP32, box [1][TW_R][TW_C * 4], zero fill outside*/,
+                      int h4, int w4, int PT, int RL, int first_poc, int n, const float4* __restrict__ sm4,
                       const int* __restrict__ cam, const float* __restrict__ wtab, float* __restrict__ Xmaps) {
-  extern __shared__ __align__(16) unsigned char t_smem[];
+  using namespace tc;
+  extern __shared__ __align__(128) unsigned char t_smem[];
+  __shared__ __align__(8) uint64_t t_bars[2 * T_STAGES];                               // full[s] (TMA landed), empty[s] (all warps done with it)
   float4* stage = reinterpret_cast<float4*>(t_smem);                                   // [T_STAGES][TW_R * TW_C]
   float4* s_w = stage + T_STAGES * TW_R * TW_C;                                        // [PT] weights
   int2* s_shift = reinterpret_cast<int2*>(s_w + PT);                                   // [TG][PT] {sx, max(sy, 0)} per (picture, j)
@@ -355,15 +387,21 @@ temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, cons
   int* s_off = reinterpret_cast<int*>(s_win + (PT - 1 + TG));                          // [nq_max][TG] offset of the pair's source tile in the window; -1 read from global; -2 no term
   const int n4 = h4 * w4;
   const int ntc = (w4 + TT_C - 1) / TT_C;
-  const int r0 = (blockIdx.x / ntc) * TT_R, c0 = (blockIdx.x % ntc) * TT_C;
-  const int f0 = blockIdx.y * TG, ng = min(TG, n - f0);
+  // grid: x = picture group (fast: the CTAs of one tile run together and find each other's ring windows in the L2), y = tile
+  const int r0 = (blockIdx.y / ntc) * TT_R, c0 = (blockIdx.y % ntc) * TT_C;
+  const int f0 = blockIdx.x * TG, ng = min(TG, n - f0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int set = warp / TT_R, wrow = warp % TT_R;                 // thread set (pictures set*TGT ..), row of the tile
   const int poc0 = first_poc + f0;
   const int q_hi = poc0 + ng - 2;                                  // newest ring picture any picture of the group reads
   const int q_lo = max(0, poc0 - (PT - 1));
   const int nq = q_hi - q_lo + 1;                                  // may be <= 0 (first picture of a clip on its own)
 
-  for (int j = threadIdx.x; j < PT; j += blockDim.x) s_w[j] = reinterpret_cast<const float4*>(wtab)[j];
+  const uint32_t bar0 = smem_u32(t_bars);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T_STAGES; s++) { mbar_init(bar0 + 8u * s, 1); mbar_init(bar0 + 8u * (T_STAGES + s), T_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp < ng) {                                 // warp g: inclusive scan of x_cammov / y_cammov over j for picture g (main.m:189-190)
     const int poc = poc0 + warp, jmax = min(PT - 1, poc);
     int cx = 0, cy = 0;
@@ -404,113 +442,111 @@ temporal_group_kernel(int h4, int w4, int PT, int RL, int first_poc, int n, cons
       if (g < ng && j >= 1 && j <= min(PT - 1, poc)) {
         const int2 sh = s_shift[g * PT + j];
         const int dx = wn.x - sh.x, dy = wn.y - sh.y;                  // >= 0
-        off = (dx + TT_C <= wn.z && dy + TT_R <= wn.w) ? dy * TW_C + dx : -1;
+        off = (dx + TT_C <= TW_C && dy + TT_R <= TW_R) ? dy * TW_C + dx : -1;     // the TMA box always has the full capacity
       }
       s_off[qi * TG + g] = off;
     }
   }
   __syncthreads();
 
-  // Warp w copies window rows w and w + 16, lane l columns l and l + 32 (the window is at most TW_R x TW_C = 24 x 48): no
-  // per-element index arithmetic.  The ring slot of the staged picture is tracked incrementally (q runs downwards).
+  // One thread (warp 0, lane 0) keeps the ring full: per ring picture one TMA box at (c0 - sxmax, r0 - symax) of its ring slot;
+  // cells outside the picture arrive as zeros (immove's zero padding).  The ring slot is tracked incrementally (q runs downwards).
   int st_slot = ((q_hi % RL) + RL) % RL;
-  const int t_idx = (r0 + warp) * w4 + c0 + lane;          // this thread's own cell; window element (lr, lc) = cell - (symax, sxmax) + (16 a, 32 b)
-  auto stage_q = [&](int qi) {
+  auto stage_q = [&](int qi) {                     // caller: the producer thread
     if (qi < nq) {
+      const int s = qi % T_STAGES;
+      mbar_wait(bar0 + 8u * (T_STAGES + s), (uint32_t)(((qi / T_STAGES) & 1) ^ 1));   // every warp is done with the window this one replaces
       const int4 wn = s_win[qi];
-      const float4* __restrict__ src = sm4 + (size_t)st_slot * n4;
-      float4* dst = stage + (qi % T_STAGES) * (TW_R * TW_C) + warp * TW_C + lane;
-      const int gr0 = r0 + warp - wn.y, gc0 = c0 + lane - wn.x, idx0 = t_idx - wn.y * w4 - wn.x;
-#pragma unroll
-      for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int b = 0; b < 2; b++) {
-          if (warp + a * TT_R < wn.w && lane + b * 32 < wn.z) {
-            const bool ok = (unsigned)(gr0 + a * TT_R) < (unsigned)h4 && (unsigned)(gc0 + b * 32) < (unsigned)w4;
-            cp_async16_zfill(dst + a * TT_R * TW_C + b * 32, src + (ok ? idx0 + a * TT_R * w4 + b * 32 : 0), ok);
-          }
-        }
+      mbar_expect_tx(bar0 + 8u * s, (uint32_t)T_STAGE_BYTES);
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(smem_u32(stage + s * (TW_R * TW_C))), "l"(&tmap), "r"((c0 - wn.x) * 4), "r"(r0 - wn.y), "r"(st_slot), "r"(bar0 + 8u * s) : "memory");
       st_slot = st_slot == 0 ? RL - 1 : st_slot - 1;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  const int r = r0 + warp, c = c0 + lane;
+  const int r = r0 + wrow, c = c0 + lane;
   const bool inside = r < h4 && c < w4;
-  float4 ref[TG];
-  float am[TG], ab[TG], ad[TG];
+  const int g0 = set * TGT;                        // this thread's first picture of the group
+  float4 ref[TGT];
+  float am[TGT], ab[TGT], ad[TGT];
 #pragma unroll
-  for (int g = 0; g < TG; g++) {
-    ref[g] = (inside && g < ng) ? sm4[(size_t)((poc0 + g) % RL) * n4 + (size_t)r * w4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-    am[g] = 0.f; ab[g] = 0.f; ad[g] = 0.f;
+  for (int k = 0; k < TGT; k++) {
+    ref[k] = (inside && g0 + k < ng) ? sm4[(size_t)((poc0 + g0 + k) % RL) * n4 + (size_t)r * w4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    am[k] = 0.f; ab[k] = 0.f; ad[k] = 0.f;
   }
-#pragma unroll
-  for (int d = 0; d < T_DIST; d++) stage_q(d);
-  const float4* __restrict__ mine = stage + warp * TW_C + lane;
+  if (warp == T_WARPS) {                          // ---- producer warp: one thread walks the ring pictures ahead of the consumers ----
+    if (lane == 0) {
+#pragma unroll 1
+      for (int w = 0; w < nq; w++) stage_q(w);     // waits for the window's buffer to be released by every consumer warp, then issues the box
+    }
+    return;
+  }
+  const float4* __restrict__ mine = stage + wrow * TW_C + lane;
   int q_slot = ((q_hi % RL) + RL) % RL;
-  // Weights of the eight pictures at ring picture q are wtab[j0 + g], j0 = poc0 - q: a sliding window kept in registers.  The loop
-  // is unrolled by TG so that the window rotates by renaming (picture g reads W[(g + u) % TG] in sub-iteration u) and the cp.async
-  // buffer index is static.  wtab's y and z columns are the same (delta 46 for bit and depth).
-  auto wload = [&](int j) { const float4 t = s_w[min(max(j, 0), PT - 1)]; return make_float2(t.x, t.y); };
-  float2 Wr[TG];
+  for (int qi0 = 0; qi0 < nq; qi0 += T_STAGES) {
 #pragma unroll
-  for (int g = 0; g < TG; g++) Wr[g] = wload(poc0 - q_hi + g);
-  for (int qi0 = 0; qi0 < nq; qi0 += TG) {
-#pragma unroll
-    for (int u = 0; u < TG; u++) {
+    for (int u = 0; u < T_STAGES; u++) {
       const int qi = qi0 + u;
       if (qi < nq) {                             // CTA-uniform
-        asm volatile("cp.async.wait_group %0;" ::"n"(T_DIST - 1) : "memory");
-        __syncthreads();                         // window qi has landed for everyone; everyone is done with window qi - 1
-        stage_q(qi + T_DIST);                    // into the buffer window qi - 1 used
+        mbar_wait(bar0 + 8u * u, (uint32_t)((qi / T_STAGES) & 1));      // window qi has landed
         const int q = q_hi - qi;
-        const float4* __restrict__ buf = mine + u * (TW_R * TW_C);       // qi % T_STAGES == u (T_STAGES == TG)
-        const int4 o03 = *reinterpret_cast<const int4*>(s_off + qi * TG), o47 = *reinterpret_cast<const int4*>(s_off + qi * TG + 4);
-        const int offs[TG] = {o03.x, o03.y, o03.z, o03.w, o47.x, o47.y, o47.z, o47.w};
-        if ((o03.x | o03.y | o03.z | o03.w | o47.x | o47.y | o47.z | o47.w) >= 0) {
-          // every picture of the group has a term for q and every source tile lies in the staged window: straight-line code
+        const int j0 = poc0 + g0 - q;                                    // j of this thread's first picture (>= 1 on the straight-line path)
+        const float4* __restrict__ buf = mine + u * (TW_R * TW_C);       // qi % T_STAGES == u
+        int offs[TGT]; int any_neg = 0;
 #pragma unroll
-          for (int g = 0; g < TG; g++) {
-            const float4 p = buf[offs[g]];
-            const float2 wj = Wr[(g + u) % TG];
-            const float ddx = ref[g].x - p.x, ddy = ref[g].y - p.y;
-            am[g] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[g]);   // main.m:195
-            ab[g] = fmaf(wj.y, fabsf(ref[g].z - p.z), ab[g]);                    // :196
-            ad[g] = fmaf(wj.y, fabsf(ref[g].w - p.w), ad[g]);                    // :197
+        for (int k4 = 0; k4 < TGT; k4 += 4) {
+          const int4 o4 = *reinterpret_cast<const int4*>(s_off + qi * TG + g0 + k4);
+          offs[k4] = o4.x; offs[k4 + 1] = o4.y; offs[k4 + 2] = o4.z; offs[k4 + 3] = o4.w;
+          any_neg |= o4.x | o4.y | o4.z | o4.w;
+        }
+        if (any_neg >= 0) {
+          // every picture of this thread has a term for q and every source tile lies in the staged window: straight-line code,
+          // all shared-memory loads first so that their latencies overlap
+          float4 pv[TGT];
+#pragma unroll
+          for (int k = 0; k < TGT; k++) pv[k] = buf[offs[k]];
+#pragma unroll
+          for (int k = 0; k < TGT; k++) {
+            const float4 p = pv[k];
+            const float2 wj = c_temporal_w[j0 + k];                              // uniform: constant bank
+            const float ddx = ref[k].x - p.x, ddy = ref[k].y - p.y;
+            am[k] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[k]);   // main.m:195
+            ab[k] = fmaf(wj.y, fabsf(ref[k].z - p.z), ab[k]);                    // :196
+            ad[k] = fmaf(wj.y, fabsf(ref[k].w - p.w), ad[k]);                    // :197
           }
         } else {
 #pragma unroll
-          for (int g = 0; g < TG; g++) {
-            const int off = offs[g];
-            if (off != -2) {                                                  // CTA-uniform
-              const int j = poc0 + g - q;
+          for (int k = 0; k < TGT; k++) {
+            const int off = offs[k];
+            if (off != -2) {                                                  // uniform per thread set
+              const int j = poc0 + g0 + k - q;
               float4 p;
               if (off >= 0) p = buf[off];
               else {                                                          // shift spread beyond the window capacity: straight from L2
-                const int2 sh = s_shift[g * PT + j];
+                const int2 sh = s_shift[(g0 + k) * PT + j];
                 const int sr = r - sh.y, sc = c - sh.x;
                 p = ((unsigned)sr < (unsigned)h4 && (unsigned)sc < (unsigned)w4) ? __ldg(sm4 + (size_t)q_slot * n4 + (size_t)sr * w4 + sc) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
-              const float2 wj = Wr[(g + u) % TG];
-              const float ddx = ref[g].x - p.x, ddy = ref[g].y - p.y;
-              am[g] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[g]);
-              ab[g] = fmaf(wj.y, fabsf(ref[g].z - p.z), ab[g]);
-              ad[g] = fmaf(wj.y, fabsf(ref[g].w - p.w), ad[g]);
+              const float2 wj = c_temporal_w[j];
+              const float ddx = ref[k].x - p.x, ddy = ref[k].y - p.y;
+              am[k] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[k]);
+              ab[k] = fmaf(wj.y, fabsf(ref[k].z - p.z), ab[k]);
+              ad[k] = fmaf(wj.y, fabsf(ref[k].w - p.w), ad[k]);
             }
           }
         }
-        Wr[u] = wload(poc0 - q + TG);            // picture 0's weight is spent: the slot takes picture 7's weight for q - 1
         q_slot = q_slot == 0 ? RL - 1 : q_slot - 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8u * (T_STAGES + u));         // this warp has read window qi
       }
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (inside) {
 #pragma unroll
-    for (int g = 0; g < TG; g++)
-      if (g < ng) {
-        float* X = Xmaps + (size_t)(f0 + g) * 9 * n4 + (size_t)r * w4 + c;
-        X[(size_t)1 * n4] = am[g]; X[(size_t)4 * n4] = ab[g]; X[(size_t)7 * n4] = ad[g];
+    for (int k = 0; k < TGT; k++)
+      if (g0 + k < ng) {
+        float* X = Xmaps + (size_t)(f0 + g0 + k) * 9 * n4 + (size_t)r * w4 + c;
+        X[(size_t)1 * n4] = am[k]; X[(size_t)4 * n4] = ab[k]; X[(size_t)7 * n4] = ad[k];
       }
   }
 }
@@ -525,11 +561,30 @@ int temporal_launch(int h4, int w4, int PT, int ring_len, int first_poc, int B, 
     CDS_LAUNCH_CHECK();
     return CDS_OK;
   }
+  {
+    static std::mutex mu; static std::map<int, bool> filled;
+    int dev = 0; CDS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (!filled[dev]) {
+      std::vector<float2> wt(TMP_MAXJ);
+      for (int j = 0; j < TMP_MAXJ; j++) wt[j] = make_float2((float)exp(-j / 26.0), (float)exp(-j / 46.0));
+      CDS_CUDA(cudaMemcpyToSymbol(c_temporal_w, wt.data(), wt.size() * sizeof(float2)));
+      filled[dev] = true;
+    }
+  }
   const int nq_max = PT - 1 + TG;
-  const size_t smem = (size_t)T_STAGES * TW_R * TW_C * 16 + (size_t)PT * 16 + (size_t)TG * PT * 8 + (size_t)nq_max * 16 + (size_t)nq_max * TG * 4;
+  const size_t smem = (size_t)T_STAGES * T_STAGE_BYTES + (size_t)PT * 16 + (size_t)TG * PT * 8 + (size_t)nq_max * 16 + (size_t)nq_max * TG * 4;
   if (int e = ensure_dyn_smem(temporal_group_kernel, smem)) return e;
-  dim3 grid(ceil_div(h4, TT_R) * ceil_div(w4, TT_C), ceil_div(B, TG));
-  temporal_group_kernel<<<grid, TT_R * TT_C, smem, st>>>(h4, w4, PT, ring_len, first_poc, B, sm4, cam_ring, wtab, Xmaps);
+  CUtensorMap tmap;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)w4 * 4, (cuuint64_t)h4, (cuuint64_t)ring_len};
+    const cuuint64_t strides[2] = {(cuuint64_t)w4 * 16, (cuuint64_t)h4 * w4 * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)TW_C * 4, (cuuint32_t)TW_R, 1};
+    if (int e = encode_tensor_map_f32_3d(sm4, dims, strides, box, &tmap)) return e;
+  }
+  dim3 grid(ceil_div(B, TG), ceil_div(h4, TT_R) * ceil_div(w4, TT_C));
+  if (grid.y > 65535) { set_error("temporal: %u tiles", grid.y); return CDS_EINVAL; }
+  temporal_group_kernel<<<grid, T_THREADS, smem, st>>>(tmap, h4, w4, PT, ring_len, first_poc, B, sm4, cam_ring, wtab, Xmaps);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }

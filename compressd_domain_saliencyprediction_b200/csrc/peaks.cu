@@ -44,6 +44,27 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, float seed, 
   if (s == 123.456f) out[0] = s;
 }
 
+// The same two opcodes with NO dependence between them: 8 FADD chains and 8 FFMA chains, interleaved.  If this reaches the pure-FFMA
+// rate, the gap between the pair mix above and pure FFMA comes from the FADD -> FFMA dependence (every FFMA of the contrast pair
+// waits for its own FADD), not from mixing the opcodes on the FMA pipe.
+__global__ void __launch_bounds__(256) fp32_indep_mix_peak_kernel(float* out, float seed, int iters) {
+  float a[8], d[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { a[k] = seed * (k + 1) + threadIdx.x * 1e-6f; d[k] = seed * (k + 2); }
+  const float m = 0.9999f + seed * 1e-9f, b = seed * 1e-3f, c = seed * 1e-7f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { d[k] = d[k] + c; a[k] = fmaf(a[k], m, b); }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k] + d[k];
+  if (s == 123.456f) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, float seed, int iters) {
   float a[8];
 #pragma unroll
@@ -146,8 +167,20 @@ using namespace cds;
 
 // Returns lane-instructions per second: fp32_pair (FADD+FFMA mix, the contrast pair), ffma (pure FFMA),
 // mufu (MUFU.EX2).  Each is the best of `reps` timed launches that fill every SM with 8 CTAs of 256 threads.
+extern "C" int cds_measure_peaks_ex(double* vals, int n);
 extern "C" int cds_measure_peaks(double* fp32_pair_ips, double* ffma_ips, double* mufu_ips) {
+  double v[4];
+  if (int e = cds_measure_peaks_ex(v, 4)) return e;
+  if (fp32_pair_ips) *fp32_pair_ips = v[0];
+  if (ffma_ips) *ffma_ips = v[1];
+  if (mufu_ips) *mufu_ips = v[2];
+  return CDS_OK;
+}
+
+// vals[0..n) = {FADD -> FFMA pair mix, pure FFMA, MUFU.EX2, FADD + FFMA without dependence} in lane-instructions per second (n <= 4)
+extern "C" int cds_measure_peaks_ex(double* vals, int n) {
   if (int e = ensure_device()) return e;
+  if (!vals || n < 1 || n > 4) { set_error("cds_measure_peaks_ex: bad arguments"); return CDS_EINVAL; }
   int dev = 0, sms = 0;
   CDS_CUDA(cudaGetDevice(&dev));
   CDS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -156,27 +189,28 @@ extern "C" int cds_measure_peaks(double* fp32_pair_ips, double* ffma_ips, double
   cudaEvent_t e0, e1;
   CDS_CUDA(cudaEventCreate(&e0)); CDS_CUDA(cudaEventCreate(&e1));
   const int grid = sms * 8, iters = 2000, reps = 5;
-  double best[3] = {0, 0, 0};
-  for (int which = 0; which < 3; which++) {
+  double best[4] = {0, 0, 0, 0};
+  for (int which = 0; which < n; which++) {
     for (int r = 0; r < reps + 1; r++) {
       CDS_CUDA(cudaEventRecord(e0));
       if (which == 0) fp32_pair_peak_kernel<<<grid, 256>>>(d, 0.5f, iters, 0.999f);
       else if (which == 1) ffma_peak_kernel<<<grid, 256>>>(d, 0.5f, iters);
-      else mufu_peak_kernel<<<grid, 256>>>(d, 0.5f, iters);
+      else if (which == 2) mufu_peak_kernel<<<grid, 256>>>(d, 0.5f, iters);
+      else fp32_indep_mix_peak_kernel<<<grid, 256>>>(d, 0.5f, iters);
       CDS_LAUNCH_CHECK();
       CDS_CUDA(cudaEventRecord(e1));
       CDS_CUDA(cudaEventSynchronize(e1));
       float ms = 0; CDS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       if (r == 0) continue;   // warm-up
-      const double per_thread = which == 0 ? (double)iters * 8 * 16 * 2 : which == 1 ? (double)iters * 16 * 16 : (double)iters * 16 * 8;
+      // pair kernel: 16 x (FADD + FFMA) + the one FADD that advances p, per inner round
+      const double per_thread = which == 0 ? (double)iters * 8 * (16 * 2 + 1) : which == 1 ? (double)iters * 16 * 16
+                              : which == 2 ? (double)iters * 16 * 8 : (double)iters * 16 * 8 * 2;
       const double ips = per_thread * grid * 256.0 / (ms * 1e-3);
       if (ips > best[which]) best[which] = ips;
     }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
-  if (fp32_pair_ips) *fp32_pair_ips = best[0];
-  if (ffma_ips) *ffma_ips = best[1];
-  if (mufu_ips) *mufu_ips = best[2];
+  for (int i = 0; i < n; i++) vals[i] = best[i];
   return CDS_OK;
 }
 

@@ -394,14 +394,23 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
     }
   } else {                                                   // ---- epilogue warps 0-7 ----
     const int quad = warp & 3, half = warp >> 2;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (TN / 2));
+    const long my_tiles = ntile_inst > (long)blockIdx.x ? (ntile_inst - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const long gtot = my_tiles * ntiles;                     // SV tiles this CTA will see over all its instance tiles
     long g = 0; int k = 0;
+    // register double buffering across tile boundaries: the first 32 columns of the NEXT accumulator are already in flight from TMEM
+    // while the MUFUs of the current one's second half issue, so a warp's exponential stream never waits for a fresh tcgen05.ld
+    uint32_t va[32], vb[32];
+    if (gtot > 0) {
+      mbar_wait(tfull(0), 0u);
+      tc_fence_after();
+      tmem_ld32(tlane, va);
+    }
     for (long tile = blockIdx.x; tile < ntile_inst; tile += gridDim.x, k++) {
       float accp[4] = {0.f, 0.f, 0.f, 0.f}, accn[4] = {0.f, 0.f, 0.f, 0.f};
       for (int t = 0; t < ntiles; t++, g++) {
         const int buf = (int)(g & 1);
-        mbar_wait(tfull(buf), (uint32_t)((g >> 1) & 1));
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TN + half * (TN / 2));
+        const uint32_t taddr = tlane + (uint32_t)(buf * TN);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         auto consume = [&](const uint32_t (&v)[32]) {
 #pragma unroll
@@ -415,15 +424,18 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
             a0 += e[0] + e[4]; a1 += e[1] + e[5]; a2 += e[2] + e[6]; a3 += e[3] + e[7];
           }
         };
-        uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
-        tmem_ld_wait();
+        tmem_ld_wait();                                      // va = columns 0..31 of this warp's half of accumulator g
         tmem_ld32(taddr + 32, vb);
         consume(va);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(buf));             // this warp's share of the accumulator is in registers
+        if (g + 1 < gtot) {
+          mbar_wait(tfull(buf ^ 1), (uint32_t)(((g + 1) >> 1) & 1));
+          tc_fence_after();
+          tmem_ld32(tlane + (uint32_t)((buf ^ 1) * TN), va);
+        }
         consume(vb);
         if (t < ntiles_pos) { accp[0] += a0; accp[1] += a1; accp[2] += a2; accp[3] += a3; }
         else                { accn[0] += a0; accn[1] += a1; accn[2] += a2; accn[3] += a3; }

@@ -219,6 +219,10 @@ int cds_profile_read(cds_ctx* ctx, double* ms, long* calls, int n);
  * contrast kernel's FADD+FFMA pair mix, pure FFMA, and MUFU.EX2.  Used as roofline denominators
  * for the FP32/MUFU-bound kernels (MEASURED_PEAKS.json has only HBM and bf16 tensor numbers). */
 int cds_measure_peaks(double* fp32_pair_ips, double* ffma_ips, double* mufu_ips);
+/* The same plus a fourth micro-kernel: vals[0..n) = {FADD -> FFMA pair mix (the contrast pair), pure FFMA, MUFU.EX2, FADD and FFMA
+ * streams WITHOUT a dependence between them}, n <= 4.  The fourth separates "mixing two opcodes on the FMA pipe" from "every FFMA
+ * waits for its own FADD" as the reason why the pair mix issues below the pure-FFMA rate. */
+int cds_measure_peaks_ex(double* vals, int n);
 /* Development probes (tools/mix_probe.py, tools/umma_probe.py): instruction-mix throughput and one tcgen05.mma with
  * caller-supplied shared-memory operand images / descriptor strides.  Not part of the drop-in surface. */
 int cds_probe_mix(int which, int ctas_per_sm, double* fma_lane_ops_per_s, double* mufu_per_s);

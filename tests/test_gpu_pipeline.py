@@ -249,3 +249,57 @@ def test_random_geometries_rates_and_batches(cds):
         worst = max(worst, err)
         assert np.array_equal(cam, wcam) and err <= REL_TOL, (i, w, h, fps, F, batch, rbf, seed, err)
     print("worst abs error over the sweep", worst)
+
+
+def test_hook_zero_copy_acquire_and_early_drain(cds):
+    """The decoder hook's own call sequence (include/cds_hm_hook.h): tokens written straight into the pinned buffers of
+    cds_acquire_frame_buffers, cds_submit_frame with those pointers, maps of batch k-1 collected after batch k was launched.
+    Same bytes as the batch entry point; a map leaves the result ring once two further batches were launched."""
+    w, h, F, fps, B = 416, 240, 14, 10.0, 4
+    packed, _ = _clip(cds, w, h, 8, F)
+    hdr, tok, base, byts = packed
+    mdl, gm = _model(cds, 64)
+    a = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=B)
+    ref_maps, ref_cam = a.process(0, *packed)
+    a.close()
+    b = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=B)
+    drained = 0
+    for f in range(F):
+        pb, ph, pt = b.acquire_frame_buffers()
+        n = int(base[f + 1] - base[f])
+        assert pt.size >= n
+        pb[:] = byts[f]; ph[:] = hdr[f]; pt[:n] = tok[base[f]:base[f + 1]]
+        b.submit_frame_acquired(f, n)
+        if f + 1 - drained >= 2 * B:                       # batch k was just launched: collect batch k-1
+            for g in range(drained, drained + B):
+                m, cam = b.get_map(g)
+                assert np.array_equal(m, ref_maps[g]) and np.array_equal(cam, ref_cam[g]), g
+            drained += B
+    for g in range(drained, F):                            # the tail: get_map launches the partial batch itself
+        m, cam = b.get_map(g)
+        assert np.array_equal(m, ref_maps[g]) and np.array_equal(cam, ref_cam[g]), g
+    with pytest.raises(cds.CdsError):
+        b.get_map(1)                                       # batch 0 has left the two result batches
+    b.close()
+
+
+def test_hook_malformed_picture_is_reported_and_does_not_wedge_the_context(cds):
+    """A corrupt token stream submitted through the hook surfaces as CDS_EFORMAT when its maps are collected; the context then
+    accepts the next pictures in order (a failed flush must not leave pending_first behind)."""
+    w, h, fps, B = 416, 240, 10.0, 4
+    packed, _ = _clip(cds, w, h, 9, 8)
+    hdr, tok, base, byts = packed
+    mdl, gm = _model(cds, 32)
+    c = cds.SaliencyClip(w, h, fps, model=gm, meanVec=MEAN9, stdVec=STD9, max_batch=B)
+    for f in range(4):
+        t = tok[base[f]:base[f + 1]].copy()
+        if f == 2:
+            t[hdr[f, 0, 0]:hdr[f, 0, 0] + hdr[f, 0, 1]] = 99       # an endless split chain in CTU 0
+        c.submit_frame(f, byts[f], hdr[f], t)
+    with pytest.raises(cds.CdsError):
+        c.get_map(3)
+    for f in range(4, 8):                                   # pictures 4..7 are still accepted in order
+        c.submit_frame(f, byts[f], hdr[f], tok[base[f]:base[f + 1]])
+    m, _ = c.get_map(7)
+    assert np.isfinite(m).all()
+    c.close()
