@@ -40,10 +40,27 @@ def build_synth(force=False):
     return SYNTH_LIB
 
 
+FEEDER = os.path.join(HERE, "cds_feeder")                # host binary: one process per GPU fed by N decoder processes (csrc_host/cds_feeder.cpp)
+FEEDER_SRC = os.path.join(HERE, "csrc_host", "cds_feeder.cpp")
+
+
+def build_feeder(force=False):
+    """g++ only; links the C ABI of libcds_b200.so (rpath $ORIGIN), so it is built after the library."""
+    deps = [FEEDER_SRC, os.path.join(HERE, "..", "include", "cds.h"), LIB]
+    if not force and os.path.exists(FEEDER) and os.path.getmtime(FEEDER) > max(os.path.getmtime(d) for d in deps):
+        return FEEDER
+    r = subprocess.run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-pthread", "-o", FEEDER, FEEDER_SRC, "-L" + HERE, "-lcds_b200",
+                        "-Wl,-rpath,$ORIGIN", "-Wl,--allow-shlib-undefined"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("cds_feeder build failed:\n" + r.stdout)
+    return FEEDER
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link libcds_b200.so next to this file."""
     build_synth(force)
     if not force and not needs_build():
+        build_feeder(force)
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -67,6 +84,7 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    build_feeder(True)
     return LIB
 
 

@@ -327,6 +327,49 @@ def test_feeder_many_streams_one_gpu_process(cds):
     assert np.array_equal(res["maps"][1][:got.shape[0]], got)
 
 
+def test_cpp_feeder_process_matches_the_direct_path(cds, tmp_path):
+    """SURVEY 8(f).3 at box scale: the C++ feeder (one process per GPU; csrc_host/cds_feeder.cpp) spawns parse-only decoder processes,
+    reads their packed syntax straight into the library's pinned staging buffers and drains the maps asynchronously.  Two streams of
+    different sizes, four producers: every video's maps equal the direct path's bytes (and through it the golden PNGs)."""
+    import json, subprocess
+    feeder = os.path.join(os.path.dirname(cds.lib_path()), "cds_feeder")
+    dumper = os.path.join(o.ROOT, "oracle", "_ref", "hm_syntax_dump")
+    sdir = os.path.join(o.ROOT, "oracle", "_ref", "streams")
+    if not (os.path.exists(feeder) and os.path.exists(dumper) and os.path.exists(os.path.join(sdir, "BasketballDrill.bin"))):
+        pytest.skip("cds_feeder / hooked HM decoder / bitstreams not built (needs the reference tree at build time)")
+    drill, bpass = os.path.join(sdir, "BasketballDrill.bin"), os.path.join(sdir, "BasketballPass.bin")
+    pre = str(tmp_path) + "/"
+    r = subprocess.run([feeder, "--producer", dumper, "--fast", "--fps", "50", "--batch", "32", "--out-prefix", pre,
+                        drill + ":832x480", bpass + ":416x240"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert [v["pictures"] for v in res["videos"]] == [500, 500] and all(v["error"] == "" for v in res["videos"])
+    print(f"cds_feeder: {res['pictures']} pictures of 2 streams in {res['seconds']:.2f} s = {res['pictures_per_s']:.0f} pictures/s")
+    maps = np.fromfile(pre + "BasketballDrill.bin.u8", np.uint8).reshape(500, 480, 832)
+    d = np.load(os.path.join(GOLD, "fast_BasketballDrill.npz"))
+    n = d["png"].shape[0]
+    clip = cds.SaliencyClip(832, 480, 50.0, fast=True, out_u8=True, max_batch=32)
+    got, _ = clip.process(0, d["hdr"], d["tok"], d["tok_base"], d["ctu_bytes"])
+    clip.close()
+    assert np.array_equal(maps[:n], got)
+    per = (maps[:n] != d["png"]).reshape(n, -1).sum(1)
+    assert per.sum() <= 3 and (per == 0).sum() >= 36
+    maps2 = np.fromfile(pre + "BasketballPass.bin.u8", np.uint8).reshape(500, 240, 416)
+    p = np.load(os.path.join(GOLD, "real_BasketballPass.npz"))
+    clip = cds.SaliencyClip(416, 240, 50.0, fast=True, out_u8=True, max_batch=32)
+    got, _ = clip.process(0, p["hdr"], p["tok"], p["tok_base"], p["ctu_bytes"])
+    clip.close()
+    assert np.array_equal(maps2[:got.shape[0]], got)
+    # the same two streams twice over (four producers): same checksums per video
+    r2 = subprocess.run([feeder, "--producer", dumper, "--fast", "--fps", "50", "--batch", "32",
+                         drill + ":832x480", bpass + ":416x240", drill + ":832x480", bpass + ":416x240"], capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    res2 = json.loads(r2.stdout.strip().splitlines()[-1])
+    cs = [v["checksum"] for v in res2["videos"]]
+    assert cs[0] == cs[2] == res["videos"][0]["checksum"] and cs[1] == cs[3] == res["videos"][1]["checksum"]
+    print(f"cds_feeder: {res2['pictures']} pictures of 4 streams in {res2['seconds']:.2f} s = {res2['pictures_per_s']:.0f} pictures/s")
+
+
 def test_fast_version_random_geometries_rates_and_batches(cds):
     """A seeded sweep over picture sizes (widths k*16, heights k*8 from 64 up), frame rates (PS / PT from cvRound, incl. 29.97 and 25 whose
     halves round to even) and batch sizes: every case bit-identical to the oracle (tools/fast_fuzz.py runs larger sweeps)."""
