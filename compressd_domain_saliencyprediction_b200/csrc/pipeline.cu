@@ -80,6 +80,13 @@ struct cds_ctx {
   cudaStream_t back_stream = nullptr;
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr}, ev_mid = nullptr;
   int xs_flip = 0, last_xs = 0; bool overlap = true;
+  // Pre stage on its own stream (RBF branch, overlap on): stages (a), (c), smoothing, thresholds, temporal and the contrast inputs of batch
+  // i+1 — latency- and bandwidth-bound kernels — run beside the map passes of batch i.  The batch-local buffers that cross from the pre
+  // stage to the main stage exist twice (set = batch parity): d_X, the three padded contrast inputs.
+  cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_c48 = nullptr, ev_call = nullptr;
+  float* d_X2[2] = {nullptr, nullptr}; float* d_padB2[2] = {nullptr, nullptr}; float* d_padD2[2] = {nullptr, nullptr}; float* d_padM2[2] = {nullptr, nullptr};
+  bool pre_ovl = true, call_open = false; int last_set = 0;
+  cudaStream_t last_pre_stream = nullptr;          // the stream the most recent batch's pre stage ran on (its camera-motion gather included)
   // Deferred back half (RBF branch, overlap on): the SVM + final-map chain of batch i is launched from the MIDDLE of batch
   // i+1's front half, right before its contrast kernels, so that the MUFU-bound persistent SVM kernel and the FP32-bound
   // contrast kernel start together and share every SM for their whole duration (or from join_back when no batch follows).
@@ -559,6 +566,14 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
   A(d_subB, (size_t)B * sbR * sbC); A(d_padB, (size_t)B * (sbR + 4) * (sbC + 4)); A(d_rawB, (size_t)B * sbR * sbC);
   A(d_subD, (size_t)B * sdR * sdC); A(d_padD, (size_t)B * (sdR + 24) * (sdC + 24)); A(d_rawD, (size_t)B * sdR * sdC);
   A(d_padM, (size_t)2 * B * (h4 + 48) * (w4 + 48)); A(d_rawM, (size_t)2 * B * n4);
+  c->d_X2[0] = c->d_X; c->d_padB2[0] = c->d_padB; c->d_padD2[0] = c->d_padD; c->d_padM2[0] = c->d_padM;
+  c->d_X2[1] = c->d_X; c->d_padB2[1] = c->d_padB; c->d_padD2[1] = c->d_padD; c->d_padM2[1] = c->d_padM;
+  { const char* ov = getenv("CDS_OVERLAP"); const char* po = getenv("CDS_PRE_OVERLAP");
+    c->pre_ovl = !(ov && ov[0] == '0') && !(po && po[0] == '0') && p->use_rbf == CDS_FUSION_RBF; }
+  if (c->pre_ovl && !fm) {
+    A(d_X2[1], (size_t)B * 9 * n4); A(d_padB2[1], (size_t)B * (sbR + 4) * (sbC + 4)); A(d_padD2[1], (size_t)B * (sdR + 24) * (sdC + 24));
+    A(d_padM2[1], (size_t)2 * B * (h4 + 48) * (w4 + 48));
+  }
   A(d_keys, (size_t)4 * B * 2); A(d_maxbits, (size_t)4 * B); A(d_w5, 64 * 64); A(d_sched, 4096);
   A(d_T, (size_t)9 * B * h4 * W);
   A(d_Y, (size_t)(p->use_rbf ? 3 : 9) * B * HW);
@@ -588,6 +603,11 @@ extern "C" int cds_create(const cds_params* p, cds_ctx** out) {
                cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming) != cudaSuccess)) { set_error("cudaEventCreate"); e = CDS_ECUDA; }
   }
   if (!e && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate copy"); e = CDS_ECUDA; }
+  if (!e && (cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking) != cudaSuccess ||
+             cudaEventCreateWithFlags(&c->ev_pre[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_pre[1], cudaEventDisableTiming) != cudaSuccess ||
+             cudaEventCreateWithFlags(&c->ev_c48, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_call, cudaEventDisableTiming) != cudaSuccess)) {
+    set_error("cudaStreamCreate pre"); e = CDS_ECUDA;
+  }
   if (!e) {           // the back stream outranks the front stream: the persistent SVM CTAs are placed before the contrast CTAs that start with them
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -626,6 +646,8 @@ extern "C" void cds_destroy(cds_ctx* c) {
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->back_stream) { cudaStreamSynchronize(c->back_stream); cudaStreamDestroy(c->back_stream); }
+  if (c->pre_stream) { cudaStreamSynchronize(c->pre_stream); cudaStreamDestroy(c->pre_stream); }
+  for (cudaEvent_t ev : {c->ev_pre[0], c->ev_pre[1], c->ev_c48, c->ev_call}) if (ev) cudaEventDestroy(ev);
   if (c->fast_front_stream) { cudaStreamSynchronize(c->fast_front_stream); cudaStreamDestroy(c->fast_front_stream); }
   if (c->ev_fstart) cudaEventDestroy(c->ev_fstart);
   if (c->ev_mid) cudaEventDestroy(c->ev_mid);
@@ -646,6 +668,8 @@ extern "C" int cds_seek(cds_ctx* c, int poc) {
   if (!c || poc < 0) { set_error("cds_seek: bad arguments"); return CDS_EINVAL; }
   join_back(c, c->stream);
   cudaStreamSynchronize(c->stream);
+  if (c->pre_stream) cudaStreamSynchronize(c->pre_stream);
+  if (c->back_stream) cudaStreamSynchronize(c->back_stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->fast) {
     if (int e = fast_clear(c->fast, c->stream)) return e;
@@ -660,6 +684,7 @@ extern "C" int cds_seek(cds_ctx* c, int poc) {
   CDS_CUDA(cudaMemset(c->r_sm4, 0, 4 * rb));
   for (double* r : {c->r_Vx, c->r_Vy}) CDS_CUDA(cudaMemset(r, 0, 2 * rb));
   CDS_CUDA(cudaMemset(c->r_cam, 0, (size_t)c->RL * 8));
+  CDS_CUDA(cudaStreamSynchronize(0));                  // the context's streams are non-blocking: they do not wait for the null stream
   c->next_poc = poc; c->pending = 0; c->pending_first = poc; c->last_first = -1; c->last_n = 0;
   hook_reset(c);
   return CDS_OK;
@@ -667,6 +692,27 @@ extern "C" int cds_seek(cds_ctx* c, int poc) {
 extern "C" int cds_reset(cds_ctx* c) { return cds_seek(c, 0); }
 
 namespace {
+
+// The stream on which this API call's ring-touching work (host->device staging, stages (a), (c), smoothing, ...) runs: the context's pre
+// stream when the pre stage overlaps the previous batch's map passes, else `st`.  The first use inside an API call orders the pre
+// stream after everything the caller had enqueued on `st` before the call; pre_join() closes the call.
+cudaStream_t pre_stream_for(cds_ctx* c, cudaStream_t st) {
+  const bool pov = c->overlap && c->pre_ovl && c->p.use_rbf == CDS_FUSION_RBF && !c->prof_on && !c->maps_in && !c->fast;
+  if (!pov) return st;
+  if (!c->call_open) {
+    if (cudaEventRecord(c->ev_call, st) != cudaSuccess || cudaStreamWaitEvent(c->pre_stream, c->ev_call, 0) != cudaSuccess) return st;
+    c->call_open = true;
+  }
+  return c->pre_stream;
+}
+// end of an API call: `st` covers whatever is still running on the pre stream
+int pre_join(cds_ctx* c, cudaStream_t st) {
+  if (!c->call_open) return CDS_OK;
+  c->call_open = false;
+  CDS_CUDA(cudaEventRecord(c->ev_call, c->pre_stream));
+  CDS_CUDA(cudaStreamWaitEvent(st, c->ev_call, 0));
+  return CDS_OK;
+}
 
 // stages (a), (c) and smoothing: everything later pictures need from this one as temporal context
 int run_context_stages(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int32_t* hdr, const int16_t* tok,
@@ -769,50 +815,71 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   c->last_xs = slot;
   float* xsvm = c->d_xsvm2[slot];
   if (!ov) if (int e = flush_pending_back(c, nullptr)) return e;          // a mode switch (profiling on) must not strand a deferred half
-  if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));      // the back half of batch i-2 has finished reading xsvm[slot]
   const int h4 = c->h4, w4 = c->w4, n4 = c->n4, H = c->h, W = c->w, RL = c->RL;
   const float* fparam = c->d_fparam;
+  // ---- PRE stage: stages (a), (c), smoothing, thresholds, temporal, contrast inputs.  With `pov` it runs on the context's pre
+  //      stream, so that batch i+1's pre stage (latency / bandwidth bound) overlaps the map passes of batch i on `st`.  It may start
+  //      when (1) the caller's inputs are ready (ev_call, once per API call), (2) the main stage of batch i-1 (same buffer set two
+  //      batches ago: ev_front[slot]) has finished reading this set of d_X / padded inputs, (3) the contrast kernels of the previous
+  //      batch are done (ev_c48: the issue-bound phase stays undisturbed).  Everything that touches the temporal rings lives here,
+  //      in one stream, in picture order. ----
+  const bool pov = ov && c->pre_ovl && !c->maps_in;
+  const int set = pov ? slot : 0;                                        // buffer set = xsvm slot: both flip once per batch
+  c->last_set = set;
+  cudaStream_t sp = pov ? pre_stream_for(c, st) : st;
+  c->last_pre_stream = sp;
+  float* dX = c->d_X2[set]; float* dPadB = c->d_padB2[set]; float* dPadD = c->d_padD2[set]; float* dPadM = c->d_padM2[set];
+  if (pov) {
+    CDS_CUDA(cudaStreamWaitEvent(sp, c->ev_front[set], 0));
+    CDS_CUDA(cudaStreamWaitEvent(sp, c->ev_c48, 0));
+  }
   // Where the previous batch's deferred back half (persistent MUFU-bound SVM, then the final-map chain) joins this batch's front
   // half (CDS_BACK_AT): 1 (default) = at the mid-point, beside the FP32-bound contrast kernels, which are then capped to
   // CDS_CO_CTAS CTAs per SM; 0 = at its start, beside stages (a), (c), smoothing, threshold, temporal; 2 = after the contrast
-  // kernels.  Measured at 1080p / nSV 4096 / 64 pictures: 11.53 ms per batch for 1, 13.1 for 0 (the resident SVM CTAs keep the
-  // register-hungry temporal and vote kernels off the SMs), 12.2 for 2, 12.7 without any overlap.
+  // kernels.  Measured at 1080p / nSV 4096 / 64 pictures: 11.3 ms per batch for 1, 12.4 for 0 (the resident SVM CTAs keep the
+  // register-hungry temporal and vote kernels off the SMs), 12.2 for 2, 12.9 without any overlap.
   static const int back_at = [] { const char* e = getenv("CDS_BACK_AT"); const int v = e ? atoi(e) : 1; return v < 0 || v > 2 ? 1 : v; }();
   if (ov && c->pb.valid && back_at == 0) {
     trace_mark(c, c->tr_batches, TR_MID, st);
     CDS_CUDA(cudaEventRecord(c->ev_mid, st));
     if (int e = flush_pending_back(c, c->ev_mid)) return e;
   }
-  if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, st)) return e;
+  if (int e = run_context_stages(c, first_poc, n, bytes, hdr, tok, tok_base, sp)) return e;
+  if (cam_out) {      // cam_out is a DEVICE pointer here: gather the ring slots of this batch (the pre stage owns the rings)
+    gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, sp>>>(c->r_cam, RL, first_poc, n, cam_out);
+    CDS_LAUNCH_CHECK();
+  }
   // ---- thresholded smoothed maps and temporal features -> X slots 0,3,6 / 1,4,7 ----
-  prof_mark(c, ST_THRESH, st);
-  if (int e = myst_small_launch(n4, H, W, RL, first_poc, n, c->d_mv_s, c->r_sm4, c->d_X, st)) return e;
-  prof_mark(c, ST_TEMPORAL, st);
-  if (int e = temporal_launch(h4, w4, c->PT, RL, first_poc, n, c->r_sm4, c->r_cam, c->d_wtab,
-                              c->d_X, st)) return e;
+  prof_mark(c, ST_THRESH, sp);
+  if (int e = myst_small_launch(n4, H, W, RL, first_poc, n, c->d_mv_s, c->r_sm4, dX, sp)) return e;
+  prof_mark(c, ST_TEMPORAL, sp);
+  if (int e = temporal_launch(h4, w4, c->PT, RL, first_poc, n, c->r_sm4, c->r_cam, c->d_wtab, dX, sp)) return e;
   // ---- (b) contrast: bit (cusize 16, delta 3, win 5), depth (2, 13, 24), mvx / mvy (1, 11, 48)  main.m:226-235 ----
   {
     const size_t nk = (size_t)2 * n * 2;
-    fill_u32_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(c->d_keys, nk, 0xffffffffu, 0u);
+    fill_u32_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, sp>>>(c->d_keys, nk, 0xffffffffu, 0u);
     CDS_LAUNCH_CHECK();
-    CDS_CUDA(cudaMemsetAsync(c->d_maxbits, 0, (size_t)4 * n * 4, st));
     unsigned *kB = c->d_keys, *kD = c->d_keys + 2 * n;
     unsigned *mB = c->d_maxbits, *mD = c->d_maxbits + n, *mX = c->d_maxbits + 2 * n, *mY = c->d_maxbits + 3 * n;
     const int sbR = (h4 + 15) / 16, sbC = (w4 + 15) / 16, sdR = (h4 + 1) / 2, sdC = (w4 + 1) / 2;
     float g[64];
-    prof_mark(c, ST_CONTRAST_PREP, st);
+    prof_mark(c, ST_CONTRAST_PREP, sp);
     // block mean (+1e-8), zero pad, pm_norm of the padded map (cu_contrast5.m:8-32, Sudoku_contrastcpp5.m:18-34)
-    if (int e = contrast_sub_launch(c->d_X + (size_t)3 * n4, (long)9 * n4, 0, 0, n, h4, w4, 16, c->d_subB, kB, st)) return e;
-    if (int e = contrast_pad_launch(c->d_subB, kB, n, sbR, sbC, 2, c->d_padB, st)) return e;
-    if (int e = contrast_sub_launch(c->d_X + (size_t)6 * n4, (long)9 * n4, 0, 0, n, h4, w4, 2, c->d_subD, kD, st)) return e;
-    if (int e = contrast_pad_launch(c->d_subD, kD, n, sdR, sdC, 12, c->d_padD, st)) return e;
+    if (int e = contrast_sub_launch(dX + (size_t)3 * n4, (long)9 * n4, 0, 0, n, h4, w4, 16, c->d_subB, kB, sp)) return e;
+    if (int e = contrast_pad_launch(c->d_subB, kB, n, sbR, sbC, 2, dPadB, sp)) return e;
+    if (int e = contrast_sub_launch(dX + (size_t)6 * n4, (long)9 * n4, 0, 0, n, h4, w4, 2, c->d_subD, kD, sp)) return e;
+    if (int e = contrast_pad_launch(c->d_subD, kD, n, sdR, sdC, 12, dPadD, sp)) return e;
     // mvx | mvy (cusize 1) in double up to the pm_norm; d_cxy holds [mvx: n maps | mvy: n maps] (written by smooth_launch)
     {
       const size_t nk64 = (size_t)2 * n * 2;
-      fill_u64_kernel<<<(unsigned)((nk64 + 255) / 256), 256, 0, st>>>(c->d_keys64, nk64, ~0ull, 0ull);
+      fill_u64_kernel<<<(unsigned)((nk64 + 255) / 256), 256, 0, sp>>>(c->d_keys64, nk64, ~0ull, 0ull);
       CDS_LAUNCH_CHECK();
-      if (int e = contrast_prep_f64_launch(c->d_cxy, 2 * n, h4, w4, 24, c->d_keys64, c->d_padM, st)) return e;
+      if (int e = contrast_prep_f64_launch(c->d_cxy, 2 * n, h4, w4, 24, c->d_keys64, dPadM, sp)) return e;
     }
+    // ---- MAIN stage on `st`: waits for this batch's pre stage and for the back half of batch i-2 (it read xsvm[slot]) ----
+    if (pov) { CDS_CUDA(cudaEventRecord(c->ev_pre[set], sp)); CDS_CUDA(cudaStreamWaitEvent(st, c->ev_pre[set], 0)); }
+    if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));
+    CDS_CUDA(cudaMemsetAsync(c->d_maxbits, 0, (size_t)4 * n * 4, st));
     // ---- mid-point: the previous batch's SVM starts together with this batch's contrast kernels.  Both are persistent; the
     //      contrast kernels then keep to `co_ctas` CTAs per SM, which leaves the shared memory, registers and warp slots of one
     //      SVM CTA free on every SM whichever of the two is placed first ----
@@ -826,31 +893,32 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     }
     // bit: 5x5 window on the CTU grid
     prof_mark(c, ST_CONTRAST_W5, st);
-    if (int e = contrast_generic_launch(c->d_padB, c->d_w5, c->d_rawB, mB, n, sbR, sbC, 5, 2, st)) return e;
+    if (int e = contrast_generic_launch(dPadB, c->d_w5, c->d_rawB, mB, n, sbR, sbC, 5, 2, st)) return e;
     // depth: 24x24 window on the 8-px grid
     prof_mark(c, ST_CONTRAST_W24, st);
     gaussian_factor(24, 13.0, g);
-    if (int e = contrast_sep_launch(c->d_padD, c->d_rawD, mD, n, sdR, sdC, 24, g, g, nullptr, st, co_ctas, co_ctas ? c->d_sched : nullptr)) return e;
+    if (int e = contrast_sep_launch(dPadD, c->d_rawD, mD, n, sdR, sdC, 24, g, g, nullptr, st, co_ctas, co_ctas ? c->d_sched : nullptr)) return e;
     // mvx | mvy as 2n maps in one launch: 48x48 window on the 4-px grid (the dominant FP32 kernel)
     prof_mark(c, ST_CONTRAST_W48, st);
     trace_mark(c, c->tr_batches, TR_C48_START, st);
     gaussian_factor(48, 11.0, g);
-    if (int e = contrast_sep_launch(c->d_padM, c->d_rawM, mX, 2 * n, h4, w4, 48, g, g, nullptr, st, co_ctas, co_ctas ? c->d_sched + 2048 : nullptr)) return e;   // mX,mY contiguous
+    if (int e = contrast_sep_launch(dPadM, c->d_rawM, mX, 2 * n, h4, w4, 48, g, g, nullptr, st, co_ctas, co_ctas ? c->d_sched + 2048 : nullptr)) return e;   // mX,mY contiguous
     trace_mark(c, c->tr_batches, TR_C48_END, st);
+    if (pov) CDS_CUDA(cudaEventRecord(c->ev_c48, st));                    // the next batch's pre stage may join from here on
     if (ov && c->pb.valid && back_at == 2) {
       trace_mark(c, c->tr_batches, TR_MID, st);
       CDS_CUDA(cudaEventRecord(c->ev_mid, st));
       if (int e = flush_pending_back(c, c->ev_mid)) return e;
     }
     prof_mark(c, ST_CONTRAST_POST, st);
-    if (int e = contrast_post_launch(c->d_rawB, mB, n, sbR, sbC, 16, h4, w4, c->d_X, 5, st)) return e;
-    if (int e = contrast_post_launch(c->d_rawD, mD, n, sdR, sdC, 2, h4, w4, c->d_X, 8, st)) return e;
-    if (int e = contrast_post_mv_launch(c->d_rawM, c->d_rawM + (size_t)n * n4, mX, mY, n, h4, w4, c->d_X, 2, st)) return e;
+    if (int e = contrast_post_launch(c->d_rawB, mB, n, sbR, sbC, 16, h4, w4, dX, 5, st)) return e;
+    if (int e = contrast_post_launch(c->d_rawD, mD, n, sdR, sdC, 2, h4, w4, dX, 8, st)) return e;
+    if (int e = contrast_post_mv_launch(c->d_rawM, c->d_rawM + (size_t)n * n4, mX, mY, n, h4, w4, dX, 2, st)) return e;
   }
   // ---- fourX2 + imfilter(gaussian) at full resolution: statistics (and the temporal maps themselves) ----
   int nb = 0;
   prof_mark(c, ST_FULLRES_H, st);
-  if (int e = fullres_hpass_launch(c->d_X, 9 * n, h4, w4, c->poly, c->d_T, st)) return e;
+  if (int e = fullres_hpass_launch(dX, 9 * n, h4, w4, c->poly, c->d_T, st)) return e;
   prof_mark(c, ST_FULLRES_V, st);
   if (int e = fullres_vpass_launch(c->d_T, 9 * n, h4, W, c->poly, c->d_Y, c->d_store_index, c->d_partial, &nb, st)) return e;
   prof_mark(c, ST_TEMPORAL_STATS, st);
@@ -862,14 +930,10 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     temporal_thresh_finalize_kernel<<<3 * n, 32, 0, st>>>(c->d_partial2, c->nblk2, c->d_stats9, c->d_xf);
     CDS_LAUNCH_CHECK();
   }
-  if (cam_out) {      // cam_out is a DEVICE pointer here: gather the ring slots of this batch (front half: it reads the ring)
-    gather_cam_kernel<<<ceil_div(2 * n, 64), 64, 0, st>>>(c->r_cam, RL, first_poc, n, cam_out);
-    CDS_LAUNCH_CHECK();
-  }
   if (c->p.use_rbf) {
     // ---- features at 200x200 (main.m:275-294) ----
     prof_mark(c, ST_RESIZE200, st);
-    if (int e = banded_rows_launch(c->d_X, 9 * n, h4, w4, c->Av, nullptr, c->d_A1, st)) return e;
+    if (int e = banded_rows_launch(dX, 9 * n, h4, w4, c->Av, nullptr, c->d_A1, st)) return e;
     if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, c->d_F200, st)) return e;
     if (int e = banded_rows_launch(c->d_Y, 3 * n, H, W, c->Rv, c->d_xf, c->d_R1, st)) return e;
     if (int e = banded_cols_launch(c->d_R1, 3 * n, 200, W, c->Rh, c->d_Ft, st)) return e;
@@ -905,6 +969,7 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
 
 // make `st` wait for every back half still in flight (end of an API call: the caller's stream then covers all the work)
 int join_back(cds_ctx* c, cudaStream_t st) {
+  if (int e = pre_join(c, st)) return e;
   if (int e = flush_pending_back(c, nullptr)) return e;     // no batch follows: the last back half runs on its own
   if (c->overlap && c->p.use_rbf)
     for (int b = 0; b < 2; b++) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[b], 0));
@@ -919,11 +984,13 @@ extern "C" int cds_clip_context_dev(cds_ctx* c, int first_poc, int nframes, cons
   if (!c || !ctu_bytes || !hdr || !tok || !tok_base || nframes < 1) { set_error("cds_clip_context_dev: bad arguments"); return CDS_EINVAL; }
   if (first_poc != c->next_poc) { set_error("cds_clip_context_dev: expected poc %d, got %d (use cds_seek)", c->next_poc, first_poc); return CDS_EINVAL; }
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  cudaStream_t sp = pre_stream_for(c, st);
   for (int done = 0; done < nframes; done += c->B) {
     const int n = std::min(c->B, nframes - done);
     if (int e = run_context_stages(c, first_poc + done, n, ctu_bytes + (size_t)done * c->nctu, hdr + (size_t)done * c->nctu * 4, tok,
-                                   tok_base + done, st)) return e;
+                                   tok_base + done, sp)) return e;
   }
+  if (int e = pre_join(c, st)) return e;
   c->next_poc = first_poc + nframes;
   return CDS_OK;
 }
@@ -1013,12 +1080,13 @@ static int process_host(cds_ctx* c, int first_poc, int nframes, const uint16_t* 
     const int64_t t0 = tok_base[done], t1 = tok_base[done + n];
     int64_t* bs = base.data() + (size_t)bi * (c->B + 1);
     for (int i = 0; i <= n; i++) bs[i] = tok_base[done + i] - t0;
-    CDS_CUDA(cudaMemcpyAsync(c->d_bytes, ctu_bytes + (size_t)done * c->nctu, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, st));
-    CDS_CUDA(cudaMemcpyAsync(c->d_hdr, hdr + (size_t)done * c->nctu * 4, (size_t)n * c->nctu * 16, cudaMemcpyHostToDevice, st));
-    CDS_CUDA(cudaMemcpyAsync(c->d_tok, tok + t0, (size_t)(t1 - t0) * 2, cudaMemcpyHostToDevice, st));
-    CDS_CUDA(cudaMemcpyAsync(c->d_tokbase, bs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    cudaStream_t sp = pre_stream_for(c, st);        // the staging buffers are read by stages (a) / (c): same stream, in order
+    CDS_CUDA(cudaMemcpyAsync(c->d_bytes, ctu_bytes + (size_t)done * c->nctu, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, sp));
+    CDS_CUDA(cudaMemcpyAsync(c->d_hdr, hdr + (size_t)done * c->nctu * 4, (size_t)n * c->nctu * 16, cudaMemcpyHostToDevice, sp));
+    CDS_CUDA(cudaMemcpyAsync(c->d_tok, tok + t0, (size_t)(t1 - t0) * 2, cudaMemcpyHostToDevice, sp));
+    CDS_CUDA(cudaMemcpyAsync(c->d_tokbase, bs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, sp));
     if (context_only) {
-      if (int e = run_context_stages(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, st)) return e;
+      if (int e = run_context_stages(c, first_poc + done, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, sp)) return e;
       continue;
     }
     const int buf = c->out_flip; c->out_flip ^= 1;
@@ -1203,11 +1271,12 @@ int hook_launch(cds_ctx* c) {
   c->hs_cur ^= 1;
   int rc = CDS_OK;
   auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && !rc) { set_error("cds_submit_frame: %s: %s", what, cudaGetErrorString(e)); rc = CDS_ECUDA; } };
-  cu(cudaMemcpyAsync(c->d_bytes, S.bytes, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, st), "copy in");
-  cu(cudaMemcpyAsync(c->d_hdr, S.hdr, (size_t)n * c->nctu * 16, cudaMemcpyHostToDevice, st), "copy in");
-  cu(cudaMemcpyAsync(c->d_tok, S.tok, S.tok_used * 2, cudaMemcpyHostToDevice, st), "copy in");
-  cu(cudaMemcpyAsync(c->d_tokbase, S.base, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st), "copy in");
-  cu(cudaEventRecord(S.h2d_done, st), "event");
+  cudaStream_t sp = pre_stream_for(c, st);          // staging is read by stages (a) / (c): same stream, in order
+  cu(cudaMemcpyAsync(c->d_bytes, S.bytes, (size_t)n * c->nctu * 2, cudaMemcpyHostToDevice, sp), "copy in");
+  cu(cudaMemcpyAsync(c->d_hdr, S.hdr, (size_t)n * c->nctu * 16, cudaMemcpyHostToDevice, sp), "copy in");
+  cu(cudaMemcpyAsync(c->d_tok, S.tok, S.tok_used * 2, cudaMemcpyHostToDevice, sp), "copy in");
+  cu(cudaMemcpyAsync(c->d_tokbase, S.base, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, sp), "copy in");
+  cu(cudaEventRecord(S.h2d_done, sp), "event");
   S.in_flight = true; S.n = 0; S.tok_used = 0;
   if (rc) return rc;
   const int slot = c->ho_cur; c->ho_cur ^= 1;
@@ -1218,9 +1287,10 @@ int hook_launch(cds_ctx* c) {
   c->retired_tag = -1;
   rc = run_batch(c, first, n, c->d_bytes, c->d_hdr, c->d_tok, c->d_tokbase, c->d_out[buf], dcam, st, c->ev_copied[buf], slot | (buf << 1));
   if (rc) { O.first = -1; O.n = 0; return rc; }
-  // camera motion: gathered by the front half on st; its copy stays on st, so the gather of batch k+2 (same slot) cannot overtake it
-  cu(cudaMemcpyAsync(O.cam, dcam, (size_t)n * 8, cudaMemcpyDeviceToHost, st), "copy out");
-  cu(cudaEventRecord(O.cam_ready, st), "event");
+  // camera motion: gathered by the pre stage; its copy stays on that stream, so the gather of batch k+2 (same slot) cannot overtake it
+  cudaStream_t sg = c->last_pre_stream ? c->last_pre_stream : st;
+  cu(cudaMemcpyAsync(O.cam, dcam, (size_t)n * 8, cudaMemcpyDeviceToHost, sg), "copy out");
+  cu(cudaEventRecord(O.cam_ready, sg), "event");
   if (rc) return rc;
   if (int e = hook_drain_retired(c)) return e;
   c->next_poc = first + n;
@@ -1353,7 +1423,7 @@ extern "C" int cds_debug_copy(cds_ctx* c, const char* which, int frame_in_batch,
   if (!c || !which || !dst || frame_in_batch < 0 || frame_in_batch >= c->B) { set_error("cds_debug_copy: bad arguments"); return CDS_EINVAL; }
   const int f = frame_in_batch; const void* src = nullptr; size_t n = 0;
   if (c->fast) return fast_debug_copy(c->fast, which, f, dst, bytes, c->stream);
-  if (!strcmp(which, "xmaps")) { src = c->d_X + (size_t)f * 9 * c->n4; n = (size_t)9 * c->n4 * 4; }
+  if (!strcmp(which, "xmaps")) { src = c->d_X2[c->last_set] + (size_t)f * 9 * c->n4; n = (size_t)9 * c->n4 * 4; }
   else if (!strcmp(which, "stats")) { src = c->d_stats9 + (size_t)f * 36; n = 36 * 4; }
   else if (!strcmp(which, "feat200")) { src = c->d_F200 + (size_t)f * 9 * 40000; n = (size_t)9 * 40000 * 4; }
   else if (!strcmp(which, "ft")) { src = c->d_Ft + (size_t)f * 3 * 40000; n = (size_t)3 * 40000 * 4; }
