@@ -3,7 +3,7 @@
 stage (a) scatter -> (c) camera-motion vote -> (e) smoothing / temporal / Gaussian map passes ->
 (b) centre-surround contrast -> (d) RBF-SVM -> final map), BASELINE.json's metric and config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (default N=1, K=10, W=3)
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (default N=1, K=40, W=3)
     python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port on the host cores
 
 A "step" is one batch of B (default 64) consecutive pictures of a synthetic 1920x1080, 50 fps clip
@@ -661,7 +661,7 @@ def run_b200(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=1920)

@@ -31,7 +31,10 @@ namespace cds {
 // =================================================================================================
 static double matlab_round(double x) { return x < 0 ? -floor(-x + 0.5) : floor(x + 0.5); }
 
-static std::vector<double> gauss1d(int k, double sigma) {   // fspecial('gaussian',k,sigma) is separable: normalised 1-D factor
+// fspecial('gaussian', k, sigma) = exp(-(x^2 + y^2) / (2 sigma^2)) with entries below eps * max zeroed, then normalised.  At the path's
+// k = round(h / 7.5), sigma = round(h / 30) the corner entry is exp(-4) of the centre, so the truncation never triggers and the kernel is
+// the outer product of this normalised 1-D factor (tests/test_matlab_semantics_cpu.py checks both statements for every BASELINE height).
+static std::vector<double> gauss1d(int k, double sigma) {
   std::vector<double> g(k);
   const double siz = (k - 1) / 2.0; double s = 0;
   for (int i = 0; i < k; i++) { const double x = i - siz; g[i] = exp(-(x * x) / (2 * sigma * sigma)); s += g[i]; }
