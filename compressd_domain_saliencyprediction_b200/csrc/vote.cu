@@ -20,7 +20,7 @@ namespace cg = cooperative_groups;
 
 namespace cds {
 
-constexpr int CM_THREADS = 512;      // 2 CTAs per SM (60 registers): more 8-CTA clusters in flight than with 1024 threads
+constexpr int CM_THREADS = 512;      // 2 CTAs per SM (60 registers): more 8-CTA clusters in flight (1024 threads: 0.56 ms per 64 pictures, 512: 0.45, 256: 0.49)
 
 __device__ __forceinline__ int med4_key(int a, int b, int c, int d) {
   // sum of the two middle values of four
