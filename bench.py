@@ -228,7 +228,7 @@ def run_reference(a):
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
-E2E_CHUNK = 3        # batches handed to cds_clip_process per call on the e2e leg (bounds the pinned output buffer)
+E2E_CHUNK = 6        # batches handed to cds_clip_process per call on the FP32 e2e leg (bounds the pinned output buffer: 3.2 GB at 1080p); the 8-bit leg hands over 4x as many
 
 
 def parity_check(a, cds, model):

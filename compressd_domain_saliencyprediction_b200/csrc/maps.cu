@@ -486,11 +486,12 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
   }
   const float4* __restrict__ mine = stage + wrow * TW_C + lane;
   int q_slot = ((q_hi % RL) + RL) % RL;
-  for (int qi0 = 0; qi0 < nq; qi0 += T_STAGES) {
-#pragma unroll
-    for (int u = 0; u < T_STAGES; u++) {
-      const int qi = qi0 + u;
-      if (qi < nq) {                             // CTA-uniform
+  // (not unrolled over the ring: eight copies of the body do not fit the instruction cache — ncu showed no_inst stalls)
+#pragma unroll 1
+  for (int qi = 0; qi < nq; qi++) {
+    {
+      const int u = qi % T_STAGES;
+      {
         mbar_wait(bar0 + 8u * u, (uint32_t)((qi / T_STAGES) & 1));      // window qi has landed
         const int q = q_hi - qi;
         const int j0 = poc0 + g0 - q;                                    // j of this thread's first picture (>= 1 on the straight-line path)
