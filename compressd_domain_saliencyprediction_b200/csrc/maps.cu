@@ -366,7 +366,7 @@ temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __r
 // from constant memory through the uniform datapath (j is warp-uniform) instead of keeping a rotating window in vector registers
 __constant__ float2 c_temporal_w[TMP_MAXJ];
 constexpr int TG = 8;                          // pictures per group (the offset table below is read as two int4)
-constexpr int TGT = 8;                         // pictures per thread (TGT = 4 = two thread sets, 992 threads at 64 registers, measured the same: 0.957 vs 0.938 ms)
+constexpr int TGT = 8;                         // pictures per thread (TGT = 4 = two thread sets, 992 threads at 64 registers: 0.95 ms against 0.89)
 constexpr int TT_R = 15, TT_C = 32;            // tile: one warp per row of 32 cells; 15 consumer warps + the producer warp = 512 threads (128 registers each)
 constexpr int TW_R = TT_R + 4, TW_C = TT_C + 8;    // staged window = the TMA box: tile + the spread of the group's shifts it can absorb
 constexpr int T_STAGES = 8;                        // TMA ring: the windows of the next 8 ring pictures in flight (most come from HBM: the ring exceeds the L2)

@@ -280,6 +280,9 @@ svm_rbf9_tc_kernel(const float* __restrict__ X, long N, const float* __restrict_
 namespace tcp {
 using namespace tc;
 constexpr int EPI_WARPS = 8;
+constexpr int NACC = 4;                                    // 128-column FP32 accumulators: all 512 TMEM columns (one CTA of this kernel per SM)
+constexpr uint32_t ACC_COLS = NACC * TN;
+static_assert(2 * STAGES + 2 * NACC + 4 <= 24, "mbarrier block");
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int RED_BYTES = 2 * 2 * TM * 4;                  // [tile parity][pos | neg][instance]
 constexpr int SMEM_BYTES = 2 * A_BYTES + STAGES * TILE_BYTES + BAR_BYTES + RED_BYTES;
@@ -300,19 +303,20 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
-  auto tempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
-  auto afull = [&](int b) { return bar0 + 8u * (2 * STAGES + 4 + b); };
-  auto aempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 6 + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * STAGES + NACC + b); };
+  auto afull = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 * NACC + b); };
+  auto aempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 * NACC + 2 + b); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long ntile_inst = (N + TM - 1) / TM;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(tfull(b), 1); mbar_init(tempty(b), EPI_WARPS); mbar_init(afull(b), 1); mbar_init(aempty(b), 1); }
+    for (int b = 0; b < NACC; b++) { mbar_init(tfull(b), 1); mbar_init(tempty(b), EPI_WARPS / 2); }
+    for (int b = 0; b < 2; b++) { mbar_init(afull(b), 1); mbar_init(aempty(b), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ACC_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -371,8 +375,8 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
         mbar_wait(afull(ab), (k >> 1) & 1);
         const uint32_t a_hi = smem_u32(sA + ab * A_BYTES), a_lo = a_hi + HALF_BYTES;
         for (int t = 0; t < ntiles; t++, g++) {
-          const int s = (int)(g % STAGES), buf = (int)(g & 1);
-          mbar_wait(tempty(buf), (uint32_t)((g >> 1) & 1) ^ 1u);
+          const int s = (int)(g % STAGES), buf = (int)(g % NACC);
+          mbar_wait(tempty(buf), (uint32_t)((g / NACC) & 1) ^ 1u);
           mbar_wait(full(s), (uint32_t)((g / STAGES) & 1));
           tc_fence_after();
           const uint32_t b_hi = smem_u32(sB + s * TILE_BYTES), b_lo = b_hi + HALF_BYTES;
@@ -393,24 +397,27 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
       }
     }
   } else {                                                   // ---- epilogue warps 0-7 ----
-    const int quad = warp & 3, half = warp >> 2;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (TN / 2));
-    const long my_tiles = ntile_inst > (long)blockIdx.x ? (ntile_inst - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    const long gtot = my_tiles * ntiles;                     // SV tiles this CTA will see over all its instance tiles
-    long g = 0; int k = 0;
-    // register double buffering across tile boundaries: the first 32 columns of the NEXT accumulator are already in flight from TMEM
-    // while the MUFUs of the current one's second half issue, so a warp's exponential stream never waits for a fresh tcgen05.ld
+    // Warp set s = warp / 4 takes every other SV tile (g & 1 == s), all 128 columns of it, from accumulator g % NACC; quad = warp % 4
+    // is its TMEM lane quadrant.  With four accumulators the MMAs of a set's next tile are done long before the set asks for it.  The two warps that share a scheduler therefore work half a tile apart: while one waits for its next
+    // accumulator (tcgen05.commit -> mbarrier -> first tcgen05.ld) the other is in the middle of its MUFU stream, so the XU pipe does
+    // not idle at tile boundaries (with both warps on the SAME accumulator, one column half each, it did: 77 % of the MUFU rate).
+    const int quad = warp & 3, set = warp >> 2;
+    const uint32_t tquad = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int g = set, k = 0;                                      // g counts this CTA's SV tiles over all its instance tiles
+    const int gtot = (ntile_inst > (long)blockIdx.x ? (int)((ntile_inst - 1 - blockIdx.x) / gridDim.x) + 1 : 0) * ntiles;
     uint32_t va[32], vb[32];
-    if (gtot > 0) {
-      mbar_wait(tfull(0), 0u);
+    auto first_chunk = [&](int gg) {                         // wait for accumulator gg % NACC and start loading its first 32 columns
+      const int b = gg % NACC;
+      mbar_wait(tfull(b), (uint32_t)((gg / NACC) & 1));
       tc_fence_after();
-      tmem_ld32(tlane, va);
-    }
+      tmem_ld32(tquad + (uint32_t)(b * TN), va);
+    };
+    if (g < gtot) first_chunk(g);
     for (long tile = blockIdx.x; tile < ntile_inst; tile += gridDim.x, k++) {
       float accp[4] = {0.f, 0.f, 0.f, 0.f}, accn[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int t = 0; t < ntiles; t++, g++) {
-        const int buf = (int)(g & 1);
-        const uint32_t taddr = tlane + (uint32_t)(buf * TN);
+      const int g_end = (k + 1) * ntiles;                    // this instance tile's SV tiles are g in [k * ntiles, g_end)
+      for (; g < g_end; g += 2) {
+        const int t = g - k * ntiles;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         auto consume = [&](const uint32_t (&v)[32]) {
 #pragma unroll
@@ -424,29 +431,35 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
             a0 += e[0] + e[4]; a1 += e[1] + e[5]; a2 += e[2] + e[6]; a3 += e[3] + e[7];
           }
         };
-        tmem_ld_wait();                                      // va = columns 0..31 of this warp's half of accumulator g
+        const int buf = g % NACC;
+        const uint32_t taddr = tquad + (uint32_t)(buf * TN);
+        // register double buffering: the next 32 columns (of the set's next tile, at the end) are in flight from TMEM while the
+        // MUFUs of the current ones issue
+        tmem_ld_wait();
         tmem_ld32(taddr + 32, vb);
+        consume(va);
+        tmem_ld_wait();
+        tmem_ld32(taddr + 64, va);
+        consume(vb);
+        tmem_ld_wait();
+        tmem_ld32(taddr + 96, vb);
         consume(va);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty(buf));             // this warp's share of the accumulator is in registers
-        if (g + 1 < gtot) {
-          mbar_wait(tfull(buf ^ 1), (uint32_t)(((g + 1) >> 1) & 1));
-          tc_fence_after();
-          tmem_ld32(tlane + (uint32_t)((buf ^ 1) * TN), va);
-        }
+        if (lane == 0) mbar_arrive(tempty(buf));             // this warp's quarter of the accumulator is in registers
+        if (g + 2 < gtot) first_chunk(g + 2);                // its MMAs were issued two tiles ago
         consume(vb);
         if (t < ntiles_pos) { accp[0] += a0; accp[1] += a1; accp[2] += a2; accp[3] += a3; }
         else                { accn[0] += a0; accn[1] += a1; accn[2] += a2; accn[3] += a3; }
       }
-      // the two column halves of an instance meet in shared memory (buffer k & 1: one named barrier per tile is enough)
+      // the two sets' partial sums of an instance meet in shared memory (buffer k & 1: one named barrier per instance tile is enough)
       const float P = (accp[0] + accp[1]) + (accp[2] + accp[3]), Q = (accn[0] + accn[1]) + (accn[2] + accn[3]);
       float* rb = red + (k & 1) * 2 * TM;
       const int inst = quad * 32 + lane;
-      if (half == 1) { rb[inst] = P; rb[TM + inst] = Q; }
+      if (set == 1) { rb[inst] = P; rb[TM + inst] = Q; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0) {
+      if (set == 0) {
         const long n = tile * TM + inst;
         if (n < N) dec[n] = (P + rb[inst]) - (Q + rb[TM + inst]) - rho;
       }
@@ -456,7 +469,7 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
   __syncthreads();
   if (warp == EPI_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ACC_COLS) : "memory");
   }
 }
 
