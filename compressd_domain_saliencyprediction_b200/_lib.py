@@ -64,6 +64,7 @@ def _declare(L):
         "cds_profile_read": (i32, [c_p, c_p, c_p, i32]),
         "cds_debug_copy": (i32, [c_p, C.c_char_p, i32, c_p, sz]),
         "cds_probe_mix": (i32, [i32, i32, c_p, c_p]),
+        "cds_probe_spin": (i32, [i32, i32, i32, i32, c_p]),
         "cds_probe_umma": (i32, [c_p, i32, c_p, i32, C.c_uint, C.c_uint, C.c_uint, C.c_uint, i32, i32, c_p]),
     }
     missing = []

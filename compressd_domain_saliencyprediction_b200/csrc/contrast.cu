@@ -87,6 +87,81 @@ __device__ __forceinline__ void sep_accumulate(const float* __restrict__ sbase, 
   }
 }
 
+// ---- packed FP32 form of the same loop (sm_100 FADD2 / FFMA2: two IEEE FP32 operations per issued instruction) ----
+// One packed operation serves the ordered pairs (centre 2m, neighbour u) and (centre 2m + 1, neighbour u + 1): both have the column
+// offset j = u - 2m, so the weight gc[j] is ONE scalar (a uniform-register operand broadcast to both halves), the centres are a
+// loop-invariant register pair and the neighbours are two adjacent values of the row.  d = p - c is one FADD2, racc += |d| * gc[j] one
+// FFMA2 (|.| is an operand modifier there as well): 1 issued instruction per pair instead of 2, the same number of FP32-pipe lane
+// cycles.  Standalone the kernel is bound by those lane cycles; the issue slots it gives up are what the MUFU-bound SVM kernel that
+// shares the SMs with it needs (pipeline.cu).  Every centre still adds its terms in ascending u, each with one rounding for the
+// product-sum: results are bitwise those of sep_accumulate.
+// Zero test: the factor [p != 0] is folded into the subtraction as t = fma(-c, m, p) with m = 1 or 0 per neighbour -- p - c when
+// p != 0, and p = 0 itself otherwise -- so the masked form costs one FSET per loaded neighbour and nothing per pair.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long abs2(unsigned long long v) { float a, b; upk2(v, a, b); return pk2(fabsf(a), fabsf(b)); }
+
+template <int WIN, int CPT, bool ZTEST>
+__device__ __forceinline__ void sep_accumulate_packed(const float* __restrict__ sbase, const int pitch,
+                                                      const float (&c)[CPT], float (&acc)[CPT],
+                                                      const SepWeights<WIN>& w) {
+  static_assert(CPT % 2 == 0, "centres are processed in pairs");
+  constexpr int NU = WIN + CPT - 1, NP = CPT / 2;
+  unsigned long long nc2[NP];
+#pragma unroll
+  for (int m = 0; m < NP; m++) nc2[m] = pk2(-c[2 * m], -c[2 * m + 1]);
+#pragma unroll 1
+  for (int i = 0; i < WIN; i++) {
+    const float* rowp = sbase + i * pitch;
+    unsigned long long racc2[NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) racc2[m] = 0ull;
+    float p_prev = 0.f, m_prev = 0.f;                      // neighbour u4 - 1 (and its mask) of the previous 16-byte load
+#pragma unroll
+    for (int u4 = 0; u4 < NU; u4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(rowp + u4);
+      const float pv[5] = {p_prev, v.x, v.y, v.z, v.w};
+      float mk[5] = {m_prev, 1.f, 1.f, 1.f, 1.f};
+      if (ZTEST) {
+#pragma unroll
+        for (int t = 1; t < 5; t++) mk[t] = pv[t] != 0.f ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) {                        // the pair (neighbour u, neighbour u + 1), u = u4 - 1 + t
+        const int u = u4 - 1 + t;
+        if (u >= 0 && u + 1 < NU) {
+          const unsigned long long p2 = pk2(pv[t], pv[t + 1]);
+          const unsigned long long m2 = ZTEST ? pk2(mk[t], mk[t + 1]) : 0ull;
+#pragma unroll
+          for (int m = 0; m < NP; m++) {
+            const int j = u - 2 * m;
+            if (j >= 0 && j < WIN) {
+              const unsigned long long d = ZTEST ? ffma2(nc2[m], m2, p2) : fadd2(p2, nc2[m]);
+              const float g = w.gc[j];
+              racc2[m] = ffma2(abs2(d), pk2(g, g), racc2[m]);
+            }
+          }
+        }
+      }
+      p_prev = v.w; m_prev = mk[4];
+    }
+    const float gi = w.gr[i];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+      float r0, r1; upk2(racc2[m], r0, r1);
+      acc[2 * m] = fmaf(gi, r0, acc[2 * m]); acc[2 * m + 1] = fmaf(gi, r1, acc[2 * m + 1]);
+    }
+  }
+}
+
 // Persistent: a CTA walks tiles t = blockIdx.x, + gridDim.x, ... of the (column tile, row tile, map) space, column tile fastest
 // so that CTAs running together stage neighbouring halos.  The grid is (SMs x CTAs per SM) at most; the pipeline caps the CTAs
 // per SM when the kernel has to leave room for the persistent SVM kernel that runs beside it (pipeline.cu, svm.cu).
@@ -95,8 +170,10 @@ __device__ __forceinline__ void sep_accumulate(const float* __restrict__ sbase, 
 // at once, so the kernel occupies exactly `cap` CTA slots on every SM wherever the block scheduler put its CTAs.
 // One tile per CTA when the grid covers the tile space (gridDim.x == ntiles: the default, and the fastest standalone form — the
 // block scheduler's own hand-out staggers the staging phases of the CTAs that share an SM); persistent otherwise.
-template <int WIN, int CPT, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32)
+// 40 registers: three CTAs of this kernel then fit beside the 320-thread, 128-register SVM CTA that shares the SM with them
+// (3 x 192 x 40 + 320 x 128 = 64 000 of 65 536); the packed form would take 58 without the cap and lose the third CTA.
+template <int WIN, int CPT, int NWARPS, bool PACKED>
+__global__ void __maxnreg__(40)
 contrast_sep_kernel(const float* __restrict__ pad, float* __restrict__ out,
                     unsigned* __restrict__ out_max_bits, int R, int C, int pr, int pc, int ntx, int nty, int ntiles,
                     unsigned* __restrict__ sched, int cap, const __grid_constant__ SepWeights<WIN> w) {
@@ -139,8 +216,13 @@ contrast_sep_kernel(const float* __restrict__ pad, float* __restrict__ out,
     float c[CPT], acc[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; k++) { c[k] = sbase[LEN * Cfg::PITCH + LEN + k]; acc[k] = 0.f; }
-    if (s_has_zero) sep_accumulate<WIN, CPT, true>(sbase, Cfg::PITCH, c, acc, w);
-    else            sep_accumulate<WIN, CPT, false>(sbase, Cfg::PITCH, c, acc, w);
+    if (PACKED) {
+      if (s_has_zero) sep_accumulate_packed<WIN, CPT, true>(sbase, Cfg::PITCH, c, acc, w);
+      else            sep_accumulate_packed<WIN, CPT, false>(sbase, Cfg::PITCH, c, acc, w);
+    } else {
+      if (s_has_zero) sep_accumulate<WIN, CPT, true>(sbase, Cfg::PITCH, c, acc, w);
+      else            sep_accumulate<WIN, CPT, false>(sbase, Cfg::PITCH, c, acc, w);
+    }
 
     const int r = tile_r0 + lr, c0 = tile_c0 + cb;
     float mx = 0.f;
@@ -210,13 +292,13 @@ contrast_generic_kernel(const float* __restrict__ pad, const float* __restrict__
   }
 }
 
-template <int WIN, int CPT, int NWARPS>
-static int launch_sep_cfg(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C,
+template <int WIN, int CPT, int NWARPS, bool PACKED>
+static int launch_sep_cfg_p(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C,
                           const float* gr, const float* gc, int ctas_per_sm, unsigned* sched, cudaStream_t st) {
   using Cfg = SepCfg<WIN, CPT, NWARPS>;
   SepWeights<WIN> w;
   for (int i = 0; i < WIN; i++) { w.gr[i] = gr[i]; w.gc[i] = gc[i]; }
-  if (int e = ensure_dyn_smem(contrast_sep_kernel<WIN, CPT, NWARPS>, Cfg::SMEM_BYTES)) return e;
+  if (int e = ensure_dyn_smem(contrast_sep_kernel<WIN, CPT, NWARPS, PACKED>, Cfg::SMEM_BYTES)) return e;
   const int len = WIN / 2;
   const int ntx = ceil_div(C, Cfg::TC), nty = ceil_div(R, Cfg::TR);
   const long ntiles = (long)ntx * nty * nmaps;
@@ -227,10 +309,23 @@ static int launch_sep_cfg(const float* pad, float* out, unsigned* mx, int nmaps,
   const int per_sm = (!sched && ctas_per_sm > 0) ? std::min(ctas_per_sm, fit) : fit;
   const unsigned grid = (sched || ctas_per_sm > 0) ? (unsigned)std::min<long>(ntiles, (long)device_sm_count() * per_sm) : (unsigned)ntiles;
   if (sched) CDS_CUDA(cudaMemsetAsync(sched, 0, CONTRAST_SCHED_WORDS * sizeof(unsigned), st));
-  contrast_sep_kernel<WIN, CPT, NWARPS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
+  contrast_sep_kernel<WIN, CPT, NWARPS, PACKED><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
       pad, out, mx, R, C, R + 2 * len, C + 2 * len, ntx, nty, (int)ntiles, sched, ctas_per_sm, w);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
+}
+
+// CDS_CONTRAST_PACKED=0 selects the scalar FADD + FFMA form of the inner loop (same results; kept for A/B timing)
+static bool contrast_packed() {
+  static const bool v = [] { const char* e = getenv("CDS_CONTRAST_PACKED"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
+template <int WIN, int CPT, int NWARPS>
+static int launch_sep_cfg(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C,
+                          const float* gr, const float* gc, int ctas_per_sm, unsigned* sched, cudaStream_t st) {
+  return contrast_packed() ? launch_sep_cfg_p<WIN, CPT, NWARPS, true>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st)
+                           : launch_sep_cfg_p<WIN, CPT, NWARPS, false>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
 }
 
 template <int WIN, int CPT>
@@ -271,6 +366,10 @@ int contrast_generic_launch(const float* pad, const float* dW, float* out, unsig
 // sched (optional, CONTRAST_SCHED_WORDS device words owned by the caller): dynamic tile hand-out and an exact per-SM cap.
 int contrast_sep_launch(const float* pad, float* out, unsigned* mx, int nmaps, int R, int C, int win,
                         const float* gr, const float* gc, float* dW_scratch, cudaStream_t st, int ctas_per_sm, unsigned* sched) {
+  // diagnosis: CDS_CONTRAST_CTAS=n runs every uncapped launch as a static persistent grid of n CTAs per SM (what the kernel can do at
+  // the occupancy it is left with beside the SVM kernel)
+  static const int diag_ctas = [] { const char* e = getenv("CDS_CONTRAST_CTAS"); return e ? atoi(e) : 0; }();
+  if (!sched && ctas_per_sm == 0 && diag_ctas > 0) ctas_per_sm = diag_ctas;
   if (win == 48) return launch_sep_win<48, 8>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
   if (win == 24) return launch_sep_win<24, 8>(pad, out, mx, nmaps, R, C, gr, gc, ctas_per_sm, sched, st);
   if (!dW_scratch) { set_error("contrast: window %d needs a weight scratch buffer", win); return CDS_EINVAL; }

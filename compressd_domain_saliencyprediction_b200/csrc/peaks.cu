@@ -216,6 +216,71 @@ extern "C" int cds_measure_peaks_ex(double* vals, int n) {
 
 // Probe: returns FP32 FMA lane-operations per second (an FFMA2 counts as 2) and MUFU per second for mix `which`
 // (see mix_probe_kernel).  ctas_per_sm CTAs of 128 threads per SM.
+// Asynchronous spinner for co-residency experiments (tools/corun_probe.py): which = 0 MUFU.EX2 only, 1 FFMA only, 2 FFMA2 only,
+// 3 MUFU.EX2 + one FADD each (the SVM epilogue's instruction mix), 4 the same with one packed FADD2 per two MUFU; `ctas_per_sm` CTAs of `threads` threads on every SM, on `stream`.
+__global__ void mufu_fadd_spin_kernel(float* out, float seed, int iters) {
+  float a[8], acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { a[k] = -seed * (k + 1) - threadIdx.x * 1e-6f; acc[k] = 0.f; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a[k])); acc[k] += y; a[k] = -y; }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k] + acc[k];
+  if (s == 123.456f) out[0] = s;
+}
+__global__ void mufu_fadd2_spin_kernel(float* out, float seed, int iters) {
+  float a[8]; unsigned long long acc2[4];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = -seed * (k + 1) - threadIdx.x * 1e-6f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) acc2[k] = 0ull;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      float y[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y[k]) : "f"(a[k])); a[k] = -y[k]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2[k]) : "l"(pk(y[2 * k], y[2 * k + 1])));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s += __uint_as_float((unsigned)acc2[k]) + __uint_as_float((unsigned)(acc2[k] >> 32)) + a[2 * k] + a[2 * k + 1];
+  if (s == 123.456f) out[0] = s;
+}
+extern "C" int cds_probe_spin(int which, int ctas_per_sm, int threads, int iters, void* stream) {
+  if (int e = ensure_device()) return e;
+  if (threads < 32 || threads > 256 || ctas_per_sm < 1) { set_error("cds_probe_spin: bad arguments"); return CDS_EINVAL; }
+  static float* d = nullptr;
+  if (!d) CDS_CUDA(cudaMalloc(&d, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = device_sm_count() * ctas_per_sm;
+  // the shared-memory carve-out of an SM cannot change while a CTA is resident: ask for the one the contrast kernel needs
+  static bool carve = false;
+  if (!carve) {
+    carve = true;
+    CDS_CUDA(cudaFuncSetAttribute(mufu_peak_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CDS_CUDA(cudaFuncSetAttribute(ffma_peak_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CDS_CUDA(cudaFuncSetAttribute(mix_probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CDS_CUDA(cudaFuncSetAttribute(mufu_fadd_spin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CDS_CUDA(cudaFuncSetAttribute(mufu_fadd2_spin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  if (which == 0) mufu_peak_kernel<<<grid, threads, 0, st>>>(d, 0.5f, iters);
+  else if (which == 1) ffma_peak_kernel<<<grid, threads, 0, st>>>(d, 0.5f, iters);
+  else if (which == 2) mix_probe_kernel<<<grid, 128, 0, st>>>(d, 0.5f, iters, 1);
+  else if (which == 4) mufu_fadd2_spin_kernel<<<grid, threads, 0, st>>>(d, 0.5f, iters);
+  else mufu_fadd_spin_kernel<<<grid, threads, 0, st>>>(d, 0.5f, iters);
+  CDS_LAUNCH_CHECK();
+  return CDS_OK;
+}
+
 extern "C" int cds_probe_mix(int which, int ctas_per_sm, double* fma_lane_ops_per_s, double* mufu_per_s) {
   if (int e = ensure_device()) return e;
   int dev = 0, sms = 0;

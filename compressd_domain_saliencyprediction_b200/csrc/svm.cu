@@ -288,6 +288,13 @@ constexpr int RED_BYTES = 2 * 2 * TM * 4;                  // [tile parity][pos 
 constexpr int SMEM_BYTES = 2 * A_BYTES + STAGES * TILE_BYTES + BAR_BYTES + RED_BYTES;
 }  // namespace tcp
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ unsigned long long fadd2_pk(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
 template <int POLY_OF_8>
 __global__ void __maxnreg__(128)
 svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict__ tiles, int ntiles, int ntiles_pos,
@@ -419,6 +426,7 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
       for (; g < g_end; g += 2) {
         const int t = g - k * ntiles;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        unsigned long long A01 = 0ull, A23 = 0ull;           // POLY_OF_8 < 0: the same four partial sums as two packed pairs (FADD2)
         auto consume = [&](const uint32_t (&v)[32]) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -428,7 +436,12 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
               const float x = __uint_as_float(v[j + q]);
               e[q] = (q < POLY_OF_8) ? ex2_poly(x) : ex2_approx(x);
             }
-            a0 += e[0] + e[4]; a1 += e[1] + e[5]; a2 += e[2] + e[6]; a3 += e[3] + e[7];
+            if (POLY_OF_8 < 0) {
+              A01 = fadd2_pk(A01, fadd2_pk(pack2(e[0], e[1]), pack2(e[4], e[5])));
+              A23 = fadd2_pk(A23, fadd2_pk(pack2(e[2], e[3]), pack2(e[6], e[7])));
+            } else {
+              a0 += e[0] + e[4]; a1 += e[1] + e[5]; a2 += e[2] + e[6]; a3 += e[3] + e[7];
+            }
           }
         };
         const int buf = g % NACC;
@@ -450,6 +463,10 @@ svm_rbf9_tcp_kernel(const float* __restrict__ X, long N, const float* __restrict
         if (lane == 0) mbar_arrive(tempty(buf));             // this warp's quarter of the accumulator is in registers
         if (g + 2 < gtot) first_chunk(g + 2);                // its MMAs were issued two tiles ago
         consume(vb);
+        if (POLY_OF_8 < 0) {
+          a0 = __uint_as_float((unsigned)A01); a1 = __uint_as_float((unsigned)(A01 >> 32));
+          a2 = __uint_as_float((unsigned)A23); a3 = __uint_as_float((unsigned)(A23 >> 32));
+        }
         if (t < ntiles_pos) { accp[0] += a0; accp[1] += a1; accp[2] += a2; accp[3] += a3; }
         else                { accn[0] += a0; accn[1] += a1; accn[2] += a2; accn[3] += a3; }
       }
@@ -526,8 +543,11 @@ int svm_predict_launch(const cds_svm_model* m, const float* X, long N, float* de
     // built to share the SMs with the FP32-bound contrast kernel of the next batch (pipeline.cu)
     static const int persist = [] { const char* e = getenv("CDS_SVM_PERSIST"); return (e && e[0] == '0') ? 0 : 1; }();
     if (persist) {
-      static const int polyp = [] { const char* e = getenv("CDS_SVM_POLY"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : v > 4 ? 4 : v; }();
-      auto kp = polyp == 0 ? svm_rbf9_tcp_kernel<0> : polyp == 1 ? svm_rbf9_tcp_kernel<1> : polyp == 2 ? svm_rbf9_tcp_kernel<2>
+      // default (-1): every exponential on the MUFU and the partial sums added as packed pairs (FADD2: half the issue slots of the
+      // scalar adds, same bits); 0 = scalar adds, 1..4 = that many of 8 exponentials as a polynomial on the FMA pipe (faster alone,
+      // slower beside the FP32-bound contrast kernel)
+      static const int polyp = [] { const char* e = getenv("CDS_SVM_POLY"); const int v = e ? atoi(e) : -1; return v < -1 ? -1 : v > 4 ? 4 : v; }();
+      auto kp = polyp < 0 ? svm_rbf9_tcp_kernel<-1> : polyp == 0 ? svm_rbf9_tcp_kernel<0> : polyp == 1 ? svm_rbf9_tcp_kernel<1> : polyp == 2 ? svm_rbf9_tcp_kernel<2>
               : polyp == 3 ? svm_rbf9_tcp_kernel<3> : svm_rbf9_tcp_kernel<4>;
       if (int e = ensure_dyn_smem(kp, tcp::SMEM_BYTES)) return e;
       const long ntile_inst = (N + tc::TM - 1) / tc::TM;

@@ -226,6 +226,9 @@ int cds_measure_peaks_ex(double* vals, int n);
 /* Development probes (tools/mix_probe.py, tools/umma_probe.py): instruction-mix throughput and one tcgen05.mma with
  * caller-supplied shared-memory operand images / descriptor strides.  Not part of the drop-in surface. */
 int cds_probe_mix(int which, int ctas_per_sm, double* fma_lane_ops_per_s, double* mufu_per_s);
+/* Asynchronous spinner on `stream` for co-residency experiments (tools/corun_probe.py): which = 0 MUFU.EX2, 1 FFMA, 2 FFMA2,
+ * 3 MUFU.EX2 + FADD; `ctas_per_sm` CTAs of `threads` (32..256) threads per SM, `iters` rounds of 128 operations per thread. */
+int cds_probe_spin(int which, int ctas_per_sm, int threads, int iters, void* stream);
 int cds_probe_umma(const float* a_img, int a_bytes, const float* b_img, int b_bytes, unsigned a_lbo, unsigned a_sbo,
                    unsigned b_lbo, unsigned b_sbo, int a_mn_major, int b_mn_major, float* D);
 /* Number of kernel launches issued by this library since the last call (bench bookkeeping). */
