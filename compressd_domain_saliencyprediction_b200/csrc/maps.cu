@@ -135,6 +135,7 @@ void banded_from_dense(const std::vector<double>& A, int n_out, int n_in, Banded
     if (i + 1 < n_out && out->start[i + 1] < out->start[i]) { out->span4 = -1; break; }
     out->span4 = std::max(out->span4, out->start[std::min(i + 3, n_out - 1)] - out->start[i]);
   }
+
 }
 
 int Banded::upload() {
@@ -1270,9 +1271,10 @@ banded_rows_kernel(const float* __restrict__ in, int in_rows, int cols, const fl
 // are staged over their common input window as float4, so one LDG.128 of inputs + one broadcast LDS.128 feed 16 FFMAs
 // and each input row is fetched once per 4 output rows.  Taps stay in ascending order; pad weights add exact zeros.
 constexpr int BR_ROWS = 4;
+template <bool XF>
 __global__ void __launch_bounds__(128)
 banded_rows4_kernel(const float* __restrict__ in, int in_rows, int cols, const float* __restrict__ w, const int* __restrict__ start,
-                    int nt, int n_out, float* __restrict__ out) {
+                    int nt, int n_out, const float* __restrict__ xf, float* __restrict__ out) {
   extern __shared__ float4 sw4[];               // [window] x 4 rows
   const int i0 = blockIdx.y * BR_ROWS, m = blockIdx.z, C4 = cols >> 2;
   const int ilast = min(i0 + BR_ROWS - 1, n_out - 1);
@@ -1291,12 +1293,15 @@ banded_rows4_kernel(const float* __restrict__ in, int in_rows, int cols, const f
   const float4* __restrict__ src = reinterpret_cast<const float4*>(in + (size_t)m * in_rows * cols);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= C4) return;
+  float fa = 0.f, fb = 1.f, fthr = INFINITY;
+  if (XF) { fa = xf[4 * m]; fb = xf[4 * m + 1]; fthr = xf[4 * m + 2]; }
   float4 acc[BR_ROWS];
 #pragma unroll
   for (int k = 0; k < BR_ROWS; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int j = 0; j < L; j++) {
-    const float4 v = __ldg(src + (size_t)(s_lo + j) * C4 + x);
+    float4 v = __ldg(src + (size_t)(s_lo + j) * C4 + x);
+    if (XF) { v.x = fminf((v.x - fa) * fb, fthr); v.y = fminf((v.y - fa) * fb, fthr); v.z = fminf((v.z - fa) * fb, fthr); v.w = fminf((v.w - fa) * fb, fthr); }
     const float4 g = sw4[j];
     acc[0].x = fmaf(g.x, v.x, acc[0].x); acc[0].y = fmaf(g.x, v.y, acc[0].y); acc[0].z = fmaf(g.x, v.z, acc[0].z); acc[0].w = fmaf(g.x, v.w, acc[0].w);
     acc[1].x = fmaf(g.y, v.x, acc[1].x); acc[1].y = fmaf(g.y, v.y, acc[1].y); acc[1].z = fmaf(g.y, v.z, acc[1].z); acc[1].w = fmaf(g.y, v.w, acc[1].w);
@@ -1340,9 +1345,14 @@ int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const 
     return CDS_OK;
   }
   const int thr = fir_threads(cols / 4);
-  if (!xf && B.span4 >= 0 && B.span4 <= B.nt / 2) {           // heavily overlapping rows: 4 output rows per CTA
+  // overlapping rows: 4 output rows per CTA, each input row fetched once for the four.  Shrinking rows (resize 1080 -> 200: 12 taps,
+  // starts 5.4 apart) overlap about two-fold; one output row per CTA re-fetched every input row twice through the L2, which was the
+  // bound of that pass (1.6 GB at 4.2 TB/s).
+  if (B.span4 >= 0 && B.span4 <= 2 * B.nt) {
     dim3 grid4(ceil_div(cols / 4, thr), ceil_div(B.n_out, BR_ROWS), nmaps);
-    banded_rows4_kernel<<<grid4, thr, (size_t)(B.nt + B.span4) * 16, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, out);
+    const size_t smem = (size_t)(B.nt + B.span4) * 16;
+    if (xf) banded_rows4_kernel<true><<<grid4, thr, smem, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
+    else    banded_rows4_kernel<false><<<grid4, thr, smem, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
     CDS_LAUNCH_CHECK();
     return CDS_OK;
   }
@@ -1353,41 +1363,85 @@ int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const 
   return CDS_OK;
 }
 
-// out[m][r][j] = sum_t w[j][t] * in[m][r][start[j]+t].  One CTA per (group of BC_ROWS rows, map): the input rows sit in
-// smem, a thread owns output column j for all BC_ROWS rows, so each (transposed, coalesced) weight load feeds BC_ROWS FFMAs.
+// out[m][r][j] = sum_t w[j][t] * f(in[m][r][start[j]+t]);  f = identity or min((v-a)*b, thr) per map (XF).
+// One CTA per (group of 8 rows, map).  The rows are staged TRANSPOSED in shared memory -- 12 floats per input column: rows 0-3,
+// rows 4-7, 4 floats of padding that spread the 16-byte bank groups -- so a thread, which owns output column j for all 8 rows,
+// feeds 8 FFMAs from two LDS.128 and one coalesced weight load (transposed weights wT[t][j]); with the rows side by side it was one
+// LDS.32 per FFMA and the kernel sat at the LSU limit.  Staging reads float4s along the rows (in_cols % 4 == 0) and turns
+// 4 rows x 4 columns into four 16-byte stores in registers.  Every input element is read once, so a column pass that comes FIRST
+// streams its input at HBM speed, however much the rows of the following row pass overlap.
 constexpr int BC_ROWS = 8;
+template <bool XF>
 __global__ void __launch_bounds__(256)
 banded_cols_kernel(const float* __restrict__ in, int rows, int in_cols, const float* __restrict__ wT, const int* __restrict__ start,
-                   int nt, int n_out, float* __restrict__ out) {
-  extern __shared__ float srow2[];              // [BC_ROWS][in_cols + 1]
-  const int r0 = blockIdx.x * BC_ROWS, m = blockIdx.y, pitch = in_cols + 1;
+                   int nt, int n_out, const float* __restrict__ xf, float* __restrict__ out) {
+  extern __shared__ float4 scol[];              // [in_cols][3]
+  const int r0 = blockIdx.x * BC_ROWS, m = blockIdx.y;
   const int nr = min(BC_ROWS, rows - r0);
   const float* __restrict__ src = in + ((size_t)m * rows + r0) * in_cols;
-  for (int i = threadIdx.x; i < BC_ROWS * in_cols; i += 256) {
-    const int r = i / in_cols, c = i - r * in_cols;
-    srow2[r * pitch + c] = r < nr ? src[i] : 0.f;
+  float fa = 0.f, fb = 1.f, fthr = INFINITY;
+  if (XF) { fa = xf[4 * m]; fb = xf[4 * m + 1]; fthr = xf[4 * m + 2]; }
+  if ((in_cols & 3) == 0) {
+    const int C4 = in_cols >> 2;
+    for (int idx = threadIdx.x; idx < 2 * C4; idx += 256) {
+      const int g = idx / C4, c4 = idx - g * C4;
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        v[k] = 4 * g + k < nr ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(4 * g + k) * in_cols) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (XF) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          v[k].x = fminf((v[k].x - fa) * fb, fthr); v[k].y = fminf((v[k].y - fa) * fb, fthr);
+          v[k].z = fminf((v[k].z - fa) * fb, fthr); v[k].w = fminf((v[k].w - fa) * fb, fthr);
+        }
+      }
+      float4* d = scol + (size_t)(4 * c4) * 3 + g;
+      d[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+      d[3] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+      d[6] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+      d[9] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < 2 * in_cols; idx += 256) {
+      const int g = idx / in_cols, c = idx - g * in_cols;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        v[k] = 4 * g + k < nr ? __ldg(src + (size_t)(4 * g + k) * in_cols + c) : 0.f;
+        if (XF) v[k] = fminf((v[k] - fa) * fb, fthr);
+      }
+      scol[(size_t)c * 3 + g] = make_float4(v[0], v[1], v[2], v[3]);
+    }
   }
   __syncthreads();
   for (int j = threadIdx.x; j < n_out; j += 256) {
     const int s0 = start[j], t_hi = min(nt, in_cols - s0);
-    float acc[BC_ROWS];
-#pragma unroll
-    for (int r = 0; r < BC_ROWS; r++) acc[r] = 0.f;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    const float4* __restrict__ sp = scol + (size_t)s0 * 3;
+#pragma unroll 4
     for (int t = 0; t < t_hi; t++) {
       const float wv = __ldg(wT + (size_t)t * n_out + j);
-#pragma unroll
-      for (int r = 0; r < BC_ROWS; r++) acc[r] = fmaf(wv, srow2[r * pitch + s0 + t], acc[r]);
+      const float4 a = sp[3 * t], b = sp[3 * t + 1];
+      lo.x = fmaf(wv, a.x, lo.x); lo.y = fmaf(wv, a.y, lo.y); lo.z = fmaf(wv, a.z, lo.z); lo.w = fmaf(wv, a.w, lo.w);
+      hi.x = fmaf(wv, b.x, hi.x); hi.y = fmaf(wv, b.y, hi.y); hi.z = fmaf(wv, b.z, hi.z); hi.w = fmaf(wv, b.w, hi.w);
     }
+    const float acc[BC_ROWS] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
     for (int r = 0; r < BC_ROWS; r++) if (r < nr) out[((size_t)m * rows + r0 + r) * n_out + j] = acc[r];
   }
 }
 
-int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st) {
+int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, const float* xf, float* out, cudaStream_t st) {
   dim3 grid(ceil_div(rows, BC_ROWS), nmaps);
-  const size_t smem = (size_t)BC_ROWS * (in_cols + 1) * 4;
-  if (int e = ensure_dyn_smem(banded_cols_kernel, smem)) return e;
-  banded_cols_kernel<<<grid, 256, smem, st>>>(in, rows, in_cols, B.d_wT, B.d_start, B.nt, B.n_out, out);
+  const size_t smem = (size_t)in_cols * 48;
+  if (xf) {
+    if (int e = ensure_dyn_smem(banded_cols_kernel<true>, smem)) return e;
+    banded_cols_kernel<true><<<grid, 256, smem, st>>>(in, rows, in_cols, B.d_wT, B.d_start, B.nt, B.n_out, xf, out);
+  } else {
+    if (int e = ensure_dyn_smem(banded_cols_kernel<false>, smem)) return e;
+    banded_cols_kernel<false><<<grid, 256, smem, st>>>(in, rows, in_cols, B.d_wT, B.d_start, B.nt, B.n_out, xf, out);
+  }
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
