@@ -284,6 +284,17 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 }
 constexpr int TMP_MAXJ = 1024;      // PT - 1 <= 7 * round(0.3 * 240) - 1 = 503
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// packed FP32 (sm_100 FADD2 / FFMA2: two IEEE operations per issued instruction; |.| and a scalar broadcast are operand modifiers)
+__device__ __forceinline__ unsigned long long tp_pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void tp_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long tp_sub2(unsigned long long a, unsigned long long b) {      // a - b
+  float b0, b1; tp_unpack(b, b0, b1);
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(tp_pack(-b0, -b1))); return d;
+}
+__device__ __forceinline__ unsigned long long tp_fma2_abs(float w, unsigned long long d, unsigned long long acc) {   // acc + w * |d|
+  float d0, d1; tp_unpack(d, d0, d1);
+  unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(tp_pack(w, w)), "l"(tp_pack(fabsf(d0), fabsf(d1))), "l"(acc)); return r;
+}
 
 __global__ void __launch_bounds__(256)
 temporal_kernel(int h4, int w4, int PT, int RL, int first_poc, const float4* __restrict__ sm4 /*{mvx, mvy, bit, depth} smoothed*/,
@@ -472,11 +483,12 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
   const bool inside = r < h4 && c < w4;
   const int g0 = set * TGT;                        // this thread's first picture of the group
   float4 ref[TGT];
-  float am[TGT], ab[TGT], ad[TGT];
+  float am[TGT];
+  unsigned long long abd[TGT];                     // (bit, depth) sums as one packed pair: the two share weight and form
 #pragma unroll
   for (int k = 0; k < TGT; k++) {
     ref[k] = (inside && g0 + k < ng) ? sm4[(size_t)((poc0 + g0 + k) % RL) * n4 + (size_t)r * w4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-    am[k] = 0.f; ab[k] = 0.f; ad[k] = 0.f;
+    am[k] = 0.f; abd[k] = 0ull;
   }
   if (warp == T_WARPS) {                          // ---- producer warp: one thread walks the ring pictures ahead of the consumers ----
     if (lane == 0) {
@@ -514,10 +526,10 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
           for (int k = 0; k < TGT; k++) {
             const float4 p = pv[k];
             const float2 wj = c_temporal_w[j0 + k];                              // uniform: constant bank
-            const float ddx = ref[k].x - p.x, ddy = ref[k].y - p.y;
+            float ddx, ddy;                                                      // the four differences as two FADD2
+            tp_unpack(tp_sub2(tp_pack(ref[k].x, ref[k].y), tp_pack(p.x, p.y)), ddx, ddy);
             am[k] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[k]);   // main.m:195
-            ab[k] = fmaf(wj.y, fabsf(ref[k].z - p.z), ab[k]);                    // :196
-            ad[k] = fmaf(wj.y, fabsf(ref[k].w - p.w), ad[k]);                    // :197
+            abd[k] = tp_fma2_abs(wj.y, tp_sub2(tp_pack(ref[k].z, ref[k].w), tp_pack(p.z, p.w)), abd[k]);   // :196, :197
           }
         } else {
 #pragma unroll
@@ -535,8 +547,7 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
               const float2 wj = c_temporal_w[j];
               const float ddx = ref[k].x - p.x, ddy = ref[k].y - p.y;
               am[k] = fmaf(wj.x, sqrt_approx(fmaf(ddx, ddx, ddy * ddy)), am[k]);
-              ab[k] = fmaf(wj.y, fabsf(ref[k].z - p.z), ab[k]);
-              ad[k] = fmaf(wj.y, fabsf(ref[k].w - p.w), ad[k]);
+              abd[k] = tp_fma2_abs(wj.y, tp_sub2(tp_pack(ref[k].z, ref[k].w), tp_pack(p.z, p.w)), abd[k]);
             }
           }
         }
@@ -551,7 +562,8 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
     for (int k = 0; k < TGT; k++)
       if (g0 + k < ng) {
         float* X = Xmaps + (size_t)(f0 + g0 + k) * 9 * n4 + (size_t)r * w4 + c;
-        X[(size_t)1 * n4] = am[k]; X[(size_t)4 * n4] = ab[k]; X[(size_t)7 * n4] = ad[k];
+        float ab, ad; tp_unpack(abd[k], ab, ad);
+        X[(size_t)1 * n4] = am[k]; X[(size_t)4 * n4] = ab; X[(size_t)7 * n4] = ad;
       }
   }
 }
