@@ -834,11 +834,13 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     CDS_CUDA(cudaStreamWaitEvent(sp, c->ev_c48, 0));
   }
   // Where the previous batch's deferred back half (persistent MUFU-bound SVM, then the final-map chain) joins this batch's front
-  // half (CDS_BACK_AT): 1 (default) = at the mid-point, beside the FP32-bound contrast kernels, which are then capped to
-  // CDS_CO_CTAS CTAs per SM; 0 = at its start, beside stages (a), (c), smoothing, threshold, temporal; 2 = after the contrast
-  // kernels.  Measured at 1080p / nSV 4096 / 64 pictures: 11.3 ms per batch for 1, 12.4 for 0 (the resident SVM CTAs keep the
-  // register-hungry temporal and vote kernels off the SMs), 12.2 for 2, 12.9 without any overlap.
-  static const int back_at = [] { const char* e = getenv("CDS_BACK_AT"); const int v = e ? atoi(e) : 1; return v < 0 || v > 2 ? 1 : v; }();
+  // half (CDS_BACK_AT): 1 (default) = at the mid-point, beside the FP32-bound contrast kernels; 0 = at its start; 2 = after the
+  // contrast kernels (beside the H pass; the V pass needs whole SMs and waits); 3 = after the V pass, beside the HBM / L2-bound
+  // statistics and resize passes.  Measured at 1080p / nSV 4096 / 64 pictures: 10.35 ms per batch for 1, 10.47 for 0, 11.4 for 2 and
+  // for 3, 13 without any overlap.  The bandwidth-bound passes are poor partners: the resident SVM CTA holds 63 % of the register
+  // file, and with a third of their usual threads in flight they crawl until it leaves (3: the 1.3 ms of passes end 1.2 ms AFTER
+  // the 3.0 ms SVM); the FP32-bound contrast kernel needs few threads to keep its pipe busy and keeps 58 % of its speed.
+  static const int back_at = [] { const char* e = getenv("CDS_BACK_AT"); const int v = e ? atoi(e) : 1; return v < 0 || v > 3 ? 1 : v; }();
   if (ov && c->pb.valid && back_at == 0) {
     trace_mark(c, c->tr_batches, TR_MID, st);
     CDS_CUDA(cudaEventRecord(c->ev_mid, st));
@@ -878,7 +880,6 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     }
     // ---- MAIN stage on `st`: waits for this batch's pre stage and for the back half of batch i-2 (it read xsvm[slot]) ----
     if (pov) { CDS_CUDA(cudaEventRecord(c->ev_pre[set], sp)); CDS_CUDA(cudaStreamWaitEvent(st, c->ev_pre[set], 0)); }
-    if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));
     CDS_CUDA(cudaMemsetAsync(c->d_maxbits, 0, (size_t)4 * n * 4, st));
     // ---- mid-point: the previous batch's persistent SVM kernel starts together with this batch's contrast kernels ----
     int co_ctas = 0;
@@ -923,6 +924,11 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   if (int e = fullres_hpass_launch(dX, 9 * n, h4, w4, c->poly, c->d_T, st)) return e;
   prof_mark(c, ST_FULLRES_V, st);
   if (int e = fullres_vpass_launch(c->d_T, 9 * n, h4, W, c->poly, c->d_Y, c->d_store_index, c->d_partial, &nb, st)) return e;
+  if (ov && c->pb.valid && back_at == 3) {        // after the V pass (which needs whole SMs): beside the HBM / L2-bound statistics and resize passes
+    trace_mark(c, c->tr_batches, TR_MID, st);
+    CDS_CUDA(cudaEventRecord(c->ev_mid, st));
+    if (int e = flush_pending_back(c, c->ev_mid)) return e;
+  }
   prof_mark(c, ST_TEMPORAL_STATS, st);
   if (int e = stats_finalize_launch(c->d_partial, 9 * n, nb, c->d_stats9, st)) return e;
   {
@@ -939,6 +945,7 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, nullptr, c->d_F200, st)) return e;
     if (int e = banded_rows_launch(c->d_Y, 3 * n, H, W, c->Rv, c->d_xf, c->d_R1, st)) return e;
     if (int e = banded_cols_launch(c->d_R1, 3 * n, 200, W, c->Rh, nullptr, c->d_Ft, st)) return e;
+    if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));     // the back half of batch i-2 read xsvm[slot]
     {
       dim3 grid(ceil_div(40000, 256), n);
       assemble_features_kernel<<<grid, 256, 0, st>>>(c->d_F200, c->d_Ft, c->d_stats9, c->d_xf, fparam, xsvm);
