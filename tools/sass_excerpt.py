@@ -1,13 +1,13 @@
 #!/usr/bin/env python3
 """Write profiles/r02_sass_<kernel>.txt: for the tcgen05 / TMA kernels of libcds_b200.so, the counts of the SASS mnemonics that prove
 the tensor-core / TMEM / TMA path (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor, UBLKCP = cp.async.bulk,
-UTCBAR = tcgen05.commit, SYNCS = mbarrier) and the first occurrences with their addresses.  CPU only (cuobjdump)."""
+UTCBAR = tcgen05.commit, SYNCS = mbarrier; FADD2 / FFMA2 = the packed FP32 forms add.f32x2 / fma.f32x2) and the first occurrences with their addresses.  CPU only (cuobjdump)."""
 import collections, os, re, subprocess, sys
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 LIB = os.path.join(ROOT, "compressd_domain_saliencyprediction_b200", "libcds_b200.so")
-KERNELS = {"svm_tc": "svm_rbf9_tcp_kernelILi0", "svm_tc_2cta": "svm_rbf9_tc_kernelILi2", "vpass_tc": "fullres_vpass_tc_kernel", "temporal_tma": "temporal_group_kernel"}
-PAT = re.compile(r"\b(UTCHMMA|UTCQMMA|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|UTCBAR|UTCATOM|SYNCS|MUFU\.EX2|MUFU\.SQRT|FFMA2|LDGSTS)\b")
+KERNELS = {"svm_tc": "svm_rbf9_tcp_kernelILin1", "contrast_packed": "contrast_sep_kernelILi48ELi8ELi6ELb1", "svm_tc_2cta": "svm_rbf9_tc_kernelILi2", "vpass_tc": "fullres_vpass_tc_kernel", "temporal_tma": "temporal_group_kernel"}
+PAT = re.compile(r"\b(UTCHMMA|UTCQMMA|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|UTCBAR|UTCATOM|SYNCS|MUFU\.EX2|MUFU\.SQRT|FFMA2|FADD2|LDGSTS)\b")
 
 
 def main():
