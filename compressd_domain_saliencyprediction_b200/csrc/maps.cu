@@ -457,7 +457,9 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
       if (g < ng && j >= 1 && j <= min(PT - 1, poc)) {
         const int2 sh = s_shift[g * PT + j];
         const int dx = wn.x - sh.x, dy = wn.y - sh.y;                  // >= 0
-        off = (dx + TT_C <= TW_C && dy + TT_R <= TW_R) ? dy * TW_C + dx : -1;     // the TMA box always has the full capacity
+        // BYTE offset of the pair's source tile from the start of the ring buffers (ring slot qi % T_STAGES included), so that a
+        // consumer adds it to its own cell address with one IADD; the TMA box always has the full capacity
+        off = (dx + TT_C <= TW_C && dy + TT_R <= TW_R) ? ((qi % T_STAGES) * (TW_R * TW_C) + dy * TW_C + dx) * 16 : -1;
       }
       s_off[qi * TG + g] = off;
     }
@@ -481,7 +483,7 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
 
   const int r = r0 + wrow, c = c0 + lane;
   const bool inside = r < h4 && c < w4;
-  const int g0 = set * TGT;                        // this thread's first picture of the group
+  const int g0 = T_SETS == 1 ? 0 : set * TGT;      // this thread's first picture of the group (a constant with one thread set: j and the weights stay uniform)
   float4 ref[TGT];
   float am[TGT];
   unsigned long long abd[TGT];                     // (bit, depth) sums as one packed pair: the two share weight and form
@@ -497,7 +499,7 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
     }
     return;
   }
-  const float4* __restrict__ mine = stage + wrow * TW_C + lane;
+  const char* __restrict__ mine = reinterpret_cast<const char*>(stage + wrow * TW_C + lane);
   int q_slot = ((q_hi % RL) + RL) % RL;
   // (not unrolled over the ring: eight copies of the body do not fit the instruction cache — ncu showed no_inst stalls)
 #pragma unroll 1
@@ -508,7 +510,6 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
         mbar_wait(bar0 + 8u * u, (uint32_t)((qi / T_STAGES) & 1));      // window qi has landed
         const int q = q_hi - qi;
         const int j0 = poc0 + g0 - q;                                    // j of this thread's first picture (>= 1 on the straight-line path)
-        const float4* __restrict__ buf = mine + u * (TW_R * TW_C);       // qi % T_STAGES == u
         int offs[TGT]; int any_neg = 0;
 #pragma unroll
         for (int k4 = 0; k4 < TGT; k4 += 4) {
@@ -521,7 +522,7 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
           // all shared-memory loads first so that their latencies overlap
           float4 pv[TGT];
 #pragma unroll
-          for (int k = 0; k < TGT; k++) pv[k] = buf[offs[k]];
+          for (int k = 0; k < TGT; k++) pv[k] = *reinterpret_cast<const float4*>(mine + offs[k]);
 #pragma unroll
           for (int k = 0; k < TGT; k++) {
             const float4 p = pv[k];
@@ -538,7 +539,7 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
             if (off != -2) {                                                  // uniform per thread set
               const int j = poc0 + g0 + k - q;
               float4 p;
-              if (off >= 0) p = buf[off];
+              if (off >= 0) p = *reinterpret_cast<const float4*>(mine + off);
               else {                                                          // shift spread beyond the window capacity: straight from L2
                 const int2 sh = s_shift[(g0 + k) * PT + j];
                 const int sr = r - sh.y, sc = c - sh.x;
