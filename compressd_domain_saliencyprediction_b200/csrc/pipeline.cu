@@ -750,7 +750,7 @@ int launch_back_rbf(cds_ctx* c, int slot, int n, void* maps_out, cudaStream_t sb
   if (mark) prof_mark(c, ST_FINAL, sb);
   dec_minmax_norm_kernel<<<n, 1024, 0, sb>>>(c->d_dec, c->d_C);
   CDS_LAUNCH_CHECK();
-  if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, nullptr, c->d_T2, sb)) return e;
+  if (int e = banded_cols_launch(c->d_C, n, 200, 200, c->Bh, c->d_T2, sb)) return e;
   const int thr = fir_threads(W / 4);
   dim3 grid(ceil_div(W / 4, thr), ceil_div(H, FR_ROWS), n);
   final_rows_kernel<<<grid, thr, (size_t)(c->Bv.nt + c->Bv.span4) * 16, sb>>>(c->d_T2, W, H, c->Bv.d_w, c->Bv.d_start, c->Bv.nt, c->d_dist, c->d_raw, c->d_fpartial);
@@ -942,9 +942,9 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
     // ---- features at 200x200 (main.m:275-294) ----
     prof_mark(c, ST_RESIZE200, st);
     if (int e = banded_rows_launch(dX, 9 * n, h4, w4, c->Av, nullptr, c->d_A1, st)) return e;
-    if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, nullptr, c->d_F200, st)) return e;
+    if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, c->d_F200, st)) return e;
     if (int e = banded_rows_launch(c->d_Y, 3 * n, H, W, c->Rv, c->d_xf, c->d_R1, st)) return e;
-    if (int e = banded_cols_launch(c->d_R1, 3 * n, 200, W, c->Rh, nullptr, c->d_Ft, st)) return e;
+    if (int e = banded_cols_launch(c->d_R1, 3 * n, 200, W, c->Rh, c->d_Ft, st)) return e;
     if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));     // the back half of batch i-2 read xsvm[slot]
     {
       dim3 grid(ceil_div(40000, 256), n);
