@@ -57,6 +57,7 @@ struct Video {
   std::string path; int w = 0, h = 0;
   pid_t pid = -1; int fd = -1;
   long pictures = 0; uint64_t checksum = 1469598103934665603ull; std::string error;
+  double t_first = 0.0, t_last = 0.0;       // first picture submitted / last map drained (the start-up before it is CUDA, the context and the decoder's own)
 };
 
 void parse9(const char* s, double* dst) {
@@ -98,10 +99,12 @@ void run_video(const Options& o, const cds_svm_model* model, Video* v) {
     if (rn != nctu || ntok < 0 || (size_t)ntok > cap) { v->error = "syntax record does not match the picture size"; break; }
     if (!read_full(v->fd, h, (size_t)nctu * 16) || !read_full(v->fd, b, (size_t)nctu * 2) || !read_full(v->fd, t, (size_t)ntok * 2)) { v->error = "truncated syntax record"; break; }
     if (cds_submit_frame(ctx, poc, b, h, t, (size_t)ntok) != CDS_OK) { v->error = std::string("cds_submit_frame: ") + cds_last_error(); break; }
+    if (submitted == 0) v->t_first = now();
     submitted = poc + 1;
     if (submitted - drained >= 2L * o.batch) drain(drained + o.batch);                  // the batch just launched keeps running
   }
   drain(submitted);                                                                     // cds_get_map launches the partial batch
+  v->t_last = now();
   v->pictures = drained;
   if (out) fclose(out);
   cds_destroy(ctx);
@@ -168,7 +171,11 @@ int main(int argc, char** argv) {
   const double sec = now() - t0;
   long total = 0; bool bad = false;
   for (Video& v : videos) { close(v.fd); int st = 0; waitpid(v.pid, &st, 0); total += v.pictures; bad |= !v.error.empty(); }
-  printf("{\"pictures\": %ld, \"seconds\": %.4f, \"pictures_per_s\": %.2f, \"videos\": [", total, sec, total / sec);
+  double first = 0.0, last = 0.0;                            // steady state: from the first picture any video submitted to the last map drained
+  for (Video& v : videos) if (v.pictures > 0) { if (first == 0.0 || v.t_first < first) first = v.t_first; if (v.t_last > last) last = v.t_last; }
+  const double steady = last > first ? last - first : sec;
+  printf("{\"pictures\": %ld, \"seconds\": %.4f, \"pictures_per_s\": %.2f, \"startup_seconds\": %.4f, \"steady_seconds\": %.4f, \"steady_pictures_per_s\": %.2f, \"videos\": [",
+         total, sec, total / sec, first > t0 ? first - t0 : 0.0, steady, total / steady);
   for (size_t i = 0; i < videos.size(); i++)
     printf("%s{\"stream\": \"%s\", \"pictures\": %ld, \"checksum\": \"%016llx\", \"error\": \"%s\"}", i ? ", " : "", videos[i].path.c_str(), videos[i].pictures,
            (unsigned long long)videos[i].checksum, videos[i].error.c_str());

@@ -28,16 +28,18 @@ def main():
         cmd += ["--svm-model", os.path.join(ROOT, "tests", "golden", "standin_svmRBFmodel.model"), "--mean", ",".join(["0.3"] * 9), "--std", ",".join(["0.2"] * 9)]
     t0 = time.time()
     procs = [subprocess.Popen(cmd + streams * copies, env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(g)), stdout=subprocess.PIPE, text=True) for g in range(gpus)]
-    total = 0
+    total = 0; steady = 0.0; startup = []
     for g, p in enumerate(procs):
         out, _ = p.communicate()
         r = json.loads(out.strip().splitlines()[-1])
-        total += r["pictures"]
+        total += r["pictures"]; steady += r.get("steady_pictures_per_s", 0.0); startup.append(r.get("startup_seconds", 0.0))
         print(f"gpu {g}: {r['pictures']} pictures of {len(r['videos'])} streams in {r['seconds']:.2f} s = {r['pictures_per_s']:.0f} pictures/s"
+              f" (start-up {r.get('startup_seconds', 0.0):.2f} s: CUDA, context, decoder; then {r.get('steady_pictures_per_s', 0.0):.0f} pictures/s)"
               + ("".join(" ERROR " + v["error"] for v in r["videos"] if v["error"])))
     sec = time.time() - t0
     print(json.dumps({"gpus": gpus, "producers": gpus * len(streams) * copies, "mode": mode, "pictures": total, "seconds": round(sec, 3),
-                      "pictures_per_s": round(total / sec, 1), "host_cores": os.cpu_count()}))
+                      "pictures_per_s": round(total / sec, 1), "steady_pictures_per_s": round(steady, 1), "startup_seconds_max": round(max(startup), 2),
+                      "host_cores": os.cpu_count()}))
 
 
 if __name__ == "__main__":
