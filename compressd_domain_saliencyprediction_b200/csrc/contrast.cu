@@ -4,8 +4,9 @@
 //     out(r,c) = sum_{i,j<win} W(i,j) * g(P(r+i, c+j), P(r+len, c+len)),  g(p,ctr) = p != 0 ? |p-ctr| : 0
 // on the zero-padded, pm_norm'ed map P built by Sudoku_contrastcpp5.m:18-34.
 //
-// B200 design: FP32 CUDA-core bound (2 FP32-pipe instructions per (cell, neighbour) pair:
-// FADD d = p - c ; FFMA acc += |d| * w  with |.| as a free operand modifier).  The reference's W
+// B200 design: FP32 CUDA-core bound (2 FP32 lane operations per (cell, neighbour) pair:
+// FADD d = p - c ; FFMA acc += |d| * w  with |.| as a free operand modifier; issued two pairs at a time
+// as FADD2 / FFMA2, see sep_accumulate_packed).  The reference's W
 // is a separable Gaussian (Sudoku_contrastcpp5.m:8-14), so the hot kernel accumulates each window
 // row with the column factor gc[j] (a constant-bank FFMA operand: the loop over j is fully
 // unrolled) and folds the row factor gr[i] in once per row.  Each thread owns CPT consecutive

@@ -272,9 +272,9 @@ svm_rbf9_tc_kernel(const float* __restrict__ X, long N, const float* __restrict_
 // Persistent variant of the kernel above: ONE CTA per SM walks the 128-instance tiles of the whole launch, so the kernel
 // can share every SM with a kernel that is bound by a different pipe (the FP32-issue-bound contrast kernel of the next
 // batch, pipeline.cu): it holds 10 warps, <= 128 registers per thread and 98 KB of shared memory per SM for its whole life
-// and leaves the rest to the co-resident CTAs.  Roles: warps 0-7 epilogue (TMEM lane quadrant = warp % 4, column half =
-// warp / 4, so two warps per scheduler alternate between tcgen05.ld latency and MUFU issue), warp 8 MMA issuer + TMEM
-// allocation, warp 9 producer (lane 0 streams the SV tile images; the whole warp builds the A tile of the NEXT instance
+// and leaves the rest to the co-resident CTAs.  Roles: warps 0-7 epilogue (TMEM lane quadrant = warp % 4, warp set =
+// warp / 4; a set takes every other SV tile, so the two warps of a scheduler run half a tile apart), warp 8 MMA issuer + TMEM
+// allocation (four accumulators), warp 9 producer (lane 0 streams the SV tile images; the whole warp builds the A tile of the NEXT instance
 // tile into the second A buffer, so the MMA pipe never waits for it).  mbarrier phases run on global counters across tiles.
 // =================================================================================================
 namespace tcp {
