@@ -499,21 +499,28 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
     }
     return;
   }
-  const char* __restrict__ mine = reinterpret_cast<const char*>(stage + wrow * TW_C + lane);
+  // The loop is bound by issued instructions (15 warps, ~120 per ring picture, of which 56 are arithmetic), so its bookkeeping is
+  // kept in loop-carried registers: 32-bit shared addresses made opaque to the compiler (it otherwise rebuilds them from
+  // %cluster_ctaid / the window base in every iteration to save registers), the ring slot, its parity and j advance by increments.
+  uint32_t mine, offp, barf;                       // this thread's cell in ring buffer 0; the offset-table row; full[0]
+  asm volatile("mov.u32 %0, %1;" : "=r"(mine) : "r"(smem_u32(stage + wrow * TW_C + lane)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(offp) : "r"(smem_u32(s_off + g0)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(barf) : "r"(bar0));
   int q_slot = ((q_hi % RL) + RL) % RL;
+  uint32_t u8 = 0, par = 0;                        // 8 * (qi % T_STAGES), (qi / T_STAGES) & 1
+  int j0 = poc0 + g0 - q_hi;                       // j of this thread's first picture for ring picture q = q_hi - qi (>= 1 on the straight-line path)
   // (not unrolled over the ring: eight copies of the body do not fit the instruction cache — ncu showed no_inst stalls)
 #pragma unroll 1
-  for (int qi = 0; qi < nq; qi++) {
+  for (int qi = 0; qi < nq; qi++, j0++, offp += TG * 4) {
     {
-      const int u = qi % T_STAGES;
       {
-        mbar_wait(bar0 + 8u * u, (uint32_t)((qi / T_STAGES) & 1));      // window qi has landed
+        mbar_wait(barf + u8, par);                                       // window qi has landed
         const int q = q_hi - qi;
-        const int j0 = poc0 + g0 - q;                                    // j of this thread's first picture (>= 1 on the straight-line path)
         int offs[TGT]; int any_neg = 0;
 #pragma unroll
         for (int k4 = 0; k4 < TGT; k4 += 4) {
-          const int4 o4 = *reinterpret_cast<const int4*>(s_off + qi * TG + g0 + k4);
+          int4 o4;
+          asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w) : "r"(offp + k4 * 4));
           offs[k4] = o4.x; offs[k4 + 1] = o4.y; offs[k4 + 2] = o4.z; offs[k4 + 3] = o4.w;
           any_neg |= o4.x | o4.y | o4.z | o4.w;
         }
@@ -522,7 +529,8 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
           // all shared-memory loads first so that their latencies overlap
           float4 pv[TGT];
 #pragma unroll
-          for (int k = 0; k < TGT; k++) pv[k] = *reinterpret_cast<const float4*>(mine + offs[k]);
+          for (int k = 0; k < TGT; k++)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pv[k].x), "=f"(pv[k].y), "=f"(pv[k].z), "=f"(pv[k].w) : "r"(mine + (uint32_t)offs[k]));
 #pragma unroll
           for (int k = 0; k < TGT; k++) {
             const float4 p = pv[k];
@@ -539,7 +547,7 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
             if (off != -2) {                                                  // uniform per thread set
               const int j = poc0 + g0 + k - q;
               float4 p;
-              if (off >= 0) p = *reinterpret_cast<const float4*>(mine + off);
+              if (off >= 0) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w) : "r"(mine + (uint32_t)off));
               else {                                                          // shift spread beyond the window capacity: straight from L2
                 const int2 sh = s_shift[(g0 + k) * PT + j];
                 const int sr = r - sh.y, sc = c - sh.x;
@@ -554,7 +562,8 @@ temporal_group_kernel(const __grid_constant__ CUtensorMap tmap /*ring as [RL][h4
         }
         q_slot = q_slot == 0 ? RL - 1 : q_slot - 1;
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 8u * (T_STAGES + u));         // this warp has read window qi
+        if (lane == 0) mbar_arrive(barf + 8u * T_STAGES + u8);          // this warp has read window qi
+        u8 += 8; if (u8 == 8u * T_STAGES) { u8 = 0; par ^= 1u; }
       }
     }
   }
