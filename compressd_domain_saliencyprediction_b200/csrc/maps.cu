@@ -1264,6 +1264,10 @@ int stats_finalize_launch(const float* partial, int nmaps, int nblocks, float* s
 // =================================================================================================
 // generic banded operators
 // =================================================================================================
+// Map selection shared by the row and column passes: with `outer_of_three` the launch covers only maps 0 and 2 of every three
+// (the 200x200 features take the middle one -- the temporal map -- from the full-resolution path, main.m:284-294).
+__device__ __forceinline__ int banded_map(int z, int outer_of_three) { return outer_of_three ? (z >> 1) * 3 + (z & 1) * 2 : z; }
+
 // out[m][i][x] = sum_t w[i][t] * f(in[m][start[i]+t][x]);  f = identity or min((v-a)*b, thr) per map.
 // A thread owns 4 adjacent columns (LDG.128 / STG.128); cols must be a multiple of 4.
 template <bool XF>
@@ -1300,9 +1304,9 @@ constexpr int BR_ROWS = 4;
 template <bool XF>
 __global__ void __launch_bounds__(128)
 banded_rows4_kernel(const float* __restrict__ in, int in_rows, int cols, const float* __restrict__ w, const int* __restrict__ start,
-                    int nt, int n_out, const float* __restrict__ xf, float* __restrict__ out) {
+                    int nt, int n_out, const float* __restrict__ xf, float* __restrict__ out, int outer_of_three) {
   extern __shared__ float4 sw4[];               // [window] x 4 rows
-  const int i0 = blockIdx.y * BR_ROWS, m = blockIdx.z, C4 = cols >> 2;
+  const int i0 = blockIdx.y * BR_ROWS, m = banded_map(blockIdx.z, outer_of_three), C4 = cols >> 2;
   const int ilast = min(i0 + BR_ROWS - 1, n_out - 1);
   const int s_lo = start[i0], L = min(start[ilast] + nt, in_rows) - s_lo;
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
@@ -1363,7 +1367,10 @@ banded_rows_scalar_kernel(const float* __restrict__ in, int in_rows, int cols, c
   }
 }
 
-int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const Banded& B, const float* xf, float* out, cudaStream_t st) {
+int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const Banded& B, const float* xf, float* out, cudaStream_t st,
+                       int outer_of_three) {
+  // `outer_of_three` is a hint (skipped maps are simply not needed): only the four-row kernel below implements it, the others do every map
+  if (nmaps % 3 != 0) outer_of_three = 0;
   if (cols % 4) {
     dim3 grid(min(ceil_div(cols, 128), 64), B.n_out, nmaps);
     banded_rows_scalar_kernel<<<grid, 128, (size_t)B.nt * 4, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
@@ -1377,8 +1384,9 @@ int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const 
   if (B.span4 >= 0 && B.span4 <= 2 * B.nt) {
     dim3 grid4(ceil_div(cols / 4, thr), ceil_div(B.n_out, BR_ROWS), nmaps);
     const size_t smem = (size_t)(B.nt + B.span4) * 16;
-    if (xf) banded_rows4_kernel<true><<<grid4, thr, smem, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
-    else    banded_rows4_kernel<false><<<grid4, thr, smem, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out);
+    if (outer_of_three) grid4.z = nmaps / 3 * 2;
+    if (xf) banded_rows4_kernel<true><<<grid4, thr, smem, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out, outer_of_three);
+    else    banded_rows4_kernel<false><<<grid4, thr, smem, st>>>(in, in_rows, cols, B.d_w, B.d_start, B.nt, B.n_out, xf, out, outer_of_three);
     CDS_LAUNCH_CHECK();
     return CDS_OK;
   }
@@ -1400,9 +1408,9 @@ int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const 
 constexpr int BC_ROWS = 8;
 __global__ void __launch_bounds__(256)
 banded_cols_kernel(const float* __restrict__ in, int rows, int in_cols, const float* __restrict__ wT, const int* __restrict__ start,
-                   int nt, int n_out, float* __restrict__ out) {
+                   int nt, int n_out, float* __restrict__ out, int outer_of_three) {
   extern __shared__ float4 scol[];              // [in_cols][3]
-  const int r0 = blockIdx.x * BC_ROWS, m = blockIdx.y;
+  const int r0 = blockIdx.x * BC_ROWS, m = banded_map(blockIdx.y, outer_of_three);
   const int nr = min(BC_ROWS, rows - r0);
   const float* __restrict__ src = in + ((size_t)m * rows + r0) * in_cols;
   if ((in_cols & 3) == 0) {
@@ -1446,11 +1454,12 @@ banded_cols_kernel(const float* __restrict__ in, int rows, int in_cols, const fl
   }
 }
 
-int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st) {
-  dim3 grid(ceil_div(rows, BC_ROWS), nmaps);
+int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st, int outer_of_three) {
+  if (nmaps % 3 != 0) outer_of_three = 0;
+  dim3 grid(ceil_div(rows, BC_ROWS), outer_of_three ? nmaps / 3 * 2 : nmaps);
   const size_t smem = (size_t)in_cols * 48;
   if (int e = ensure_dyn_smem(banded_cols_kernel, smem)) return e;
-  banded_cols_kernel<<<grid, 256, smem, st>>>(in, rows, in_cols, B.d_wT, B.d_start, B.nt, B.n_out, out);
+  banded_cols_kernel<<<grid, 256, smem, st>>>(in, rows, in_cols, B.d_wT, B.d_start, B.nt, B.n_out, out, outer_of_three);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }

@@ -72,7 +72,8 @@ int fir_threads(int W4);                      // CTA width (96 or 128 threads of
 int fullres_vpass_nblocks(int h4, int W);   // partial blocks per map written by fullres_vpass_launch
 int stats_finalize_launch(const float* partial, int nmaps, int nblocks, float* stats /*[nmaps][4] min,max,sum_lo,sum_hi*/, cudaStream_t st);
 // generic banded operators, batched over nmaps; xf (optional, [nmaps][4] = a,b,thr,unused): v = min((in - a) * b, thr)
-int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const Banded& B, const float* xf, float* out, cudaStream_t st);
-int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st);
+int banded_rows_launch(const float* in, int nmaps, int in_rows, int cols, const Banded& B, const float* xf, float* out, cudaStream_t st,
+                       int outer_of_three = 0);
+int banded_cols_launch(const float* in, int nmaps, int rows, int in_cols, const Banded& B, float* out, cudaStream_t st, int outer_of_three = 0);
 
 }  // namespace cds

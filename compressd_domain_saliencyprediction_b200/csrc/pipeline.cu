@@ -941,8 +941,9 @@ int run_batch(cds_ctx* c, int first_poc, int n, const uint16_t* bytes, const int
   if (c->p.use_rbf) {
     // ---- features at 200x200 (main.m:275-294) ----
     prof_mark(c, ST_RESIZE200, st);
-    if (int e = banded_rows_launch(dX, 9 * n, h4, w4, c->Av, nullptr, c->d_A1, st)) return e;
-    if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, c->d_F200, st)) return e;
+    // the cell path serves features 0, 2 of every triple only: the middle one (temporal) comes from the full-resolution path below
+    if (int e = banded_rows_launch(dX, 9 * n, h4, w4, c->Av, nullptr, c->d_A1, st, 1)) return e;
+    if (int e = banded_cols_launch(c->d_A1, 9 * n, 200, w4, c->Ah, c->d_F200, st, 1)) return e;
     if (int e = banded_rows_launch(c->d_Y, 3 * n, H, W, c->Rv, c->d_xf, c->d_R1, st)) return e;
     if (int e = banded_cols_launch(c->d_R1, 3 * n, 200, W, c->Rh, c->d_Ft, st)) return e;
     if (ov) CDS_CUDA(cudaStreamWaitEvent(st, c->ev_back[slot], 0));     // the back half of batch i-2 read xsvm[slot]
