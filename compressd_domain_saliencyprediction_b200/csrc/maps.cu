@@ -185,34 +185,57 @@ struct OpAddI { __device__ int operator()(int a, int b) const { return a + b; } 
 // =================================================================================================
 // smoothing: causal mean over the last PS pictures (main.m:144-165)
 // =================================================================================================
-__global__ void __launch_bounds__(256)
+// A thread owns one cell for a group of SG consecutive pictures: their windows are almost the same ring pictures, so each ring value
+// is loaded once and added into every picture of the group whose window holds it (uniform predicates).  Every picture still adds its
+// own values in ascending picture order -- the reference's loop order; the two FP64 sums must match the oracle to the bit -- while the
+// loads drop from SG x PS to PS + SG - 1 per cell and map (one picture per thread read 3.5 GB per batch out of the L2 at 1080p / 50 fps).
+// Measured per 64 pictures: one picture per thread 0.27 ms; groups of 8 (103 registers, a quarter of the warps resident: latency
+// bound) 0.30 ms; groups of 4 (64 registers) 0.17 ms.
+constexpr int SG = 4;
+__global__ void __launch_bounds__(128)
 smooth_kernel(int n4, int PS, int RL, int first_poc, const double* __restrict__ Vx, const double* __restrict__ Vy,
               const float* __restrict__ mvn, const float* __restrict__ bitn, const float* __restrict__ depn,
               float4* __restrict__ sm4 /*ring [RL][n4]: {mvx, mvy, bit, depth} smoothed*/,
               float* __restrict__ mv_s, double* __restrict__ cxy, int B) {
-  const int o = blockIdx.x * 256 + threadIdx.x, f = blockIdx.y;
+  const int o = blockIdx.x * 128 + threadIdx.x, f0 = blockIdx.y * SG;
   if (o >= n4) return;
-  const int poc = first_poc + f;
-  const int cnt = min(PS, poc + 1);
-  float a = 0.f, d = 0.f, e = 0.f;
-  double b = 0.0, c = 0.0;                                         // mv_x / mv_y stay double: see camera_motion_kernel<double>
-  for (int ii = poc - cnt + 1; ii <= poc; ii++) {                 // ascending, like the reference loop
-    const size_t s = (size_t)(ii % RL) * n4 + o;
-    a += mvn[s]; b += Vx[s]; c += Vy[s]; d += bitn[s]; e += depn[s];
+  const int ng = min(SG, B - f0), poc0 = first_poc + f0;
+  float a[SG], d[SG], e[SG];
+  double b[SG], c[SG];                                             // mv_x / mv_y stay double: see camera_motion_kernel<double>
+#pragma unroll
+  for (int g = 0; g < SG; g++) { a[g] = 0.f; d[g] = 0.f; e[g] = 0.f; b[g] = 0.0; c[g] = 0.0; }
+  const int q_lo = max(0, poc0 - PS + 1), q_hi = poc0 + ng - 1;
+#pragma unroll 6
+  for (int q = q_lo; q <= q_hi; q++) {                            // ascending, like the reference loop
+    const size_t s = (size_t)(q % RL) * n4 + o;
+    const float va = __ldg(mvn + s), vd = __ldg(bitn + s), ve = __ldg(depn + s);
+    const double vb = __ldg(Vx + s), vc = __ldg(Vy + s);
+#pragma unroll
+    for (int g = 0; g < SG; g++) {
+      const int poc = poc0 + g;                                    // window of picture g: [poc - min(PS, poc + 1) + 1, poc]
+      if (g < ng && q <= poc && q > poc - PS) { a[g] += va; b[g] += vb; c[g] += vc; d[g] += vd; e[g] += ve; }
+    }
   }
-  const float fc = (float)cnt;
-  b /= (double)cnt; c /= (double)cnt;
-  const size_t so = (size_t)(poc % RL) * n4 + o;
-  mv_s[(size_t)f * n4 + o] = a / fc;
-  sm4[so] = make_float4((float)b, (float)c, d / fc, e / fc);
-  if (cxy) { cxy[(size_t)f * n4 + o] = b; cxy[((size_t)B + f) * n4 + o] = c; }     // [mvx: B maps | mvy: B maps]
+#pragma unroll
+  for (int g = 0; g < SG; g++) {
+    if (g < ng) {
+      const int poc = poc0 + g, f = f0 + g;
+      const int cnt = min(PS, poc + 1);
+      const float fc = (float)cnt;
+      const double bm = b[g] / (double)cnt, cm = c[g] / (double)cnt;
+      const size_t so = (size_t)(poc % RL) * n4 + o;
+      mv_s[(size_t)f * n4 + o] = a[g] / fc;
+      sm4[so] = make_float4((float)bm, (float)cm, d[g] / fc, e[g] / fc);
+      if (cxy) { cxy[(size_t)f * n4 + o] = bm; cxy[((size_t)B + f) * n4 + o] = cm; }     // [mvx: B maps | mvy: B maps]
+    }
+  }
 }
 
 int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const double* Vx, const double* Vy, const float* mvn,
                   const float* bitn, const float* depn, float4* sm4, float* mv_s,
                   double* cxy, cudaStream_t st) {
-  dim3 grid(ceil_div(n4, 256), B);
-  smooth_kernel<<<grid, 256, 0, st>>>(n4, PS, ring_len, first_poc, Vx, Vy, mvn, bitn, depn, sm4, mv_s, cxy, B);
+  dim3 grid(ceil_div(n4, 128), ceil_div(B, SG));
+  smooth_kernel<<<grid, 128, 0, st>>>(n4, PS, ring_len, first_poc, Vx, Vy, mvn, bitn, depn, sm4, mv_s, cxy, B);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
