@@ -16,6 +16,7 @@
 // All of these passes are bandwidth/latency class (HBM / L2), not FLOP class.
 #include "maps.cuh"
 #include "tc_common.cuh"
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -243,37 +244,60 @@ int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const doub
 // =================================================================================================
 // mysterythrehold.m:3-7 on the smoothed h4 x w4 maps (main.m:170-172).  One CTA per (picture, map).
 // =================================================================================================
-__global__ void __launch_bounds__(1024)
+// One thread-block CLUSTER of MS_CLUSTER CTAs per (picture, map): the three sweeps over a map are latency bound, and one CTA per map
+// (192 CTAs for 64 pictures: barely one per SM, 0.14 ms) left most of the GPU idle.  A CTA owns a contiguous slice (its re-reads hit
+// the L1); the partial statistics of the slices meet in the rank-0 CTA's shared memory, one slot per rank, and every CTA adds them in
+// rank order -- no atomics, so the result does not depend on timing.
+constexpr int MS_CLUSTER = 8, MS_THREADS = 512;
+struct MsShared { double s[MS_CLUSTER], sb[MS_CLUSTER]; float mx[MS_CLUSTER]; int nb[MS_CLUSTER]; };
+__global__ void __cluster_dims__(MS_CLUSTER, 1, 1) __launch_bounds__(MS_THREADS)
 myst_small_kernel(int n4, double inv_hw, int RL, int first_poc, const float* __restrict__ mv_s,
                   const float4* __restrict__ sm4, float* __restrict__ Xmaps) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ MsShared sh;
   __shared__ float redf[32];
   __shared__ double redd[32];
   __shared__ int redi[32];
-  const int f = blockIdx.x, which = blockIdx.y;       // 0 mv, 1 bit, 2 depth
+  MsShared* S0 = cluster.map_shared_rank(&sh, 0);
+  const int crank = (int)cluster.block_rank();
+  const int f = blockIdx.x / MS_CLUSTER, which = blockIdx.y;       // 0 mv, 1 bit, 2 depth
   const size_t slot = (size_t)((first_poc + f) % RL) * n4;
   // which == 0: the batch's smoothed mv_norm (stride 1); 1 / 2: components z / w of the interleaved ring (stride 4)
   const float* __restrict__ src = which == 0 ? mv_s + (size_t)f * n4 : reinterpret_cast<const float*>(sm4 + slot) + (which + 1);
   const int sst = which == 0 ? 1 : 4;
   float* __restrict__ dst = Xmaps + ((size_t)f * 9 + which * 3) * n4;
+  const int per = (n4 + MS_CLUSTER - 1) / MS_CLUSTER, o0 = crank * per, o1 = min(n4, o0 + per);
   double s = 0; float mx = -INFINITY;
-  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[(size_t)o * sst]; s += v; mx = fmaxf(mx, v); }
+  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) { const float v = src[(size_t)o * sst]; s += v; mx = fmaxf(mx, v); }
   s = block_reduce(s, redd, OpAddD());
   mx = block_reduce(mx, redf, OpMax());
+  if (threadIdx.x == 0) { S0->s[crank] = s; S0->mx[crank] = mx; }
+  cluster.sync();
+  s = 0; mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MS_CLUSTER; k++) { s += S0->s[k]; mx = fmaxf(mx, S0->mx[k]); }
   const float lim = mx - (float)(s * inv_hw);                     // max - ave, ave over im_height*im_width (:3-4)
   double sb = 0; int nb = 0;
-  for (int o = threadIdx.x; o < n4; o += 1024) { const float v = src[(size_t)o * sst]; if (v > lim) { sb += v; nb++; } }
+  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) { const float v = src[(size_t)o * sst]; if (v > lim) { sb += v; nb++; } }
   sb = block_reduce(sb, redd, OpAddD());
   nb = block_reduce(nb, redi, OpAddI());
+  if (threadIdx.x == 0) { S0->sb[crank] = sb; S0->nb[crank] = nb; }
+  cluster.sync();
+  sb = 0; nb = 0;
+#pragma unroll
+  for (int k = 0; k < MS_CLUSTER; k++) { sb += S0->sb[k]; nb += S0->nb[k]; }
   const float thresh = nb > 0 ? (float)(sb / nb) : NAN;           // :5
   const float M = nb > 0 ? fminf(thresh, mx) : mx;                // max after the clamp
   const float inv = 1.f / (M + 0.000001f);                        // :7
-  for (int o = threadIdx.x; o < n4; o += 1024) { float v = src[(size_t)o * sst]; if (v > thresh) v = thresh; dst[o] = v * inv; }
+  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) { float v = src[(size_t)o * sst]; if (v > thresh) v = thresh; dst[o] = v * inv; }
+  cluster.sync();                  // rank 0's shared memory must outlive every remote read
 }
 
 int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float4* sm4,
                       float* Xmaps, cudaStream_t st) {
-  dim3 grid(B, 3);
-  myst_small_kernel<<<grid, 1024, 0, st>>>(n4, 1.0 / ((double)H * W), ring_len, first_poc, mv_s, sm4, Xmaps);
+  dim3 grid(B * MS_CLUSTER, 3);
+  myst_small_kernel<<<grid, MS_THREADS, 0, st>>>(n4, 1.0 / ((double)H * W), ring_len, first_poc, mv_s, sm4, Xmaps);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
 }
