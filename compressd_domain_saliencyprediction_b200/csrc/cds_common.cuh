@@ -17,6 +17,16 @@ int ensure_dyn_smem_impl(const void* func, size_t bytes);
 template <typename K> inline int ensure_dyn_smem(K kernel, size_t bytes) { return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kernel), bytes); }
 int device_sm_count();          // multiprocessors of the current device (cached per device)
 
+#ifdef __CUDACC__
+// One 256-bit store (sm_100: STG.256): a thread that owns 32 contiguous bytes writes a whole 32-byte sector with one instruction --
+// two 128-bit stores from lanes that are 64 bytes or a picture row apart leave every sector half written per instruction.
+// `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(float* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+#endif
+
 #define CDS_CUDA(expr)                                                              \
   do {                                                                              \
     cudaError_t _e = (expr);                                                        \

@@ -865,8 +865,15 @@ fullres_hpass_kernel(const float* __restrict__ X, int h4, int w4, int dmin, int 
       }
       w0 = w1;
     }
+    if (c0 + HP_CPT <= w4 && (w4 & 1) == 0) {      // the thread's 64 output bytes as two 256-bit stores (whole sectors)
 #pragma unroll
-    for (int k = 0; k < HP_CPT; k++) if (c0 + k < w4) out[c0 + k] = make_float4(lo2(alo[k]), hi2(alo[k]), lo2(ahi[k]), hi2(ahi[k]));
+      for (int k = 0; k < HP_CPT; k += 2)
+        st_global_256(reinterpret_cast<float*>(out + c0 + k), make_float4(lo2(alo[k]), hi2(alo[k]), lo2(ahi[k]), hi2(ahi[k])),
+                      make_float4(lo2(alo[k + 1]), hi2(alo[k + 1]), lo2(ahi[k + 1]), hi2(ahi[k + 1])));
+    } else {
+#pragma unroll
+      for (int k = 0; k < HP_CPT; k++) if (c0 + k < w4) out[c0 + k] = make_float4(lo2(alo[k]), hi2(alo[k]), lo2(ahi[k]), hi2(ahi[k]));
+    }
   }
 }
 
@@ -1172,14 +1179,18 @@ fullres_vpass_tc_kernel(const __grid_constant__ CUtensorMap tmap /*T as [maps][h
           tmem_ld_wait();
           if (y < H) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < 32; j += 8) {
               const int x = x0 + c + j;
-              if (x < W) {
+              if (x < W) {                                     // W is a multiple of 8: a group of 8 columns is inside or outside as a whole
                 const float4 a = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                const float4 b = make_float4(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]), __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
                 mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
                 mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
                 tsum += (a.x + a.y) + (a.z + a.w);
-                if (Ys) *reinterpret_cast<float4*>(Ys + (size_t)y * W + x) = a;
+                mn = fminf(mn, fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
+                mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+                tsum += (b.x + b.y) + (b.z + b.w);
+                if (Ys) st_global_256(Ys + (size_t)y * W + x, a, b);      // a lane owns a row: 32 bytes = one whole sector per store
               }
             }
           }
