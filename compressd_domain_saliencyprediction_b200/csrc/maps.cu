@@ -1029,7 +1029,7 @@ constexpr int NCONV = 8;                          // converter warps: WPS per K 
 constexpr int WPS = NCONV / 4;                    // measured: 8 warps 1.46 ms, 16 warps 1.66 ms per 64 pictures (shared-memory bandwidth is the wall)
 constexpr int CBLK = 32 / (WPS / 2);              // 8-column blocks per converter warp
 constexpr int THREADS = (6 + NCONV) * 32;         // warps 0-3 epilogue, warp 4 MMA + TMEM alloc, then NCONV converter warps, then the producer warp
-constexpr int RSTAGES = 4;                        // raw FP32 input ring filled by TMA; == number of converter groups, so a group sees every phase of its stage
+constexpr int RSTAGES = 4, RSTAGES_MAX = 8;       // raw FP32 input ring filled by TMA: a multiple of the number of converter groups (4), so a stage always belongs to the same group, which then sees every phase of its barrier.  8 where shared memory allows: with 4 boxes of 8 KB in flight per SM the loop waited on TMA latency (~1000 cycles per K step against ~530 of shared-memory traffic)
 constexpr int RAW_PITCH = TN * 4;                 // dense TMA box
 constexpr int RAW_STAGE = 8 * RAW_PITCH;
 constexpr int BAR_BYTES = 1024;
@@ -1039,15 +1039,15 @@ constexpr uint32_t IDESC = idesc_tf32(TM, TN, 0, 0);   // both operands K-major
 
 __global__ void __launch_bounds__(vtc::THREADS, 1)
 fullres_vpass_tc_kernel(const __grid_constant__ CUtensorMap tmap /*T as [maps][h4][W] FP32, box [1][8][256]*/, int nmaps, int h4, int W, int dmin,
-                        int kp, int nstages, const float* __restrict__ aimg, float* __restrict__ Ystore, const int* __restrict__ store_index,
+                        int kp, int nstages, int rstages, const float* __restrict__ aimg, float* __restrict__ Ystore, const int* __restrict__ store_index,
                         float* __restrict__ partial) {
   using namespace vtc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int a_half = kp * TM * 4;                 // bytes of A hi (then A lo)
   uint8_t* sA = smem;                             // [hi|lo][k chunk of 4][128 rows][4]   (K-major, no swizzle)
   uint8_t* sB = smem + 2 * a_half;                // STAGES x [hi|lo][k chunk of 4][256 columns][4]   (K-major, no swizzle)
-  uint8_t* sR = sB + nstages * STAGE_BYTES;       // RSTAGES x [8 rows][128] raw FP32 inputs (TMA boxes)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + RSTAGES * RAW_STAGE);
+  uint8_t* sR = sB + nstages * STAGE_BYTES;       // rstages x [8 rows][256] raw FP32 inputs (TMA boxes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + rstages * RAW_STAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
   float* red = reinterpret_cast<float*>(bars + 52);     // [4 warps][4]: min, max, sum as double
   const uint32_t bar0 = smem_u32(bars);
@@ -1058,7 +1058,7 @@ fullres_vpass_tc_kernel(const __grid_constant__ CUtensorMap tmap /*T as [maps][h
   auto tempty = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
   const uint32_t abar = bar0 + 8u * (2 * STAGES + 4);
   auto rfull = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + s); };
-  auto rempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + RSTAGES + s); };
+  auto rempty = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + RSTAGES_MAX + s); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = 4 * h4;
   const int ntile = (H + TM - 1) / TM, ksteps = kp >> 3, total = ntile * ksteps;   // per work item
@@ -1071,7 +1071,7 @@ fullres_vpass_tc_kernel(const __grid_constant__ CUtensorMap tmap /*T as [maps][h
     for (int s = 0; s < nstages; s++) { mbar_init(full(s), WPS); mbar_init(empty(s), 1); }   // WPS converter warps fill one stage
     for (int b = 0; b < 2; b++) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 4); }
     mbar_init(abar, 1);
-    for (int r = 0; r < RSTAGES; r++) { mbar_init(rfull(r), 1); mbar_init(rempty(r), WPS); }
+    for (int r = 0; r < rstages; r++) { mbar_init(rfull(r), 1); mbar_init(rempty(r), WPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(abar, 2u * a_half);
     bulk_g2s(smem_u32(sA), aimg, 2u * a_half, abar);
@@ -1091,8 +1091,8 @@ fullres_vpass_tc_kernel(const __grid_constant__ CUtensorMap tmap /*T as [maps][h
       for (int wi = blockIdx.x; wi < nitems; wi += gridDim.x) {
         const int m = wi / nstrips, x0 = (wi - m * nstrips) * TN;
         for (int it = 0; it < total; it++, g++) {
-          const int t = it / ksteps, ks = it - t * ksteps, rs = g % RSTAGES;
-          mbar_wait(rempty(rs), ((g / RSTAGES) & 1) ^ 1);
+          const int t = it / ksteps, ks = it - t * ksteps, rs = g % rstages;
+          mbar_wait(rempty(rs), ((g / rstages) & 1) ^ 1);
           mbar_expect_tx(rfull(rs), (uint32_t)RAW_STAGE);
           const int r0 = CELLS * t + dmin + ks * 8;
           asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -1108,8 +1108,8 @@ fullres_vpass_tc_kernel(const __grid_constant__ CUtensorMap tmap /*T as [maps][h
     int nsteps = 0;
     for (int wi = blockIdx.x; wi < nitems; wi += gridDim.x) nsteps += total;
     for (int g = pr; g < nsteps; g += 4) {
-      const int rs = g % RSTAGES, s = g % nstages;
-      mbar_wait(rfull(rs), (g / RSTAGES) & 1);
+      const int rs = g % rstages, s = g % nstages;
+      mbar_wait(rfull(rs), (g / rstages) & 1);
       mbar_wait(empty(s), ((g / nstages) & 1) ^ 1);
       const uint8_t* raw = sR + rs * RAW_STAGE;
       const float* __restrict__ src = reinterpret_cast<const float*>(raw + (kc * 4 + kk) * RAW_PITCH) + ch * (CBLK * 8) + c;
@@ -1275,7 +1275,13 @@ int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polypha
   if (impl == 1) {
     int kp = 0; const float* img = nullptr;
     if (int e = vpass_tc_prepare(P, &kp, &img)) return e;
-    const size_t fixed = (size_t)2 * kp * vtc::TM * 4 + (size_t)vtc::RSTAGES * vtc::RAW_STAGE + vtc::BAR_BYTES;
+    static const int rs_env = [] { const char* e = getenv("CDS_VPASS_RSTAGES"); return e ? atoi(e) : 0; }();
+    int rstages = rs_env == 4 || rs_env == 8 ? rs_env : vtc::RSTAGES_MAX;
+    size_t fixed = (size_t)2 * kp * vtc::TM * 4 + (size_t)rstages * vtc::RAW_STAGE + vtc::BAR_BYTES;
+    if (fixed + (size_t)vtc::MAX_STAGES * vtc::STAGE_BYTES > 220 * 1024) {      // wide filters (4K: kp = 104): the weight tile leaves room for 4 raw stages only
+      rstages = vtc::RSTAGES;
+      fixed = (size_t)2 * kp * vtc::TM * 4 + (size_t)rstages * vtc::RAW_STAGE + vtc::BAR_BYTES;
+    }
     const int nstages = (int)std::min<size_t>(vtc::MAX_STAGES, fixed < 220 * 1024 ? (220 * 1024 - fixed) / vtc::STAGE_BYTES : 0);
     const size_t smem = fixed + (size_t)nstages * vtc::STAGE_BYTES;
     if (nstages >= 4) {
@@ -1285,7 +1291,7 @@ int fullres_vpass_launch(const float* T, int nmaps, int h4, int W, const Polypha
       if (int e = vpass_tc_tensor_map(T, nmaps, h4, W, &tmap)) return e;
       const int sms = device_sm_count();
       dim3 grid(std::min(sms, nstrips * nmaps));
-fullres_vpass_tc_kernel<<<grid, vtc::THREADS, smem, st>>>(tmap, nmaps, h4, W, P.dmin, kp, nstages, img, Ystore, store_index, partial);
+fullres_vpass_tc_kernel<<<grid, vtc::THREADS, smem, st>>>(tmap, nmaps, h4, W, P.dmin, kp, nstages, rstages, img, Ystore, store_index, partial);
       CDS_LAUNCH_CHECK();
       *nblocks_out = nstrips;
       return CDS_OK;
