@@ -273,22 +273,29 @@ temporal_thresh_finalize_kernel(const float* __restrict__ partial2, int nb2, con
 __global__ void __launch_bounds__(256)
 assemble_features_kernel(const float* __restrict__ F200, const float* __restrict__ Ft, const float* __restrict__ stats9,
                          const float* __restrict__ xf, const float* __restrict__ fparam /*[9][4] = mean, 1/std, weight, 0*/, float* __restrict__ xsvm) {
-  const int f = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= 40000) return;
-  float* o = xsvm + ((size_t)f * 40000 + n) * 9;
+  // a thread computes the nine features of one pixel; the CTA's 256 x 9 floats are one contiguous piece of xsvm, so they go out
+  // through shared memory as coalesced stores (nine scalar stores per thread 36 bytes apart wrote 4 bytes per sector per instruction)
+  __shared__ float so[256 * 9];
+  const int f = blockIdx.y, n0 = blockIdx.x * 256, n = n0 + threadIdx.x;
+  if (n < 40000) {
 #pragma unroll
-  for (int i = 0; i < 9; i++) {
-    float v;
-    if (i % 3 == 1) {
-      const int tm = f * 3 + i / 3;
-      v = Ft[(size_t)tm * 40000 + n] * xf[(size_t)tm * 4 + 3];
-    } else {
-      const float* st = stats9 + (size_t)(f * 9 + i) * 4;
-      const float mn = st[0], mx = st[1];
-      v = mx > mn ? (F200[(size_t)(f * 9 + i) * 40000 + n] - mn) / (mx - mn) : 0.f;     // pm_norm, NaN -> 0
+    for (int i = 0; i < 9; i++) {
+      float v;
+      if (i % 3 == 1) {
+        const int tm = f * 3 + i / 3;
+        v = Ft[(size_t)tm * 40000 + n] * xf[(size_t)tm * 4 + 3];
+      } else {
+        const float* st = stats9 + (size_t)(f * 9 + i) * 4;
+        const float mn = st[0], mx = st[1];
+        v = mx > mn ? (F200[(size_t)(f * 9 + i) * 40000 + n] - mn) / (mx - mn) : 0.f;     // pm_norm, NaN -> 0
+      }
+      so[threadIdx.x * 9 + i] = (v - fparam[4 * i]) * fparam[4 * i + 1];
     }
-    o[i] = (v - fparam[4 * i]) * fparam[4 * i + 1];
   }
+  __syncthreads();
+  const int cnt = min(256, 40000 - n0) * 9;
+  float* __restrict__ o = xsvm + ((size_t)f * 40000 + n0) * 9;
+  for (int i = threadIdx.x; i < cnt; i += 256) o[i] = so[i];
 }
 
 __global__ void __launch_bounds__(1024)
