@@ -249,7 +249,9 @@ int smooth_launch(int n4, int PS, int ring_len, int first_poc, int B, const doub
 // the L1); the partial statistics of the slices meet in the rank-0 CTA's shared memory, one slot per rank, and every CTA adds them in
 // rank order -- no atomics, so the result does not depend on timing.
 constexpr int MS_CLUSTER = 8, MS_THREADS = 512;
-struct MsShared { double s[MS_CLUSTER], sb[MS_CLUSTER]; float mx[MS_CLUSTER]; int nb[MS_CLUSTER]; };
+struct MsShared { double s[2][MS_CLUSTER], sb[2][MS_CLUSTER]; float mx[2][MS_CLUSTER]; int nb[2][MS_CLUSTER]; };
+// blockIdx.y = 0: the smoothed mv_norm map (planar); 1: the bit AND depth maps together -- they are components z / w of the
+// interleaved ring, so one 16-byte load per cell serves both (one map per launch row read 4 of every 16 bytes, three times).
 __global__ void __cluster_dims__(MS_CLUSTER, 1, 1) __launch_bounds__(MS_THREADS)
 myst_small_kernel(int n4, double inv_hw, int RL, int first_poc, const float* __restrict__ mv_s,
                   const float4* __restrict__ sm4, float* __restrict__ Xmaps) {
@@ -261,42 +263,67 @@ myst_small_kernel(int n4, double inv_hw, int RL, int first_poc, const float* __r
   __shared__ int redi[32];
   MsShared* S0 = cluster.map_shared_rank(&sh, 0);
   const int crank = (int)cluster.block_rank();
-  const int f = blockIdx.x / MS_CLUSTER, which = blockIdx.y;       // 0 mv, 1 bit, 2 depth
-  const size_t slot = (size_t)((first_poc + f) % RL) * n4;
-  // which == 0: the batch's smoothed mv_norm (stride 1); 1 / 2: components z / w of the interleaved ring (stride 4)
-  const float* __restrict__ src = which == 0 ? mv_s + (size_t)f * n4 : reinterpret_cast<const float*>(sm4 + slot) + (which + 1);
-  const int sst = which == 0 ? 1 : 4;
-  float* __restrict__ dst = Xmaps + ((size_t)f * 9 + which * 3) * n4;
+  const int f = blockIdx.x / MS_CLUSTER;
+  const bool two = blockIdx.y == 1;                                // uniform over the cluster
+  const int nm = two ? 2 : 1;
+  const float* __restrict__ p1 = mv_s + (size_t)f * n4;
+  const float4* __restrict__ p4 = sm4 + (size_t)((first_poc + f) % RL) * n4;
+  float* __restrict__ dst0 = Xmaps + ((size_t)f * 9 + (two ? 3 : 0)) * n4;      // maps 0 | 3 and 6
+  float* __restrict__ dst1 = Xmaps + ((size_t)f * 9 + 6) * n4;
   const int per = (n4 + MS_CLUSTER - 1) / MS_CLUSTER, o0 = crank * per, o1 = min(n4, o0 + per);
-  double s = 0; float mx = -INFINITY;
-  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) { const float v = src[(size_t)o * sst]; s += v; mx = fmaxf(mx, v); }
-  s = block_reduce(s, redd, OpAddD());
-  mx = block_reduce(mx, redf, OpMax());
-  if (threadIdx.x == 0) { S0->s[crank] = s; S0->mx[crank] = mx; }
+  auto load2 = [&](int o, float& v0, float& v1) { if (two) { const float4 q = p4[o]; v0 = q.z; v1 = q.w; } else { v0 = p1[o]; v1 = 0.f; } };
+  double s[2] = {0, 0}; float mx[2] = {-INFINITY, -INFINITY};
+  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) {
+    float v0, v1; load2(o, v0, v1);
+    s[0] += v0; mx[0] = fmaxf(mx[0], v0); s[1] += v1; mx[1] = fmaxf(mx[1], v1);
+  }
+  for (int k = 0; k < nm; k++) {
+    s[k] = block_reduce(s[k], redd, OpAddD());
+    mx[k] = block_reduce(mx[k], redf, OpMax());
+    if (threadIdx.x == 0) { S0->s[k][crank] = s[k]; S0->mx[k][crank] = mx[k]; }
+  }
   cluster.sync();
-  s = 0; mx = -INFINITY;
+  float lim[2] = {0.f, 0.f};
+  for (int k = 0; k < nm; k++) {
+    double t = 0; float m = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < MS_CLUSTER; k++) { s += S0->s[k]; mx = fmaxf(mx, S0->mx[k]); }
-  const float lim = mx - (float)(s * inv_hw);                     // max - ave, ave over im_height*im_width (:3-4)
-  double sb = 0; int nb = 0;
-  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) { const float v = src[(size_t)o * sst]; if (v > lim) { sb += v; nb++; } }
-  sb = block_reduce(sb, redd, OpAddD());
-  nb = block_reduce(nb, redi, OpAddI());
-  if (threadIdx.x == 0) { S0->sb[crank] = sb; S0->nb[crank] = nb; }
+    for (int c = 0; c < MS_CLUSTER; c++) { t += S0->s[k][c]; m = fmaxf(m, S0->mx[k][c]); }
+    mx[k] = m;
+    lim[k] = m - (float)(t * inv_hw);                              // max - ave, ave over im_height*im_width (:3-4)
+  }
+  double sb[2] = {0, 0}; int nb[2] = {0, 0};
+  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) {
+    float v0, v1; load2(o, v0, v1);
+    if (v0 > lim[0]) { sb[0] += v0; nb[0]++; }
+    if (two && v1 > lim[1]) { sb[1] += v1; nb[1]++; }
+  }
+  for (int k = 0; k < nm; k++) {
+    sb[k] = block_reduce(sb[k], redd, OpAddD());
+    nb[k] = block_reduce(nb[k], redi, OpAddI());
+    if (threadIdx.x == 0) { S0->sb[k][crank] = sb[k]; S0->nb[k][crank] = nb[k]; }
+  }
   cluster.sync();
-  sb = 0; nb = 0;
+  float thresh[2] = {NAN, NAN}, inv[2] = {0.f, 0.f};
+  for (int k = 0; k < nm; k++) {
+    double t = 0; int n = 0;
 #pragma unroll
-  for (int k = 0; k < MS_CLUSTER; k++) { sb += S0->sb[k]; nb += S0->nb[k]; }
-  const float thresh = nb > 0 ? (float)(sb / nb) : NAN;           // :5
-  const float M = nb > 0 ? fminf(thresh, mx) : mx;                // max after the clamp
-  const float inv = 1.f / (M + 0.000001f);                        // :7
-  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) { float v = src[(size_t)o * sst]; if (v > thresh) v = thresh; dst[o] = v * inv; }
+    for (int c = 0; c < MS_CLUSTER; c++) { t += S0->sb[k][c]; n += S0->nb[k][c]; }
+    thresh[k] = n > 0 ? (float)(t / n) : NAN;                      // :5
+    const float M = n > 0 ? fminf(thresh[k], mx[k]) : mx[k];       // max after the clamp
+    inv[k] = 1.f / (M + 0.000001f);                                // :7
+  }
+  for (int o = o0 + threadIdx.x; o < o1; o += MS_THREADS) {
+    float v0, v1; load2(o, v0, v1);
+    if (v0 > thresh[0]) v0 = thresh[0];
+    dst0[o] = v0 * inv[0];
+    if (two) { if (v1 > thresh[1]) v1 = thresh[1]; dst1[o] = v1 * inv[1]; }
+  }
   cluster.sync();                  // rank 0's shared memory must outlive every remote read
 }
 
 int myst_small_launch(int n4, int H, int W, int ring_len, int first_poc, int B, const float* mv_s, const float4* sm4,
                       float* Xmaps, cudaStream_t st) {
-  dim3 grid(B * MS_CLUSTER, 3);
+  dim3 grid(B * MS_CLUSTER, 2);
   myst_small_kernel<<<grid, MS_THREADS, 0, st>>>(n4, 1.0 / ((double)H * W), ring_len, first_poc, mv_s, sm4, Xmaps);
   CDS_LAUNCH_CHECK();
   return CDS_OK;
