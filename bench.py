@@ -364,7 +364,7 @@ def run_b200(a):
         return t
     h_hdr, h_tok, h_base, h_byts = pinned(c_hdr), pinned(c_tok), pinned(c_base), pinned(c_byts)
     d_hdr, d_tok, d_base, d_byts = (t.to(dev) for t in (h_hdr, h_tok, h_base, h_byts))
-    DEV_CHUNK = 8                                  # batches per device-resident call (bounds the output buffer)
+    DEV_CHUNK = 20                                 # batches per device-resident call (bounds the output buffer: 10.6 GB of FP32 maps at 1080p; the last batch of every call cannot overlap a next one)
     d_maps = torch.empty((min(max(a.steps, a.warmup, nprof), DEV_CHUNK) * B, h, w), dtype=torch.float32, device=dev)
     h_maps = torch.empty((E2E_CHUNK * B, h, w), dtype=torch.float32).pin_memory()
     h_cam = torch.zeros((4 * E2E_CHUNK * B, 2), dtype=torch.int32)
